@@ -1,0 +1,184 @@
+/*
+ * b200_demod.h — C ABI of the Blackwell-native Mode-S demodulator.
+ *
+ * This library replaces exactly one path of wiedehopf/readsb: the 2.4 MSPS Mode-S
+ * demodulator (uc8 IQ -> magnitude -> preamble detect -> 5-phase bit slice ->
+ * CRC-24 + 1-bit fix -> accepted frames).  Everything else in readsb stays the
+ * unchanged C host.  Reference interfaces replaced (file:line in the reference tree):
+ *
+ *   convert.h:34-39      iq_convert_fn(void *iq, uint16_t *mag, unsigned n, state*,
+ *                        double *mean_level, double *mean_power)      -> b200_demod_submit_iq_uc8
+ *   demod_2400.h:38      void demodulate2400(struct mag_buf *mag)    -> b200_demod_submit_mag_u16
+ *                                                                       + b200_demod_run + b200_demod_fetch
+ *   readsb.h:450-464     struct mag_buf {sampleTimestamp, mean_level, mean_power, length, data}
+ *                                                                    -> submit arguments + b200_buffer_result
+ *   demod_2400.c:401-471 netGetMM / fill timestamp,score,msg,signalLevel / decodeModesMessage
+ *                        accept test / netUseMessage                 -> b200_frame (one per accepted frame)
+ *   icao_filter.h        icaoFilterAdd / icaoFilterTest / icaoFilterExpire
+ *                                                                    -> b200_demod_icao_*
+ *   stats.h:62-83        struct stats demod_* counters              -> b200_demod_stats
+ *
+ * All entry points are plain C (extern "C"), take plain pointers and sizes, and return 0 on
+ * success or a negative B200_E_* code; b200_demod_last_error() gives the text.  There is no CPU
+ * fallback: if no sm_100-class CUDA device is usable, b200_demod_create() fails.
+ */
+#ifndef B200_DEMOD_H
+#define B200_DEMOD_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_DEMOD_ABI_VERSION 1
+
+/* readsb.c:288  trailing_samples = (8 + 112 + 16) us * 2.4 = 326 */
+#define B200_TRAILING_SAMPLES 326
+/* demod_2400.h:31 PREAMBLE_THRESHOLD_DEFAULT */
+#define B200_PREAMBLE_THRESHOLD_DEFAULT 58
+/* readsb.h MODES_ICAO_FILTER_TTL: two tables flipped every 60 s (readsb.c:1227-1231) */
+#define B200_ICAO_TTL_MS 60000
+
+enum {
+    B200_OK = 0,
+    B200_E_INVAL = -1,      /* bad argument */
+    B200_E_NODEV = -2,      /* no usable CUDA device (no CPU fallback exists) */
+    B200_E_CUDA = -3,       /* CUDA runtime error, see b200_demod_last_error */
+    B200_E_NOMEM = -4,
+    B200_E_STATE = -5,      /* call sequence error (e.g. submit queue full) */
+    B200_E_OVERFLOW = -6    /* caller-provided output array too small */
+};
+
+/* One accepted Mode-S frame: what demodulate2400() hands to netUseMessage()
+ * (demod_2400.c:401-471) restricted to the fields the demodulator itself produces. */
+typedef struct b200_frame {
+    int64_t  timestamp;     /* 12 MHz: sampleTimestamp + j*5 + (8+56)*12 + phase   (demod_2400.c:406) */
+    uint64_t sigpow_sum;    /* sum of mag^2 over signal_len samples from data[j+19] (demod_2400.c:443-446);
+                               signalLevel = sigpow_sum / 65535.0 / 65535.0 / signal_len */
+    uint32_t j;             /* preamble start: index into mag_buf.data (halo included) */
+    uint32_t crc;           /* mm->crc: syndrome after DF repair, before the bit fix (mode_s.c:466) */
+    uint32_t addr;          /* mm->addr: AA (DF11/17/18) or CRC-derived address (DF0/4/5/16/20/21) */
+    int32_t  score;         /* scoreModesMessage() value of the winning phase (mode_s.c:309) */
+    uint32_t buffer_seq;    /* per-stream running number of the buffer this frame was found in */
+    uint16_t signal_len;    /* msglen*12/5 with msglen taken from the UNrepaired DF (demod_2400.c:399,439) */
+    uint8_t  phase;         /* winning try_phase 4..8 */
+    uint8_t  msgtype;       /* DF after DF17 repair (mm->msgtype) */
+    uint8_t  msgbits;       /* 56 or 112 (mm->msgbits) */
+    uint8_t  correctedbits; /* 0 or 1 (mm->correctedbits) */
+    int8_t   fix_bit;       /* -1: none; 0..4: repaired DF bit; 5..111: CRC-corrected bit.
+                               raw (as-received) frame = msg with this message bit flipped back */
+    uint8_t  flags;         /* B200_FRAME_* */
+    uint8_t  msg[14];       /* corrected frame (mm->msg after decodeModesMessage); bytes >= msgbits/8 are 0 */
+    uint8_t  pad_[6];
+} b200_frame;
+
+#define B200_FRAME_ICAO_ADDED 0x01 /* this frame caused icaoFilterAdd(addr) (mode_s.c:766-779) */
+
+/* Per (stream, buffer) scalars: what convert_uc8_nodc() returns (convert.c:100-107) and what
+ * demodulate2400() folds into noise stats (demod_2400.c:474-479), kept as exact integers. */
+typedef struct b200_buffer_result {
+    int64_t  sample_timestamp;  /* as submitted */
+    uint64_t sum_level;         /* sum of mag over the buffer's new samples; mean_level = sum/65536.0/length */
+    uint64_t sum_power;         /* sum of mag^2;  mean_power = sum/65535.0/65535.0/length */
+    uint64_t sum_signal_power;  /* sum of sigpow_sum over frames accepted in this buffer */
+    uint32_t length;            /* new samples in this buffer */
+    uint32_t n_frames;          /* frames accepted in this buffer */
+    uint32_t buffer_seq;
+    uint32_t icao_flipped;      /* 1 if the ICAO filter tables were flipped after this buffer */
+} b200_buffer_result;
+
+/* Cumulative per-stream counters = Modes.stats_current demod_* (stats.h:62-83). */
+typedef struct b200_demod_stats {
+    uint64_t samples_processed;
+    uint64_t demod_preambles;
+    uint64_t demod_rejected_bad;
+    uint64_t demod_rejected_unknown_icao;
+    uint64_t demod_accepted[2];       /* by correctedbits */
+    uint64_t demod_preamblePhase[5];  /* every phase tried (demod_2400.c:216) */
+    uint64_t demod_bestPhase[5];
+    uint64_t signal_power_count;      /* sum of signal_len */
+    uint64_t sum_signal_power;        /* sum of sigpow_sum (integer form of signal_power_sum) */
+    uint64_t strong_signal_count;     /* signalLevel > 0.50119 */
+    uint64_t peak_sigpow_sum;         /* sigpow_sum and signal_len of the frame with the highest signalLevel */
+    uint64_t peak_signal_len;
+    uint64_t buffers;
+    uint64_t icao_flips;
+} b200_demod_stats;
+
+typedef struct b200_demod_config {
+    uint32_t struct_size;           /* = sizeof(b200_demod_config) */
+    int32_t  device;                /* CUDA ordinal; -1 = current device */
+    uint32_t n_streams;             /* independent receivers handled by this context */
+    uint32_t buf_samples;           /* Modes.sdr_buf_samples: max new samples per buffer (readsb.c:2212) */
+    uint32_t max_buffers_per_run;   /* how many buffers per stream one b200_demod_run may process */
+    int32_t  preamble_threshold;    /* Modes.preambleThreshold, 0 -> 58 (readsb.c:2268-2270) */
+    int32_t  nfix_crc;              /* 0 or 1 (--fix / --no-fix, readsb.c:1460-1464) */
+    int32_t  fix_df;                /* 0 or 1 (--no-fix-df, readsb.c:1467) */
+    int32_t  icao_ttl_ms;           /* automatic filter flip period in stream time, <0 = never, 0 -> 60000 */
+    uint32_t flags;                 /* reserved, 0 */
+} b200_demod_config;
+
+typedef struct b200_demod_ctx b200_demod_ctx;
+
+/* lifecycle ------------------------------------------------------------------------------------ */
+int  b200_demod_abi_version(void);
+int  b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out);
+void b200_demod_destroy(b200_demod_ctx *ctx);
+const char *b200_demod_last_error(const b200_demod_ctx *ctx); /* ctx may be NULL: last create error */
+
+/* pinned host memory for zero-staging submits (optional; any host pointer is accepted) */
+void *b200_demod_host_alloc(size_t bytes);
+void  b200_demod_host_free(void *p);
+
+/* host-buffer path (the drop-in) ---------------------------------------------------------------
+ * submit_iq_uc8 replaces the converter call a frontend makes (sdr_ifile.c:241, sdr_rtlsdr.c:395):
+ * `iq` holds nsamples interleaved unsigned 8-bit I,Q pairs; the halo of 326 preceding samples is
+ * kept by the library (zeros for the first buffer of a stream, sdr_ifile.c:209-213).
+ * submit_mag_u16 replaces demodulate2400(mag): `data` is mag_buf.data, i.e. 326 halo magnitudes
+ * followed by `length` new ones.  Buffers of one stream are processed in submission order.
+ * A stream must not mix the two submit kinds. */
+int b200_demod_submit_iq_uc8(b200_demod_ctx *ctx, uint32_t stream, const uint8_t *iq,
+                             uint32_t nsamples, int64_t sample_timestamp);
+int b200_demod_submit_mag_u16(b200_demod_ctx *ctx, uint32_t stream, const uint16_t *data,
+                              uint32_t length, int64_t sample_timestamp);
+/* Process everything submitted since the last run; returns when frames are in host memory. */
+int b200_demod_run(b200_demod_ctx *ctx);
+
+/* device-resident path (inputs already in HBM) ------------------------------------------------
+ * d_iq: device pointer; stream s starts at d_iq + s*stream_stride_bytes and holds
+ * n_buffers*buf_len contiguous uc8 IQ samples which are processed as n_buffers consecutive
+ * buffers of buf_len samples.  `continues` != 0 means the 326 samples before each stream's first
+ * sample (at negative offset) are valid halo from the previous call; 0 means stream start (zero halo).
+ * first_sample_timestamp applies to every stream.  Frames are fetched as for b200_demod_run. */
+int b200_demod_run_device_uc8(b200_demod_ctx *ctx, const uint8_t *d_iq, uint64_t stream_stride_bytes,
+                              uint32_t n_buffers, uint32_t buf_len, int continues,
+                              int64_t first_sample_timestamp);
+
+/* results of the last run ---------------------------------------------------------------------- */
+int b200_demod_frame_count(b200_demod_ctx *ctx, uint32_t stream, uint32_t *n);
+int b200_demod_fetch(b200_demod_ctx *ctx, uint32_t stream, b200_frame *out, uint32_t cap, uint32_t *n);
+int b200_demod_buffer_results(b200_demod_ctx *ctx, uint32_t stream, b200_buffer_result *out,
+                              uint32_t cap, uint32_t *n);
+int b200_demod_total_frames(b200_demod_ctx *ctx, uint64_t *n); /* all streams, last run */
+int b200_demod_get_stats(b200_demod_ctx *ctx, uint32_t stream, b200_demod_stats *out);
+
+/* ICAO address filter (icao_filter.h) — per stream, lives next to the resolver on the device */
+int b200_demod_icao_add(b200_demod_ctx *ctx, uint32_t stream, uint32_t addr);
+int b200_demod_icao_test(b200_demod_ctx *ctx, uint32_t stream, uint32_t addr, int *present);
+int b200_demod_icao_expire(b200_demod_ctx *ctx, uint32_t stream);
+int b200_demod_icao_reset(b200_demod_ctx *ctx, uint32_t stream);
+
+/* instrumentation: device time (ms) of the last run, by CUDA events on the library's stream:
+ * [0] whole run, [1] scan kernel (stage A), [2] resolve kernel (stage B), [3] H2D, [4] D2H.
+ * kernel_launches = number of the library's own kernel launches in the last run. */
+int b200_demod_last_timing(b200_demod_ctx *ctx, float ms[5], uint32_t *kernel_launches);
+
+/* UC8 lookup table the device uses (convert.c:35-62), 65536 entries, index = I*256+Q. */
+int b200_demod_uc8_lut(uint16_t *out65536);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_DEMOD_H */

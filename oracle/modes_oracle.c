@@ -1,0 +1,442 @@
+/*
+ * modes_oracle.c — CPU restatement of readsb's 2.4 MSPS Mode-S demodulator (TEST INFRASTRUCTURE).
+ *
+ * See modes_oracle.h for the role of this file and how it is pinned against the reference.
+ * Written from the behaviour of the reference (file:line cited per function), not from its text:
+ * the bit slicer uses the closed form  u = phase + 12*k, sample = j + 19 + u/5, correlator = u%5
+ * instead of the reference's unrolled slice_byte switch, the error tables are a direct
+ * syndrome scan, and the ICAO filter is a plain two-generation set.
+ *
+ * Build:  gcc -O2 -std=c11 -ffp-contract=off -fPIC -shared modes_oracle.c -o libmodes_oracle.so -lm
+ *         (-ffp-contract=off matters: the LUT arithmetic must round mul and add separately,
+ *          like the reference built with plain -O2 on x86-64.)
+ */
+#include "modes_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define TRAIL B200_TRAILING_SAMPLES
+
+/* ------------------------------------------------------------------ convert.c:35-62 */
+static uint16_t g_lut[65536];
+static int g_lut_ready;
+
+static void build_lut(void) {
+    if (g_lut_ready) return;
+    for (int i = 0; i < 256; i++) {
+        for (int q = 0; q < 256; q++) {
+            float fi = (float)((i - 127.5) / 127.5); /* double divide, then narrowed (convert.c:49) */
+            float fq = (float)((q - 127.5) / 127.5);
+            float magsq = fi * fi + fq * fq;          /* float mul, float add, no contraction */
+            if (magsq > 1) magsq = 1;
+            float mag = sqrtf(magsq);
+            /* index: the reference reads each I,Q byte pair as a little-endian uint16 (convert.c:70,78)
+             * into a table filled at [i*256+q]; the table is symmetric in i<->q so either order
+             * gives the same value. */
+            g_lut[i * 256 + q] = (uint16_t)(mag * 65535.0f + 0.5f);
+        }
+    }
+    g_lut_ready = 1;
+}
+
+void oracle_uc8_lut(uint16_t *out) {
+    build_lut();
+    memcpy(out, g_lut, sizeof(g_lut));
+}
+
+/* ------------------------------------------------------------------ convert.c:64-108 */
+void oracle_convert_uc8(const uint8_t *iq, uint16_t *mag, unsigned n, uint64_t *sum_level, uint64_t *sum_power) {
+    build_lut();
+    uint64_t sl = 0, sp = 0;
+    for (unsigned k = 0; k < n; k++) {
+        /* little-endian uint16 read of (I,Q): index = I + 256*Q */
+        unsigned idx = (unsigned)iq[2 * k] | ((unsigned)iq[2 * k + 1] << 8);
+        uint16_t m = g_lut[idx];
+        mag[k] = m;
+        sl += m;
+        sp += (uint64_t)((uint32_t)m * (uint32_t)m);
+    }
+    if (sum_level) *sum_level = sl;
+    if (sum_power) *sum_power = sp;
+}
+
+/* ------------------------------------------------------------------ crc.c:42-82 */
+#define POLY 0xfff409u
+static uint32_t g_crc_tab[256];
+static uint32_t g_bit_syn[112]; /* syndrome of a single set bit i of a 112-bit frame (crc.c:59-64) */
+static int g_crc_ready;
+
+uint32_t oracle_crc24(const uint8_t *msg, int bits) {
+    int n = bits / 8;
+    uint32_t rem = 0;
+    for (int i = 0; i < n - 3; i++)
+        rem = ((rem << 8) ^ g_crc_tab[msg[i] ^ ((rem >> 16) & 0xff)]) & 0xffffff;
+    return rem ^ ((uint32_t)msg[n - 3] << 16) ^ ((uint32_t)msg[n - 2] << 8) ^ msg[n - 1];
+}
+
+static void build_crc(void) {
+    if (g_crc_ready) return;
+    for (int i = 0; i < 256; i++) {
+        uint32_t c = (uint32_t)i << 16;
+        for (int j = 0; j < 8; j++) c = (c & 0x800000) ? ((c << 1) ^ POLY) : (c << 1);
+        g_crc_tab[i] = c & 0xffffff;
+    }
+    uint8_t m[14];
+    for (int i = 0; i < 112; i++) {
+        memset(m, 0, sizeof m);
+        m[i >> 3] = (uint8_t)(1u << (7 - (i & 7)));
+        g_bit_syn[i] = oracle_crc24(m, 112);
+    }
+    g_crc_ready = 1;
+}
+
+/* crc.c:180-406 with max_correct = 1: the table holds the syndromes of single-bit errors at message
+ * bits 5..bits-1 (DF bits are never corrected, crc.c:210-211); a short frame's bit i has the
+ * syndrome of long-frame bit i+56 (offset = 112-bits).  All 107 / 51 syndromes are distinct, so
+ * the bsearch is equivalent to this scan. */
+int oracle_crc_diagnose1(uint32_t syndrome, int bits) {
+    build_crc();
+    if (syndrome == 0) return -1;
+    int off = 112 - bits;
+    for (int b = 5; b < bits; b++)
+        if (g_bit_syn[b + off] == syndrome) return b;
+    return -2;
+}
+
+/* ------------------------------------------------------------------ icao_filter.c semantics
+ * Two generations; Test looks in both (icao_filter.c:132-154), Add goes to the active one
+ * (:112-130), Expire clears the other one and makes it active (:96-110).  The hash layout of
+ * the reference is unobservable; this is a growable open-addressed set of its own design. */
+typedef struct { uint32_t *slot; uint32_t cap, n; } aset;
+
+static void aset_init(aset *s) { s->cap = 1024; s->n = 0; s->slot = malloc(s->cap * 4); memset(s->slot, 0xff, s->cap * 4); }
+static void aset_clear(aset *s) { memset(s->slot, 0xff, s->cap * 4); s->n = 0; }
+static uint32_t aset_h(uint32_t a) { a *= 0x9E3779B1u; return a ^ (a >> 15); }
+static int aset_has(const aset *s, uint32_t a) {
+    uint32_t h = aset_h(a) & (s->cap - 1);
+    while (s->slot[h] != 0xffffffffu) { if (s->slot[h] == a) return 1; h = (h + 1) & (s->cap - 1); }
+    return 0;
+}
+static void aset_add(aset *s, uint32_t a) {
+    if (aset_has(s, a)) return;
+    if ((s->n + 1) * 2 > s->cap) {
+        aset t = { malloc(s->cap * 2 * 4), s->cap * 2, 0 };
+        memset(t.slot, 0xff, t.cap * 4);
+        for (uint32_t i = 0; i < s->cap; i++) if (s->slot[i] != 0xffffffffu) {
+            uint32_t h = aset_h(s->slot[i]) & (t.cap - 1);
+            while (t.slot[h] != 0xffffffffu) h = (h + 1) & (t.cap - 1);
+            t.slot[h] = s->slot[i]; t.n++;
+        }
+        free(s->slot); *s = t;
+    }
+    uint32_t h = aset_h(a) & (s->cap - 1);
+    while (s->slot[h] != 0xffffffffu) h = (h + 1) & (s->cap - 1);
+    s->slot[h] = a; s->n++;
+}
+
+struct oracle_ctx {
+    int thr, nfix, fixdf, ttl_ms;
+    uint32_t long_set, short_set;     /* demod_2400.c:98-128 */
+    aset gen[2]; int active;
+    int64_t next_flip; int flip_armed;
+    /* stream state for oracle_run_stream_uc8 */
+    uint16_t halo[TRAIL]; int halo_valid;
+    uint32_t buffer_seq;
+    b200_demod_stats st;
+    double peak_level;
+};
+
+void oracle_icao_add(oracle_ctx *o, uint32_t a) { aset_add(&o->gen[o->active], a); }
+int oracle_icao_test(const oracle_ctx *o, uint32_t a) { return aset_has(&o->gen[0], a) || aset_has(&o->gen[1], a); }
+void oracle_icao_expire(oracle_ctx *o) { o->active ^= 1; aset_clear(&o->gen[o->active]); o->st.icao_flips++; }
+
+oracle_ctx *oracle_create(int thr, int nfix, int fixdf, int ttl_ms) {
+    build_lut(); build_crc();
+    oracle_ctx *o = calloc(1, sizeof *o);
+    o->thr = thr ? thr : B200_PREAMBLE_THRESHOLD_DEFAULT;
+    o->nfix = nfix ? 1 : 0; o->fixdf = fixdf ? 1 : 0;
+    o->ttl_ms = ttl_ms == 0 ? B200_ICAO_TTL_MS : ttl_ms;
+    /* demod_2400.c:112-127: DFs understood directly, plus every DF one bit away from 17 when
+     * DF repair is on (generate_damage_set(17,1) = {17,16,19,21,25,1}). */
+    o->short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
+    o->long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
+    if (o->fixdf && o->nfix) {
+        o->long_set |= 1u << 17;
+        for (int b = 0; b < 5; b++) o->long_set |= 1u << (17 ^ (1 << b));
+    }
+    aset_init(&o->gen[0]); aset_init(&o->gen[1]);
+    return o;
+}
+
+void oracle_destroy(oracle_ctx *o) { if (!o) return; free(o->gen[0].slot); free(o->gen[1].slot); free(o); }
+void oracle_get_stats(const oracle_ctx *o, b200_demod_stats *out) { *out = o->st; }
+
+/* ------------------------------------------------------------------ demod_2400.c:74-93, 133-213
+ * Correlator u%5 applied at sample j+19+u/5 for u = try_phase + 12*bit. */
+static inline int slice_bit(const uint16_t *m, int row) {
+    switch (row) {
+        case 0: return 18 * m[0] - 15 * m[1] - 3 * m[2] > 0;
+        case 1: return 14 * m[0] - 5 * m[1] - 9 * m[2] > 0;
+        case 2: return 16 * m[0] + 5 * m[1] - 20 * m[2] > 0;
+        case 3: return 7 * m[0] + 11 * m[1] - 18 * m[2] > 0;
+        default: return 4 * m[0] + 15 * m[1] - 20 * m[2] + m[3] > 0;
+    }
+}
+
+static void slice_bytes(const uint16_t *pa, int phase, int first_byte, int nbytes, uint8_t *msg) {
+    for (int by = first_byte; by < nbytes; by++) {
+        unsigned v = 0;
+        for (int b = 0; b < 8; b++) {
+            int u = phase + 12 * (by * 8 + b);
+            v = (v << 1) | (unsigned)slice_bit(pa + 19 + u / 5, u % 5);
+        }
+        msg[by] = (uint8_t)v;
+    }
+}
+
+static inline uint32_t aa_field(const uint8_t *m) { return ((uint32_t)m[1] << 16) | ((uint32_t)m[2] << 8) | m[3]; }
+
+/* What one sliced phase looks like before the ICAO filter is consulted. */
+typedef struct {
+    uint8_t msg[14];
+    int df;          /* DF as sliced */
+    int nbytes;      /* bytes sliced (7/14) */
+    int dfrepair;    /* fixDF17msgtype would succeed (mode_s.c:276-301) */
+    uint32_t crc;    /* syndrome over modesMessageLenByType(df) bits of the unrepaired frame */
+    int fixbit;      /* -1 crc==0 (or IID-only for DF11), >=5 correctable bit, -2 uncorrectable */
+} sliced;
+
+/* mode_s.c:309-419.  Returns the score; *addr_out = address that was looked up (for diagnostics). */
+static int score_sliced(const oracle_ctx *o, const sliced *s) {
+    const uint8_t *msg = s->msg;
+    if (s->dfrepair) /* mode_s.c:319-329 */
+        return oracle_icao_test(o, aa_field(msg)) ? 900 : 700;
+    int df = s->df;
+    /* validbits < msgbits cannot happen: nbytes was chosen from the DF. mode_s.c:336-338: */
+    static const uint8_t z[7] = {0};
+    if (!memcmp(msg, z, 7)) return -2;
+    uint32_t crc = s->crc;
+    switch (df) {
+        case 0: case 4: case 5: case 16: case 20: case 21:
+            return oracle_icao_test(o, crc) ? 1000 : -1;
+        case 11: {
+            uint32_t addr = aa_field(msg);
+            if (crc & 0xffff80) {
+                if (s->fixbit < 5) return -2;                       /* no table entry (or nfix=0) */
+                if (s->fixbit >= 8 && s->fixbit <= 31) addr ^= 1u << (31 - s->fixbit); /* mode_s.c:230-245 */
+                return oracle_icao_test(o, addr) ? 800 : -1;
+            }
+            if ((crc & 0x7f) == 0) return oracle_icao_test(o, addr) ? 1600 : 750;
+            return oracle_icao_test(o, addr) ? 1000 : -1;
+        }
+        case 17: case 18: {
+            if (s->fixbit == -2) return -2;
+            uint32_t addr = aa_field(msg);
+            int e = s->fixbit >= 5 ? 1 : 0;
+            if (e && s->fixbit >= 8 && s->fixbit <= 31) addr ^= 1u << (31 - s->fixbit);
+            return oracle_icao_test(o, addr) ? 1800 / (e + 1) : 1400 / (e + 1);
+        }
+        default:
+            return -2;
+    }
+}
+
+/* demod_2400.c:215-258 up to the score: slice, DF gate, CRC work that does not depend on the filter. */
+static int slice_phase(const oracle_ctx *o, const uint16_t *pa, int phase, sliced *s) {
+    slice_bytes(pa, phase, 0, 1, s->msg);
+    int df = s->msg[0] >> 3;
+    s->df = df;
+    if (o->long_set & (1u << df)) s->nbytes = 14;
+    else if (o->short_set & (1u << df)) s->nbytes = 7;
+    else return 0; /* score -2 without slicing further */
+    slice_bytes(pa, phase, 1, s->nbytes, s->msg);
+    memset(s->msg + s->nbytes, 0, 14 - s->nbytes);
+    s->dfrepair = 0;
+    if (s->nbytes == 14 && o->fixdf && o->nfix && (df == 1 || df == 25 || df == 21 || df == 19 || df == 16)) {
+        uint8_t t[14];
+        memcpy(t, s->msg, 14);
+        t[0] = (uint8_t)((t[0] & 7) | (17 << 3));
+        if (oracle_crc24(t, 112) == 0) s->dfrepair = 1;
+    }
+    int bits = (df & 0x10) ? 112 : 56; /* mode_s.h:124 */
+    s->crc = oracle_crc24(s->msg, bits);
+    s->fixbit = -2;
+    if (df == 11) {
+        if (!(s->crc & 0xffff80)) s->fixbit = -1;
+        else if (o->nfix) s->fixbit = oracle_crc_diagnose1(s->crc, bits);
+    } else if (df == 17 || df == 18) {
+        if (s->crc == 0) s->fixbit = -1;
+        else if (o->nfix) s->fixbit = oracle_crc_diagnose1(s->crc, bits);
+    }
+    return 1;
+}
+
+/* ------------------------------------------------------------------ demod_2400.c:264-482 */
+int oracle_demodulate2400(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64_t sample_ts,
+                          uint64_t sum_level, uint64_t sum_power,
+                          b200_frame *out, unsigned cap, unsigned *n_out, b200_buffer_result *res) {
+    b200_demod_stats *st = &o->st;
+    uint64_t sum_sig = 0;
+    unsigned nfr = 0;
+    int overflow = 0;
+    int64_t now_ms = sample_ts / 12000; /* synthetic clock: buffer start (demod_2400.c:283-285) */
+
+    for (unsigned j = 0; j < mlen; j++) {
+        const uint16_t *pa = m + j;
+        /* pre-check, demod_2400.c:311-320 (the reference's unroll tests every position) */
+        if (!(pa[1] > pa[7] && pa[12] > pa[14] && pa[12] > pa[15])) continue;
+        /* demod_2400.c:330-340 (samples_dropped never set on this path) */
+        int32_t base_noise = pa[5] + pa[8] + pa[16] + pa[17] + pa[18];
+        int32_t ref_level = (int32_t)((uint32_t)base_noise * (uint32_t)o->thr) >> 5;
+        int32_t d23 = pa[2] - pa[3], s14 = pa[1] + pa[4], d1011 = pa[10] - pa[11];
+        int32_t common = s14 - d23 + pa[9] + pa[12];
+        int tryp[5], ntry = 0;
+        if (common - d1011 >= ref_level) { tryp[ntry++] = 4; tryp[ntry++] = 5; }
+        if (common + d1011 >= ref_level) { tryp[ntry++] = 6; tryp[ntry++] = 7; }
+        if (s14 + 2 * d23 + d1011 + pa[12] >= ref_level) tryp[ntry++] = 8;
+        if (!ntry) continue;
+
+        int bestscore = -42, bestphase = 0;
+        sliced best, cur;
+        memset(&best, 0, sizeof best);
+        for (int t = 0; t < ntry; t++) {
+            st->demod_preamblePhase[tryp[t] - 4]++;
+            int score = -2;
+            if (slice_phase(o, pa, tryp[t], &cur)) score = score_sliced(o, &cur);
+            if (score > bestscore) { /* strictly greater: earliest phase wins ties (demod_2400.c:243) */
+                bestscore = score;
+                if (score > -2) { best = cur; bestphase = tryp[t]; }
+            }
+        }
+        st->demod_preambles++;
+        if (bestscore < 0) {
+            if (bestscore == -1) st->demod_rejected_unknown_icao++; else st->demod_rejected_bad++;
+            continue;
+        }
+
+        /* accept part of decodeModesMessage, mode_s.c:443-596 + :766-779 */
+        int msgtype = best.df, corrected = 0, fix_bit = -1;
+        uint8_t msg[14];
+        memcpy(msg, best.msg, 14);
+        if (best.dfrepair) {
+            fix_bit = 0; /* which DF bit differs from 17 */
+            int x = best.df ^ 17;
+            while (!((x << fix_bit) & 0x10)) fix_bit++;
+            msg[0] = (uint8_t)((msg[0] & 7) | (17 << 3));
+            msgtype = 17; corrected = 1;
+        }
+        int msgbits = (msgtype & 0x10) ? 112 : 56;
+        uint32_t crc = best.dfrepair ? 0 : best.crc; /* mode_s.c:466 recomputed after repair */
+        uint32_t addr;
+        int result = 0, add_to_filter = 0;
+        switch (msgtype) {
+            case 0: case 4: case 5: case 16: case 20: case 21:
+                addr = crc;
+                if (!oracle_icao_test(o, crc)) result = -1;
+                break;
+            case 11:
+                if (crc & 0xffff80) {
+                    if (best.fixbit < 5) { result = -2; addr = 0; break; }
+                    corrected = 1; fix_bit = best.fixbit;
+                    msg[fix_bit >> 3] ^= (uint8_t)(1u << (7 - (fix_bit & 7)));
+                    addr = aa_field(msg);
+                    if (!oracle_icao_test(o, addr)) result = -1;
+                } else {
+                    addr = aa_field(msg);
+                    if ((crc & 0x7f) == 0) add_to_filter = 1; /* IID == 0, no corrected bits */
+                }
+                break;
+            case 17: case 18:
+                addr = aa_field(msg);
+                if (crc != 0) {
+                    if (best.fixbit < 5) { result = -2; break; }
+                    uint32_t addr1 = addr;
+                    corrected = 1; fix_bit = best.fixbit;
+                    msg[fix_bit >> 3] ^= (uint8_t)(1u << (7 - (fix_bit & 7)));
+                    addr = aa_field(msg);
+                    if (addr1 != addr && !oracle_icao_test(o, addr)) result = -1;
+                } else if (msgtype == 17 && !corrected) {
+                    add_to_filter = 1;
+                }
+                break;
+            default:
+                result = -2; addr = 0;
+        }
+        if (result < 0) {
+            if (result == -1) st->demod_rejected_unknown_icao++; else st->demod_rejected_bad++;
+            continue; /* no skip, demod_2400.c:422-428 */
+        }
+        if (add_to_filter) oracle_icao_add(o, addr);
+        st->demod_accepted[corrected]++;
+        st->demod_bestPhase[bestphase - 4]++;
+
+        /* demod_2400.c:399,436-457: msglen comes from the DF as sliced (score restored byte 0) */
+        int msglen = (best.df & 0x10) ? 112 : 56;
+        int signal_len = msglen * 12 / 5;
+        uint64_t sp = 0;
+        for (int k = 0; k < signal_len; k++) { uint32_t v = pa[19 + k]; sp += (uint64_t)(v * v); }
+        sum_sig += sp;
+        st->signal_power_count += (uint64_t)signal_len;
+        st->sum_signal_power += sp;
+        double level = (double)sp / 65535.0 / 65535.0 / signal_len;
+        if (level > o->peak_level) { o->peak_level = level; st->peak_sigpow_sum = sp; st->peak_signal_len = (uint64_t)signal_len; }
+        if (level > 0.50119) st->strong_signal_count++;
+
+        int64_t ts = sample_ts + (int64_t)j * 5 + (8 + 56) * 12 + bestphase; /* demod_2400.c:406 */
+        now_ms = sample_ts / 12000 + (ts - sample_ts) / 12000;             /* :409-414 */
+        if (*n_out < cap) {
+            b200_frame *f = &out[(*n_out)++];
+            memset(f, 0, sizeof *f);
+            f->timestamp = ts; f->sigpow_sum = sp; f->j = j; f->crc = crc; f->addr = addr;
+            f->score = bestscore; f->buffer_seq = o->buffer_seq; f->signal_len = (uint16_t)signal_len;
+            f->phase = (uint8_t)bestphase; f->msgtype = (uint8_t)msgtype; f->msgbits = (uint8_t)msgbits;
+            f->correctedbits = (uint8_t)corrected; f->fix_bit = (int8_t)fix_bit;
+            f->flags = add_to_filter ? B200_FRAME_ICAO_ADDED : 0;
+            memcpy(f->msg, msg, (size_t)msgbits / 8);
+        } else overflow = 1;
+        nfr++;
+        j += (unsigned)msglen * 2; /* demod_2400.c:468; the loop adds the +1 */
+    }
+
+    st->samples_processed += mlen;
+    st->buffers++;
+    int flipped = 0;
+    /* readsb.c:901,1227-1231: backgroundTasks() after each buffer, on the synthetic clock */
+    if (o->ttl_ms > 0 && (!o->flip_armed || now_ms >= o->next_flip)) {
+        oracle_icao_expire(o);
+        o->next_flip = now_ms + o->ttl_ms; o->flip_armed = 1; flipped = 1;
+    }
+    if (res) {
+        res->sample_timestamp = sample_ts; res->sum_level = sum_level; res->sum_power = sum_power;
+        res->sum_signal_power = sum_sig; res->length = mlen; res->n_frames = nfr;
+        res->buffer_seq = o->buffer_seq; res->icao_flipped = (uint32_t)flipped;
+    }
+    o->buffer_seq++;
+    return overflow ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------ sdr_ifile.c:169-259 */
+long oracle_run_stream_uc8(oracle_ctx *o, const uint8_t *iq, uint64_t nsamples, unsigned buf_samples,
+                           int64_t first_ts, b200_frame *frames, unsigned frame_cap,
+                           b200_buffer_result *bufres, unsigned bufres_cap, unsigned *n_bufres) {
+    uint16_t *data = malloc(((size_t)buf_samples + TRAIL) * 2);
+    unsigned nf = 0, nb = 0;
+    int bad = 0;
+    for (uint64_t off = 0; off < nsamples; off += buf_samples) {
+        unsigned len = (unsigned)((nsamples - off < buf_samples) ? nsamples - off : buf_samples);
+        /* overlap copy, zeros when the previous buffer was too short (sdr_ifile.c:209-213) */
+        if (o->halo_valid) memcpy(data, o->halo, TRAIL * 2); else memset(data, 0, TRAIL * 2);
+        uint64_t sl, sp;
+        oracle_convert_uc8(iq + off * 2, data + TRAIL, len, &sl, &sp);
+        b200_buffer_result r;
+        if (oracle_demodulate2400(o, data, len, first_ts + (int64_t)off * 5, sl, sp, frames, frame_cap, &nf, &r) < 0) bad = 1;
+        if (nb < bufres_cap && bufres) bufres[nb] = r;
+        nb++;
+        if (len >= TRAIL) { memcpy(o->halo, data + len, TRAIL * 2); o->halo_valid = 1; } else o->halo_valid = 0;
+    }
+    free(data);
+    if (n_bufres) *n_bufres = nb;
+    return bad ? -1 : (long)nf;
+}

@@ -1,0 +1,225 @@
+"""ctypes front ends of the parity oracle (oracle/libmodes_oracle.so) and of the reference built as a
+library (oracle/_ref/libreadsb_ref.so).  TEST INFRASTRUCTURE — never imported by readsb_b200."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+from readsb_b200.abi import BUFRES_DTYPE, FRAME_DTYPE, BufferResult, Stats
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_SO = ROOT / "oracle" / "libmodes_oracle.so"
+REF_SO = ROOT / "oracle" / "_ref" / "libreadsb_ref.so"
+
+
+def _ensure_built():
+    if not ORACLE_SO.exists() or (Path("/root/reference/demod_2400.c").exists() and not REF_SO.exists()):
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "CC=gcc"], check=True, capture_output=True)
+
+
+def have_ref() -> bool:
+    _ensure_built()
+    return REF_SO.exists()
+
+
+class Oracle:
+    """One receiver's worth of the CPU restatement."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            _ensure_built()
+            L = C.CDLL(str(ORACLE_SO))
+            L.oracle_create.restype = C.c_void_p
+            L.oracle_create.argtypes = [C.c_int] * 4
+            L.oracle_destroy.argtypes = [C.c_void_p]
+            L.oracle_uc8_lut.argtypes = [C.c_void_p]
+            L.oracle_convert_uc8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+            L.oracle_crc24.restype = C.c_uint32
+            L.oracle_crc24.argtypes = [C.c_void_p, C.c_int]
+            L.oracle_crc_diagnose1.argtypes = [C.c_uint32, C.c_int]
+            L.oracle_demodulate2400.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int64, C.c_uint64, C.c_uint64,
+                                                C.c_void_p, C.c_uint, C.POINTER(C.c_uint), C.POINTER(BufferResult)]
+            L.oracle_run_stream_uc8.restype = C.c_long
+            L.oracle_run_stream_uc8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int64, C.c_void_p,
+                                                C.c_uint, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
+            L.oracle_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+            L.oracle_icao_add.argtypes = [C.c_void_p, C.c_uint32]
+            L.oracle_icao_test.argtypes = [C.c_void_p, C.c_uint32]
+            L.oracle_icao_expire.argtypes = [C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, preamble_threshold=58, nfix_crc=1, fix_df=1, icao_ttl_ms=60000):
+        self.L = self.lib()
+        self.h = self.L.oracle_create(preamble_threshold, nfix_crc, fix_df, icao_ttl_ms)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.oracle_destroy(self.h)
+            self.h = None
+
+    @classmethod
+    def lut(cls) -> np.ndarray:
+        out = np.empty(65536, dtype=np.uint16)
+        cls.lib().oracle_uc8_lut(out.ctypes.data)
+        return out
+
+    @classmethod
+    def convert(cls, iq: np.ndarray):
+        n = iq.size // 2
+        mag = np.empty(n, dtype=np.uint16)
+        sl, sp = C.c_uint64(), C.c_uint64()
+        cls.lib().oracle_convert_uc8(iq.ctypes.data, mag.ctypes.data, n, C.byref(sl), C.byref(sp))
+        return mag, sl.value, sp.value
+
+    @classmethod
+    def crc24(cls, msg: bytes) -> int:
+        buf = (C.c_uint8 * len(msg)).from_buffer_copy(msg)
+        return cls.lib().oracle_crc24(buf, len(msg) * 8)
+
+    @classmethod
+    def diagnose1(cls, syndrome: int, bits: int) -> int:
+        return cls.lib().oracle_crc_diagnose1(syndrome, bits)
+
+    def demodulate(self, data: np.ndarray, length: int, sample_ts: int, sum_level=0, sum_power=0, cap=8192):
+        assert data.dtype == np.uint16 and data.size >= length + 326
+        frames = np.zeros(cap, dtype=FRAME_DTYPE)
+        n = C.c_uint(0)
+        res = BufferResult()
+        rc = self.L.oracle_demodulate2400(self.h, data.ctypes.data, length, sample_ts, sum_level, sum_power,
+                                          frames.ctypes.data, cap, C.byref(n), C.byref(res))
+        assert rc == 0
+        return frames[: n.value].copy(), res
+
+    def run_stream(self, iq: np.ndarray, buf_samples: int, first_ts: int = 0, cap: int | None = None):
+        nsamples = iq.size // 2
+        cap = cap or max(1024, nsamples // 100)
+        nbuf_cap = nsamples // buf_samples + 2
+        frames = np.zeros(cap, dtype=FRAME_DTYPE)
+        bufres = np.zeros(nbuf_cap, dtype=BUFRES_DTYPE)
+        nb = C.c_uint(0)
+        n = self.L.oracle_run_stream_uc8(self.h, iq.ctypes.data, nsamples, buf_samples, first_ts, frames.ctypes.data,
+                                         cap, bufres.ctypes.data, nbuf_cap, C.byref(nb))
+        assert n >= 0, "oracle frame capacity exceeded"
+        return frames[:n].copy(), bufres[: nb.value].copy()
+
+    def stats(self) -> dict:
+        s = Stats()
+        self.L.oracle_get_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    def icao_add(self, a):
+        self.L.oracle_icao_add(self.h, a)
+
+    def icao_test(self, a) -> bool:
+        return bool(self.L.oracle_icao_test(self.h, a))
+
+    def icao_expire(self):
+        self.L.oracle_icao_expire(self.h)
+
+
+class Reference:
+    """The reference's own demodulator (one receiver per loaded copy: readsb keeps its state in globals,
+    so every instance dlopens a private copy of the library)."""
+
+    def __init__(self, preamble_threshold=58, nfix_crc=1, fix_df=1, icao_ttl_ms=60000):
+        assert have_ref(), "reference library not built (needs /root/reference)"
+        self._tmp = tempfile.NamedTemporaryFile(prefix="readsb_ref_", suffix=".so", delete=False)
+        self._tmp.close()
+        shutil.copyfile(REF_SO, self._tmp.name)
+        L = self.L = C.CDLL(self._tmp.name)
+        os.unlink(self._tmp.name)
+        L.ref_init.argtypes = [C.c_int] * 4
+        L.ref_uc8_lut.argtypes = [C.c_void_p]
+        L.ref_convert_uc8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_crc24.restype = C.c_uint32
+        L.ref_crc24.argtypes = [C.c_void_p, C.c_int]
+        L.ref_crc_diagnose1.argtypes = [C.c_uint32, C.c_int]
+        L.ref_score.argtypes = [C.c_void_p, C.c_int]
+        L.ref_icao_add.argtypes = [C.c_uint32]
+        L.ref_icao_test.argtypes = [C.c_uint32]
+        L.ref_demodulate2400.argtypes = [C.c_void_p, C.c_uint, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.c_uint, C.POINTER(C.c_uint), C.POINTER(BufferResult)]
+        L.ref_run_stream_uc8.restype = C.c_long
+        L.ref_run_stream_uc8.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
+        L.ref_get_stats.argtypes = [C.POINTER(Stats), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_time_stream_uc8.restype = C.c_double
+        L.ref_time_stream_uc8.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.POINTER(C.c_uint)]
+        assert L.ref_init(preamble_threshold, nfix_crc, fix_df, icao_ttl_ms) == 0
+
+    def lut(self) -> np.ndarray:
+        out = np.empty(65536, dtype=np.uint16)
+        self.L.ref_uc8_lut(out.ctypes.data)
+        return out
+
+    def convert(self, iq: np.ndarray):
+        n = iq.size // 2
+        mag = np.empty(n, dtype=np.uint16)
+        ml, mp = C.c_double(), C.c_double()
+        self.L.ref_convert_uc8(iq.ctypes.data, mag.ctypes.data, n, C.byref(ml), C.byref(mp))
+        return mag, ml.value, mp.value
+
+    def crc24(self, msg: bytes) -> int:
+        buf = (C.c_uint8 * len(msg)).from_buffer_copy(msg)
+        return self.L.ref_crc24(buf, len(msg) * 8)
+
+    def diagnose1(self, syndrome: int, bits: int) -> int:
+        return self.L.ref_crc_diagnose1(syndrome, bits)
+
+    def score(self, msg: bytes, validbits: int) -> int:
+        buf = (C.c_uint8 * 14).from_buffer_copy(msg.ljust(14, b"\0"))
+        return self.L.ref_score(buf, validbits)
+
+    def demodulate(self, data: np.ndarray, length: int, sample_ts: int, mean_level=0.0, mean_power=0.0, cap=8192):
+        frames = np.zeros(cap, dtype=FRAME_DTYPE)
+        levels = np.zeros(cap, dtype=np.float64)
+        n = C.c_uint(0)
+        res = BufferResult()
+        rc = self.L.ref_demodulate2400(data.ctypes.data, length, sample_ts, mean_level, mean_power, frames.ctypes.data,
+                                       levels.ctypes.data, cap, C.byref(n), C.byref(res))
+        assert rc == 0
+        return frames[: n.value].copy(), levels[: n.value].copy(), res
+
+    def run_stream(self, iq: np.ndarray, buf_samples: int, first_ts: int = 0, cap: int | None = None):
+        nsamples = iq.size // 2
+        cap = cap or max(1024, nsamples // 100)
+        nbuf_cap = nsamples // buf_samples + 2
+        frames = np.zeros(cap, dtype=FRAME_DTYPE)
+        levels = np.zeros(cap, dtype=np.float64)
+        bufres = np.zeros(nbuf_cap, dtype=BUFRES_DTYPE)
+        ml = np.zeros(nbuf_cap)
+        mp = np.zeros(nbuf_cap)
+        nb = C.c_uint(0)
+        n = self.L.ref_run_stream_uc8(iq.ctypes.data, nsamples, buf_samples, first_ts, frames.ctypes.data,
+                                      levels.ctypes.data, cap, bufres.ctypes.data, ml.ctypes.data, mp.ctypes.data,
+                                      nbuf_cap, C.byref(nb))
+        assert n >= 0
+        k = nb.value
+        return frames[:n].copy(), levels[:n].copy(), bufres[:k].copy(), ml[:k].copy(), mp[:k].copy()
+
+    def stats(self):
+        s = Stats()
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.L.ref_get_stats(C.byref(s), C.byref(a), C.byref(b), C.byref(c))
+        return s.as_dict(), {"signal_power_sum": a.value, "noise_power_sum": b.value, "peak_signal_power": c.value}
+
+    def icao_add(self, a):
+        self.L.ref_icao_add(a)
+
+    def icao_test(self, a) -> bool:
+        return bool(self.L.ref_icao_test(a))
+
+    def time_stream(self, iq: np.ndarray, buf_samples: int):
+        nf = C.c_uint(0)
+        secs = self.L.ref_time_stream_uc8(iq.ctypes.data, iq.size // 2, buf_samples, C.byref(nf))
+        return secs, nf.value
