@@ -101,8 +101,8 @@ typedef struct b200_demod_stats {
     uint64_t signal_power_count;      /* sum of signal_len */
     uint64_t sum_signal_power;        /* sum of sigpow_sum (integer form of signal_power_sum) */
     uint64_t strong_signal_count;     /* signalLevel > 0.50119 */
-    uint64_t peak_sigpow_sum;         /* sigpow_sum and signal_len of the frame with the highest signalLevel */
-    uint64_t peak_signal_len;
+    double   peak_signal_power;       /* highest signalLevel seen (stats.h peak_signal_power) */
+    uint64_t reserved_;
     uint64_t buffers;
     uint64_t icao_flips;
 } b200_demod_stats;
@@ -174,6 +174,10 @@ int b200_demod_icao_reset(b200_demod_ctx *ctx, uint32_t stream);
  * [0] whole run, [1] scan kernel (stage A), [2] resolve kernel (stage B), [3] H2D, [4] D2H.
  * kernel_launches = number of the library's own kernel launches in the last run. */
 int b200_demod_last_timing(b200_demod_ctx *ctx, float ms[5], uint32_t *kernel_launches);
+
+/* test instrumentation: [0] tiles, [1] threshold-passing positions, [2] filter-dependent records,
+ * [3] record pool use, [4] overflow flags, [5] segments, [6] buffers, [7] frames — of the last run */
+int b200_demod_debug_counters(b200_demod_ctx *ctx, uint64_t out[8]);
 
 /* UC8 lookup table the device uses (convert.c:35-62), 65536 entries, index = I*256+Q. */
 int b200_demod_uc8_lut(uint16_t *out65536);

@@ -145,7 +145,6 @@ struct oracle_ctx {
     uint16_t halo[TRAIL]; int halo_valid;
     uint32_t buffer_seq;
     b200_demod_stats st;
-    double peak_level;
 };
 
 void oracle_icao_add(oracle_ctx *o, uint32_t a) { aset_add(&o->gen[o->active], a); }
@@ -381,7 +380,7 @@ int oracle_demodulate2400(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64
         st->signal_power_count += (uint64_t)signal_len;
         st->sum_signal_power += sp;
         double level = (double)sp / 65535.0 / 65535.0 / signal_len;
-        if (level > o->peak_level) { o->peak_level = level; st->peak_sigpow_sum = sp; st->peak_signal_len = (uint64_t)signal_len; }
+        if (level > st->peak_signal_power) st->peak_signal_power = level;
         if (level > 0.50119) st->strong_signal_count++;
 
         int64_t ts = sample_ts + (int64_t)j * 5 + (8 + 56) * 12 + bestphase; /* demod_2400.c:406 */

@@ -216,6 +216,7 @@ void ref_get_stats(b200_demod_stats *out, double *signal_power_sum, double *nois
     for (int i = 0; i < 5; i++) { out->demod_preamblePhase[i] = s->demod_preamblePhase[i]; out->demod_bestPhase[i] = s->demod_bestPhase[i]; }
     out->signal_power_count = s->signal_power_count;
     out->strong_signal_count = s->strong_signal_count;
+    out->peak_signal_power = s->peak_signal_power;
     out->buffers = g_buffers;
     out->icao_flips = g_flips;
     if (signal_power_sum) *signal_power_sum = s->signal_power_sum;

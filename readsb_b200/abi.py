@@ -28,14 +28,14 @@ class Stats(C.Structure):
                 ("demod_accepted", C.c_uint64 * 2), ("demod_preamblePhase", C.c_uint64 * 5),
                 ("demod_bestPhase", C.c_uint64 * 5), ("signal_power_count", C.c_uint64),
                 ("sum_signal_power", C.c_uint64), ("strong_signal_count", C.c_uint64),
-                ("peak_sigpow_sum", C.c_uint64), ("peak_signal_len", C.c_uint64), ("buffers", C.c_uint64),
+                ("peak_signal_power", C.c_double), ("reserved_", C.c_uint64), ("buffers", C.c_uint64),
                 ("icao_flips", C.c_uint64)]
 
     def as_dict(self):
         d = {}
         for name, typ in self._fields_:
             v = getattr(self, name)
-            d[name] = list(v) if hasattr(v, "__len__") else int(v)
+            d[name] = list(v) if hasattr(v, "__len__") else (float(v) if isinstance(v, float) else int(v))
         return d
 
 

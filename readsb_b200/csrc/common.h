@@ -1,0 +1,182 @@
+// common.h — structures shared by the kernels (demod_kernels.cu) and the C ABI (demod_api.cu).
+//
+// Data layout in HBM:
+//   * input: 2 bytes per sample either way (uc8 I,Q pair, or one uint16 magnitude), so one
+//     address rule serves both: byte address of data index d = seg.base + 2*d, where data index 0 is
+//     the first of the 326 halo samples (readsb.h:450-464 `mag_buf.data`).
+//   * a SEGMENT is a run of consecutive preamble start positions of one receiver whose samples are
+//     contiguous in memory; it may span several reference "buffers" (boundary every buf_len
+//     positions) because consecutive mag_bufs tile the sample axis without gaps
+//     (sdr_ifile.c:209-213: the halo of buffer b+1 is the tail of buffer b).
+//   * stage A (scan kernel) is stateless per position and writes, per tile of TILE positions, an
+//     ordered list of PosEntry (every position that passed a preamble threshold) and an ordered
+//     list of Rec (every sliced phase whose score depends on the ICAO filter).
+//   * stage B (resolve kernel) walks those lists sequentially per receiver with the receiver's
+//     ICAO filter and emits frames.
+#pragma once
+#include <stdint.h>
+#include "b200_demod.h"
+
+#define B200_TRAIL 326
+
+// ---- stage A tiling ----------------------------------------------------------------------------
+#define SCAN_TILE      8192          // preamble start positions per tile
+#define SCAN_THREADS   512
+#define SCAN_LOOKAHEAD 328           // samples kept after the last position of a tile: >= 291 for the slicer, >= 326 so the last tile of a segment sees (and sums) the tail; multiple of 8
+#define SCAN_NMAG      (SCAN_TILE + SCAN_LOOKAHEAD)
+#define SCAN_Q1_CAP    (SCAN_TILE / 4)   // positions passing the pre-check, per tile
+#define SCAN_ITEM_CAP  (SCAN_TILE / 8)   // (position, phase) pairs passing a threshold, per tile
+#define SCAN_FULL_CAP  768             // live records per tile staged in shared memory
+
+// ---- segment descriptor ------------------------------------------------------------------------
+#define SEG_MAG        0x1u   // input samples are uint16 magnitudes (demodulate2400 hand-off), not uc8 IQ
+#define SEG_HALO_ZERO  0x2u   // data indices [0,326) are zeros (first buffer of a stream); memory not read
+
+struct Segment {
+    const uint8_t *base;   // byte address of data index 0 (may be unaligned by a multiple of 2)
+    int64_t  first_ts;     // 12 MHz timestamp of the first NEW sample (data index 326)
+    uint32_t npos;         // preamble start positions = new samples in the segment
+    uint32_t buf_len;      // reference buffer length: skip state resets every buf_len positions
+    uint32_t lead;         // ((uintptr_t)base & 15) / 2: dummy positions so tile origins are 16B aligned
+    uint32_t flags;        // SEG_*
+    uint32_t stream;
+    uint32_t first_buf;    // index of this segment's first buffer in the run's BufAcc / BufOut arrays
+    uint32_t n_bufs;
+    uint32_t tile_begin;   // global index of this segment's first tile
+    uint32_t n_tiles;
+    uint32_t first_seq;    // buffer_seq of the segment's first buffer
+    uint32_t pad_[2];
+};
+
+// One position whose preamble correlation reached the threshold (demod_2400.c:344-378).
+//   bits 0..12  position relative to the tile origin (tile coordinates x = data index + lead)
+//   bits 16..20 phases tried  (bit p = try_phase 4+p)
+//   bits 21..25 phases whose score depends on the filter (a Rec follows for each, ascending phase)
+typedef uint32_t PosEntry;
+
+// Stateless result of slicing one phase (demod_2400.c:215-258 up to the filter lookups).
+enum RecKind : uint8_t {
+    K_AP = 1,        // DF0/4/5/16/20/21: score = known(crc) ? 1000 : -1
+    K_DFREPAIR = 2,  // DF one bit away from 17 and CRC clean as DF17: known(AA) ? 900 : 700
+    K_DF11_FIX = 3,  // DF11, 1-bit error under IID=0: known(AA') ? 800 : -1
+    K_DF11_IID0 = 4, // DF11, syndrome 0: known(AA) ? 1600 : 750
+    K_DF11_IID = 5,  // DF11, only the IID bits set: known(AA) ? 1000 : -1
+    K_ES_OK = 6,     // DF17/18, syndrome 0: known(AA) ? 1800 : 1400
+    K_ES_FIX = 7     // DF17/18, 1-bit error: known(AA') ? 900 : 700; rejected later if AA changed and unknown
+};
+
+struct __align__(16) Rec {
+    uint8_t  msg[14];  // as sliced (uncorrected); bytes 7..13 zero for short frames
+    uint8_t  kind;     // RecKind
+    int8_t   fixbit;   // K_*_FIX: corrected message bit; K_DFREPAIR: repaired DF bit; else -1
+    uint32_t crc;      // syndrome over the frame length of the DF as sliced
+    uint32_t addr;     // 24-bit address the filter is asked about
+    uint32_t pad_[2];
+};
+
+struct TileOut {
+    uint32_t n_pos;    // PosEntry count; entries live at pos_pool[tile * SCAN_TILE ...]
+    uint32_t n_rec;
+    uint32_t rec_off;  // first Rec in rec_pool
+    uint32_t pad_;
+};
+
+struct BufAcc {        // exact per-buffer sums (convert.c:75-79), zeroed at the start of a run
+    unsigned long long sum_level;
+    unsigned long long sum_power;
+    unsigned long long sum_signal_power;
+    unsigned long long pad_;
+};
+
+// ---- per-receiver persistent state (device) -----------------------------------------------------
+#define ICAO_CAP_LOG2 12
+#define ICAO_CAP      (1u << ICAO_CAP_LOG2)   // slots per generation
+#define ICAO_EMPTY    0xffffffffu
+
+struct StreamState {
+    uint32_t gen[2][ICAO_CAP];   // two generations of the address filter (icao_filter.c)
+    uint32_t gen_count[2];
+    uint32_t active;             // generation that receives adds
+    uint32_t flip_armed;         // 0 until the first flip (readsb.c:1227: next_flip starts at 0)
+    int64_t  next_flip_ms;
+    uint32_t buffer_seq;         // running buffer number
+    uint32_t error;              // sticky: 1 = filter generation full
+    b200_demod_stats stats;
+};
+
+// ---- run-wide control block (device) ------------------------------------------------------------
+struct RunCtl {
+    uint32_t rec_alloc;      // atomic bump pointer into rec_pool
+    uint32_t rec_cap;
+    uint32_t overflow;       // bit0: rec_pool exhausted, bit1: per-tile queue capacity exceeded, bit2: frame capacity
+    uint32_t tile_counter;   // dynamic tile scheduler
+    uint32_t total_frames;
+    uint32_t pad_[3];
+};
+
+struct ScanParams {
+    const Segment *segs;
+    const uint32_t *tile_seg;    // tile -> segment index
+    uint32_t n_tiles;
+    PosEntry *pos_pool;
+    Rec *rec_pool;
+    TileOut *tile_out;
+    BufAcc *buf_acc;
+    RunCtl *ctl;
+    int32_t thr;                 // Modes.preambleThreshold
+    uint32_t long_set, short_set; // valid DF bitsets (demod_2400.c:98-128)
+    int32_t nfix, fixdf;
+};
+
+struct ResolveParams {
+    const Segment *segs;
+    const uint32_t *stream_seg_begin; // per stream: first segment index (segments sorted by stream); [n_streams+1]
+    uint32_t n_streams;
+    const PosEntry *pos_pool;
+    const Rec *rec_pool;
+    const TileOut *tile_out;
+    BufAcc *buf_acc;
+    b200_buffer_result *buf_out;      // per run buffer results (n_frames, flip flag, ...)
+    StreamState *state;
+    b200_frame *frames;               // [n_streams][frame_cap]
+    uint32_t *frame_count;            // [n_streams]
+    uint32_t frame_cap;
+    RunCtl *ctl;
+    int32_t ttl_ms;
+};
+
+struct FinalizeParams {
+    const Segment *segs;
+    const uint32_t *stream_seg_begin;
+    uint32_t n_streams;
+    b200_frame *frames;
+    const uint32_t *frame_count;
+    const uint32_t *frame_prefix;     // exclusive prefix of frame_count (device computed)
+    uint32_t frame_cap;
+    b200_frame *packed;               // all frames of the run, stream-major
+    BufAcc *buf_acc;
+    StreamState *state;
+    const uint16_t *lut_full;         // 65536-entry UC8 table in global memory
+};
+
+// ---- host-built constant tables, uploaded once ---------------------------------------------------
+struct DeviceTables {
+    uint16_t lut_fold[128 * 128];  // folded + bank-swizzled UC8 magnitude table (see modes_tables.h)
+    uint32_t crc_tab[256];         // byte-wise CRC-24 table (crc.c:46-57)
+    uint32_t bit_syn[112];         // syndrome of each single bit of a 112-bit frame (crc.c:59-64)
+    uint32_t syn_hash[512];        // perfect hash: (syndrome*mul)>>23 -> syndrome<<8 | bit
+    uint32_t syn_hash_mul;
+    uint32_t pad_[3];
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+// kernel launch wrappers implemented in demod_kernels.cu (stream is a cudaStream_t)
+int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream);
+int b200_launch_resolve(const ResolveParams *p, void *stream);
+int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream);
+int b200_launch_icao_op(StreamState *state, uint32_t stream, int op, uint32_t addr, int *d_result, void *cstream);
+#ifdef __cplusplus
+}
+#endif

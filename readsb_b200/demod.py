@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference interface for the demodulator path, over the C ABI.
+
+`Demodulator` is a thin ctypes front end of include/b200_demod.h: `submit_iq` stands where a
+readsb frontend calls its converter and publishes a mag_buf (sdr_ifile.c:241-259), `submit_mag`
++ `run` + `frames` stand where the decode thread calls demodulate2400(buf) (readsb.c:871) and the
+frames reach netUseMessage().  There is no CPU implementation behind this class: if the CUDA
+library is missing or no B200-class device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from .abi import BUFRES_DTYPE, FRAME_DTYPE, Config, Stats
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parent / "libb200demod.so"
+
+
+class DemodError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the in-tree CUDA library.  Never builds silently on a GPU box: the .so travels with the tree."""
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise DemodError(f"{LIB_PATH} is missing: run `python -m readsb_b200.build` (nvcc, sm_100a). "
+                             "There is no CPU fallback for the demodulator.")
+        L = C.CDLL(str(LIB_PATH))
+        vp, u32, i64, u64 = C.c_void_p, C.c_uint32, C.c_int64, C.c_uint64
+        L.b200_demod_abi_version.restype = C.c_int
+        L.b200_demod_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.b200_demod_destroy.argtypes = [vp]
+        L.b200_demod_last_error.restype = C.c_char_p
+        L.b200_demod_last_error.argtypes = [vp]
+        L.b200_demod_host_alloc.restype = vp
+        L.b200_demod_host_alloc.argtypes = [C.c_size_t]
+        L.b200_demod_host_free.argtypes = [vp]
+        L.b200_demod_submit_iq_uc8.argtypes = [vp, u32, vp, u32, i64]
+        L.b200_demod_submit_mag_u16.argtypes = [vp, u32, vp, u32, i64]
+        L.b200_demod_run.argtypes = [vp]
+        L.b200_demod_run_device_uc8.argtypes = [vp, vp, u64, u32, u32, C.c_int, i64]
+        L.b200_demod_frame_count.argtypes = [vp, u32, C.POINTER(u32)]
+        L.b200_demod_fetch.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+        L.b200_demod_buffer_results.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+        L.b200_demod_total_frames.argtypes = [vp, C.POINTER(u64)]
+        L.b200_demod_get_stats.argtypes = [vp, u32, C.POINTER(Stats)]
+        L.b200_demod_icao_add.argtypes = [vp, u32, u32]
+        L.b200_demod_icao_test.argtypes = [vp, u32, u32, C.POINTER(C.c_int)]
+        L.b200_demod_icao_expire.argtypes = [vp, u32]
+        L.b200_demod_icao_reset.argtypes = [vp, u32]
+        L.b200_demod_last_timing.argtypes = [vp, C.POINTER(C.c_float * 5), C.POINTER(u32)]
+        L.b200_demod_uc8_lut.argtypes = [vp]
+        L.b200_demod_debug_counters.argtypes = [vp, C.POINTER(u64 * 8)]
+        _LIB = L
+    return _LIB
+
+
+EXPORTED_SYMBOLS = [
+    "b200_demod_abi_version", "b200_demod_create", "b200_demod_destroy", "b200_demod_last_error",
+    "b200_demod_host_alloc", "b200_demod_host_free", "b200_demod_submit_iq_uc8", "b200_demod_submit_mag_u16",
+    "b200_demod_run", "b200_demod_run_device_uc8", "b200_demod_frame_count", "b200_demod_fetch",
+    "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
+    "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
+    "b200_demod_uc8_lut", "b200_demod_debug_counters",
+]
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the library (cudaHostAlloc), exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        self._L = lib()
+        self.ptr = self._L.b200_demod_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError(f"cannot pin {nbytes} bytes")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._L.b200_demod_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Demodulator:
+    def __init__(self, n_streams: int = 1, buf_samples: int = 131072, max_buffers_per_run: int = 1,
+                 preamble_threshold: int = 58, nfix_crc: int = 1, fix_df: int = 1, icao_ttl_ms: int = 60000,
+                 device: int = -1):
+        self.L = lib()
+        self.cfg = Config(C.sizeof(Config), device, n_streams, buf_samples, max_buffers_per_run,
+                          preamble_threshold, nfix_crc, fix_df, icao_ttl_ms, 0)
+        self.n_streams, self.buf_samples, self.max_buffers_per_run = n_streams, buf_samples, max_buffers_per_run
+        h = C.c_void_p()
+        rc = self.L.b200_demod_create(C.byref(self.cfg), C.byref(h))
+        if rc != 0:
+            raise DemodError(f"b200_demod_create failed ({rc}): {self.L.b200_demod_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200_demod_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise DemodError(f"error {rc}: {self.L.b200_demod_last_error(self.h).decode()}")
+
+    # -- host-buffer path ----------------------------------------------------------------------
+    def submit_iq(self, stream: int, iq: np.ndarray, sample_timestamp: int):
+        """iq: uint8 array of interleaved I,Q; one reference buffer (<= buf_samples samples)."""
+        assert iq.dtype == np.uint8 and iq.flags.c_contiguous and iq.size % 2 == 0
+        self._check(self.L.b200_demod_submit_iq_uc8(self.h, stream, iq.ctypes.data, iq.size // 2, sample_timestamp))
+
+    def submit_iq_ptr(self, stream: int, ptr: int, nsamples: int, sample_timestamp: int):
+        self._check(self.L.b200_demod_submit_iq_uc8(self.h, stream, ptr, nsamples, sample_timestamp))
+
+    def submit_mag(self, stream: int, data: np.ndarray, length: int, sample_timestamp: int):
+        """data: uint16 mag_buf.data = 326 halo magnitudes followed by `length` new ones."""
+        assert data.dtype == np.uint16 and data.flags.c_contiguous and data.size >= length + 326
+        self._check(self.L.b200_demod_submit_mag_u16(self.h, stream, data.ctypes.data, length, sample_timestamp))
+
+    def run(self):
+        self._check(self.L.b200_demod_run(self.h))
+
+    # -- device-resident path --------------------------------------------------------------------
+    def run_device(self, d_ptr: int, stream_stride_bytes: int, n_buffers: int, buf_len: int, continues: bool,
+                   first_sample_timestamp: int):
+        self._check(self.L.b200_demod_run_device_uc8(self.h, d_ptr, stream_stride_bytes, n_buffers, buf_len,
+                                                     1 if continues else 0, first_sample_timestamp))
+
+    # -- results -----------------------------------------------------------------------------------
+    def frames(self, stream: int) -> np.ndarray:
+        n = C.c_uint32()
+        self._check(self.L.b200_demod_frame_count(self.h, stream, C.byref(n)))
+        out = np.zeros(n.value, dtype=FRAME_DTYPE)
+        self._check(self.L.b200_demod_fetch(self.h, stream, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def total_frames(self) -> int:
+        n = C.c_uint64()
+        self._check(self.L.b200_demod_total_frames(self.h, C.byref(n)))
+        return n.value
+
+    def buffer_results(self, stream: int) -> np.ndarray:
+        out = np.zeros(self.max_buffers_per_run, dtype=BUFRES_DTYPE)
+        n = C.c_uint32()
+        self._check(self.L.b200_demod_buffer_results(self.h, stream, out.ctypes.data, out.size, C.byref(n)))
+        return out[: n.value].copy()
+
+    def stats(self, stream: int) -> dict:
+        s = Stats()
+        self._check(self.L.b200_demod_get_stats(self.h, stream, C.byref(s)))
+        return s.as_dict()
+
+    def timing(self):
+        ms = (C.c_float * 5)()
+        n = C.c_uint32()
+        self._check(self.L.b200_demod_last_timing(self.h, C.byref(ms), C.byref(n)))
+        return {"run_ms": ms[0], "scan_ms": ms[1], "resolve_ms": ms[2], "h2d_ms": ms[3], "d2h_ms": ms[4], "launches": n.value}
+
+    def debug_counters(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        self._check(self.L.b200_demod_debug_counters(self.h, C.byref(out)))
+        return dict(zip(("tiles", "positions", "records", "rec_alloc", "overflow", "segments", "buffers", "frames"), list(out)))
+
+    # -- ICAO filter -------------------------------------------------------------------------------
+    def icao_add(self, stream: int, addr: int):
+        self._check(self.L.b200_demod_icao_add(self.h, stream, addr))
+
+    def icao_test(self, stream: int, addr: int) -> bool:
+        r = C.c_int()
+        self._check(self.L.b200_demod_icao_test(self.h, stream, addr, C.byref(r)))
+        return bool(r.value)
+
+    def icao_expire(self, stream: int):
+        self._check(self.L.b200_demod_icao_expire(self.h, stream))
+
+    def icao_reset(self, stream: int):
+        self._check(self.L.b200_demod_icao_reset(self.h, stream))
+
+    # -- convenience: replay a whole capture like `--device-type ifile` --------------------------------
+    def replay(self, iq: np.ndarray, first_ts: int = 0, stream: int = 0):
+        """Feeds a uc8 capture as consecutive buffers of buf_samples (last one partial), max_buffers_per_run
+        at a time; returns (frames, buffer_results) concatenated in order."""
+        nsamples = iq.size // 2
+        frames, bufres = [], []
+        off = 0
+        while off < nsamples:
+            for _ in range(self.max_buffers_per_run):
+                if off >= nsamples:
+                    break
+                n = min(self.buf_samples, nsamples - off)
+                self.submit_iq(stream, iq[2 * off: 2 * (off + n)], first_ts + off * 5)
+                off += n
+            self.run()
+            frames.append(self.frames(stream))
+            bufres.append(self.buffer_results(stream))
+        return np.concatenate(frames) if frames else np.zeros(0, FRAME_DTYPE), \
+            np.concatenate(bufres) if bufres else np.zeros(0, BUFRES_DTYPE)
+
+
+def uc8_lut() -> np.ndarray:
+    out = np.empty(65536, dtype=np.uint16)
+    rc = lib().b200_demod_uc8_lut(out.ctypes.data)
+    if rc != 0:
+        raise DemodError("b200_demod_uc8_lut failed")
+    return out

@@ -16,11 +16,14 @@ from readsb_b200.abi import BUFRES_DTYPE, FRAME_DTYPE, BufferResult, Stats
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_SO = ROOT / "oracle" / "libmodes_oracle.so"
 REF_SO = ROOT / "oracle" / "_ref" / "libreadsb_ref.so"
+_BUILT = False
 
 
 def _ensure_built():
-    if not ORACLE_SO.exists() or (Path("/root/reference/demod_2400.c").exists() and not REF_SO.exists()):
+    global _BUILT
+    if not _BUILT:   # make is a no-op when everything is up to date
         subprocess.run(["make", "-C", str(ROOT / "oracle"), "CC=gcc"], check=True, capture_output=True)
+        _BUILT = True
 
 
 def have_ref() -> bool:

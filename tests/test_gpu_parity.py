@@ -1,0 +1,165 @@
+"""-m gpu: the CUDA path, called through the C ABI, must equal the CPU oracle bit for bit.
+
+Sizes here are chosen so the oracle finishes in seconds; BASELINE-size runs are covered through
+size-independent properties in test_gpu_fullsize.py.
+"""
+import numpy as np
+import pytest
+
+from oraclelib import Oracle
+from paritylib import diff_bufres, diff_frames, diff_stats
+from readsb_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GENS = {"cfg2": synth.config2_stream, "cfg5": synth.config5_stream, "mixed": synth.mixed_stream}
+
+
+def _check(d, o, fg, bg, fo, bo, stream=0):
+    problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(stream), o.stats())
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.parametrize("kind", ["cfg2", "cfg5", "mixed"])
+@pytest.mark.parametrize("buf,K", [(65536, 1), (65536, 4), (131072, 2)])
+def test_replay_matches_oracle(cuda, kind, buf, K):
+    from readsb_b200.demod import Demodulator
+    iq = GENS[kind](11, 1_000_000)          # ends in a partial buffer
+    o = Oracle()
+    fo, bo = o.run_stream(iq, buf)
+    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=K)
+    fg, bg = d.replay(iq)
+    assert len(fo) > 10
+    _check(d, o, fg, bg, fo, bo)
+    d.close()
+
+
+@pytest.mark.parametrize("thr,nfix,fixdf", [(58, 0, 1), (58, 1, 0), (40, 1, 1), (120, 1, 1), (58, 0, 0)])
+def test_option_variants(cuda, thr, nfix, fixdf):
+    """--preamble-threshold, --no-fix, --no-fix-df (readsb.c:1460-1473)."""
+    from readsb_b200.demod import Demodulator
+    iq = synth.mixed_stream(5, 700_000)
+    o = Oracle(thr, nfix, fixdf)
+    fo, bo = o.run_stream(iq, 65536)
+    d = Demodulator(n_streams=1, buf_samples=65536, max_buffers_per_run=3, preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf)
+    fg, bg = d.replay(iq)
+    _check(d, o, fg, bg, fo, bo)
+    d.close()
+
+
+def test_many_streams_independent(cuda):
+    """Receivers are independent: own halo, own ICAO filter, own skip state."""
+    from readsb_b200.demod import Demodulator
+    S, buf, nb = 6, 65536, 3
+    kinds = ["cfg2", "cfg5", "mixed"]
+    iqs = [GENS[kinds[s % 3]](100 + s, buf * nb) for s in range(S)]
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=nb)
+    for b in range(nb):
+        for s in range(S):
+            d.submit_iq(s, iqs[s][2 * b * buf: 2 * (b + 1) * buf], b * buf * 5)
+    d.run()
+    for s in range(S):
+        o = Oracle()
+        fo, bo = o.run_stream(iqs[s], buf)
+        _check(d, o, d.frames(s), d.buffer_results(s), fo, bo, stream=s)
+    d.close()
+
+
+def test_magnitude_handoff(cuda):
+    """demodulate2400(struct mag_buf*) boundary: uint16 magnitudes with their 326-sample halo."""
+    from readsb_b200.demod import Demodulator
+    buf = 65536
+    iq = synth.mixed_stream(21, 3 * buf + 1234)
+    mag, _, _ = Oracle.convert(iq)
+    o = Oracle()
+    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=2)
+    halo = np.zeros(326, dtype=np.uint16)
+    fg_all, fo_all = [], []
+    off = 0
+    n = len(mag)
+    pending = []
+    while off < n:
+        ln = min(buf, n - off)
+        data = np.concatenate([halo, mag[off:off + ln]])
+        sl, sp = int(mag[off:off + ln].astype(np.uint64).sum()), int((mag[off:off + ln].astype(np.uint64) ** 2).sum())
+        fo, ro = o.demodulate(data, ln, off * 5, sl, sp)
+        fo_all.append(fo)
+        d.submit_mag(0, data, ln, off * 5)
+        pending.append((sl, sp, ln))
+        if len(pending) == 2 or off + ln >= n:
+            d.run()
+            fg_all.append(d.frames(0))
+            br = d.buffer_results(0)
+            assert [int(x) for x in br["sum_level"]] == [p[0] for p in pending]
+            assert [int(x) for x in br["sum_power"]] == [p[1] for p in pending]
+            pending = []
+        if ln >= 326:
+            halo = data[ln:ln + 326].copy()
+        else:
+            halo = np.zeros(326, dtype=np.uint16)
+        off += ln
+    fg, fo = np.concatenate(fg_all), np.concatenate(fo_all)
+    problems = diff_frames(fg, fo) + diff_stats(d.stats(0), o.stats())
+    assert not problems, "\n".join(problems)
+    d.close()
+
+
+def test_device_resident_batches(cuda):
+    """Inputs already in HBM: streams contiguous in device memory, several buffers per call, continuation."""
+    import torch
+    from readsb_b200.demod import Demodulator
+    S, buf, nb, calls = 5, 65536, 2, 3
+    total = buf * nb * calls
+    iqs = [GENS[["cfg5", "mixed", "cfg2"][s % 3]](300 + s, total) for s in range(S)]
+    pad = 1024  # room for the 326-sample halo in front of stream 0
+    stride = total * 2 + 4096
+    dev = torch.zeros(pad + S * stride, dtype=torch.uint8, device="cuda")
+    for s in range(S):
+        dev[pad + s * stride: pad + s * stride + 2 * total] = torch.from_numpy(iqs[s]).cuda()
+    torch.cuda.synchronize()
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=nb)
+    got = [[] for _ in range(S)]
+    gotb = [[] for _ in range(S)]
+    for c in range(calls):
+        base = dev.data_ptr() + pad + c * nb * buf * 2
+        d.run_device(base, stride, nb, buf, continues=c > 0, first_sample_timestamp=c * nb * buf * 5)
+        for s in range(S):
+            got[s].append(d.frames(s))
+            gotb[s].append(d.buffer_results(s))
+    for s in range(S):
+        o = Oracle()
+        fo, bo = o.run_stream(iqs[s], buf)
+        _check(d, o, np.concatenate(got[s]), np.concatenate(gotb[s]), fo, bo, stream=s)
+    d.close()
+
+
+def test_icao_filter_api(cuda):
+    """icaoFilterAdd/Test/Expire semantics: an address lives until the second flip after its add."""
+    from readsb_b200.demod import Demodulator
+    d = Demodulator(n_streams=2, buf_samples=4096, max_buffers_per_run=1)
+    assert not d.icao_test(0, 0x4840D6)
+    d.icao_add(0, 0x4840D6)
+    assert d.icao_test(0, 0x4840D6) and not d.icao_test(1, 0x4840D6)
+    d.icao_expire(0)
+    assert d.icao_test(0, 0x4840D6)
+    d.icao_expire(0)
+    assert not d.icao_test(0, 0x4840D6)
+    d.close()
+
+
+def test_seeded_filter_accepts_address_parity_replies(cuda):
+    """DF0/4/5/16/20/21 are only accepted from known aircraft (mode_s.c:343-360): seeding the filter through the
+    API must have the same effect as the oracle's."""
+    from readsb_b200.demod import Demodulator
+    iq = synth.generate(400_000, seed=9, frames_per_sec=3000, df_mask=synth.AP, n_icao=4)
+    _, truth = synth.generate(400_000, seed=9, frames_per_sec=3000, df_mask=synth.AP, n_icao=4, want_truth=True)
+    addrs = {Oracle.crc24(m) for _, m, _ in truth}
+    assert 1 <= len(addrs) <= 4
+    o = Oracle(); d = Demodulator(n_streams=1, buf_samples=131072, max_buffers_per_run=1)
+    for a in addrs:
+        o.icao_add(a); d.icao_add(0, a)
+    fo, bo = o.run_stream(iq, 131072)
+    fg, bg = d.replay(iq)
+    assert len(fo) > 100
+    _check(d, o, fg, bg, fo, bo)
+    d.close()
