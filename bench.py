@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — IQ Msamples/s demodulated (BASELINE.json metric) on N B200s, one process per GPU.
+
+A *step* is one pass of the hot path over one batch: for every one of the GPU's receivers, the next
+`--buffers` reference buffers of 65536 samples (128 KiB mag_buf, `--sdr-buffer-size=128`) of its synthetic
+2.4 MSPS uc8 stream.  Default workload = BASELINE.json configs[2] per GPU (256 concurrent streams, DF17
+injected at 100/s), which at N GPUs is configs[3] (256 streams per GPU, independent, no collective).
+
+  value  whole-job throughput with the IQ already resident in HBM (device ring larger than L2)
+  e2e    same metric through the C-ABI with HOST buffers: pinned host -> H2D -> kernels -> frames D2H
+  roofline  scan kernel: 2 B/sample x samples per launch / CUDA-event duration, vs measured HBM peak
+  cpu_baseline  the reference's own convert_uc8_nodc + demodulate2400 (oracle/_ref, built from
+             /root/reference) on all host cores, on a bounded sample of the same batch (rank 0, N=1)
+
+`--impl reference` runs only that CPU arm and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BUF = 65536                      # samples per reference buffer: 128 KiB of uint16 magnitudes
+ALG_BYTES_PER_SAMPLE = 2         # uc8 I + Q, read once
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--streams", type=int, default=256, help="receivers per GPU")
+    ap.add_argument("--buffers", type=int, default=8, help="reference buffers per receiver per step")
+    ap.add_argument("--ring", type=int, default=4, help="distinct steps of input kept resident (ring > L2)")
+    ap.add_argument("--workload", choices=["config3_256streams", "config5_dense"], default="config3_256streams")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic input
+# ---------------------------------------------------------------------------------------------------------
+def generate_streams(n_streams: int, samples_per_stream: int, seed0: int, workload: str, out: np.ndarray):
+    """out: uint8 [n_streams, 2*samples_per_stream] (may be pinned). One distinct seeded stream per receiver."""
+    from readsb_b200 import synth
+    gen = synth.config5_stream if workload == "config5_dense" else synth.config2_stream
+    synth.lib()
+
+    def one(s):
+        gen(seed0 + s, samples_per_stream, out=out[s])
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(one, range(n_streams)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref: the reference's own translation units, see oracle/Makefile)
+# ---------------------------------------------------------------------------------------------------------
+class ReferencePool:
+    """One private copy of the reference library per worker thread (readsb keeps its state in globals)."""
+
+    def __init__(self, n_threads: int):
+        sys.path.insert(0, str(ROOT / "tests"))
+        import oraclelib
+        self.kind = "reference" if oraclelib.REF_SO.exists() else "port"
+        self.n_threads = n_threads
+        if self.kind == "reference":
+            self.workers = [oraclelib.Reference() for _ in range(n_threads)]
+        else:   # /root/reference was absent when oracle/_ref would have been built: time the C restatement instead
+            self.workers = [None] * n_threads
+            self.oraclelib = oraclelib
+        self.pool = ThreadPoolExecutor(max_workers=n_threads)
+
+    def _run(self, w, iq_rows):
+        n = 0
+        for row in iq_rows:
+            if self.kind == "reference":
+                self.workers[w].time_stream(row, BUF)
+            else:
+                self.oraclelib.Oracle().run_stream(row, BUF)
+            n += row.size // 2
+        return n
+
+    def step(self, rows):
+        """Demodulates every row (one receiver's uc8 samples for this step) once; returns samples processed."""
+        shards = [rows[w::self.n_threads] for w in range(self.n_threads)]
+        return sum(self.pool.map(self._run, range(self.n_threads), shards))
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    # bounded sample of the b200 arm's batch: the same streams, but only as many as keep a step around a second
+    n_streams = min(args.streams * args.gpus, max(cores, 64))
+    n_buf = args.buffers
+    host = np.empty((n_streams, 2 * n_buf * BUF), dtype=np.uint8)
+    generate_streams(n_streams, n_buf * BUF, 1, args.workload, host)
+    pool = ReferencePool(cores)
+    rows = [host[s] for s in range(n_streams)]
+    for _ in range(args.warmup):
+        pool.step(rows)
+    t0 = time.perf_counter()
+    samples = 0
+    for _ in range(args.steps):
+        samples += pool.step(rows)
+    dt = time.perf_counter() - t0
+    value = samples / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "iq_msamples_per_s_demodulated", "value": value, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->u16/int32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": pool.kind,
+                         "sample": f"{n_streams} of the {args.streams * args.gpus} streams x {n_buf} buffers of {BUF} samples per step, "
+                                   f"one receiver per thread (the reference demodulator is single-threaded per receiver)"},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+def workload_config(args, n_gpus):
+    desc = ("BASELINE configs[2]/[3]: 256 concurrent synthetic 2.4 MSPS uc8 streams per GPU, DF17 injected at 100/s"
+            if args.workload == "config3_256streams" else
+            "BASELINE configs[4]: dense-preamble stress, 10k DF11+DF17/s per stream with overlaps, --fix on")
+    return {"workload": desc, "streams_per_gpu": args.streams, "streams_total": args.streams * n_gpus,
+            "buffers_per_stream_per_step": args.buffers, "buf_samples": BUF, "sample_rate_hz": 2400000,
+            "samples_per_step_per_gpu": args.streams * args.buffers * BUF,
+            "parallelism": f"{n_gpus} independent GPU(s), streams sharded {args.streams}/GPU, no collective",
+            "l2": f"device inputs cycle through a ring of {args.ring} distinct steps "
+                  f"({args.ring * args.streams * args.buffers * BUF * 2 / 2**20:.0f} MiB per GPU, L2 is 126 MB); each step reads bytes not touched for {args.ring - 1} steps"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        if shutil.which("nvidia-smi"):
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def b200_arm(args, rank, world, local):
+    import torch
+    from readsb_b200.demod import Demodulator, PinnedBuffer
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the demodulator has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    S, B, R = args.streams, args.buffers, args.ring
+    step_samples = S * B * BUF
+    per_stream = R * B * BUF                       # samples of one receiver resident in the ring
+    # --- inputs: pinned host slab [S, 2*per_stream] (for e2e) and a device copy (for value) -------------------
+    pin = PinnedBuffer(S * 2 * per_stream)
+    host = pin.array.reshape(S, 2 * per_stream)
+    generate_streams(S, per_stream, 1 + rank * S, args.workload, host)
+    pad = 4096                                      # room in front of receiver 0 for the 326-sample halo
+    dev = torch.empty(pad + S * 2 * per_stream + 256, dtype=torch.uint8, device="cuda")
+    dev[pad: pad + S * 2 * per_stream] = torch.from_numpy(host.reshape(-1)).cuda()
+    dev[:pad] = 0
+    torch.cuda.synchronize()
+    stride = 2 * per_stream
+
+    d = Demodulator(n_streams=S, buf_samples=BUF, max_buffers_per_run=B, device=local)
+    d.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def device_step(k):
+        slot = k % R
+        d.run_device(dev.data_ptr() + pad + slot * B * BUF * 2, stride, B, BUF, continues=slot > 0,
+                     first_sample_timestamp=k * B * BUF * 5)
+
+    def host_step(k):
+        slot = k % R
+        d.submit_iq_strided(0, S, pin.ptr + slot * B * BUF * 2, stride, B, BUF, k * B * BUF * 5)
+        d.run()
+        return d.total_frames()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, k0):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scan_ms, launches, frames = 0.0, 0, 0
+        barrier()
+        ev0.record()
+        for k in range(k0, k0 + steps):
+            fn(k)
+            t = d.timing()
+            scan_ms += t["scan_ms"]; launches += t["launches"]; frames += d.total_frames()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            tmax = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
+        barrier()
+        return ms, scan_ms, launches, frames
+
+    # --- value: inputs resident in HBM -------------------------------------------------------------------------
+    for k in range(args.warmup):
+        device_step(k)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, scan_ms, launches, frames = timed(device_step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else {}
+    value = world * step_samples * args.steps / (ms * 1e-3) / 1e6
+
+    # --- e2e: host buffers through the C ABI ----------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        # a fresh context so that receiver state (halo, ICAO filter) starts clean for the host path
+        d2 = Demodulator(n_streams=S, buf_samples=BUF, max_buffers_per_run=B, device=local)
+        d2.set_stream(torch.cuda.current_stream().cuda_stream)
+        d_dev, d = d, d2
+        for k in range(args.warmup):
+            host_step(k)
+        ms_e, _, launches_e, frames_e = timed(host_step, args.steps, args.warmup)
+        e2e = {"value": world * step_samples * args.steps / (ms_e * 1e-3) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": step_samples * 2 + S * 64 + 64,           # IQ slab + segment table + control block
+               "d2h_bytes_per_step": int(frames_e / args.steps * 64) + S * 4 + S * B * 80 + 32,   # frames + counts + buffer results
+               "ms_per_step": ms_e / args.steps, "frames_per_step": frames_e / args.steps}
+        d = d_dev
+        d2.close()
+
+    if rank != 0:
+        return 0
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    scan_avg_s = scan_ms / args.steps * 1e-3
+    achieved = ALG_BYTES_PER_SAMPLE * step_samples / scan_avg_s / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "scan_traffic.json"      # per-launch DRAM bytes from the committed ncu capture, if any
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "iq_msamples_per_s_demodulated", "value": value, "unit": "Msamples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8->u16/int32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "frames_per_step_per_gpu": frames / args.steps,
+        "roofline": {"bound": "hbm", "kernel": "scan_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "kernel_ms_per_launch": scan_ms / args.steps, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * step_samples},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu and world == 1:
+        # bounded CPU sample on this box's host cores, timed beside the GPU run
+        try:
+            cores = os.cpu_count() or 1
+            n_cpu_streams = min(S, max(cores, 64))
+            pool = ReferencePool(cores)
+            rows = [host[s][: 2 * B * BUF] for s in range(n_cpu_streams)]
+            pool.step(rows)
+            t0 = time.perf_counter(); n = 0; reps = 0
+            while time.perf_counter() - t0 < 8.0 and reps < 50:
+                n += pool.step(rows); reps += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": pool.kind,
+                                    "sample": f"{n_cpu_streams} of the {S} streams x {B} buffers of {BUF} samples, {reps} passes, one receiver per thread"}
+        except Exception as e:   # the CPU arm must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+    return b200_arm(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -128,6 +128,10 @@ int  b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out);
 void b200_demod_destroy(b200_demod_ctx *ctx);
 const char *b200_demod_last_error(const b200_demod_ctx *ctx); /* ctx may be NULL: last create error */
 
+/* Run all work of this context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the
+ * context's own stream).  Lets a caller bracket runs with its own events. */
+int b200_demod_set_stream(b200_demod_ctx *ctx, void *cuda_stream);
+
 /* pinned host memory for zero-staging submits (optional; any host pointer is accepted) */
 void *b200_demod_host_alloc(size_t bytes);
 void  b200_demod_host_free(void *p);
@@ -143,6 +147,12 @@ int b200_demod_submit_iq_uc8(b200_demod_ctx *ctx, uint32_t stream, const uint8_t
                              uint32_t nsamples, int64_t sample_timestamp);
 int b200_demod_submit_mag_u16(b200_demod_ctx *ctx, uint32_t stream, const uint16_t *data,
                               uint32_t length, int64_t sample_timestamp);
+/* Many receivers in one call (a multi-channel frontend's slab): stream first_stream+i has n_buffers*buf_len
+ * samples at iq + i*host_stride_bytes, submitted as n_buffers consecutive buffers with timestamps
+ * first_sample_timestamp + b*buf_len*5.  One strided DMA instead of n_streams*n_buffers copies. */
+int b200_demod_submit_iq_uc8_strided(b200_demod_ctx *ctx, uint32_t first_stream, uint32_t n_streams,
+                                     const uint8_t *iq, uint64_t host_stride_bytes, uint32_t n_buffers,
+                                     uint32_t buf_len, int64_t first_sample_timestamp);
 /* Process everything submitted since the last run; returns when frames are in host memory. */
 int b200_demod_run(b200_demod_ctx *ctx);
 

@@ -27,6 +27,8 @@
 #define SCAN_Q1_CAP    (SCAN_TILE / 4)   // positions passing the pre-check, per tile
 #define SCAN_ITEM_CAP  (SCAN_TILE / 8)   // (position, phase) pairs passing a threshold, per tile
 #define SCAN_FULL_CAP  768             // live records per tile staged in shared memory
+// worst-case candidate queues of one tile in global memory (dense-input slow path), see process_candidates<true>
+#define SCAN_SCRATCH_BYTES (184u * SCAN_TILE)
 
 // ---- segment descriptor ------------------------------------------------------------------------
 #define SEG_MAG        0x1u   // input samples are uint16 magnitudes (demodulate2400 hand-off), not uc8 IQ
@@ -126,6 +128,7 @@ struct ScanParams {
     int32_t thr;                 // Modes.preambleThreshold
     uint32_t long_set, short_set; // valid DF bitsets (demod_2400.c:98-128)
     int32_t nfix, fixdf;
+    uint8_t *scratch;            // nullptr, or SCAN_SCRATCH_BYTES per CTA of the scan grid
 };
 
 struct ResolveParams {
@@ -173,6 +176,7 @@ struct DeviceTables {
 extern "C" {
 #endif
 // kernel launch wrappers implemented in demod_kernels.cu (stream is a cudaStream_t)
+int b200_scan_grid(int n_sm);   // CTAs the scan kernel is launched with (persistent, occupancy-sized)
 int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream);
 int b200_launch_resolve(const ResolveParams *p, void *stream);
 int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream);

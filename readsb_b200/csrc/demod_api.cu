@@ -29,7 +29,7 @@ struct Pending {
 struct b200_demod_ctx {
     b200_demod_config cfg;
     int device = 0, n_sm = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     std::string err;
 
     DeviceTables *d_tables = nullptr;
@@ -58,6 +58,7 @@ struct b200_demod_ctx {
     b200_frame *d_frames = nullptr, *d_packed = nullptr, *h_packed = nullptr;
     uint32_t *d_frame_count = nullptr, *d_frame_prefix = nullptr, *h_frame_prefix = nullptr;
     uint32_t *d_carry_src = nullptr, *h_carry_src = nullptr;
+    uint8_t *d_scratch = nullptr;     // dense-input slow path arena, allocated on first need
     int *d_result = nullptr;
 
     // results of the last run
@@ -130,12 +131,12 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     cudaFree(c->d_segs); cudaFree(c->d_tile_seg); cudaFree(c->d_stream_seg_begin); cudaFree(c->d_pos_pool);
     cudaFree(c->d_rec_pool); cudaFree(c->d_tile_out); cudaFree(c->d_buf_acc); cudaFree(c->d_buf_out);
     cudaFree(c->d_frames); cudaFree(c->d_packed); cudaFree(c->d_frame_count); cudaFree(c->d_frame_prefix);
-    cudaFree(c->d_carry_src); cudaFree(c->d_result);
+    cudaFree(c->d_carry_src); cudaFree(c->d_result); cudaFree(c->d_scratch);
     cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_segs); cudaFreeHost(c->h_tile_seg); cudaFreeHost(c->h_stream_seg_begin);
     cudaFreeHost(c->h_buf_acc); cudaFreeHost(c->h_buf_out); cudaFreeHost(c->h_packed); cudaFreeHost(c->h_frame_prefix);
     cudaFreeHost(c->h_carry_src);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -159,7 +160,8 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     CUC(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
-    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     for (auto &e : c->ev) CUC(cudaEventCreate(&e));
 
     const uint32_t S = cfg->n_streams, K = cfg->max_buffers_per_run, BUF = cfg->buf_samples;
@@ -245,6 +247,41 @@ static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32
     return B200_OK;
 }
 
+API int b200_demod_set_stream(b200_demod_ctx *c, void *cuda_stream) {
+    if (!c) return B200_E_INVAL;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return B200_OK;
+}
+
+API int b200_demod_submit_iq_uc8_strided(b200_demod_ctx *c, uint32_t first, uint32_t ns, const uint8_t *iq, uint64_t host_stride,
+                                         uint32_t n_buffers, uint32_t buf_len, int64_t ts) {
+    if (!c || !iq) return B200_E_INVAL;
+    if (ns == 0 || first + ns > c->cfg.n_streams || n_buffers == 0 || buf_len == 0 || buf_len > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "bad stream range or buffer length");
+    if (n_buffers > 1 && buf_len != c->cfg.buf_samples) return fail(c, B200_E_INVAL, "several buffers per call need buf_len == buf_samples");
+    const size_t row = (size_t)n_buffers * buf_len * 2;
+    if (host_stride < row) return fail(c, B200_E_INVAL, "host_stride_bytes smaller than one stream's data");
+    for (uint32_t s = first; s < first + ns; s++) {
+        if (c->kind[s] == 2) return fail(c, B200_E_STATE, "stream %u mixes IQ and magnitude submits in one run", s);
+        if (c->pending[s].size() + n_buffers > c->cfg.max_buffers_per_run) return fail(c, B200_E_STATE, "stream %u would exceed max_buffers_per_run", s);
+        if (c->kind[s] && c->cursor[s] != c->cursor[first]) return fail(c, B200_E_STATE, "strided submit needs all streams of the range at the same fill level");
+    }
+    CU(c, cudaSetDevice(c->device));
+    const size_t off0 = c->kind[first] ? c->cursor[first] : (size_t)B200_TRAIL * 2;
+    CU(c, cudaMemcpy2DAsync(c->d_arena + (size_t)first * c->stream_stride + off0, c->stream_stride, iq, host_stride, row, ns,
+                            cudaMemcpyHostToDevice, c->stream));
+    for (uint32_t s = first; s < first + ns; s++) {
+        c->kind[s] = 1;
+        for (uint32_t b = 0; b < n_buffers; b++) {
+            Pending p; p.n = buf_len; p.ts = ts + (int64_t)b * buf_len * 5; p.off = off0 + (size_t)b * buf_len * 2;
+            c->pending[s].push_back(p);
+        }
+        c->cursor[s] = off0 + row;
+    }
+    return B200_OK;
+}
+
 API int b200_demod_submit_iq_uc8(b200_demod_ctx *c, uint32_t s, const uint8_t *iq, uint32_t n, int64_t ts) { return submit_common(c, s, iq, n, ts, false); }
 API int b200_demod_submit_mag_u16(b200_demod_ctx *c, uint32_t s, const uint16_t *data, uint32_t n, int64_t ts) { return submit_common(c, s, data, n, ts, true); }
 
@@ -278,7 +315,7 @@ static int execute(b200_demod_ctx *c, uint32_t nseg, uint32_t ntile, uint32_t nb
         ScanParams sp;
         sp.segs = c->d_segs; sp.tile_seg = c->d_tile_seg; sp.n_tiles = ntile; sp.pos_pool = c->d_pos_pool; sp.rec_pool = c->d_rec_pool;
         sp.tile_out = c->d_tile_out; sp.buf_acc = c->d_buf_acc; sp.ctl = c->d_ctl; sp.thr = c->cfg.preamble_threshold;
-        sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df;
+        sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df; sp.scratch = c->d_scratch;
         // demod_2400.c:112-127
         sp.short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
         sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
@@ -314,6 +351,12 @@ static int execute(b200_demod_ctx *c, uint32_t nseg, uint32_t ntile, uint32_t nb
             cudaFree(c->d_rec_pool); c->d_rec_pool = nullptr;
             c->rec_cap = need;
             if (dev_alloc(&c->d_rec_pool, c->rec_cap) != cudaSuccess) return fail(c, B200_E_NOMEM, "cannot grow the record pool to %u records", need);
+            continue;
+        }
+        if ((c->h_ctl->overflow & 2u) && !c->d_scratch) {   // a tile denser than the shared-memory queues: give the kernel its slow-path arena
+            const int grid = b200_scan_grid(c->n_sm);
+            if (grid <= 0 || cudaMalloc((void **)&c->d_scratch, (size_t)grid * SCAN_SCRATCH_BYTES) != cudaSuccess)
+                return fail(c, B200_E_NOMEM, "cannot allocate the dense-input scratch arena");
             continue;
         }
         break;

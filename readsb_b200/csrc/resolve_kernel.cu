@@ -1,0 +1,352 @@
+// resolve_kernel.cu — stage B and the frame finaliser.
+//
+//   resolve_kernel  one warp per receiver: the sequential part of demodulate2400() (ICAO-filter dependent
+//                   scoring mode_s.c:309-419, best-phase pick demod_2400.c:241-258, the accept test of
+//                   decodeModesMessage mode_s.c:443-596,:766-779, skip-ahead demod_2400.c:468, the filter flip
+//                   readsb.c:1227-1231), walked speculatively 32 candidates at a time with the receiver's two
+//                   filter generations (icao_filter.c) in shared memory.
+//   finalize_kernel one warp per accepted frame: signal power (demod_2400.c:436-457), per-buffer / per-receiver
+//                   power statistics, packing of the frame list for a single D2H copy.
+#include "common.h"
+#include "device_utils.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// stage B
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t icao_slot(uint32_t a) { return (a * 0x9E3779B1u) >> (32 - ICAO_CAP_LOG2); }
+
+__device__ __forceinline__ bool gen_has(const uint32_t *g, uint32_t a) {
+    uint32_t h = icao_slot(a);
+    for (;;) {
+        const uint32_t v = g[h];
+        if (v == a) return true;
+        if (v == ICAO_EMPTY) return false;
+        h = (h + 1) & (ICAO_CAP - 1);
+    }
+}
+
+__device__ __forceinline__ bool gen_add(uint32_t *g, uint32_t *count, uint32_t a) {   // false when full
+    uint32_t h = icao_slot(a);
+    for (;;) {
+        const uint32_t v = g[h];
+        if (v == a) return true;
+        if (v == ICAO_EMPTY) break;
+        h = (h + 1) & (ICAO_CAP - 1);
+    }
+    if (*count >= ICAO_CAP / 2) return false;
+    g[h] = a; (*count)++;
+    return true;
+}
+
+struct ResolveSmem {
+    uint32_t gen[2][ICAO_CAP];
+};
+
+// Score of one record under the current filter (mode_s.c:309-419).
+__device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
+    switch (kind) {
+        case K_AP: return known ? 1000 : -1;
+        case K_DFREPAIR: return known ? 900 : 700;
+        case K_DF11_FIX: return known ? 800 : -1;
+        case K_DF11_IID0: return known ? 1600 : 750;
+        case K_DF11_IID: return known ? 1000 : -1;
+        case K_ES_OK: return known ? 1800 : 1400;
+        case K_ES_FIX: return known ? 900 : 700;
+        default: return -2;
+    }
+}
+
+__global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
+    __shared__ ResolveSmem S;
+    const uint32_t stream = blockIdx.x, lane = threadIdx.x;
+    StreamState *st = &P.state[stream];
+    if (P.ctl->overflow & 3u) return;     // stage A failed: leave every receiver's state untouched, the host redoes the run
+
+    for (uint32_t i = lane; i < 2 * ICAO_CAP; i += 32) (&S.gen[0][0])[i] = (&st->gen[0][0])[i];
+    uint32_t gcount[2] = {st->gen_count[0], st->gen_count[1]};
+    uint32_t active = st->active, armed = st->flip_armed, seq = st->buffer_seq, err = st->error;
+    int64_t next_flip = st->next_flip_ms;
+    bool dirty[2] = {false, false};
+    __syncwarp();
+
+    // per-lane partial counters, reduced at the end
+    uint32_t c_pre = 0, c_bad = 0, c_unk = 0, c_acc0 = 0, c_acc1 = 0, c_tp[5] = {0, 0, 0, 0, 0}, c_bp[5] = {0, 0, 0, 0, 0};
+    unsigned long long c_samples = 0;
+    uint32_t c_bufs = 0, c_flips = 0;
+    uint32_t nframes = 0;
+    b200_frame *fout = P.frames + (size_t)stream * P.frame_cap;
+
+    for (uint32_t si = P.stream_seg_begin[stream]; si < P.stream_seg_begin[stream + 1]; si++) {
+        const Segment seg = P.segs[si];
+        uint32_t tile = seg.tile_begin, idx = 0;
+        const uint32_t tile_end = seg.tile_begin + seg.n_tiles;
+        TileOut to = {0, 0, 0, 0};
+        if (seg.n_tiles) to = P.tile_out[tile];
+        uint32_t rec_cursor = to.rec_off;
+
+        for (uint32_t b = 0; b < seg.n_bufs; b++) {
+            const uint32_t d_begin = b * seg.buf_len;
+            const uint32_t d_end = min(d_begin + seg.buf_len, seg.npos);
+            const int64_t buf_ts = seg.first_ts + (int64_t)d_begin * 5;
+            int64_t now_ms = buf_ts / 12000;          // demod_2400.c:283-285
+            uint32_t skip_until = d_begin;            // data-index form of the reference's `pa` skip
+            uint32_t nfr_buf = 0;
+
+            for (;;) {
+                while (idx >= to.n_pos && tile + 1 < tile_end) { tile++; idx = 0; to = P.tile_out[tile]; rec_cursor = to.rec_off; }
+                if (idx >= to.n_pos) break;
+                const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;
+                const bool has = idx + lane < to.n_pos;
+                const PosEntry pe = has ? P.pos_pool[(size_t)tile * SCAN_TILE + idx + lane] : 0;
+                const uint32_t d = x0 + (pe & 0x1fffu) - seg.lead;          // data index = position in the segment
+                const bool inbuf = has && d < d_end;                        // entries are ascending: a prefix of lanes
+                const uint32_t n_in = __popc(__ballot_sync(FULLMASK, inbuf));
+                if (n_in == 0) break;                                       // next entry belongs to the next buffer
+                const uint32_t tried = (pe >> 16) & 31u, live = (pe >> 21) & 31u;
+                const uint32_t nlive = inbuf ? __popc(live) : 0;
+                uint32_t dummy;
+                const uint32_t rprefix = warp_excl_scan(nlive, lane, &dummy);
+                const bool valid = inbuf && d >= skip_until;
+
+                // score every tried phase with the current filter; first strictly greatest wins (demod_2400.c:243)
+                int best = -2; uint32_t best_rec = 0, best_phase = 0, best_kind = 0; bool best_known = false; int best_fix = -1;
+                if (valid && live) {
+                    uint32_t lb = live, k = 0;
+                    while (lb) {
+                        const uint32_t ph = __ffs(lb) - 1; lb &= lb - 1;
+                        const uint32_t ri = rec_cursor + rprefix + k; k++;
+                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(&P.rec_pool[ri]);
+                        const uint32_t meta = rw[3], addr = rw[5];
+                        const uint32_t kind = (meta >> 16) & 0xffu;
+                        const bool known = gen_has(S.gen[0], addr) || gen_has(S.gen[1], addr);
+                        const int sc = rec_score(kind, known);
+                        if (sc > best) { best = sc; best_rec = ri; best_phase = ph; best_kind = kind; best_known = known; best_fix = (int)(int8_t)(meta >> 24); }
+                    }
+                }
+                // accept test of decodeModesMessage (mode_s.c:443-596): only a corrected AA that is unknown rejects
+                const bool decode_ok = best >= 0 && !(best_kind == K_ES_FIX && best_fix >= 8 && best_fix <= 31 && !best_known);
+                const uint32_t acc_mask = __ballot_sync(FULLMASK, valid && decode_ok);
+                const uint32_t f = acc_mask ? (uint32_t)__ffs(acc_mask) - 1 : 32u;
+                const uint32_t consumed = acc_mask ? f + 1 : n_in;
+
+                if (valid && lane < f) {       // rejected preambles before the first accepted one
+                    c_pre++;
+#pragma unroll
+                    for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
+                    if (best == -2) c_bad++; else c_unk++;       // -1, or decode result -1
+                }
+                if (acc_mask) {
+                    uint32_t msglen = 0;
+                    if (lane == f) {
+                        c_pre++;
+#pragma unroll
+                        for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
+                        const uint4 r0 = reinterpret_cast<const uint4 *>(&P.rec_pool[best_rec])[0];
+                        const uint4 r1 = reinterpret_cast<const uint4 *>(&P.rec_pool[best_rec])[1];
+                        uint8_t msg[16];
+                        *reinterpret_cast<uint4 *>(msg) = r0;
+                        const uint32_t crc_raw = r1.x;
+                        const uint32_t df_raw = msg[0] >> 3;
+                        msglen = (df_raw & 0x10) ? 112 : 56;                 // demod_2400.c:399 (DF as sliced)
+                        uint32_t msgtype = df_raw, corrected = 0, crc = crc_raw;
+                        int fix_bit = -1;
+                        bool add = false;
+                        if (best_kind == K_DFREPAIR) { msg[0] = (uint8_t)((msg[0] & 7) | (17 << 3)); msgtype = 17; corrected = 1; fix_bit = best_fix; crc = 0; }
+                        else if (best_kind == K_DF11_FIX || best_kind == K_ES_FIX) { corrected = 1; fix_bit = best_fix; msg[fix_bit >> 3] ^= (uint8_t)(1u << (7 - (fix_bit & 7))); }
+                        else if (best_kind == K_DF11_IID0 || (best_kind == K_ES_OK && msgtype == 17)) add = true;   // mode_s.c:766-779
+                        const uint32_t msgbits = (msgtype & 0x10) ? 112 : 56;
+                        const uint32_t aa = ((uint32_t)msg[1] << 16) | ((uint32_t)msg[2] << 8) | msg[3];
+                        const uint32_t addr = best_kind == K_AP ? crc : aa;
+                        const uint32_t j = d - d_begin;
+                        const int64_t ts = buf_ts + (int64_t)j * 5 + (8 + 56) * 12 + (4 + best_phase);   // demod_2400.c:406
+                        if (nframes < P.frame_cap) {
+                            b200_frame fr;
+                            fr.timestamp = ts; fr.sigpow_sum = 0; fr.j = j; fr.crc = crc; fr.addr = addr; fr.score = best;
+                            fr.buffer_seq = seq; fr.signal_len = (uint16_t)(msglen * 12 / 5); fr.phase = (uint8_t)(4 + best_phase);
+                            fr.msgtype = (uint8_t)msgtype; fr.msgbits = (uint8_t)msgbits; fr.correctedbits = (uint8_t)corrected;
+                            fr.fix_bit = (int8_t)fix_bit; fr.flags = add ? B200_FRAME_ICAO_ADDED : 0;
+#pragma unroll
+                            for (int i = 0; i < 14; i++) fr.msg[i] = (uint32_t)i < msgbits / 8 ? msg[i] : 0;
+                            // pad_: segment index and data index for finalize_kernel (cleared there)
+                            fr.pad_[0] = 0; fr.pad_[1] = 0;
+                            *reinterpret_cast<uint16_t *>(&fr.pad_[0]) = (uint16_t)(si & 0xffffu);
+                            *reinterpret_cast<uint32_t *>(&fr.pad_[2]) = d;
+                            // pad_[0..1] hold only 16 bits of the segment index; the upper bits ride in flags' spare bits
+                            fout[nframes] = fr;
+                        } else atomicOr(&P.ctl->overflow, 4u);
+                        if (corrected) c_acc1++; else c_acc0++;
+                        c_bp[best_phase]++;
+                        if (add) { if (!gen_add(S.gen[active], &gcount[active], addr)) err = 1; dirty[active] = true; }
+                        now_ms = buf_ts / 12000 + (ts - buf_ts) / 12000;      // demod_2400.c:409-414
+                    }
+                    __syncwarp();
+                    // broadcast the state the accepting lane changed
+                    msglen = __shfl_sync(FULLMASK, msglen, f);
+                    now_ms = __shfl_sync(FULLMASK, now_ms, f);
+                    gcount[0] = __shfl_sync(FULLMASK, gcount[0], f); gcount[1] = __shfl_sync(FULLMASK, gcount[1], f);
+                    dirty[0] = __shfl_sync(FULLMASK, (int)dirty[0], f); dirty[1] = __shfl_sync(FULLMASK, (int)dirty[1], f);
+                    err = __shfl_sync(FULLMASK, err, f);
+                    const uint32_t d_f = __shfl_sync(FULLMASK, d, f);
+                    skip_until = d_f + msglen * 2 + 1;                          // demod_2400.c:468 + loop increment
+                    nframes++; nfr_buf++;
+                }
+                // advance the cursors past the consumed entries
+                const uint32_t last = consumed - 1;
+                rec_cursor += __shfl_sync(FULLMASK, rprefix + nlive, last);
+                idx += consumed;
+            }
+
+            // end of buffer: readsb.c:876, then backgroundTasks' filter flip (readsb.c:1227-1231)
+            c_samples += d_end - d_begin; c_bufs++;
+            uint32_t flipped = 0;
+            if (P.ttl_ms > 0 && (!armed || now_ms >= next_flip)) {
+                const uint32_t other = active ^ 1u;
+                for (uint32_t i = lane; i < ICAO_CAP; i += 32) S.gen[other][i] = ICAO_EMPTY;
+                gcount[other] = 0; dirty[other] = true; active = other;
+                next_flip = now_ms + P.ttl_ms; armed = 1; flipped = 1; c_flips++;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                b200_buffer_result r;
+                r.sample_timestamp = buf_ts; r.sum_level = 0; r.sum_power = 0; r.sum_signal_power = 0;
+                r.length = d_end - d_begin; r.n_frames = nfr_buf; r.buffer_seq = seq; r.icao_flipped = flipped;
+                P.buf_out[seg.first_buf + b] = r;
+            }
+            seq++;
+        }
+    }
+
+    // write back
+    for (int g = 0; g < 2; g++)
+        if (dirty[g]) for (uint32_t i = lane; i < ICAO_CAP; i += 32) st->gen[g][i] = S.gen[g][i];
+    uint32_t red[15] = {c_pre, c_bad, c_unk, c_acc0, c_acc1, c_tp[0], c_tp[1], c_tp[2], c_tp[3], c_tp[4], c_bp[0], c_bp[1], c_bp[2], c_bp[3], c_bp[4]};
+#pragma unroll
+    for (int k = 0; k < 15; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) red[k] += __shfl_xor_sync(FULLMASK, red[k], o);
+    if (lane == 0) {
+        st->gen_count[0] = gcount[0]; st->gen_count[1] = gcount[1];
+        st->active = active; st->flip_armed = armed; st->next_flip_ms = next_flip; st->buffer_seq = seq; st->error = err;
+        b200_demod_stats &s = st->stats;
+        s.samples_processed += c_samples; s.demod_preambles += red[0]; s.demod_rejected_bad += red[1];
+        s.demod_rejected_unknown_icao += red[2]; s.demod_accepted[0] += red[3]; s.demod_accepted[1] += red[4];
+        for (int p = 0; p < 5; p++) { s.demod_preamblePhase[p] += red[5 + p]; s.demod_bestPhase[p] += red[10 + p]; }
+        s.buffers += c_bufs; s.icao_flips += c_flips;
+        P.frame_count[stream] = min(nframes, P.frame_cap);
+        if (err) atomicOr(&P.ctl->overflow, 8u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: prefix of per-stream frame counts, then one warp per frame
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *count, uint32_t *prefix, uint32_t n, RunCtl *ctl) {
+    const uint32_t n_all = n;
+    __shared__ uint32_t scratch[40];
+    uint32_t base = 0;
+    if (ctl->overflow & 3u) n = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t v = i < n ? count[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(v, scratch, &total);
+        if (i < n) prefix[i] = base + ex;
+        base += total;
+    }
+    if (threadIdx.x == 0) { prefix[n_all] = base; ctl->total_frames = base; }
+}
+
+__device__ __forceinline__ unsigned long long dmax_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t total = P.frame_prefix[P.n_streams];
+    for (uint32_t fi = warp_global; fi < total; fi += n_warps) {
+        // stream = last s with prefix[s] <= fi
+        uint32_t lo = 0, hi = P.n_streams;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.frame_prefix[mid] <= fi) lo = mid; else hi = mid; }
+        const uint32_t stream = lo, k = fi - P.frame_prefix[lo];
+        b200_frame *src = &P.frames[(size_t)stream * P.frame_cap + k];
+        const uint32_t d = *reinterpret_cast<const uint32_t *>(&src->pad_[2]);
+        // locate the segment: frames carry the low 16 bits of the segment index; segments of one stream are few
+        uint32_t seg_i = P.stream_seg_begin[stream];
+        {
+            const uint32_t low = *reinterpret_cast<const uint16_t *>(&src->pad_[0]);
+            while ((seg_i & 0xffffu) != low) seg_i++;
+        }
+        const Segment seg = P.segs[seg_i];
+        const uint32_t len = src->signal_len;
+        unsigned long long sum = 0;
+        for (uint32_t i = lane; i < len; i += 32) {
+            const uint32_t dd = d + 19 + i;                      // data index of the sample (demod_2400.c:443)
+            uint32_t m;
+            if ((seg.flags & SEG_HALO_ZERO) && dd < B200_TRAIL) m = 0;
+            else {
+                const uint16_t raw = *reinterpret_cast<const uint16_t *>(seg.base + 2 * (size_t)dd);
+                m = (seg.flags & SEG_MAG) ? raw : P.lut_full[(raw & 0xffu) * 256 + (raw >> 8)];
+            }
+            sum += (unsigned long long)(m * m);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULLMASK, sum, o);
+        if (lane == 0) {
+            b200_frame fr = *src;
+            fr.sigpow_sum = sum;
+#pragma unroll
+            for (int i = 0; i < 6; i++) fr.pad_[i] = 0;
+            P.packed[fi] = fr;
+            const uint32_t b = seg.first_buf + d / seg.buf_len;
+            atomicAdd(&P.buf_acc[b].sum_signal_power, sum);
+            b200_demod_stats &s = P.state[stream].stats;
+            atomicAdd((unsigned long long *)&s.signal_power_count, (unsigned long long)len);
+            atomicAdd((unsigned long long *)&s.sum_signal_power, sum);
+            const double level = (double)sum / 65535.0 / 65535.0 / (double)len;      // demod_2400.c:448-449
+            if (level > 0.50119) atomicAdd((unsigned long long *)&s.strong_signal_count, 1ull);
+            atomicMax((unsigned long long *)&s.peak_signal_power, dmax_bits(level));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiny control-plane kernels: ICAO filter operations from the host API
+// ------------------------------------------------------------------------------------------------
+__global__ void icao_op_kernel(StreamState *state, uint32_t stream, int op, uint32_t addr, int *result) {
+    StreamState *st = &state[stream];
+    if (threadIdx.x != 0) return;
+    int r = 0;
+    if (op == 0) {            // add (icao_filter.c:112-130)
+        r = gen_add(st->gen[st->active], &st->gen_count[st->active], addr) ? 0 : -1;
+    } else if (op == 1) {     // test (icao_filter.c:132-154)
+        r = (gen_has(st->gen[0], addr) || gen_has(st->gen[1], addr)) ? 1 : 0;
+    } else if (op == 2) {     // expire (icao_filter.c:96-110)
+        const uint32_t other = st->active ^ 1u;
+        for (uint32_t i = 0; i < ICAO_CAP; i++) st->gen[other][i] = ICAO_EMPTY;
+        st->gen_count[other] = 0; st->active = other; st->stats.icao_flips++;
+    } else if (op == 3) {     // reset (icaoFilterInit)
+        for (uint32_t i = 0; i < ICAO_CAP; i++) { st->gen[0][i] = ICAO_EMPTY; st->gen[1][i] = ICAO_EMPTY; }
+        st->gen_count[0] = st->gen_count[1] = 0; st->active = 0; st->flip_armed = 0; st->next_flip_ms = 0;
+    }
+    if (result) *result = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_launch_resolve(const ResolveParams *p, void *stream) {
+    if (p->n_streams == 0) return 0;
+    resolve_kernel<<<p->n_streams, 32, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream) {
+    frame_prefix_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->frame_count, d_frame_prefix, p->n_streams, ctl);
+    finalize_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200_launch_icao_op(StreamState *state, uint32_t stream, int op, uint32_t addr, int *d_result, void *cstream) {
+    icao_op_kernel<<<1, 32, 0, (cudaStream_t)cstream>>>(state, stream, op, addr, d_result);
+    return (int)cudaGetLastError();
+}

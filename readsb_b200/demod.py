@@ -42,6 +42,8 @@ def lib():
         L.b200_demod_host_free.argtypes = [vp]
         L.b200_demod_submit_iq_uc8.argtypes = [vp, u32, vp, u32, i64]
         L.b200_demod_submit_mag_u16.argtypes = [vp, u32, vp, u32, i64]
+        L.b200_demod_submit_iq_uc8_strided.argtypes = [vp, u32, u32, vp, u64, u32, u32, i64]
+        L.b200_demod_set_stream.argtypes = [vp, vp]
         L.b200_demod_run.argtypes = [vp]
         L.b200_demod_run_device_uc8.argtypes = [vp, vp, u64, u32, u32, C.c_int, i64]
         L.b200_demod_frame_count.argtypes = [vp, u32, C.POINTER(u32)]
@@ -66,7 +68,7 @@ EXPORTED_SYMBOLS = [
     "b200_demod_run", "b200_demod_run_device_uc8", "b200_demod_frame_count", "b200_demod_fetch",
     "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
     "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
-    "b200_demod_uc8_lut", "b200_demod_debug_counters",
+    "b200_demod_uc8_lut", "b200_demod_debug_counters", "b200_demod_submit_iq_uc8_strided", "b200_demod_set_stream",
 ]
 
 
@@ -135,6 +137,14 @@ class Demodulator:
         """data: uint16 mag_buf.data = 326 halo magnitudes followed by `length` new ones."""
         assert data.dtype == np.uint16 and data.flags.c_contiguous and data.size >= length + 326
         self._check(self.L.b200_demod_submit_mag_u16(self.h, stream, data.ctypes.data, length, sample_timestamp))
+
+    def submit_iq_strided(self, first_stream: int, n_streams: int, ptr: int, host_stride_bytes: int, n_buffers: int,
+                          buf_len: int, first_sample_timestamp: int):
+        self._check(self.L.b200_demod_submit_iq_uc8_strided(self.h, first_stream, n_streams, ptr, host_stride_bytes,
+                                                            n_buffers, buf_len, first_sample_timestamp))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.L.b200_demod_set_stream(self.h, cuda_stream))
 
     def run(self):
         self._check(self.L.b200_demod_run(self.h))
