@@ -77,55 +77,72 @@ def generate_streams(n_streams: int, samples_per_stream: int, seed0: int, worklo
 # ---------------------------------------------------------------------------------------------------------
 # reference CPU arm (oracle/_ref: the reference's own translation units, see oracle/Makefile)
 # ---------------------------------------------------------------------------------------------------------
-class ReferencePool:
-    """One private copy of the reference library per worker thread (readsb keeps its state in globals)."""
+# Worker processes (fork, started before any CUDA call): readsb keeps its demodulator state in globals, so every
+# receiver shard gets its own process with its own copy of the reference library, like one readsb per receiver.
+_W = {}
 
-    def __init__(self, n_threads: int):
+
+def _worker_init(workload, n_buf):
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oraclelib
+    _W["kind"] = "reference" if oraclelib.have_ref() else "port"
+    _W["ref"] = oraclelib.Reference() if _W["kind"] == "reference" else None
+    _W["oraclelib"] = oraclelib
+    _W["workload"], _W["n_buf"], _W["rows"] = workload, n_buf, {}
+
+
+def _worker_run(task):
+    """task = (seeds, passes): demodulate each seed's stream `passes` times; returns (samples, cpu seconds)."""
+    from readsb_b200 import synth
+    seeds, passes = task
+    gen = synth.config5_stream if _W["workload"] == "config5_dense" else synth.config2_stream
+    for sd in seeds:
+        if sd not in _W["rows"]:
+            _W["rows"][sd] = gen(sd, _W["n_buf"] * BUF)
+    n = 0
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        for sd in seeds:
+            row = _W["rows"][sd]
+            if _W["ref"] is not None:
+                _W["ref"].time_stream(row, BUF)          # convert_uc8_nodc + demodulate2400 per buffer (ifile loop)
+            else:
+                _W["oraclelib"].Oracle().run_stream(row, BUF)
+            n += row.size // 2
+    return n, time.perf_counter() - t0
+
+
+class ReferencePool:
+    def __init__(self, n_workers: int, workload: str, n_buf: int):
+        import multiprocessing as mp
+        self.n = n_workers
+        self.pool = mp.get_context("fork").Pool(n_workers, initializer=_worker_init, initargs=(workload, n_buf))
         sys.path.insert(0, str(ROOT / "tests"))
         import oraclelib
-        self.kind = "reference" if oraclelib.REF_SO.exists() else "port"
-        self.n_threads = n_threads
-        if self.kind == "reference":
-            self.workers = [oraclelib.Reference() for _ in range(n_threads)]
-        else:   # /root/reference was absent when oracle/_ref would have been built: time the C restatement instead
-            self.workers = [None] * n_threads
-            self.oraclelib = oraclelib
-        self.pool = ThreadPoolExecutor(max_workers=n_threads)
+        self.kind = "reference" if oraclelib.have_ref() else "port"
 
-    def _run(self, w, iq_rows):
-        n = 0
-        for row in iq_rows:
-            if self.kind == "reference":
-                self.workers[w].time_stream(row, BUF)
-            else:
-                self.oraclelib.Oracle().run_stream(row, BUF)
-            n += row.size // 2
-        return n
+    def run(self, seeds, passes):
+        """All seeds' streams, `passes` times, sharded over the workers; returns (samples, wall seconds)."""
+        shards = [(seeds[w::self.n], passes) for w in range(self.n) if seeds[w::self.n]]
+        t0 = time.perf_counter()
+        res = self.pool.map(_worker_run, shards, chunksize=1)
+        return sum(r[0] for r in res), time.perf_counter() - t0
 
-    def step(self, rows):
-        """Demodulates every row (one receiver's uc8 samples for this step) once; returns samples processed."""
-        shards = [rows[w::self.n_threads] for w in range(self.n_threads)]
-        return sum(self.pool.map(self._run, range(self.n_threads), shards))
+    def close(self):
+        self.pool.terminate()
 
 
 def reference_arm(args, rank, world):
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    # bounded sample of the b200 arm's batch: the same streams, but only as many as keep a step around a second
+    cores = usable_cores()
+    # bounded sample of the b200 arm's batch: the same seeded streams (rank 0's first receivers), one step = one pass
     n_streams = min(args.streams * args.gpus, max(cores, 64))
-    n_buf = args.buffers
-    host = np.empty((n_streams, 2 * n_buf * BUF), dtype=np.uint8)
-    generate_streams(n_streams, n_buf * BUF, 1, args.workload, host)
-    pool = ReferencePool(cores)
-    rows = [host[s] for s in range(n_streams)]
-    for _ in range(args.warmup):
-        pool.step(rows)
-    t0 = time.perf_counter()
-    samples = 0
-    for _ in range(args.steps):
-        samples += pool.step(rows)
-    dt = time.perf_counter() - t0
+    seeds = [1 + s for s in range(n_streams)]
+    pool = ReferencePool(cores, args.workload, args.buffers)
+    pool.run(seeds, max(1, args.warmup))            # generates the streams in the workers and warms up
+    samples, dt = pool.run(seeds, args.steps)
+    pool.close()
     value = samples / dt / 1e6
     line = {
         "impl": "reference", "metric": "iq_msamples_per_s_demodulated", "value": value, "unit": "Msamples/s",
@@ -133,8 +150,8 @@ def reference_arm(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->u16/int32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": pool.kind,
-                         "sample": f"{n_streams} of the {args.streams * args.gpus} streams x {n_buf} buffers of {BUF} samples per step, "
-                                   f"one receiver per thread (the reference demodulator is single-threaded per receiver)"},
+                         "sample": f"{n_streams} of the {args.streams * args.gpus} streams x {args.buffers} buffers of {BUF} samples per step, "
+                                   f"one receiver per process (the reference demodulator is single-threaded per receiver), {cores} processes"},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -153,6 +170,63 @@ def workload_config(args, n_gpus):
             "parallelism": f"{n_gpus} independent GPU(s), streams sharded {args.streams}/GPU, no collective",
             "l2": f"device inputs cycle through a ring of {args.ring} distinct steps "
                   f"({args.ring * args.streams * args.buffers * BUF * 2 / 2**20:.0f} MiB per GPU, L2 is 126 MB); each step reads bytes not touched for {args.ring - 1} steps"}
+
+
+def usable_cores() -> int:
+    """Host threads this process may really use: affinity mask and cgroup CPU quota, not the machine's core count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+class NvmlClockSampler:
+    """SM clock and throttle reasons sampled through NVML every few ms DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.samples, self.reasons, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], set(), False, None, None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self) -> dict:
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 class ClockSampler:
@@ -201,6 +275,12 @@ class ClockSampler:
 
 
 def b200_arm(args, rank, world, local):
+    cpu_pool = None
+    if not args.no_cpu and world == 1 and rank == 0:
+        try:    # fork the CPU-baseline workers before this process creates a CUDA context
+            cpu_pool = ReferencePool(usable_cores(), args.workload, args.buffers)
+        except Exception:
+            cpu_pool = None
     import torch
     from readsb_b200.demod import Demodulator, PinnedBuffer
     if not torch.cuda.is_available():
@@ -266,7 +346,7 @@ def b200_arm(args, rank, world, local):
     # --- value: inputs resident in HBM -------------------------------------------------------------------------
     for k in range(args.warmup):
         device_step(k)
-    sampler = ClockSampler(local)
+    sampler = NvmlClockSampler(local)
     if rank == 0:
         sampler.start()
     ms, scan_ms, launches, frames = timed(device_step, args.steps, args.warmup)
@@ -321,22 +401,23 @@ def b200_arm(args, rank, world, local):
     }
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu and world == 1:
-        # bounded CPU sample on this box's host cores, timed beside the GPU run
+    if cpu_pool is not None:
+        # bounded CPU sample on this box's host cores, timed beside the GPU run: the same seeded streams
         try:
-            cores = os.cpu_count() or 1
+            cores = cpu_pool.n
             n_cpu_streams = min(S, max(cores, 64))
-            pool = ReferencePool(cores)
-            rows = [host[s][: 2 * B * BUF] for s in range(n_cpu_streams)]
-            pool.step(rows)
-            t0 = time.perf_counter(); n = 0; reps = 0
-            while time.perf_counter() - t0 < 8.0 and reps < 50:
-                n += pool.step(rows); reps += 1
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": pool.kind,
-                                    "sample": f"{n_cpu_streams} of the {S} streams x {B} buffers of {BUF} samples, {reps} passes, one receiver per thread"}
+            seeds = [1 + s for s in range(n_cpu_streams)]
+            cpu_pool.run(seeds, 1)
+            passes = 4
+            n, dt = cpu_pool.run(seeds, passes)
+            while dt < 3.0 and passes < 256:
+                passes *= 4
+                n, dt = cpu_pool.run(seeds, passes)
+            line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": cpu_pool.kind,
+                                    "sample": f"{n_cpu_streams} of the {S} streams x {B} buffers of {BUF} samples, {passes} passes, one receiver per process"}
         except Exception as e:   # the CPU arm must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+        cpu_pool.close()
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -25,10 +25,10 @@
 #define SCAN_LOOKAHEAD 328           // samples kept after the last position of a tile: >= 291 for the slicer, >= 326 so the last tile of a segment sees (and sums) the tail; multiple of 8
 #define SCAN_NMAG      (SCAN_TILE + SCAN_LOOKAHEAD)
 #define SCAN_Q1_CAP    (SCAN_TILE / 4)   // positions passing the pre-check, per tile
-#define SCAN_ITEM_CAP  (SCAN_TILE / 8)   // (position, phase) pairs passing a threshold, per tile
+#define SCAN_PASS_CAP  (SCAN_TILE / 8)   // positions reaching a preamble threshold, per tile
 #define SCAN_FULL_CAP  768             // live records per tile staged in shared memory
 // worst-case candidate queues of one tile in global memory (dense-input slow path), see process_candidates<true>
-#define SCAN_SCRATCH_BYTES (184u * SCAN_TILE)
+#define SCAN_SCRATCH_BYTES (204u * SCAN_TILE)
 
 // ---- segment descriptor ------------------------------------------------------------------------
 #define SEG_MAG        0x1u   // input samples are uint16 magnitudes (demodulate2400 hand-off), not uc8 IQ
@@ -76,6 +76,12 @@ struct __align__(16) Rec {
     uint32_t pad_[2];
 };
 
+// Score key of a Rec (key_pool, parallel to rec_pool): everything the sequential resolver needs.
+#define KEY_AA_CHANGED 0x80000000u   // K_ES_FIX whose corrected bit lies in the AA field (mode_s.c:560)
+#define KEY_DF17       0x10000000u   // DF as sliced is 17
+#define KEY_LONG       0x08000000u   // DF as sliced is a 112-bit type (demod_2400.c:399)
+// bits 24..26 RecKind, bits 0..23 the address the filter is asked about
+
 struct TileOut {
     uint32_t n_pos;    // PosEntry count; entries live at pos_pool[tile * SCAN_TILE ...]
     uint32_t n_rec;
@@ -122,6 +128,7 @@ struct ScanParams {
     uint32_t n_tiles;
     PosEntry *pos_pool;
     Rec *rec_pool;
+    uint32_t *key_pool;          // per Rec: aa_changed << 31 | kind << 24 | addr — all stage B needs to score it
     TileOut *tile_out;
     BufAcc *buf_acc;
     RunCtl *ctl;
@@ -137,6 +144,7 @@ struct ResolveParams {
     uint32_t n_streams;
     const PosEntry *pos_pool;
     const Rec *rec_pool;
+    const uint32_t *key_pool;
     const TileOut *tile_out;
     BufAcc *buf_acc;
     b200_buffer_result *buf_out;      // per run buffer results (n_frames, flip flag, ...)
@@ -157,6 +165,7 @@ struct FinalizeParams {
     const uint32_t *frame_prefix;     // exclusive prefix of frame_count (device computed)
     uint32_t frame_cap;
     b200_frame *packed;               // all frames of the run, stream-major
+    const Rec *rec_pool;
     BufAcc *buf_acc;
     StreamState *state;
     const uint16_t *lut_full;         // 65536-entry UC8 table in global memory

@@ -52,6 +52,7 @@ struct b200_demod_ctx {
     uint64_t cached_layout_key = 0;
     PosEntry *d_pos_pool = nullptr;
     Rec *d_rec_pool = nullptr;
+    uint32_t *d_key_pool = nullptr;
     TileOut *d_tile_out = nullptr;
     BufAcc *d_buf_acc = nullptr, *h_buf_acc = nullptr;
     b200_buffer_result *d_buf_out = nullptr, *h_buf_out = nullptr;
@@ -129,7 +130,7 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_lut_full); cudaFree(c->d_state); cudaFree(c->d_ctl); cudaFree(c->d_arena);
     cudaFree(c->d_segs); cudaFree(c->d_tile_seg); cudaFree(c->d_stream_seg_begin); cudaFree(c->d_pos_pool);
-    cudaFree(c->d_rec_pool); cudaFree(c->d_tile_out); cudaFree(c->d_buf_acc); cudaFree(c->d_buf_out);
+    cudaFree(c->d_rec_pool); cudaFree(c->d_key_pool); cudaFree(c->d_tile_out); cudaFree(c->d_buf_acc); cudaFree(c->d_buf_out);
     cudaFree(c->d_frames); cudaFree(c->d_packed); cudaFree(c->d_frame_count); cudaFree(c->d_frame_prefix);
     cudaFree(c->d_carry_src); cudaFree(c->d_result); cudaFree(c->d_scratch);
     cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_segs); cudaFreeHost(c->h_tile_seg); cudaFreeHost(c->h_stream_seg_begin);
@@ -203,6 +204,7 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     CUC(dev_alloc(&c->d_stream_seg_begin, S + 1)); CUC(pin_alloc(&c->h_stream_seg_begin, S + 1));
     CUC(dev_alloc(&c->d_pos_pool, (size_t)c->tile_cap * SCAN_TILE));
     CUC(dev_alloc(&c->d_rec_pool, c->rec_cap));
+    CUC(dev_alloc(&c->d_key_pool, c->rec_cap));
     CUC(dev_alloc(&c->d_tile_out, c->tile_cap));
     CUC(dev_alloc(&c->d_buf_acc, c->buf_cap)); CUC(pin_alloc(&c->h_buf_acc, c->buf_cap));
     CUC(dev_alloc(&c->d_buf_out, c->buf_cap)); CUC(pin_alloc(&c->h_buf_out, c->buf_cap));
@@ -313,7 +315,7 @@ static int execute(b200_demod_ctx *c, uint32_t nseg, uint32_t ntile, uint32_t nb
         c->launches = 0;
 
         ScanParams sp;
-        sp.segs = c->d_segs; sp.tile_seg = c->d_tile_seg; sp.n_tiles = ntile; sp.pos_pool = c->d_pos_pool; sp.rec_pool = c->d_rec_pool;
+        sp.segs = c->d_segs; sp.tile_seg = c->d_tile_seg; sp.n_tiles = ntile; sp.pos_pool = c->d_pos_pool; sp.rec_pool = c->d_rec_pool; sp.key_pool = c->d_key_pool;
         sp.tile_out = c->d_tile_out; sp.buf_acc = c->d_buf_acc; sp.ctl = c->d_ctl; sp.thr = c->cfg.preamble_threshold;
         sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df; sp.scratch = c->d_scratch;
         // demod_2400.c:112-127
@@ -326,7 +328,7 @@ static int execute(b200_demod_ctx *c, uint32_t nseg, uint32_t ntile, uint32_t nb
 
         ResolveParams rp;
         rp.segs = c->d_segs; rp.stream_seg_begin = c->d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = c->d_pos_pool;
-        rp.rec_pool = c->d_rec_pool; rp.tile_out = c->d_tile_out; rp.buf_acc = c->d_buf_acc; rp.buf_out = c->d_buf_out;
+        rp.rec_pool = c->d_rec_pool; rp.key_pool = c->d_key_pool; rp.tile_out = c->d_tile_out; rp.buf_acc = c->d_buf_acc; rp.buf_out = c->d_buf_out;
         rp.state = c->d_state; rp.frames = c->d_frames; rp.frame_count = c->d_frame_count; rp.frame_cap = c->frame_cap;
         rp.ctl = c->d_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms;
         { int r = b200_launch_resolve(&rp, c->stream); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); c->launches++; }
@@ -335,7 +337,7 @@ static int execute(b200_demod_ctx *c, uint32_t nseg, uint32_t ntile, uint32_t nb
         FinalizeParams fp;
         fp.segs = c->d_segs; fp.stream_seg_begin = c->d_stream_seg_begin; fp.n_streams = S; fp.frames = c->d_frames;
         fp.frame_count = c->d_frame_count; fp.frame_prefix = c->d_frame_prefix; fp.frame_cap = c->frame_cap; fp.packed = c->d_packed;
-        fp.buf_acc = c->d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full;
+        fp.buf_acc = c->d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = c->d_rec_pool;
         { int r = b200_launch_finalize(&fp, c->d_frame_prefix, c->d_ctl, c->stream); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); c->launches += 2; }
         CU(c, cudaEventRecord(c->ev[4], c->stream));
 
@@ -349,8 +351,9 @@ static int execute(b200_demod_ctx *c, uint32_t nseg, uint32_t ntile, uint32_t nb
         if (c->h_ctl->overflow & 1u) {        // record pool too small: stage A is stateless, stage B did nothing -> grow and redo
             const uint32_t need = c->h_ctl->rec_alloc + c->h_ctl->rec_alloc / 4 + 65536;
             cudaFree(c->d_rec_pool); c->d_rec_pool = nullptr;
+            cudaFree(c->d_key_pool); c->d_key_pool = nullptr;
             c->rec_cap = need;
-            if (dev_alloc(&c->d_rec_pool, c->rec_cap) != cudaSuccess) return fail(c, B200_E_NOMEM, "cannot grow the record pool to %u records", need);
+            if (dev_alloc(&c->d_rec_pool, c->rec_cap) != cudaSuccess || dev_alloc(&c->d_key_pool, c->rec_cap) != cudaSuccess) return fail(c, B200_E_NOMEM, "cannot grow the record pool to %u records", need);
             continue;
         }
         if ((c->h_ctl->overflow & 2u) && !c->d_scratch) {   // a tile denser than the shared-memory queues: give the kernel its slow-path arena

@@ -4,14 +4,17 @@
 //                   scoring mode_s.c:309-419, best-phase pick demod_2400.c:241-258, the accept test of
 //                   decodeModesMessage mode_s.c:443-596,:766-779, skip-ahead demod_2400.c:468, the filter flip
 //                   readsb.c:1227-1231), walked speculatively 32 candidates at a time with the receiver's two
-//                   filter generations (icao_filter.c) in shared memory.
-//   finalize_kernel one warp per accepted frame: signal power (demod_2400.c:436-457), per-buffer / per-receiver
-//                   power statistics, packing of the frame list for a single D2H copy.
+//                   filter generations (icao_filter.c) in shared memory.  The walk touches only staged data:
+//                   each tile's PosEntry list and 32-bit score keys arrive through a cp.async ring three tiles
+//                   ahead, so no dependent global load sits on the sequential path.
+//   finalize_kernel one warp per accepted frame (fully parallel): assembles the frame from its 32-byte record
+//                   (bit fix / DF17 repair, mode_s.c:443-596), signal power (demod_2400.c:436-457), per-buffer /
+//                   per-receiver power statistics, packing of the frame list for a single D2H copy.
 #include "common.h"
 #include "device_utils.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// stage B
+// ICAO address filter: two generations of an open-addressed set (icao_filter.c semantics)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t icao_slot(uint32_t a) { return (a * 0x9E3779B1u) >> (32 - ICAO_CAP_LOG2); }
 
@@ -38,9 +41,20 @@ __device__ __forceinline__ bool gen_add(uint32_t *g, uint32_t *count, uint32_t a
     return true;
 }
 
+#define RS_STAGE 384          // PosEntry / score keys of one tile staged in shared memory (bigger tiles are read in place)
+#define RS_RING  4            // staging buffers: the current tile plus three in flight
+
 struct ResolveSmem {
     uint32_t gen[2][ICAO_CAP];
+    PosEntry pos[RS_RING][RS_STAGE];
+    uint32_t key[RS_RING][RS_STAGE];
 };
+
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 
 // Score of one record under the current filter (mode_s.c:309-419).
 __device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
@@ -78,11 +92,41 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
 
     for (uint32_t si = P.stream_seg_begin[stream]; si < P.stream_seg_begin[stream + 1]; si++) {
         const Segment seg = P.segs[si];
-        uint32_t tile = seg.tile_begin, idx = 0;
         const uint32_t tile_end = seg.tile_begin + seg.n_tiles;
-        TileOut to = {0, 0, 0, 0};
-        if (seg.n_tiles) to = P.tile_out[tile];
-        uint32_t rec_cursor = to.rec_off;
+        // Tile cursor with a staging ring: tile t's lists live in ring slot (t - tile_begin) % RS_RING; at any time the
+        // current tile is complete and up to three more are in flight.  TileOut descriptors run one step further ahead
+        // in registers (t1..t4).
+        uint32_t tile = seg.tile_begin, idx = 0, rec_rel = 0;
+        TileOut to = {0, 0, 0, 0}, t1 = to, t2 = to, t3 = to, t4 = to;
+        const PosEntry *pe_ptr = nullptr;
+        const uint32_t *key_ptr = nullptr;
+        auto stageable = [](const TileOut &o) { return o.n_pos <= RS_STAGE && o.n_rec <= RS_STAGE; };
+        auto issue_stage = [&](uint32_t t, const TileOut &o) {      // always commits a group, so group counting stays uniform
+            if (t < tile_end && stageable(o)) {
+                const uint32_t buf = (t - seg.tile_begin) % RS_RING;
+                for (uint32_t e = lane; e < o.n_pos; e += 32) cp_async4(&S.pos[buf][e], &P.pos_pool[(size_t)t * SCAN_TILE + e]);
+                for (uint32_t e = lane; e < o.n_rec; e += 32) cp_async4(&S.key[buf][e], &P.key_pool[o.rec_off + e]);
+            }
+            cp_async_commit();
+        };
+        auto enter_tile = [&](uint32_t t) {          // make tile t current (t1 describes it)
+            to = t1; t1 = t2; t2 = t3; t3 = t4;
+            if (t + 4 < tile_end) t4 = P.tile_out[t + 4];
+            cp_async_wait_2();                       // everything but the two newest groups has landed: tile t is complete
+            __syncwarp();
+            if (stageable(to)) { const uint32_t buf = (t - seg.tile_begin) % RS_RING; pe_ptr = S.pos[buf]; key_ptr = S.key[buf]; }
+            else { pe_ptr = P.pos_pool + (size_t)t * SCAN_TILE; key_ptr = P.key_pool + to.rec_off; }
+            issue_stage(t + 3, t3);                  // reuses the slot of tile t - 1, which is finished
+            idx = 0; rec_rel = 0;
+        };
+        if (seg.n_tiles) {
+            t1 = P.tile_out[tile];
+            if (tile + 1 < tile_end) t2 = P.tile_out[tile + 1];
+            if (tile + 2 < tile_end) t3 = P.tile_out[tile + 2];
+            if (tile + 3 < tile_end) t4 = P.tile_out[tile + 3];
+            issue_stage(tile, t1); issue_stage(tile + 1, t2); issue_stage(tile + 2, t3);
+            enter_tile(tile);
+        }
 
         for (uint32_t b = 0; b < seg.n_bufs; b++) {
             const uint32_t d_begin = b * seg.buf_len;
@@ -93,11 +137,11 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
             uint32_t nfr_buf = 0;
 
             for (;;) {
-                while (idx >= to.n_pos && tile + 1 < tile_end) { tile++; idx = 0; to = P.tile_out[tile]; rec_cursor = to.rec_off; }
+                while (idx >= to.n_pos && tile + 1 < tile_end) { tile++; enter_tile(tile); }
                 if (idx >= to.n_pos) break;
                 const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;
                 const bool has = idx + lane < to.n_pos;
-                const PosEntry pe = has ? P.pos_pool[(size_t)tile * SCAN_TILE + idx + lane] : 0;
+                const PosEntry pe = has ? pe_ptr[idx + lane] : 0;
                 const uint32_t d = x0 + (pe & 0x1fffu) - seg.lead;          // data index = position in the segment
                 const bool inbuf = has && d < d_end;                        // entries are ascending: a prefix of lanes
                 const uint32_t n_in = __popc(__ballot_sync(FULLMASK, inbuf));
@@ -109,22 +153,22 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                 const bool valid = inbuf && d >= skip_until;
 
                 // score every tried phase with the current filter; first strictly greatest wins (demod_2400.c:243)
-                int best = -2; uint32_t best_rec = 0, best_phase = 0, best_kind = 0; bool best_known = false; int best_fix = -1;
+                int best = -2; uint32_t best_rel = 0, best_phase = 0, best_key = 0; bool best_known = false;
                 if (valid && live) {
-                    uint32_t lb = live, k = 0;
-                    while (lb) {
-                        const uint32_t ph = __ffs(lb) - 1; lb &= lb - 1;
-                        const uint32_t ri = rec_cursor + rprefix + k; k++;
-                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(&P.rec_pool[ri]);
-                        const uint32_t meta = rw[3], addr = rw[5];
-                        const uint32_t kind = (meta >> 16) & 0xffu;
-                        const bool known = gen_has(S.gen[0], addr) || gen_has(S.gen[1], addr);
-                        const int sc = rec_score(kind, known);
-                        if (sc > best) { best = sc; best_rec = ri; best_phase = ph; best_kind = kind; best_known = known; best_fix = (int)(int8_t)(meta >> 24); }
+                    uint32_t k = rec_rel + rprefix;
+#pragma unroll
+                    for (uint32_t ph = 0; ph < 5; ph++) {
+                        if ((live >> ph) & 1u) {
+                            const uint32_t key = key_ptr[k];
+                            const bool known = gen_has(S.gen[0], key & 0xffffffu) || gen_has(S.gen[1], key & 0xffffffu);
+                            const int sc = rec_score((key >> 24) & 7u, known);
+                            if (sc > best) { best = sc; best_rel = k; best_phase = ph; best_key = key; best_known = known; }
+                            k++;
+                        }
                     }
                 }
                 // accept test of decodeModesMessage (mode_s.c:443-596): only a corrected AA that is unknown rejects
-                const bool decode_ok = best >= 0 && !(best_kind == K_ES_FIX && best_fix >= 8 && best_fix <= 31 && !best_known);
+                const bool decode_ok = best >= 0 && !((best_key & KEY_AA_CHANGED) && !best_known);
                 const uint32_t acc_mask = __ballot_sync(FULLMASK, valid && decode_ok);
                 const uint32_t f = acc_mask ? (uint32_t)__ffs(acc_mask) - 1 : 32u;
                 const uint32_t consumed = acc_mask ? f + 1 : n_in;
@@ -141,42 +185,29 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                         c_pre++;
 #pragma unroll
                         for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
-                        const uint4 r0 = reinterpret_cast<const uint4 *>(&P.rec_pool[best_rec])[0];
-                        const uint4 r1 = reinterpret_cast<const uint4 *>(&P.rec_pool[best_rec])[1];
-                        uint8_t msg[16];
-                        *reinterpret_cast<uint4 *>(msg) = r0;
-                        const uint32_t crc_raw = r1.x;
-                        const uint32_t df_raw = msg[0] >> 3;
-                        msglen = (df_raw & 0x10) ? 112 : 56;                 // demod_2400.c:399 (DF as sliced)
-                        uint32_t msgtype = df_raw, corrected = 0, crc = crc_raw;
-                        int fix_bit = -1;
-                        bool add = false;
-                        if (best_kind == K_DFREPAIR) { msg[0] = (uint8_t)((msg[0] & 7) | (17 << 3)); msgtype = 17; corrected = 1; fix_bit = best_fix; crc = 0; }
-                        else if (best_kind == K_DF11_FIX || best_kind == K_ES_FIX) { corrected = 1; fix_bit = best_fix; msg[fix_bit >> 3] ^= (uint8_t)(1u << (7 - (fix_bit & 7))); }
-                        else if (best_kind == K_DF11_IID0 || (best_kind == K_ES_OK && msgtype == 17)) add = true;   // mode_s.c:766-779
-                        const uint32_t msgbits = (msgtype & 0x10) ? 112 : 56;
-                        const uint32_t aa = ((uint32_t)msg[1] << 16) | ((uint32_t)msg[2] << 8) | msg[3];
-                        const uint32_t addr = best_kind == K_AP ? crc : aa;
+                        const uint32_t kind = (best_key >> 24) & 7u;
+                        msglen = (best_key & KEY_LONG) ? 112 : 56;              // demod_2400.c:399 (DF as sliced)
+                        const bool corrected = kind == K_DFREPAIR || kind == K_DF11_FIX || kind == K_ES_FIX;
+                        // mode_s.c:766-779: clean DF17, or DF11 with IID 0, teaches the filter its address
+                        const bool add = kind == K_DF11_IID0 || (kind == K_ES_OK && (best_key & KEY_DF17));
                         const uint32_t j = d - d_begin;
                         const int64_t ts = buf_ts + (int64_t)j * 5 + (8 + 56) * 12 + (4 + best_phase);   // demod_2400.c:406
                         if (nframes < P.frame_cap) {
+                            // accept record; finalize_kernel turns it into the full frame from the 32-byte Rec
                             b200_frame fr;
-                            fr.timestamp = ts; fr.sigpow_sum = 0; fr.j = j; fr.crc = crc; fr.addr = addr; fr.score = best;
+                            fr.timestamp = ts; fr.sigpow_sum = 0; fr.j = j; fr.crc = to.rec_off + best_rel; fr.addr = 0; fr.score = best;
                             fr.buffer_seq = seq; fr.signal_len = (uint16_t)(msglen * 12 / 5); fr.phase = (uint8_t)(4 + best_phase);
-                            fr.msgtype = (uint8_t)msgtype; fr.msgbits = (uint8_t)msgbits; fr.correctedbits = (uint8_t)corrected;
-                            fr.fix_bit = (int8_t)fix_bit; fr.flags = add ? B200_FRAME_ICAO_ADDED : 0;
+                            fr.msgtype = 0; fr.msgbits = 0; fr.correctedbits = 0; fr.fix_bit = -1; fr.flags = add ? B200_FRAME_ICAO_ADDED : 0;
 #pragma unroll
-                            for (int i = 0; i < 14; i++) fr.msg[i] = (uint32_t)i < msgbits / 8 ? msg[i] : 0;
-                            // pad_: segment index and data index for finalize_kernel (cleared there)
+                            for (int i = 0; i < 14; i++) fr.msg[i] = 0;
                             fr.pad_[0] = 0; fr.pad_[1] = 0;
-                            *reinterpret_cast<uint16_t *>(&fr.pad_[0]) = (uint16_t)(si & 0xffffu);
+                            *reinterpret_cast<uint16_t *>(&fr.pad_[0]) = (uint16_t)(si & 0xffffu);   // segment (low 16 bits) and data index
                             *reinterpret_cast<uint32_t *>(&fr.pad_[2]) = d;
-                            // pad_[0..1] hold only 16 bits of the segment index; the upper bits ride in flags' spare bits
                             fout[nframes] = fr;
                         } else atomicOr(&P.ctl->overflow, 4u);
                         if (corrected) c_acc1++; else c_acc0++;
                         c_bp[best_phase]++;
-                        if (add) { if (!gen_add(S.gen[active], &gcount[active], addr)) err = 1; dirty[active] = true; }
+                        if (add) { if (!gen_add(S.gen[active], &gcount[active], best_key & 0xffffffu)) err = 1; dirty[active] = true; }
                         now_ms = buf_ts / 12000 + (ts - buf_ts) / 12000;      // demod_2400.c:409-414
                     }
                     __syncwarp();
@@ -192,7 +223,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                 }
                 // advance the cursors past the consumed entries
                 const uint32_t last = consumed - 1;
-                rec_cursor += __shfl_sync(FULLMASK, rprefix + nlive, last);
+                rec_rel += __shfl_sync(FULLMASK, rprefix + nlive, last);
                 idx += consumed;
             }
 
@@ -214,6 +245,8 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
             }
             seq++;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing of this segment may land after the ring is reused
+        __syncwarp();
     }
 
     // write back
@@ -253,6 +286,7 @@ __global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *coun
         if (i < n) prefix[i] = base + ex;
         base += total;
     }
+    for (uint32_t i = n + threadIdx.x; i < n_all; i += blockDim.x) prefix[i] = base;
     if (threadIdx.x == 0) { prefix[n_all] = base; ctl->total_frames = base; }
 }
 
@@ -268,9 +302,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
         uint32_t lo = 0, hi = P.n_streams;
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.frame_prefix[mid] <= fi) lo = mid; else hi = mid; }
         const uint32_t stream = lo, k = fi - P.frame_prefix[lo];
-        b200_frame *src = &P.frames[(size_t)stream * P.frame_cap + k];
+        const b200_frame *src = &P.frames[(size_t)stream * P.frame_cap + k];
         const uint32_t d = *reinterpret_cast<const uint32_t *>(&src->pad_[2]);
-        // locate the segment: frames carry the low 16 bits of the segment index; segments of one stream are few
+        // locate the segment: accept records carry the low 16 bits of the segment index; a stream has few segments
         uint32_t seg_i = P.stream_seg_begin[stream];
         {
             const uint32_t low = *reinterpret_cast<const uint16_t *>(&src->pad_[0]);
@@ -293,6 +327,23 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULLMASK, sum, o);
         if (lane == 0) {
             b200_frame fr = *src;
+            // the accept part of decodeModesMessage (mode_s.c:443-596) on the record the resolver picked
+            const uint4 r0 = reinterpret_cast<const uint4 *>(&P.rec_pool[fr.crc])[0];
+            const uint4 r1 = reinterpret_cast<const uint4 *>(&P.rec_pool[fr.crc])[1];
+            uint8_t msg[16];
+            *reinterpret_cast<uint4 *>(msg) = r0;
+            const uint32_t kind = msg[14];
+            const int rec_fix = (int)(int8_t)msg[15];
+            uint32_t msgtype = msg[0] >> 3, corrected = 0, crc = r1.x;
+            int fix_bit = -1;
+            if (kind == K_DFREPAIR) { msg[0] = (uint8_t)((msg[0] & 7) | (17 << 3)); msgtype = 17; corrected = 1; fix_bit = rec_fix; crc = 0; }   // mode_s.c:276-301
+            else if (kind == K_DF11_FIX || kind == K_ES_FIX) { corrected = 1; fix_bit = rec_fix; msg[fix_bit >> 3] ^= (uint8_t)(1u << (7 - (fix_bit & 7))); }   // crc.c:410-418
+            const uint32_t msgbits = (msgtype & 0x10) ? 112 : 56;
+            const uint32_t aa = ((uint32_t)msg[1] << 16) | ((uint32_t)msg[2] << 8) | msg[3];
+            fr.crc = crc; fr.addr = kind == K_AP ? crc : aa;
+            fr.msgtype = (uint8_t)msgtype; fr.msgbits = (uint8_t)msgbits; fr.correctedbits = (uint8_t)corrected; fr.fix_bit = (int8_t)fix_bit;
+#pragma unroll
+            for (int i = 0; i < 14; i++) fr.msg[i] = (uint32_t)i < msgbits / 8 ? msg[i] : 0;
             fr.sigpow_sum = sum;
 #pragma unroll
             for (int i = 0; i < 6; i++) fr.pad_[i] = 0;
