@@ -1,0 +1,121 @@
+/*
+ * readsb_shim.c — the reference-side binding for the demodulator path.
+ *
+ * Not part of the library and not built by this repository's build(): it is glue a readsb maintainer adds,
+ * compiled against readsb's own headers.  Link an UNMODIFIED readsb with
+ *
+ *     gcc -c -I<readsb> -I<this repo>/include readsb_shim.c
+ *     ... readsb objects ... readsb_shim.o -Wl,--wrap=demodulate2400 -Wl,--wrap=icaoFilterAdd \
+ *         -Wl,--wrap=icaoFilterExpire -L<this repo>/readsb_b200 -lb200demod
+ *
+ * readsb.o's call `demodulate2400(buf)` (readsb.c:871) then resolves to __wrap_demodulate2400 below;
+ * demodulate2400AC and every other symbol of demod_2400.o stay as they are, and __real_demodulate2400
+ * remains available (it is never used as a fallback here: if the GPU path fails the shim calls setExit(2),
+ * readsb.h:406-409 style).
+ *
+ * What stays on the host, unchanged: netGetMM / decodeModesMessage (field decoding, comm_b, CPR) /
+ * netUseMessage / netDrainMessageBuffers, the tracker, all network I/O.  What moves to the GPU: everything
+ * demodulate2400() computes up to the accept decision, including the ICAO filter lookups.  The host filter
+ * (icao_filter.c) keeps existing for network-input decoding (net_io.c:3916); the two are kept in step by
+ * forwarding host-side adds and the 60 s flip (readsb.c:1227-1231) to the library.
+ */
+#include "readsb.h"
+#include "b200_demod.h"
+
+static b200_demod_ctx *g_ctx;
+static b200_demod_stats g_prev;      /* cumulative counters at the previous buffer */
+static int g_in_shim;                /* adds that come from our own decodeModesMessage calls are already on the device */
+static b200_frame g_frames[2048];
+
+void __real_icaoFilterAdd(uint32_t addr);
+void __real_icaoFilterExpire(void);
+
+void __wrap_icaoFilterAdd(uint32_t addr) {
+    __real_icaoFilterAdd(addr);
+    if (g_ctx && !g_in_shim) b200_demod_icao_add(g_ctx, 0, addr);      /* learned from network input */
+}
+
+void __wrap_icaoFilterExpire(void) {
+    __real_icaoFilterExpire();
+    if (g_ctx) b200_demod_icao_expire(g_ctx, 0);
+}
+
+static int shim_open(void) {
+    b200_demod_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.device = -1;
+    cfg.n_streams = 1;                                   /* one receiver per readsb process */
+    cfg.buf_samples = Modes.sdr_buf_samples;             /* readsb.c:2212 */
+    cfg.max_buffers_per_run = 1;                         /* the decode loop hands over one mag_buf at a time */
+    cfg.preamble_threshold = (int32_t) Modes.preambleThreshold;
+    cfg.nfix_crc = Modes.nfix_crc ? 1 : 0;
+    cfg.fix_df = Modes.fixDF;
+    cfg.icao_ttl_ms = -1;                                /* flips are driven by backgroundTasks through the wrap above */
+    if (b200_demod_create(&cfg, &g_ctx) != B200_OK) {
+        fprintf(stderr, "b200 demodulator: %s\n", b200_demod_last_error(NULL));
+        return -1;
+    }
+    memset(&g_prev, 0, sizeof g_prev);
+    return 0;
+}
+
+void __wrap_demodulate2400(struct mag_buf *mag) {
+    if (!g_ctx && shim_open() < 0) { setExit(2); return; }
+
+    /* demod_2400.c:283-285 */
+    if (Modes.sdr_type == SDR_IFILE && Modes.synthetic_now) Modes.synthetic_now = mag->sysTimestamp;
+
+    uint32_t n = 0;
+    if (b200_demod_submit_mag_u16(g_ctx, 0, mag->data, mag->length, mag->sampleTimestamp) != B200_OK ||
+        b200_demod_run(g_ctx) != B200_OK ||
+        b200_demod_fetch(g_ctx, 0, g_frames, sizeof g_frames / sizeof g_frames[0], &n) != B200_OK) {
+        fprintf(stderr, "b200 demodulator: %s\n", b200_demod_last_error(g_ctx));
+        setExit(2);
+        return;
+    }
+
+    uint64_t sum_scaled_signal_power = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const b200_frame *f = &g_frames[i];
+        struct modesMessage *mm = netGetMM(&Modes.netMessageBuffer[0]);          /* demod_2400.c:401 */
+        mm->timestamp = f->timestamp;                                            /* :406 */
+        mm->sysTimestamp = mag->sysTimestamp + receiveclock_ms_elapsed(mag->sampleTimestamp, mm->timestamp);
+        if (Modes.sdr_type == SDR_IFILE && Modes.synthetic_now) Modes.synthetic_now = mm->sysTimestamp;
+        mm->score = f->score;
+        /* decodeModesMessage wants the frame as received: undo the library's correction */
+        memcpy(mm->msg, f->msg, MODES_LONG_MSG_BYTES);
+        if (f->fix_bit >= 0) mm->msg[f->fix_bit >> 3] ^= (unsigned char) (1 << (7 - (f->fix_bit & 7)));
+        g_in_shim = 1;
+        int result = decodeModesMessage(mm);                                     /* :421, field decoding stays on the host */
+        g_in_shim = 0;
+        if (result < 0) continue;                      /* cannot happen while the two filters are in step */
+        Modes.stats_current.demod_accepted[mm->correctedbits]++;
+        Modes.stats_current.demod_bestPhase[f->phase - 4]++;
+        double signal_power = f->sigpow_sum / 65535.0 / 65535.0;                 /* :448-457 */
+        mm->signalLevel = signal_power / f->signal_len;
+        Modes.stats_current.signal_power_sum += signal_power;
+        Modes.stats_current.signal_power_count += f->signal_len;
+        sum_scaled_signal_power += f->sigpow_sum;
+        if (mm->signalLevel > Modes.stats_current.peak_signal_power) Modes.stats_current.peak_signal_power = mm->signalLevel;
+        if (mm->signalLevel > 0.50119) Modes.stats_current.strong_signal_count++;
+        netUseMessage(mm);                                                       /* :471 */
+    }
+
+    /* the counters the scan itself increments (stats.h:62-83) */
+    b200_demod_stats s;
+    if (b200_demod_get_stats(g_ctx, 0, &s) == B200_OK) {
+        Modes.stats_current.demod_preambles += (uint32_t) (s.demod_preambles - g_prev.demod_preambles);
+        Modes.stats_current.demod_rejected_bad += (uint32_t) (s.demod_rejected_bad - g_prev.demod_rejected_bad);
+        Modes.stats_current.demod_rejected_unknown_icao += (uint32_t) (s.demod_rejected_unknown_icao - g_prev.demod_rejected_unknown_icao);
+        for (int p = 0; p < 5; p++)
+            Modes.stats_current.demod_preamblePhase[p] += (uint32_t) (s.demod_preamblePhase[p] - g_prev.demod_preamblePhase[p]);
+        g_prev = s;
+    }
+    /* demod_2400.c:474-479 */
+    double sum_signal_power = sum_scaled_signal_power / 65535.0 / 65535.0;
+    Modes.stats_current.noise_power_sum += (mag->mean_power * mag->length - sum_signal_power);
+    Modes.stats_current.noise_power_count += mag->length;
+
+    netDrainMessageBuffers();                                                    /* :481 */
+}

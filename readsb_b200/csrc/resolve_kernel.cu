@@ -169,18 +169,22 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                 }
                 // accept test of decodeModesMessage (mode_s.c:443-596): only a corrected AA that is unknown rejects
                 const bool decode_ok = best >= 0 && !((best_key & KEY_AA_CHANGED) && !best_known);
-                const uint32_t acc_mask = __ballot_sync(FULLMASK, valid && decode_ok);
-                const uint32_t f = acc_mask ? (uint32_t)__ffs(acc_mask) - 1 : 32u;
-                const uint32_t consumed = acc_mask ? f + 1 : n_in;
-
-                if (valid && lane < f) {       // rejected preambles before the first accepted one
-                    c_pre++;
+                // Commit the chunk in order.  After an accept the skip-ahead (demod_2400.c:468) silently consumes the
+                // following lanes inside the frame; the lanes beyond keep their scores as long as the accepted frame did
+                // not teach the filter a NEW address, so one loaded chunk can yield several frames.
+                uint32_t pending = __ballot_sync(FULLMASK, inbuf), consumed = n_in;
+                for (;;) {
+                    const bool live_lane = ((pending >> lane) & 1u) && d >= skip_until;
+                    const uint32_t acc_mask = __ballot_sync(FULLMASK, live_lane && decode_ok);
+                    const uint32_t f = acc_mask ? (uint32_t)__ffs(acc_mask) - 1 : 32u;
+                    if (live_lane && lane < f) {       // rejected preambles before the next accepted one
+                        c_pre++;
 #pragma unroll
-                    for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
-                    if (best == -2) c_bad++; else c_unk++;       // -1, or decode result -1
-                }
-                if (acc_mask) {
-                    uint32_t msglen = 0;
+                        for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
+                        if (best == -2) c_bad++; else c_unk++;       // -1, or decode result -1
+                    }
+                    if (!acc_mask) break;
+                    uint32_t msglen = 0, relearn = 0;
                     if (lane == f) {
                         c_pre++;
 #pragma unroll
@@ -207,12 +211,17 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                         } else atomicOr(&P.ctl->overflow, 4u);
                         if (corrected) c_acc1++; else c_acc0++;
                         c_bp[best_phase]++;
-                        if (add) { if (!gen_add(S.gen[active], &gcount[active], best_key & 0xffffffu)) err = 1; dirty[active] = true; }
+                        if (add) {
+                            if (!gen_add(S.gen[active], &gcount[active], best_key & 0xffffffu)) err = 1;
+                            dirty[active] = true;
+                            relearn = best_known ? 0u : 1u;      // membership changed: later scores are stale
+                        }
                         now_ms = buf_ts / 12000 + (ts - buf_ts) / 12000;      // demod_2400.c:409-414
                     }
                     __syncwarp();
                     // broadcast the state the accepting lane changed
                     msglen = __shfl_sync(FULLMASK, msglen, f);
+                    relearn = __shfl_sync(FULLMASK, relearn, f);
                     now_ms = __shfl_sync(FULLMASK, now_ms, f);
                     gcount[0] = __shfl_sync(FULLMASK, gcount[0], f); gcount[1] = __shfl_sync(FULLMASK, gcount[1], f);
                     dirty[0] = __shfl_sync(FULLMASK, (int)dirty[0], f); dirty[1] = __shfl_sync(FULLMASK, (int)dirty[1], f);
@@ -220,6 +229,9 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                     const uint32_t d_f = __shfl_sync(FULLMASK, d, f);
                     skip_until = d_f + msglen * 2 + 1;                          // demod_2400.c:468 + loop increment
                     nframes++; nfr_buf++;
+                    pending &= ~((2u << f) - 1u);                               // lanes up to the accepted one are done
+                    if (relearn) { consumed = f + 1; break; }                   // re-score the rest of the chunk with the new filter
+                    if (!pending) break;
                 }
                 // advance the cursors past the consumed entries
                 const uint32_t last = consumed - 1;
