@@ -1,0 +1,143 @@
+"""-m gpu: edge cases of the boundary — ragged / tiny / empty buffers, timestamp discontinuities, receivers with different
+amounts of data in one run, random buffer sizes (seeded fuzz) — always against the oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from oraclelib import Oracle
+from paritylib import diff_bufres, diff_frames, diff_stats
+from readsb_b200 import synth
+from readsb_b200.abi import BUFRES_DTYPE, FRAME_DTYPE
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_buffers(o, iq, cuts, ts_of):
+    """Feed the oracle buffer by buffer exactly like sdr_ifile.c:209-241 (halo carried iff the previous buffer had >= 326 samples)."""
+    halo = np.zeros(326, dtype=np.uint16)
+    frames, bufres = [], []
+    for b, (lo, hi) in enumerate(cuts):
+        mag, sl, sp = Oracle.convert(iq[2 * lo: 2 * hi]) if hi > lo else (np.zeros(0, np.uint16), 0, 0)
+        data = np.concatenate([halo, mag]).astype(np.uint16)
+        f, r = o.demodulate(data, hi - lo, ts_of(b, lo), sl, sp)
+        frames.append(f)
+        bufres.append(np.array([(r.sample_timestamp, r.sum_level, r.sum_power, r.sum_signal_power, r.length, r.n_frames, r.buffer_seq,
+                                 r.icao_flipped)], dtype=BUFRES_DTYPE))
+        halo = data[hi - lo: hi - lo + 326].copy() if hi - lo >= 326 else np.zeros(326, dtype=np.uint16)
+    return (np.concatenate(frames) if frames else np.zeros(0, FRAME_DTYPE)), (np.concatenate(bufres) if bufres else np.zeros(0, BUFRES_DTYPE))
+
+
+def _gpu_buffers(d, iq, cuts, ts_of, per_run, stream=0):
+    frames, bufres = [], []
+    for i in range(0, len(cuts), per_run):
+        for b in range(i, min(i + per_run, len(cuts))):
+            lo, hi = cuts[b]
+            d.submit_iq(stream, iq[2 * lo: 2 * hi], ts_of(b, lo))
+        d.run()
+        frames.append(d.frames(stream)); bufres.append(d.buffer_results(stream))
+    return np.concatenate(frames), np.concatenate(bufres)
+
+
+def test_ragged_and_tiny_buffers(cuda):
+    from readsb_b200.demod import Demodulator
+    iq = synth.mixed_stream(31, 260_000, frames_per_sec=4000)
+    # full, partial, shorter than the halo, empty, full again, odd sizes (also not multiples of 8)
+    sizes = [65536, 1000, 200, 0, 65536, 325, 326, 327, 12345, 65536, 7, 33333]
+    cuts, pos = [], 0
+    for n in sizes:
+        cuts.append((pos, pos + n)); pos += n
+    assert pos <= 260_000
+    ts_of = lambda b, lo: lo * 5
+    o = Oracle(); fo, bo = _oracle_buffers(o, iq, cuts, ts_of)
+    for per_run in (1, 4):
+        d = Demodulator(n_streams=1, buf_samples=65536, max_buffers_per_run=per_run)
+        fg, bg = _gpu_buffers(d, iq, cuts, ts_of, per_run)
+        problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(0), o.stats())
+        assert not problems, f"per_run={per_run}\n" + "\n".join(problems)
+        d.close()
+    assert len(fo) > 50
+
+
+def test_timestamp_discontinuity_starts_a_new_segment(cuda):
+    """Buffers whose sampleTimestamps are not contiguous (dropped samples upstream) must not be glued into one segment:
+    frame timestamps come from each buffer's own sampleTimestamp (demod_2400.c:406)."""
+    from readsb_b200.demod import Demodulator
+    iq = synth.mixed_stream(32, 4 * 32768, frames_per_sec=5000)
+    cuts = [(i * 32768, (i + 1) * 32768) for i in range(4)]
+    ts_of = lambda b, lo: lo * 5 + (0, 0, 777_000, 777_000)[b]
+    o = Oracle(); fo, bo = _oracle_buffers(o, iq, cuts, ts_of)
+    d = Demodulator(n_streams=1, buf_samples=32768, max_buffers_per_run=4)
+    fg, bg = _gpu_buffers(d, iq, cuts, ts_of, 4)
+    problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(0), o.stats())
+    assert not problems, "\n".join(problems)
+    d.close()
+
+
+def test_receivers_with_unequal_work_in_one_run(cuda):
+    """Some receivers idle, some with one buffer, some with several, some ending in a partial buffer."""
+    from readsb_b200.demod import Demodulator
+    S, BUF, K = 7, 32768, 3
+    plan = [[], [BUF], [BUF, BUF, BUF], [BUF, 500], [100], [BUF, BUF], [BUF, BUF, 9999]]
+    d = Demodulator(n_streams=S, buf_samples=BUF, max_buffers_per_run=K)
+    iqs = [synth.mixed_stream(40 + s, K * BUF, frames_per_sec=5000) for s in range(S)]
+    for rnd in range(2):                                   # two runs: halo + filter state carry per receiver
+        for s in range(S):
+            pos = rnd * K * BUF // 2
+            for n in plan[s]:
+                d.submit_iq(s, iqs[s][2 * pos: 2 * (pos + n)], pos * 5); pos += n
+        d.run()
+        for s in range(S):
+            fr = d.frames(s)
+            assert len(d.buffer_results(s)) == len(plan[s])
+            if not plan[s]:
+                assert len(fr) == 0
+        if rnd == 0:
+            first = [(d.frames(s).copy(), d.buffer_results(s).copy()) for s in range(S)]
+    # compare run 0 of every receiver with a fresh oracle fed the same buffers
+    for s in range(S):
+        o = Oracle()
+        cuts, pos = [], 0
+        for n in plan[s]:
+            cuts.append((pos, pos + n)); pos += n
+        fo, bo = _oracle_buffers(o, iqs[s], cuts, lambda b, lo: lo * 5)
+        problems = diff_frames(first[s][0], fo) + diff_bufres(first[s][1], bo)
+        assert not problems, f"receiver {s}\n" + "\n".join(problems)
+    d.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_buffer_sizes_fuzz(cuda, seed):
+    from readsb_b200.demod import Demodulator
+    rng = np.random.default_rng(seed)
+    BUF = int(rng.choice([4096, 8192, 20000, 65536]))
+    total = 150_000
+    iq = synth.generate(total, seed=100 + seed, frames_per_sec=float(rng.choice([300, 3000, 12000])),
+                        df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.DF18 | synth.DF11_IID, n_icao=int(rng.integers(1, 40)),
+                        amp=(0.05, 0.95), noise_sigma=float(rng.uniform(0.5, 6.0)), p_bit_error=0.3, p_two_bit_error=0.1)
+    cuts, pos = [], 0
+    while pos < total:
+        n = int(min(total - pos, rng.integers(0, BUF + 1) if rng.random() < 0.4 else BUF))
+        cuts.append((pos, pos + n)); pos += n
+        if len(cuts) > 200:
+            break
+    thr = int(rng.choice([40, 58, 58, 90]))
+    o = Oracle(thr); fo, bo = _oracle_buffers(o, iq, cuts, lambda b, lo: lo * 5)
+    K = int(rng.integers(1, 6))
+    d = Demodulator(n_streams=1, buf_samples=BUF, max_buffers_per_run=K, preamble_threshold=thr)
+    fg, bg = _gpu_buffers(d, iq, cuts, lambda b, lo: lo * 5, K)
+    problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(0), o.stats())
+    assert not problems, f"BUF={BUF} K={K} thr={thr} buffers={len(cuts)}\n" + "\n".join(problems)
+    d.close()
+
+
+def test_filter_flip_on_the_stream_clock(cuda):
+    """Two-generation ICAO filter flipped by stream time (readsb.c:1227-1231), with a short TTL so several flips happen."""
+    from readsb_b200.demod import Demodulator
+    ttl = 40   # ms of stream time
+    iq = synth.generate(1_200_000, seed=77, frames_per_sec=400, df_mask=synth.DF17 | synth.AP | synth.DF11, n_icao=3)
+    o = Oracle(icao_ttl_ms=ttl); fo, bo = o.run_stream(iq, 32768)
+    d = Demodulator(n_streams=1, buf_samples=32768, max_buffers_per_run=5, icao_ttl_ms=ttl)
+    fg, bg = d.replay(iq)
+    assert bo["icao_flipped"].sum() >= 8
+    problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(0), o.stats())
+    assert not problems, "\n".join(problems)
+    d.close()
