@@ -166,6 +166,15 @@ int b200_demod_run_device_uc8(b200_demod_ctx *ctx, const uint8_t *d_iq, uint64_t
                               uint32_t n_buffers, uint32_t buf_len, int continues,
                               int64_t first_sample_timestamp);
 
+/* Asynchronous form of the call above: returns once the step is enqueued; at most two steps may be in flight.
+ * b200_demod_wait() completes the OLDEST step in flight and makes its results current for the fetch calls below.
+ * Stage A of step n+1 overlaps stage B of step n on the GPU; per-receiver state still advances strictly in step order.
+ * The host-buffer calls, get_stats and the icao_* calls need an empty pipeline. */
+int b200_demod_run_device_uc8_async(b200_demod_ctx *ctx, const uint8_t *d_iq, uint64_t stream_stride_bytes,
+                                    uint32_t n_buffers, uint32_t buf_len, int continues,
+                                    int64_t first_sample_timestamp);
+int b200_demod_wait(b200_demod_ctx *ctx);
+
 /* results of the last run ---------------------------------------------------------------------- */
 int b200_demod_frame_count(b200_demod_ctx *ctx, uint32_t stream, uint32_t *n);
 int b200_demod_fetch(b200_demod_ctx *ctx, uint32_t stream, b200_frame *out, uint32_t cap, uint32_t *n);

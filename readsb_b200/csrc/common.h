@@ -116,7 +116,8 @@ struct StreamState {
 struct RunCtl {
     uint32_t rec_alloc;      // atomic bump pointer into rec_pool
     uint32_t rec_cap;
-    uint32_t overflow;       // bit0: rec_pool exhausted, bit1: per-tile queue capacity exceeded, bit2: frame capacity
+    uint32_t overflow;       // bit0: rec_pool exhausted, bit1: per-tile queue capacity exceeded, bit2: frame capacity,
+                             // bit3: ICAO filter full, bit4: stage B skipped because the step ahead has to be repeated
     uint32_t tile_counter;   // dynamic tile scheduler
     uint32_t total_frames;
     uint32_t pad_[3];
@@ -153,6 +154,7 @@ struct ResolveParams {
     uint32_t *frame_count;            // [n_streams]
     uint32_t frame_cap;
     RunCtl *ctl;
+    const RunCtl *prev_ctl;           // asynchronous pipeline: control block of the step ahead of this one (or nullptr)
     int32_t ttl_ms;
 };
 

@@ -1,15 +1,21 @@
 // demod_api.cu — the C ABI declared in include/b200_demod.h: context, device memory, the
-// host-buffer (drop-in) path and the device-resident path around the kernels in demod_kernels.cu.
+// host-buffer (drop-in) path and the device-resident path around the kernels in scan_kernel.cu / resolve_kernel.cu.
 //
 // Host side of the boundary (reference tree): a frontend's converter call + mag_buf hand-off
 // (sdr_ifile.c:194-259, convert.h:34-39) becomes b200_demod_submit_iq_uc8; the decode thread's
 // demodulate2400(buf) (readsb.c:871, demod_2400.h:38) becomes submit_mag_u16 / run / fetch.
+//
+// A run owns one SLOT (segment tables, candidate pools, result buffers).  The blocking calls use slot 0 on one
+// CUDA stream.  The asynchronous device-resident pair (run_device_uc8_async / wait) alternates two slots: stage A
+// of step n+1 (scan stream) overlaps stage B + finalize + D2H of step n (resolve stream); stage B kernels stay
+// ordered among themselves, which is all the per-receiver state needs.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -26,30 +32,19 @@ struct Pending {
     size_t off;          // byte offset of data index 0 (mag) or of the first new sample (iq) in the stream's arena region
 };
 
-struct b200_demod_ctx {
-    b200_demod_config cfg;
-    int device = 0, n_sm = 148;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
-    std::string err;
+struct DeviceArgs {      // what a device-resident step was asked to do (kept for a repeat after a pool regrowth)
+    const uint8_t *d_iq; uint64_t stride; uint32_t n_buffers, buf_len; int continues; int64_t first_ts;
+};
 
-    DeviceTables *d_tables = nullptr;
-    uint16_t *d_lut_full = nullptr;
-    StreamState *d_state = nullptr;
-    RunCtl *d_ctl = nullptr, *h_ctl = nullptr;
-
-    uint8_t *d_arena = nullptr;
-    size_t stream_stride = 0;
-    std::vector<std::vector<Pending>> pending;
-    std::vector<uint8_t> kind;        // per stream this run: 0 none, 1 iq, 2 mag
-    std::vector<uint8_t> halo_valid;  // iq streams: saved 326-sample tail is valid
-    std::vector<size_t> cursor;       // append offset in the stream's arena region
-
-    uint32_t seg_cap = 0, tile_cap = 0, buf_cap = 0, frame_cap = 0, rec_cap = 0;
+struct Slot {
+    bool allocated = false, in_flight = false, completed = false;
+    uint32_t rec_cap = 0;
     Segment *d_segs = nullptr, *h_segs = nullptr;
     uint32_t *d_tile_seg = nullptr, *h_tile_seg = nullptr;
     uint32_t *d_stream_seg_begin = nullptr, *h_stream_seg_begin = nullptr;
     uint32_t cached_tiles = 0;        // tile_seg on the device is valid for this many tiles (device-resident path)
     uint64_t cached_layout_key = 0;
+    RunCtl *d_ctl = nullptr, *h_ctl = nullptr;
     PosEntry *d_pos_pool = nullptr;
     Rec *d_rec_pool = nullptr;
     uint32_t *d_key_pool = nullptr;
@@ -58,16 +53,40 @@ struct b200_demod_ctx {
     b200_buffer_result *d_buf_out = nullptr, *h_buf_out = nullptr;
     b200_frame *d_frames = nullptr, *d_packed = nullptr, *h_packed = nullptr;
     uint32_t *d_frame_count = nullptr, *d_frame_prefix = nullptr, *h_frame_prefix = nullptr;
+    // the run this slot holds
+    uint32_t nseg = 0, ntile = 0, nbuf = 0, run_frames = 0;
+    bool upload_tiles = true, is_device = false;
+    DeviceArgs dargs = {};
+    std::vector<uint32_t> stream_buf_begin;   // [n_streams+1] into h_buf_out
+    cudaEvent_t ev[6] = {};                   // 0 scan begin, 1 scan end, 2 resolve end, 3 finalize end, 4 results on host, 5 spare
+    float ms[5] = {0, 0, 0, 0, 0};
+    uint32_t launches = 0;
+};
+
+struct b200_demod_ctx {
+    b200_demod_config cfg;
+    int device = 0, n_sm = 148;
+    cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr;
+    std::string err;
+
+    DeviceTables *d_tables = nullptr;
+    uint16_t *d_lut_full = nullptr;
+    StreamState *d_state = nullptr;
+
+    uint8_t *d_arena = nullptr;
+    size_t stream_stride = 0;
+    std::vector<std::vector<Pending>> pending;
+    std::vector<uint8_t> kind;        // per stream this run: 0 none, 1 iq, 2 mag
+    std::vector<uint8_t> halo_valid;  // iq streams: saved 326-sample tail is valid
+    std::vector<size_t> cursor;       // append offset in the stream's arena region
+
+    uint32_t seg_cap = 0, tile_cap = 0, buf_cap = 0, frame_cap = 0;
+    Slot slot[2];
+    int cur = 0;                      // slot whose results fetch / buffer_results / timing report
+    int next_async = 0;               // slot the next asynchronous step takes
     uint32_t *d_carry_src = nullptr, *h_carry_src = nullptr;
     uint8_t *d_scratch = nullptr;     // dense-input slow path arena, allocated on first need
     int *d_result = nullptr;
-
-    // results of the last run
-    uint32_t run_segs = 0, run_tiles = 0, run_bufs = 0, run_frames = 0;
-    std::vector<uint32_t> stream_buf_begin;   // [n_streams+1] into h_buf_out
-    cudaEvent_t ev[6] = {};
-    float ms[5] = {0, 0, 0, 0, 0};
-    uint32_t launches = 0;
 };
 
 static int fail(b200_demod_ctx *c, int code, const char *fmt, ...) {
@@ -124,20 +143,54 @@ API int b200_demod_uc8_lut(uint16_t *out) {
     return B200_OK;
 }
 
+static void free_slot(Slot &s) {
+    cudaFree(s.d_segs); cudaFree(s.d_tile_seg); cudaFree(s.d_stream_seg_begin); cudaFree(s.d_ctl); cudaFree(s.d_pos_pool);
+    cudaFree(s.d_rec_pool); cudaFree(s.d_key_pool); cudaFree(s.d_tile_out); cudaFree(s.d_buf_acc); cudaFree(s.d_buf_out);
+    cudaFree(s.d_frames); cudaFree(s.d_packed); cudaFree(s.d_frame_count); cudaFree(s.d_frame_prefix);
+    cudaFreeHost(s.h_segs); cudaFreeHost(s.h_tile_seg); cudaFreeHost(s.h_stream_seg_begin); cudaFreeHost(s.h_ctl);
+    cudaFreeHost(s.h_buf_acc); cudaFreeHost(s.h_buf_out); cudaFreeHost(s.h_packed); cudaFreeHost(s.h_frame_prefix);
+    for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+    s = Slot();
+}
+
+static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
+    const uint32_t S = c->cfg.n_streams;
+#define A(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+    for (auto &e : s.ev) A(cudaEventCreate(&e));
+    s.rec_cap = rec_cap;
+    A(dev_alloc(&s.d_segs, c->seg_cap)); A(pin_alloc(&s.h_segs, c->seg_cap));
+    A(dev_alloc(&s.d_tile_seg, c->tile_cap)); A(pin_alloc(&s.h_tile_seg, c->tile_cap));
+    A(dev_alloc(&s.d_stream_seg_begin, S + 1)); A(pin_alloc(&s.h_stream_seg_begin, S + 1));
+    A(dev_alloc(&s.d_ctl, 1)); A(pin_alloc(&s.h_ctl, 1));
+    A(dev_alloc(&s.d_pos_pool, (size_t)c->tile_cap * SCAN_TILE));
+    A(dev_alloc(&s.d_rec_pool, s.rec_cap)); A(dev_alloc(&s.d_key_pool, s.rec_cap));
+    A(dev_alloc(&s.d_tile_out, c->tile_cap));
+    A(dev_alloc(&s.d_buf_acc, c->buf_cap)); A(pin_alloc(&s.h_buf_acc, c->buf_cap));
+    A(dev_alloc(&s.d_buf_out, c->buf_cap)); A(pin_alloc(&s.h_buf_out, c->buf_cap));
+    A(dev_alloc(&s.d_frames, (size_t)S * c->frame_cap));
+    A(dev_alloc(&s.d_packed, (size_t)S * c->frame_cap)); A(pin_alloc(&s.h_packed, (size_t)S * c->frame_cap));
+    A(dev_alloc(&s.d_frame_count, S)); A(cudaMemset(s.d_frame_count, 0, S * 4));
+    A(dev_alloc(&s.d_frame_prefix, S + 1)); A(pin_alloc(&s.h_frame_prefix, S + 1));
+    A(cudaMemset(s.d_ctl, 0, sizeof(RunCtl)));
+#undef A
+    memset(s.h_frame_prefix, 0, (S + 1) * 4);
+    memset(s.h_ctl, 0, sizeof(RunCtl));
+    s.stream_buf_begin.assign(S + 1, 0);
+    s.allocated = true;
+    return cudaSuccess;
+}
+
 API void b200_demod_destroy(b200_demod_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_tables); cudaFree(c->d_lut_full); cudaFree(c->d_state); cudaFree(c->d_ctl); cudaFree(c->d_arena);
-    cudaFree(c->d_segs); cudaFree(c->d_tile_seg); cudaFree(c->d_stream_seg_begin); cudaFree(c->d_pos_pool);
-    cudaFree(c->d_rec_pool); cudaFree(c->d_key_pool); cudaFree(c->d_tile_out); cudaFree(c->d_buf_acc); cudaFree(c->d_buf_out);
-    cudaFree(c->d_frames); cudaFree(c->d_packed); cudaFree(c->d_frame_count); cudaFree(c->d_frame_prefix);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_tables); cudaFree(c->d_lut_full); cudaFree(c->d_state); cudaFree(c->d_arena);
     cudaFree(c->d_carry_src); cudaFree(c->d_result); cudaFree(c->d_scratch);
-    cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_segs); cudaFreeHost(c->h_tile_seg); cudaFreeHost(c->h_stream_seg_begin);
-    cudaFreeHost(c->h_buf_acc); cudaFreeHost(c->h_buf_out); cudaFreeHost(c->h_packed); cudaFreeHost(c->h_frame_prefix);
     cudaFreeHost(c->h_carry_src);
-    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    free_slot(c->slot[0]); free_slot(c->slot[1]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->res_stream) cudaStreamDestroy(c->res_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -162,8 +215,9 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
     CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->res_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    for (auto &e : c->ev) CUC(cudaEventCreate(&e));
 
     const uint32_t S = cfg->n_streams, K = cfg->max_buffers_per_run, BUF = cfg->buf_samples;
     // tables
@@ -182,8 +236,6 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     CUC(dev_alloc(&c->d_state, S));
     init_state_kernel<<<S, 256, 0, c->stream>>>(c->d_state, S);
     CUC(cudaGetLastError());
-    CUC(dev_alloc(&c->d_ctl, 1));
-    CUC(pin_alloc(&c->h_ctl, 1));
     CUC(dev_alloc(&c->d_result, 1));
 
     // arena for host submits: [326-sample halo][K buffers, each with room for its own halo when magnitudes are submitted]
@@ -198,29 +250,15 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     c->buf_cap = S * K;
     c->frame_cap = K * (BUF / 113 + 2);
     const size_t positions = (size_t)S * K * BUF;
-    c->rec_cap = (uint32_t)std::max<size_t>(65536, positions / 16);
-    CUC(dev_alloc(&c->d_segs, c->seg_cap)); CUC(pin_alloc(&c->h_segs, c->seg_cap));
-    CUC(dev_alloc(&c->d_tile_seg, c->tile_cap)); CUC(pin_alloc(&c->h_tile_seg, c->tile_cap));
-    CUC(dev_alloc(&c->d_stream_seg_begin, S + 1)); CUC(pin_alloc(&c->h_stream_seg_begin, S + 1));
-    CUC(dev_alloc(&c->d_pos_pool, (size_t)c->tile_cap * SCAN_TILE));
-    CUC(dev_alloc(&c->d_rec_pool, c->rec_cap));
-    CUC(dev_alloc(&c->d_key_pool, c->rec_cap));
-    CUC(dev_alloc(&c->d_tile_out, c->tile_cap));
-    CUC(dev_alloc(&c->d_buf_acc, c->buf_cap)); CUC(pin_alloc(&c->h_buf_acc, c->buf_cap));
-    CUC(dev_alloc(&c->d_buf_out, c->buf_cap)); CUC(pin_alloc(&c->h_buf_out, c->buf_cap));
-    CUC(dev_alloc(&c->d_frames, (size_t)S * c->frame_cap));
-    CUC(dev_alloc(&c->d_packed, (size_t)S * c->frame_cap)); CUC(pin_alloc(&c->h_packed, (size_t)S * c->frame_cap));
-    CUC(dev_alloc(&c->d_frame_count, S));
-    CUC(cudaMemsetAsync(c->d_frame_count, 0, S * 4, c->stream));
-    CUC(dev_alloc(&c->d_frame_prefix, S + 1)); CUC(pin_alloc(&c->h_frame_prefix, S + 1));
+    CUC(alloc_slot(c, c->slot[0], (uint32_t)std::max<size_t>(65536, positions / 16)));
     CUC(dev_alloc(&c->d_carry_src, S)); CUC(pin_alloc(&c->h_carry_src, S));
-    c->stream_buf_begin.assign(S + 1, 0);
-    memset(c->h_frame_prefix, 0, (S + 1) * 4);
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
     *out = c;
     return B200_OK;
 }
+
+static bool any_in_flight(const b200_demod_ctx *c) { return c->slot[0].in_flight || c->slot[1].in_flight; }
 
 // ---- submits ---------------------------------------------------------------------------------
 static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32_t n, int64_t ts, bool mag) {
@@ -228,6 +266,7 @@ static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32
     if (s >= c->cfg.n_streams || (!host && n)) return fail(c, B200_E_INVAL, "bad stream or buffer");
     if (n > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "buffer of %u samples exceeds buf_samples=%u", n, c->cfg.buf_samples);
     if (c->pending[s].size() >= c->cfg.max_buffers_per_run) return fail(c, B200_E_STATE, "stream %u already has max_buffers_per_run buffers queued", s);
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     const uint8_t want = mag ? 2 : 1;
     if (c->kind[s] && c->kind[s] != want) return fail(c, B200_E_STATE, "stream %u mixes IQ and magnitude submits in one run", s);
     CU(c, cudaSetDevice(c->device));
@@ -251,6 +290,7 @@ static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32
 
 API int b200_demod_set_stream(b200_demod_ctx *c, void *cuda_stream) {
     if (!c) return B200_E_INVAL;
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
@@ -262,6 +302,7 @@ API int b200_demod_submit_iq_uc8_strided(b200_demod_ctx *c, uint32_t first, uint
     if (!c || !iq) return B200_E_INVAL;
     if (ns == 0 || first + ns > c->cfg.n_streams || n_buffers == 0 || buf_len == 0 || buf_len > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "bad stream range or buffer length");
     if (n_buffers > 1 && buf_len != c->cfg.buf_samples) return fail(c, B200_E_INVAL, "several buffers per call need buf_len == buf_samples");
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     const size_t row = (size_t)n_buffers * buf_len * 2;
     if (host_stride < row) return fail(c, B200_E_INVAL, "host_stride_bytes smaller than one stream's data");
     for (uint32_t s = first; s < first + ns; s++) {
@@ -288,118 +329,157 @@ API int b200_demod_submit_iq_uc8(b200_demod_ctx *c, uint32_t s, const uint8_t *i
 API int b200_demod_submit_mag_u16(b200_demod_ctx *c, uint32_t s, const uint16_t *data, uint32_t n, int64_t ts) { return submit_common(c, s, data, n, ts, true); }
 
 // ---- the pipeline ------------------------------------------------------------------------------
-static void add_segment(b200_demod_ctx *c, uint32_t &nseg, uint32_t &ntile, uint32_t &nbuf, uint32_t stream, const uint8_t *base,
-                        uint32_t npos, uint32_t buf_len, uint32_t n_bufs, uint32_t flags, int64_t first_ts) {
-    Segment &g = c->h_segs[nseg];
+static void add_segment(b200_demod_ctx *c, Slot &sl, uint32_t stream, const uint8_t *base, uint32_t npos, uint32_t buf_len, uint32_t n_bufs,
+                        uint32_t flags, int64_t first_ts) {
+    (void)c;
+    Segment &g = sl.h_segs[sl.nseg];
     memset(&g, 0, sizeof g);
     g.base = base; g.first_ts = first_ts; g.npos = npos; g.buf_len = buf_len ? buf_len : 1;
     g.lead = (uint32_t)(((uintptr_t)base & 15) / 2); g.flags = flags; g.stream = stream;
-    g.first_buf = nbuf; g.n_bufs = n_bufs; g.tile_begin = ntile;
+    g.first_buf = sl.nbuf; g.n_bufs = n_bufs; g.tile_begin = sl.ntile;
     g.n_tiles = npos ? (g.lead + npos + SCAN_TILE - 1) / SCAN_TILE : 0;
-    for (uint32_t t = 0; t < g.n_tiles; t++) c->h_tile_seg[ntile + t] = nseg;
-    ntile += g.n_tiles; nbuf += n_bufs; nseg++;
+    for (uint32_t t = 0; t < g.n_tiles; t++) sl.h_tile_seg[sl.ntile + t] = sl.nseg;
+    sl.ntile += g.n_tiles; sl.nbuf += n_bufs; sl.nseg++;
 }
 
-static int execute(b200_demod_ctx *c, uint32_t nseg, uint32_t ntile, uint32_t nbuf, bool upload_tiles) {
+// Enqueue one run held by `sl`: tables up, stage A on `scan`, stage B + finalize + first result copy on `res`
+// (the same stream in blocking mode).  `prev_ctl`: control block of the step in flight before this one (async mode).
+static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t res, const RunCtl *prev_ctl) {
     const uint32_t S = c->cfg.n_streams;
-    c->run_segs = nseg; c->run_tiles = ntile; c->run_bufs = nbuf; c->run_frames = 0;
-    CU(c, cudaMemcpyAsync(c->d_segs, c->h_segs, nseg * sizeof(Segment), cudaMemcpyHostToDevice, c->stream));
-    if (upload_tiles && ntile) CU(c, cudaMemcpyAsync(c->d_tile_seg, c->h_tile_seg, ntile * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_stream_seg_begin, c->h_stream_seg_begin, (S + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(sl.d_segs, sl.h_segs, sl.nseg * sizeof(Segment), cudaMemcpyHostToDevice, scan));
+    if (sl.upload_tiles && sl.ntile) CU(c, cudaMemcpyAsync(sl.d_tile_seg, sl.h_tile_seg, sl.ntile * 4, cudaMemcpyHostToDevice, scan));
+    CU(c, cudaMemcpyAsync(sl.d_stream_seg_begin, sl.h_stream_seg_begin, (S + 1) * 4, cudaMemcpyHostToDevice, scan));
+    memset(sl.h_ctl, 0, sizeof(RunCtl));
+    sl.h_ctl->rec_cap = sl.rec_cap;
+    CU(c, cudaMemcpyAsync(sl.d_ctl, sl.h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, scan));
+    CU(c, cudaMemsetAsync(sl.d_buf_acc, 0, (size_t)sl.nbuf * sizeof(BufAcc), scan));
+    sl.launches = 0;
 
-    for (int attempt = 0; attempt < 6; attempt++) {
-        memset(c->h_ctl, 0, sizeof(RunCtl));
-        c->h_ctl->rec_cap = c->rec_cap;
-        CU(c, cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemsetAsync(c->d_buf_acc, 0, (size_t)nbuf * sizeof(BufAcc), c->stream));
-        c->launches = 0;
+    ScanParams sp;
+    sp.segs = sl.d_segs; sp.tile_seg = sl.d_tile_seg; sp.n_tiles = sl.ntile; sp.pos_pool = sl.d_pos_pool; sp.rec_pool = sl.d_rec_pool;
+    sp.key_pool = sl.d_key_pool; sp.tile_out = sl.d_tile_out; sp.buf_acc = sl.d_buf_acc; sp.ctl = sl.d_ctl; sp.thr = c->cfg.preamble_threshold;
+    sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df; sp.scratch = c->d_scratch;
+    // demod_2400.c:112-127
+    sp.short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
+    sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
+    if (sp.nfix && sp.fixdf) for (int b = 0; b < 5; b++) sp.long_set |= 1u << (17 ^ (1 << b));
+    CU(c, cudaEventRecord(sl.ev[0], scan));
+    if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, c->n_sm, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
+    CU(c, cudaEventRecord(sl.ev[1], scan));
+    if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[1], 0));
 
-        ScanParams sp;
-        sp.segs = c->d_segs; sp.tile_seg = c->d_tile_seg; sp.n_tiles = ntile; sp.pos_pool = c->d_pos_pool; sp.rec_pool = c->d_rec_pool; sp.key_pool = c->d_key_pool;
-        sp.tile_out = c->d_tile_out; sp.buf_acc = c->d_buf_acc; sp.ctl = c->d_ctl; sp.thr = c->cfg.preamble_threshold;
-        sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df; sp.scratch = c->d_scratch;
-        // demod_2400.c:112-127
-        sp.short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
-        sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
-        if (sp.nfix && sp.fixdf) for (int b = 0; b < 5; b++) sp.long_set |= 1u << (17 ^ (1 << b));
-        CU(c, cudaEventRecord(c->ev[1], c->stream));
-        if (ntile) { int r = b200_launch_scan(&sp, c->d_tables, c->n_sm, c->stream); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); c->launches++; }
-        CU(c, cudaEventRecord(c->ev[2], c->stream));
+    ResolveParams rp;
+    rp.segs = sl.d_segs; rp.stream_seg_begin = sl.d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = sl.d_pos_pool;
+    rp.rec_pool = sl.d_rec_pool; rp.key_pool = sl.d_key_pool; rp.tile_out = sl.d_tile_out; rp.buf_acc = sl.d_buf_acc; rp.buf_out = sl.d_buf_out;
+    rp.state = c->d_state; rp.frames = sl.d_frames; rp.frame_count = sl.d_frame_count; rp.frame_cap = c->frame_cap;
+    rp.ctl = sl.d_ctl; rp.prev_ctl = prev_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms;
+    { int r = b200_launch_resolve(&rp, res); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
+    CU(c, cudaEventRecord(sl.ev[2], res));
 
-        ResolveParams rp;
-        rp.segs = c->d_segs; rp.stream_seg_begin = c->d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = c->d_pos_pool;
-        rp.rec_pool = c->d_rec_pool; rp.key_pool = c->d_key_pool; rp.tile_out = c->d_tile_out; rp.buf_acc = c->d_buf_acc; rp.buf_out = c->d_buf_out;
-        rp.state = c->d_state; rp.frames = c->d_frames; rp.frame_count = c->d_frame_count; rp.frame_cap = c->frame_cap;
-        rp.ctl = c->d_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms;
-        { int r = b200_launch_resolve(&rp, c->stream); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); c->launches++; }
-        CU(c, cudaEventRecord(c->ev[3], c->stream));
+    FinalizeParams fp;
+    fp.segs = sl.d_segs; fp.stream_seg_begin = sl.d_stream_seg_begin; fp.n_streams = S; fp.frames = sl.d_frames;
+    fp.frame_count = sl.d_frame_count; fp.frame_prefix = sl.d_frame_prefix; fp.frame_cap = c->frame_cap; fp.packed = sl.d_packed;
+    fp.buf_acc = sl.d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = sl.d_rec_pool;
+    { int r = b200_launch_finalize(&fp, sl.d_frame_prefix, sl.d_ctl, res); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
+    CU(c, cudaEventRecord(sl.ev[3], res));
 
-        FinalizeParams fp;
-        fp.segs = c->d_segs; fp.stream_seg_begin = c->d_stream_seg_begin; fp.n_streams = S; fp.frames = c->d_frames;
-        fp.frame_count = c->d_frame_count; fp.frame_prefix = c->d_frame_prefix; fp.frame_cap = c->frame_cap; fp.packed = c->d_packed;
-        fp.buf_acc = c->d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = c->d_rec_pool;
-        { int r = b200_launch_finalize(&fp, c->d_frame_prefix, c->d_ctl, c->stream); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); c->launches += 2; }
-        CU(c, cudaEventRecord(c->ev[4], c->stream));
-
-        CU(c, cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaMemcpyAsync(c->h_frame_prefix, c->d_frame_prefix, (S + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (nbuf) {
-            CU(c, cudaMemcpyAsync(c->h_buf_out, c->d_buf_out, (size_t)nbuf * sizeof(b200_buffer_result), cudaMemcpyDeviceToHost, c->stream));
-            CU(c, cudaMemcpyAsync(c->h_buf_acc, c->d_buf_acc, (size_t)nbuf * sizeof(BufAcc), cudaMemcpyDeviceToHost, c->stream));
-        }
-        CU(c, cudaStreamSynchronize(c->stream));
-        if (c->h_ctl->overflow & 1u) {        // record pool too small: stage A is stateless, stage B did nothing -> grow and redo
-            const uint32_t need = c->h_ctl->rec_alloc + c->h_ctl->rec_alloc / 4 + 65536;
-            cudaFree(c->d_rec_pool); c->d_rec_pool = nullptr;
-            cudaFree(c->d_key_pool); c->d_key_pool = nullptr;
-            c->rec_cap = need;
-            if (dev_alloc(&c->d_rec_pool, c->rec_cap) != cudaSuccess || dev_alloc(&c->d_key_pool, c->rec_cap) != cudaSuccess) return fail(c, B200_E_NOMEM, "cannot grow the record pool to %u records", need);
-            continue;
-        }
-        if ((c->h_ctl->overflow & 2u) && !c->d_scratch) {   // a tile denser than the shared-memory queues: give the kernel its slow-path arena
-            const int grid = b200_scan_grid(c->n_sm);
-            if (grid <= 0 || cudaMalloc((void **)&c->d_scratch, (size_t)grid * SCAN_SCRATCH_BYTES) != cudaSuccess)
-                return fail(c, B200_E_NOMEM, "cannot allocate the dense-input scratch arena");
-            continue;
-        }
-        break;
+    CU(c, cudaMemcpyAsync(sl.h_ctl, sl.d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, res));
+    CU(c, cudaMemcpyAsync(sl.h_frame_prefix, sl.d_frame_prefix, (S + 1) * 4, cudaMemcpyDeviceToHost, res));
+    if (sl.nbuf) {
+        CU(c, cudaMemcpyAsync(sl.h_buf_out, sl.d_buf_out, (size_t)sl.nbuf * sizeof(b200_buffer_result), cudaMemcpyDeviceToHost, res));
+        CU(c, cudaMemcpyAsync(sl.h_buf_acc, sl.d_buf_acc, (size_t)sl.nbuf * sizeof(BufAcc), cudaMemcpyDeviceToHost, res));
     }
-    if (c->h_ctl->overflow & 1u) return fail(c, B200_E_NOMEM, "record pool still too small after regrowth");
-    if (c->h_ctl->overflow & 2u) return fail(c, B200_E_OVERFLOW, "a tile exceeded the in-kernel candidate capacity (input denser than the kernel is sized for)");
-    if (c->h_ctl->overflow & 4u) return fail(c, B200_E_OVERFLOW, "per-stream frame capacity exceeded");
-    if (c->h_ctl->overflow & 8u) return fail(c, B200_E_OVERFLOW, "a receiver's ICAO filter generation is full (%u addresses)", ICAO_CAP / 2);
-    const uint32_t total = c->h_frame_prefix[S];
-    c->run_frames = total;
-    if (total) CU(c, cudaMemcpyAsync(c->h_packed, c->d_packed, (size_t)total * sizeof(b200_frame), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaEventRecord(c->ev[5], c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    for (uint32_t b = 0; b < nbuf; b++) {
-        c->h_buf_out[b].sum_level = c->h_buf_acc[b].sum_level;
-        c->h_buf_out[b].sum_power = c->h_buf_acc[b].sum_power;
-        c->h_buf_out[b].sum_signal_power = c->h_buf_acc[b].sum_signal_power;
-    }
-    cudaEventElapsedTime(&c->ms[1], c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&c->ms[2], c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&c->ms[0], c->ev[1], c->ev[5]);
-    cudaEventElapsedTime(&c->ms[4], c->ev[4], c->ev[5]);
-    c->ms[3] = 0;
+    CU(c, cudaEventRecord(sl.ev[4], res));
     return B200_OK;
+}
+
+// Second half: wait for the first result copy, fetch the frames, derive the timings.  Returns B200_OK, or a positive
+// value when the run has to be repeated: 1 = record pool too small, 2 = dense-tile scratch arena needed, 3 = skipped
+// because the step before it had to be repeated.
+static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
+    const uint32_t S = c->cfg.n_streams;
+    CU(c, cudaEventSynchronize(sl.ev[4]));
+    const uint32_t ov = sl.h_ctl->overflow;
+    if (ov & 1u) return 1;
+    if ((ov & 2u) && !c->d_scratch) return 2;
+    if (ov & 16u) return 3;
+    if (ov & 2u) return fail(c, B200_E_OVERFLOW, "a tile exceeded the in-kernel candidate capacity even with the scratch arena");
+    if (ov & 4u) return fail(c, B200_E_OVERFLOW, "per-stream frame capacity exceeded");
+    if (ov & 8u) return fail(c, B200_E_OVERFLOW, "a receiver's ICAO filter generation is full (%u addresses)", ICAO_CAP / 2);
+    const uint32_t total = sl.h_frame_prefix[S];
+    sl.run_frames = total;
+    if (total) {
+        // The frame copy must not queue behind the NEXT step's stage B on the resolve stream: its own stream,
+        // ordered after this slot's finalize only (ev[4] already completed: finalize is done).
+        (void)res;
+        CU(c, cudaMemcpyAsync(sl.h_packed, sl.d_packed, (size_t)total * sizeof(b200_frame), cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(c, cudaEventRecord(sl.ev[5], c->copy_stream));
+        CU(c, cudaEventSynchronize(sl.ev[5]));
+    }
+    for (uint32_t b = 0; b < sl.nbuf; b++) {
+        sl.h_buf_out[b].sum_level = sl.h_buf_acc[b].sum_level;
+        sl.h_buf_out[b].sum_power = sl.h_buf_acc[b].sum_power;
+        sl.h_buf_out[b].sum_signal_power = sl.h_buf_acc[b].sum_signal_power;
+    }
+    cudaEventElapsedTime(&sl.ms[1], sl.ev[0], sl.ev[1]);
+    cudaEventElapsedTime(&sl.ms[2], sl.ev[1], sl.ev[2]);
+    cudaEventElapsedTime(&sl.ms[0], sl.ev[0], total ? sl.ev[5] : sl.ev[4]);
+    cudaEventElapsedTime(&sl.ms[4], sl.ev[3], total ? sl.ev[5] : sl.ev[4]);
+    sl.ms[3] = 0;
+    return B200_OK;
+}
+
+// Repairs after collect() asked for a repeat.  Every slot gets the new capacity so that later steps do not trip again.
+static int regrow(b200_demod_ctx *c, Slot &sl, int why) {
+    if (why == 1) {
+        const uint32_t need = std::max(sl.h_ctl->rec_alloc + sl.h_ctl->rec_alloc / 4 + 65536, sl.rec_cap);
+        for (Slot &s : c->slot) {
+            if (!s.allocated || s.rec_cap >= need) continue;
+            cudaFree(s.d_rec_pool); s.d_rec_pool = nullptr;
+            cudaFree(s.d_key_pool); s.d_key_pool = nullptr;
+            s.rec_cap = need;
+            if (dev_alloc(&s.d_rec_pool, s.rec_cap) != cudaSuccess || dev_alloc(&s.d_key_pool, s.rec_cap) != cudaSuccess)
+                return fail(c, B200_E_NOMEM, "cannot grow the record pool to %u records", need);
+        }
+    } else if (why == 2 && !c->d_scratch) {   // a tile denser than the shared-memory queues: give the kernel its slow-path arena
+        const int grid = b200_scan_grid(c->n_sm);
+        if (grid <= 0 || cudaMalloc((void **)&c->d_scratch, (size_t)grid * SCAN_SCRATCH_BYTES) != cudaSuccess)
+            return fail(c, B200_E_NOMEM, "cannot allocate the dense-input scratch arena");
+    }
+    return B200_OK;
+}
+
+// Blocking execution of the run held by `sl` on the context's stream, repeated after pool regrowth (stage A is
+// stateless and stage B refuses to run after a stage A failure, so a repeat is exact).
+static int execute_blocking(b200_demod_ctx *c, Slot &sl) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int rc = enqueue(c, sl, c->stream, c->stream, nullptr);
+        if (rc != B200_OK) return rc;
+        rc = collect(c, sl, c->stream);
+        if (rc <= 0) return rc;
+        rc = regrow(c, sl, rc);
+        if (rc != B200_OK) return rc;
+    }
+    return fail(c, B200_E_NOMEM, "record pool still too small after regrowth");
 }
 
 API int b200_demod_run(b200_demod_ctx *c) {
     if (!c) return B200_E_INVAL;
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     CU(c, cudaSetDevice(c->device));
     const uint32_t S = c->cfg.n_streams, BUF = c->cfg.buf_samples;
-    uint32_t nseg = 0, ntile = 0, nbuf = 0;
+    Slot &sl = c->slot[0];
+    c->cur = 0;
+    sl.nseg = sl.ntile = sl.nbuf = 0; sl.is_device = false; sl.upload_tiles = true; sl.cached_tiles = 0;
     for (uint32_t s = 0; s < S; s++) {
-        c->h_stream_seg_begin[s] = nseg;
-        c->stream_buf_begin[s] = nbuf;
+        sl.h_stream_seg_begin[s] = sl.nseg;
+        sl.stream_buf_begin[s] = sl.nbuf;
         c->h_carry_src[s] = 0xffffffffu;
         const auto &pl = c->pending[s];
         if (pl.empty()) continue;
         const uint8_t *region = c->d_arena + (size_t)s * c->stream_stride;
         if (c->kind[s] == 2) {
-            for (const Pending &p : pl) add_segment(c, nseg, ntile, nbuf, s, region + p.off, p.n, p.n, 1, SEG_MAG, p.ts);
+            for (const Pending &p : pl) add_segment(c, sl, s, region + p.off, p.n, p.n, 1, SEG_MAG, p.ts);
         } else {
             // consecutive full buffers with contiguous timestamps form one segment; a partial buffer ends it
             size_t i = 0;
@@ -414,7 +494,7 @@ API int b200_demod_run(b200_demod_ctx *c) {
                     j++;
                 }
                 const uint32_t nb = (uint32_t)(j - i + 1);
-                add_segment(c, nseg, ntile, nbuf, s, region + pl[i].off - (size_t)B200_TRAIL * 2, npos, nb > 1 ? BUF : pl[i].n, nb,
+                add_segment(c, sl, s, region + pl[i].off - (size_t)B200_TRAIL * 2, npos, nb > 1 ? BUF : pl[i].n, nb,
                             halo_ok ? 0 : SEG_HALO_ZERO, pl[i].ts);
                 halo_ok = pl[j].n >= B200_TRAIL;      // sdr_ifile.c:209-213
                 i = j + 1;
@@ -423,74 +503,138 @@ API int b200_demod_run(b200_demod_ctx *c) {
             if (halo_ok) c->h_carry_src[s] = (uint32_t)(c->cursor[s] - (size_t)B200_TRAIL * 2);
         }
     }
-    c->h_stream_seg_begin[S] = nseg;
-    c->stream_buf_begin[S] = nbuf;
-    c->cached_tiles = 0;
-    int rc = execute(c, nseg, ntile, nbuf, true);
+    sl.h_stream_seg_begin[S] = sl.nseg;
+    sl.stream_buf_begin[S] = sl.nbuf;
+    int rc = execute_blocking(c, sl);
     // next run: move each IQ stream's tail to the front of its region
     if (rc == B200_OK) {
         cudaMemcpyAsync(c->d_carry_src, c->h_carry_src, S * 4, cudaMemcpyHostToDevice, c->stream);
         carry_halo_kernel<<<S, 128, 0, c->stream>>>(c->d_arena, c->stream_stride, c->d_carry_src, S);
-        c->launches++;
+        sl.launches++;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, B200_E_CUDA, "halo carry failed");
     }
     for (uint32_t s = 0; s < S; s++) { c->pending[s].clear(); c->kind[s] = 0; c->cursor[s] = 0; }
     return rc;
 }
 
+static int build_device_run(b200_demod_ctx *c, Slot &sl, const DeviceArgs &a) {
+    const uint32_t S = c->cfg.n_streams;
+    if (((uintptr_t)a.d_iq & 15) || (a.stride & 15) || (a.buf_len & 7)) return fail(c, B200_E_INVAL, "d_iq and stream_stride_bytes must be 16-byte aligned and buf_len a multiple of 8");
+    if (a.n_buffers == 0 || a.n_buffers > c->cfg.max_buffers_per_run || a.buf_len == 0 || a.buf_len > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "n_buffers/buf_len exceed the context's configuration");
+    if ((uint64_t)a.n_buffers * a.buf_len * 2 > a.stride && S > 1) return fail(c, B200_E_INVAL, "stream_stride_bytes smaller than one stream's data");
+    sl.nseg = sl.ntile = sl.nbuf = 0; sl.is_device = true; sl.dargs = a;
+    for (uint32_t s = 0; s < S; s++) {
+        sl.h_stream_seg_begin[s] = sl.nseg;
+        sl.stream_buf_begin[s] = sl.nbuf;
+        add_segment(c, sl, s, a.d_iq + (size_t)s * a.stride - (size_t)B200_TRAIL * 2, a.n_buffers * a.buf_len, a.buf_len, a.n_buffers,
+                    a.continues ? 0 : SEG_HALO_ZERO, a.first_ts);
+    }
+    sl.h_stream_seg_begin[S] = sl.nseg;
+    sl.stream_buf_begin[S] = sl.nbuf;
+    // the tile -> segment table only depends on the layout; skip its upload when nothing changed
+    const uint64_t key = ((uint64_t)a.n_buffers << 40) ^ ((uint64_t)a.buf_len << 8) ^ (((uintptr_t)a.d_iq >> 4) & 15) ^ (a.stride << 20);
+    sl.upload_tiles = !(sl.cached_tiles == sl.ntile && sl.cached_layout_key == key);
+    sl.cached_tiles = sl.ntile; sl.cached_layout_key = key;
+    return B200_OK;
+}
+
 API int b200_demod_run_device_uc8(b200_demod_ctx *c, const uint8_t *d_iq, uint64_t stride, uint32_t n_buffers, uint32_t buf_len,
                                   int continues, int64_t first_ts) {
     if (!c || !d_iq) return B200_E_INVAL;
-    const uint32_t S = c->cfg.n_streams;
-    if (((uintptr_t)d_iq & 15) || (stride & 15) || (buf_len & 7)) return fail(c, B200_E_INVAL, "d_iq and stream_stride_bytes must be 16-byte aligned and buf_len a multiple of 8");
-    if (n_buffers == 0 || n_buffers > c->cfg.max_buffers_per_run || buf_len == 0 || buf_len > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "n_buffers/buf_len exceed the context's configuration");
-    if ((uint64_t)n_buffers * buf_len * 2 > stride && S > 1) return fail(c, B200_E_INVAL, "stream_stride_bytes smaller than one stream's data");
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     CU(c, cudaSetDevice(c->device));
-    uint32_t nseg = 0, ntile = 0, nbuf = 0;
-    for (uint32_t s = 0; s < S; s++) {
-        c->h_stream_seg_begin[s] = nseg;
-        c->stream_buf_begin[s] = nbuf;
-        add_segment(c, nseg, ntile, nbuf, s, d_iq + (size_t)s * stride - (size_t)B200_TRAIL * 2, n_buffers * buf_len, buf_len, n_buffers,
-                    continues ? 0 : SEG_HALO_ZERO, first_ts);
+    Slot &sl = c->slot[0];
+    c->cur = 0;
+    const DeviceArgs a = {d_iq, stride, n_buffers, buf_len, continues, first_ts};
+    int rc = build_device_run(c, sl, a);
+    if (rc != B200_OK) return rc;
+    return execute_blocking(c, sl);
+}
+
+// ---- asynchronous device-resident steps: at most two in flight ---------------------------------------------------
+API int b200_demod_run_device_uc8_async(b200_demod_ctx *c, const uint8_t *d_iq, uint64_t stride, uint32_t n_buffers, uint32_t buf_len,
+                                        int continues, int64_t first_ts) {
+    if (!c || !d_iq) return B200_E_INVAL;
+    CU(c, cudaSetDevice(c->device));
+    Slot &sl = c->slot[c->next_async];
+    if (sl.in_flight) return fail(c, B200_E_STATE, "two steps are already in flight: call b200_demod_wait");
+    if (!sl.allocated) {
+        cudaError_t e = alloc_slot(c, sl, c->slot[0].rec_cap);
+        if (e != cudaSuccess) return fail(c, B200_E_NOMEM, "second pipeline slot: %s", cudaGetErrorString(e));
     }
-    c->h_stream_seg_begin[S] = nseg;
-    c->stream_buf_begin[S] = nbuf;
-    // the tile -> segment table only depends on the layout; skip its upload when nothing changed
-    const uint64_t key = ((uint64_t)n_buffers << 40) ^ ((uint64_t)buf_len << 8) ^ (((uintptr_t)d_iq >> 4) & 15) ^ (stride << 20);
-    const bool upload = !(c->cached_tiles == ntile && c->cached_layout_key == key);
-    c->cached_tiles = ntile; c->cached_layout_key = key;
-    return execute(c, nseg, ntile, nbuf, upload);
+    const DeviceArgs a = {d_iq, stride, n_buffers, buf_len, continues, first_ts};
+    int rc = build_device_run(c, sl, a);
+    if (rc != B200_OK) return rc;
+    Slot &other = c->slot[c->next_async ^ 1];
+    rc = enqueue(c, sl, c->stream, c->res_stream, other.in_flight ? other.d_ctl : nullptr);
+    if (rc != B200_OK) return rc;
+    sl.in_flight = true; sl.completed = false;
+    c->next_async ^= 1;
+    return B200_OK;
+}
+
+API int b200_demod_wait(b200_demod_ctx *c) {
+    if (!c) return B200_E_INVAL;
+    CU(c, cudaSetDevice(c->device));
+    // the oldest step in flight is the one in the slot the next submit would NOT take, if both are busy
+    int idx = c->next_async;
+    if (!c->slot[idx].in_flight) idx ^= 1;
+    Slot &sl = c->slot[idx];
+    if (!sl.in_flight) return fail(c, B200_E_STATE, "no asynchronous step in flight");
+    c->cur = idx;
+    if (sl.completed) { sl.in_flight = false; return B200_OK; }     // already repeated synchronously (see below)
+    int rc = collect(c, sl, c->res_stream);
+    if (rc > 0) {
+        // This step (and therefore the one behind it, which saw our failure flag and skipped its stage B) must be
+        // repeated.  Drain the pipeline and redo both, in order, synchronously.
+        Slot &next = c->slot[idx ^ 1];
+        if (next.in_flight) CU(c, cudaEventSynchronize(next.ev[4]));
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaStreamSynchronize(c->res_stream));
+        rc = regrow(c, sl, rc);
+        if (rc == B200_OK) rc = execute_blocking(c, sl);
+        if (rc == B200_OK && next.in_flight) {
+            int rc2 = execute_blocking(c, next);
+            if (rc2 != B200_OK) rc = rc2; else next.completed = true;
+        }
+    }
+    sl.in_flight = false;
+    return rc;
 }
 
 // ---- results -----------------------------------------------------------------------------------
-API int b200_demod_total_frames(b200_demod_ctx *c, uint64_t *n) { if (!c || !n) return B200_E_INVAL; *n = c->run_frames; return B200_OK; }
+API int b200_demod_total_frames(b200_demod_ctx *c, uint64_t *n) { if (!c || !n) return B200_E_INVAL; *n = c->slot[c->cur].run_frames; return B200_OK; }
 
 API int b200_demod_frame_count(b200_demod_ctx *c, uint32_t s, uint32_t *n) {
     if (!c || !n || s >= c->cfg.n_streams) return B200_E_INVAL;
-    *n = c->h_frame_prefix[s + 1] - c->h_frame_prefix[s];
+    const Slot &sl = c->slot[c->cur];
+    *n = sl.h_frame_prefix[s + 1] - sl.h_frame_prefix[s];
     return B200_OK;
 }
 
 API int b200_demod_fetch(b200_demod_ctx *c, uint32_t s, b200_frame *out, uint32_t cap, uint32_t *n) {
     if (!c || !n || s >= c->cfg.n_streams) return B200_E_INVAL;
-    const uint32_t cnt = c->h_frame_prefix[s + 1] - c->h_frame_prefix[s];
+    const Slot &sl = c->slot[c->cur];
+    const uint32_t cnt = sl.h_frame_prefix[s + 1] - sl.h_frame_prefix[s];
     *n = cnt;
     if (cnt > cap) return fail(c, B200_E_OVERFLOW, "stream %u has %u frames, output holds %u", s, cnt, cap);
-    if (cnt) memcpy(out, c->h_packed + c->h_frame_prefix[s], (size_t)cnt * sizeof(b200_frame));
+    if (cnt) memcpy(out, sl.h_packed + sl.h_frame_prefix[s], (size_t)cnt * sizeof(b200_frame));
     return B200_OK;
 }
 
 API int b200_demod_buffer_results(b200_demod_ctx *c, uint32_t s, b200_buffer_result *out, uint32_t cap, uint32_t *n) {
     if (!c || !n || s >= c->cfg.n_streams) return B200_E_INVAL;
-    const uint32_t b0 = c->stream_buf_begin[s], cnt = c->stream_buf_begin[s + 1] - b0;
+    const Slot &sl = c->slot[c->cur];
+    const uint32_t b0 = sl.stream_buf_begin[s], cnt = sl.stream_buf_begin[s + 1] - b0;
     *n = cnt;
     if (cnt > cap) return fail(c, B200_E_OVERFLOW, "stream %u has %u buffer results, output holds %u", s, cnt, cap);
-    if (cnt) memcpy(out, c->h_buf_out + b0, (size_t)cnt * sizeof(b200_buffer_result));
+    if (cnt) memcpy(out, sl.h_buf_out + b0, (size_t)cnt * sizeof(b200_buffer_result));
     return B200_OK;
 }
 
 API int b200_demod_get_stats(b200_demod_ctx *c, uint32_t s, b200_demod_stats *out) {
     if (!c || !out || s >= c->cfg.n_streams) return B200_E_INVAL;
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaMemcpyAsync(out, &c->d_state[s].stats, sizeof(b200_demod_stats), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -499,8 +643,8 @@ API int b200_demod_get_stats(b200_demod_ctx *c, uint32_t s, b200_demod_stats *ou
 
 API int b200_demod_last_timing(b200_demod_ctx *c, float ms[5], uint32_t *launches) {
     if (!c) return B200_E_INVAL;
-    if (ms) memcpy(ms, c->ms, sizeof(c->ms));
-    if (launches) *launches = c->launches;
+    if (ms) memcpy(ms, c->slot[c->cur].ms, sizeof(c->slot[c->cur].ms));
+    if (launches) *launches = c->slot[c->cur].launches;
     return B200_OK;
 }
 
@@ -509,18 +653,20 @@ API int b200_demod_last_timing(b200_demod_ctx *c, float ms[5], uint32_t *launche
 API int b200_demod_debug_counters(b200_demod_ctx *c, uint64_t out[8]) {
     if (!c || !out) return B200_E_INVAL;
     CU(c, cudaSetDevice(c->device));
-    std::vector<TileOut> t(c->run_tiles);
-    if (c->run_tiles) CU(c, cudaMemcpy(t.data(), c->d_tile_out, c->run_tiles * sizeof(TileOut), cudaMemcpyDeviceToHost));
+    const Slot &sl = c->slot[c->cur];
+    std::vector<TileOut> t(sl.ntile);
+    if (sl.ntile) CU(c, cudaMemcpy(t.data(), sl.d_tile_out, sl.ntile * sizeof(TileOut), cudaMemcpyDeviceToHost));
     uint64_t np = 0, nr = 0;
     for (auto &x : t) { np += x.n_pos; nr += x.n_rec; }
-    out[0] = c->run_tiles; out[1] = np; out[2] = nr; out[3] = c->h_ctl->rec_alloc; out[4] = c->h_ctl->overflow;
-    out[5] = c->run_segs; out[6] = c->run_bufs; out[7] = c->run_frames;
+    out[0] = sl.ntile; out[1] = np; out[2] = nr; out[3] = sl.h_ctl->rec_alloc; out[4] = sl.h_ctl->overflow;
+    out[5] = sl.nseg; out[6] = sl.nbuf; out[7] = sl.run_frames;
     return B200_OK;
 }
 
 // ---- ICAO filter control -------------------------------------------------------------------------
 static int icao_op(b200_demod_ctx *c, uint32_t s, int op, uint32_t addr, int *result) {
     if (!c || s >= c->cfg.n_streams) return B200_E_INVAL;
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     CU(c, cudaSetDevice(c->device));
     int r = b200_launch_icao_op(c->d_state, s, op, addr & 0xffffffu, c->d_result, c->stream);
     if (r) return fail(c, B200_E_CUDA, "icao op launch: %s", cudaGetErrorString((cudaError_t)r));

@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
     __shared__ ResolveSmem S;
     const uint32_t stream = blockIdx.x, lane = threadIdx.x;
     StreamState *st = &P.state[stream];
-    if (P.ctl->overflow & 3u) return;     // stage A failed: leave every receiver's state untouched, the host redoes the run
+    // Stage A failed (record pool / dense tile), or the step ahead of this one in the asynchronous pipeline has to be
+    // repeated: leave every receiver's state untouched; the host repeats the run(s) in order.
+    if (P.ctl->overflow & 3u) return;
+    if (P.prev_ctl && (P.prev_ctl->overflow & 19u)) { if (lane == 0) atomicOr(&P.ctl->overflow, 16u); return; }
 
     for (uint32_t i = lane; i < 2 * ICAO_CAP; i += 32) (&S.gen[0][0])[i] = (&st->gen[0][0])[i];
     uint32_t gcount[2] = {st->gen_count[0], st->gen_count[1]};
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *coun
     const uint32_t n_all = n;
     __shared__ uint32_t scratch[40];
     uint32_t base = 0;
-    if (ctl->overflow & 3u) n = 0;
+    if (ctl->overflow & 19u) n = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
         const uint32_t v = i < n ? count[i] : 0;

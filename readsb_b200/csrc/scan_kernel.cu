@@ -27,7 +27,7 @@
 #define TICK_WORDS ((5 * (SCAN_NMAG + 24) + 31) / 32 + 8)
 #define MAG_PAD 40                      // the register-window pass may read this far past SCAN_NMAG
 
-#define WQ1_CAP   512                   // pre-check passers per warp range (worst case: every position)
+#define WQ1_CAP   448                   // pre-check passers per warp range kept in shared memory (of 512 positions)
 #define WPASS_CAP 64                    // threshold passers per warp range kept in shared memory
 #define WFULL_CAP 96                    // DF-gate survivors per warp range kept in shared memory
 
@@ -459,7 +459,7 @@ __device__ __forceinline__ uint32_t window_pass(ScanSmem &S, uint32_t i0, uint32
     return mask;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
+__global__ void __maxnreg__(56) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
     extern __shared__ uint4 smem_raw[];
     ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -535,6 +535,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
             uint32_t n_wq1;
             uint32_t off = warp_excl_scan(__popc(mask), lane, &n_wq1);
             uint32_t mb = mask;
+            if (n_wq1 > WQ1_CAP) { wover = true; n_wq1 = 0; mb = 0; }
             while (mb) { const uint32_t b = __ffs(mb) - 1; mb &= mb - 1; wq1[off++] = (uint16_t)(i0 + b); }
             __syncwarp();
             for (uint32_t r0 = 0; r0 < n_wq1; r0 += 32) {

@@ -46,6 +46,8 @@ def lib():
         L.b200_demod_set_stream.argtypes = [vp, vp]
         L.b200_demod_run.argtypes = [vp]
         L.b200_demod_run_device_uc8.argtypes = [vp, vp, u64, u32, u32, C.c_int, i64]
+        L.b200_demod_run_device_uc8_async.argtypes = [vp, vp, u64, u32, u32, C.c_int, i64]
+        L.b200_demod_wait.argtypes = [vp]
         L.b200_demod_frame_count.argtypes = [vp, u32, C.POINTER(u32)]
         L.b200_demod_fetch.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_buffer_results.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
@@ -69,6 +71,7 @@ EXPORTED_SYMBOLS = [
     "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
     "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
     "b200_demod_uc8_lut", "b200_demod_debug_counters", "b200_demod_submit_iq_uc8_strided", "b200_demod_set_stream",
+    "b200_demod_run_device_uc8_async", "b200_demod_wait",
 ]
 
 
@@ -154,6 +157,14 @@ class Demodulator:
                    first_sample_timestamp: int):
         self._check(self.L.b200_demod_run_device_uc8(self.h, d_ptr, stream_stride_bytes, n_buffers, buf_len,
                                                      1 if continues else 0, first_sample_timestamp))
+
+    def run_device_async(self, d_ptr: int, stream_stride_bytes: int, n_buffers: int, buf_len: int, continues: bool,
+                         first_sample_timestamp: int):
+        self._check(self.L.b200_demod_run_device_uc8_async(self.h, d_ptr, stream_stride_bytes, n_buffers, buf_len,
+                                                           1 if continues else 0, first_sample_timestamp))
+
+    def wait(self):
+        self._check(self.L.b200_demod_wait(self.h))
 
     # -- results -----------------------------------------------------------------------------------
     def frames(self, stream: int) -> np.ndarray:

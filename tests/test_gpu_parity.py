@@ -163,3 +163,60 @@ def test_seeded_filter_accepts_address_parity_replies(cuda):
     assert len(fo) > 100
     _check(d, o, fg, bg, fo, bo)
     d.close()
+
+
+def _device_streams(iqs, total, pad=1024):
+    import torch
+    stride = total * 2 + 4096
+    dev = torch.zeros(pad + len(iqs) * stride, dtype=torch.uint8, device="cuda")
+    for s, iq in enumerate(iqs):
+        dev[pad + s * stride: pad + s * stride + 2 * total] = torch.from_numpy(iq).cuda()
+    torch.cuda.synchronize()
+    return dev, stride, pad
+
+
+def test_async_pipeline_matches_oracle(cuda):
+    """run_device_uc8_async / wait: two steps in flight, stage A of step n+1 overlapping stage B of step n."""
+    from readsb_b200.demod import Demodulator
+    S, buf, nb, calls = 4, 65536, 2, 5
+    total = buf * nb * calls
+    iqs = [GENS[["cfg5", "mixed", "cfg2", "mixed"][s]](700 + s, total) for s in range(S)]
+    dev, stride, pad = _device_streams(iqs, total)
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=nb)
+    got = [[] for _ in range(S)]; gotb = [[] for _ in range(S)]
+
+    def collect():
+        d.wait()
+        for s in range(S):
+            got[s].append(d.frames(s)); gotb[s].append(d.buffer_results(s))
+    for c in range(calls):
+        d.run_device_async(dev.data_ptr() + pad + c * nb * buf * 2, stride, nb, buf, continues=c > 0, first_sample_timestamp=c * nb * buf * 5)
+        if c >= 1:
+            collect()
+    collect()
+    for s in range(S):
+        o = Oracle()
+        fo, bo = o.run_stream(iqs[s], buf)
+        _check(d, o, np.concatenate(got[s]), np.concatenate(gotb[s]), fo, bo, stream=s)
+    d.close()
+
+
+def test_async_pipeline_repeats_steps_exactly_after_a_pool_failure(cuda):
+    """A dense capture makes the FIRST pipelined step ask for the scratch arena while the second is already in flight:
+    both must be repeated in order and stay bit-exact (stage B of the second must not have run on stale state)."""
+    from readsb_b200.demod import Demodulator
+    buf, nb, calls = 32768, 1, 4
+    total = buf * nb * calls
+    storm = synth.generate(total, seed=8, frames_per_sec=40000, df_mask=synth.DF17 | synth.DF11 | synth.AP, n_icao=4,
+                           amp=(0.3, 0.9), p_bit_error=0.3)
+    dev, stride, pad = _device_streams([storm], total)
+    o = Oracle(40); fo, bo = o.run_stream(storm, buf)
+    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=nb, preamble_threshold=40)
+    got, gotb = [], []
+    for c in range(calls):
+        d.run_device_async(dev.data_ptr() + pad + c * nb * buf * 2, stride, nb, buf, continues=c > 0, first_sample_timestamp=c * nb * buf * 5)
+        if c >= 1:
+            d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0))
+    d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0))
+    _check(d, o, np.concatenate(got), np.concatenate(gotb), fo, bo)
+    d.close()
