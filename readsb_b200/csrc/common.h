@@ -21,7 +21,8 @@
 
 // ---- stage A tiling ----------------------------------------------------------------------------
 #define SCAN_TILE      8192          // preamble start positions per tile
-#define SCAN_THREADS   512
+#define SCAN_MAIN_THREADS 512        // 16 warps: convert + window pass + candidate discovery, 16 positions per lane
+#define SCAN_THREADS   (SCAN_MAIN_THREADS + 32)   // + one helper warp: look-ahead samples, tile prefetch
 #define SCAN_LOOKAHEAD 328           // samples kept after the last position of a tile: >= 291 for the slicer, >= 326 so the last tile of a segment sees (and sums) the tail; multiple of 8
 #define SCAN_NMAG      (SCAN_TILE + SCAN_LOOKAHEAD)
 #define SCAN_Q1_CAP    (SCAN_TILE / 4)   // positions passing the pre-check, per tile

@@ -24,6 +24,7 @@
 #include "device_utils.cuh"
 
 #define SCAN_WARPS (SCAN_THREADS / 32)
+#define MAIN_WARPS (SCAN_MAIN_THREADS / 32)
 #define TICK_WORDS ((5 * (SCAN_NMAG + 24) + 31) / 32 + 8)
 #define MAG_PAD 40                      // the register-window pass may read this far past SCAN_NMAG
 
@@ -31,11 +32,13 @@
 #define WPASS_CAP 64                    // threshold passers per warp range kept in shared memory
 #define WFULL_CAP 96                    // DF-gate survivors per warp range kept in shared memory
 
+struct TileInfo { uint32_t x0, interior, p_lo, p_hi; };
+
 struct WarpQueues {                     // candidate discovery is warp-local: warp w owns positions [512w, 512w+512)
-    uint16_t q1[SCAN_WARPS][WQ1_CAP];
-    uint16_t pass_pos[SCAN_WARPS][WPASS_CAP];
-    uint8_t  pass_tried[SCAN_WARPS][WPASS_CAP];
-    uint32_t full[SCAN_WARPS][WFULL_CAP];
+    uint16_t q1[MAIN_WARPS][WQ1_CAP];
+    uint16_t pass_pos[MAIN_WARPS][WPASS_CAP];
+    uint8_t  pass_tried[MAIN_WARPS][WPASS_CAP];
+    uint32_t full[MAIN_WARPS][WFULL_CAP];
 };
 
 struct ScanSmem {
@@ -55,7 +58,8 @@ struct ScanSmem {
         Rec recs[SCAN_FULL_CAP];        // one record per fully sliced phase (kind 0 = score -2 regardless of the filter)
     };
     Segment seg, seg_next;              // descriptor of the current / prefetched tile's segment
-    uint32_t wcnt[SCAN_WARPS];          // per warp: passers | survivors << 16
+    TileInfo info, info_next;           // per-tile scalars, computed once by the helper warp
+    uint32_t wcnt[MAIN_WARPS];          // per warp: passers | survivors << 16
     uint32_t scratch[40];
     uint32_t syn_mul;
     uint32_t rec_off, tile_next, overflow;
@@ -319,10 +323,11 @@ __device__ __forceinline__ void load_convert(ScanSmem &S, const ScanParams &P, c
 
     unsigned long long acc_level = 0, acc_power = 0;
     uint32_t acc_buf = INTERIOR ? seg.first_buf + nb0 : 0xffffffffu;
+    // 16 main warps: chunks [0, SCAN_TILE/8) in two rounds; helper warp: the look-ahead chunks — two rounds each, balanced
+    const bool helper = tid >= SCAN_MAIN_THREADS;
 #pragma unroll 1
-    for (uint32_t k = 0; k < (SCAN_NMAG / 8 + SCAN_THREADS - 1) / SCAN_THREADS; k++) {
-        // the few look-ahead chunks of the last round go to the LAST threads: warp 0 already does the extra window pass
-        const uint32_t c = k * SCAN_THREADS + ((k + 1) * SCAN_THREADS <= SCAN_NMAG / 8 ? tid : SCAN_THREADS - 1 - tid);
+    for (uint32_t k = 0; k < 2; k++) {
+        const uint32_t c = helper ? SCAN_TILE / 8 + k * 32 + lane : k * SCAN_MAIN_THREADS + tid;
         if (c >= SCAN_NMAG / 8) continue;
         const uint32_t xc = x0 + c * 8;
         uint32_t m[8];
@@ -459,6 +464,24 @@ __device__ __forceinline__ uint32_t window_pass(ScanSmem &S, uint32_t i0, uint32
     return mask;
 }
 
+// Per-tile scalars every thread needs, computed by one lane while the previous tile is being processed.
+__device__ __forceinline__ TileInfo make_tile_info(const Segment &seg, uint32_t tile) {
+    TileInfo t;
+    t.x0 = (tile - seg.tile_begin) * SCAN_TILE;                           // tile origin in tile coordinates
+    const int64_t n_first = (int64_t)t.x0 - seg.lead - B200_TRAIL;
+    const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;
+    bool interior = t.x0 >= x_zero_end && t.x0 + SCAN_NMAG <= seg.lead + seg.npos + B200_TRAIL && n_first >= 0 &&
+                    tile + 1 != seg.tile_begin + seg.n_tiles;
+    if (interior) {   // all owned samples in one reference buffer?
+        const uint32_t nb0 = (uint32_t)n_first / seg.buf_len;
+        interior = (uint64_t)n_first + SCAN_TILE <= (uint64_t)(nb0 + 1) * seg.buf_len;
+    }
+    t.interior = interior;
+    t.p_lo = seg.lead > t.x0 ? seg.lead - t.x0 : 0;                        // first real position
+    t.p_hi = min((uint32_t)SCAN_TILE, seg.lead + seg.npos > t.x0 ? seg.lead + seg.npos - t.x0 : 0u);
+    return t;
+}
+
 __global__ void __maxnreg__(56) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
     extern __shared__ uint4 smem_raw[];
     ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
@@ -477,60 +500,53 @@ __global__ void __maxnreg__(56) scan_kernel(const ScanParams P, const DeviceTabl
             S.syn_mul = tables->syn_hash_mul;
             const uint32_t t = atomicAdd(&P.ctl->tile_counter, 1u);
             S.tile_next = t;
-            if (t < P.n_tiles) S.seg_next = P.segs[P.tile_seg[t]];
+            if (t < P.n_tiles) { const Segment sg = P.segs[P.tile_seg[t]]; S.seg_next = sg; S.info_next = make_tile_info(sg, t); }
         }
     }
+    const bool helper_lane0 = tid == SCAN_MAIN_THREADS;
 
     for (;;) {
         __syncthreads();
         const uint32_t tile = S.tile_next;
         if (tile >= P.n_tiles) break;
         if (tid < sizeof(Segment) / 4) reinterpret_cast<uint32_t *>(&S.seg)[tid] = reinterpret_cast<const uint32_t *>(&S.seg_next)[tid];
+        if (tid >= 32 && tid < 32 + sizeof(TileInfo) / 4) reinterpret_cast<uint32_t *>(&S.info)[tid - 32] = reinterpret_cast<const uint32_t *>(&S.info_next)[tid - 32];
         __syncthreads();
-        // Software-pipelined tile fetch (thread 0 only): the atomic is issued here, its result is first used after
-        // phase 1, the segment it names is loaded after phase 2 — three round trips hidden behind this tile's work.
+        // Software-pipelined tile fetch (lane 0 of the helper warp only): the atomic is issued here, its result is first
+        // used after phase 1, the segment it names is loaded after phase 2 — three round trips hidden behind this tile's work.
         uint32_t nxt = 0;
-        if (tid == 0) nxt = atomicAdd(&P.ctl->tile_counter, 1u);
+        if (helper_lane0) nxt = atomicAdd(&P.ctl->tile_counter, 1u);
 
         const Segment &seg = S.seg;
-        const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;         // tile origin in tile coordinates
+        const uint32_t x0 = S.info.x0;
 
         // ---- phase 1: load + convert ----------------------------------------------------------------
-        {
-            const int64_t n_first = (int64_t)x0 - seg.lead - B200_TRAIL;
-            const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;
-            bool interior = x0 >= x_zero_end && x0 + SCAN_NMAG <= seg.lead + seg.npos + B200_TRAIL && n_first >= 0 &&
-                            tile + 1 != seg.tile_begin + seg.n_tiles;
-            if (interior) {   // all owned samples in one reference buffer?
-                const uint32_t nb0 = (uint32_t)n_first / seg.buf_len;
-                interior = (uint64_t)n_first + SCAN_TILE <= (uint64_t)(nb0 + 1) * seg.buf_len;
-            }
-            if (interior) load_convert<true>(S, P, seg, tile, x0); else load_convert<false>(S, P, seg, tile, x0);
-        }
+        if (S.info.interior) load_convert<true>(S, P, seg, tile, x0); else load_convert<false>(S, P, seg, tile, x0);
         uint32_t nxt_seg = 0;
-        if (tid == 0) { S.tile_next = nxt; if (nxt < P.n_tiles) nxt_seg = P.tile_seg[nxt]; }
+        if (helper_lane0) { S.tile_next = nxt; if (nxt < P.n_tiles) nxt_seg = P.tile_seg[nxt]; }
         __syncthreads();                                                   // B: magnitudes complete
 
-        // ---- phase 2: pre-check masks + tick map, 16 positions per lane; warp w owns positions [512w, 512w+512) ----
-        const uint32_t i0 = tid * 16;
-        uint32_t mask = window_pass(S, i0, lane, true);
-        {
-            const uint32_t p_lo = seg.lead > x0 ? seg.lead - x0 : 0;                              // first real position
-            const uint32_t p_hi = min((uint32_t)SCAN_TILE, seg.lead + seg.npos > x0 ? seg.lead + seg.npos - x0 : 0u);
+        // ---- phase 2: pre-check masks + tick map, 16 positions per lane; main warp w owns positions [512w, 512w+512),
+        //      the helper warp the look-ahead samples SCAN_TILE .. SCAN_NMAG-1 (ticks only) ------------------------------
+        const bool is_main = tid < SCAN_MAIN_THREADS;
+        const uint32_t i0 = is_main ? tid * 16 : SCAN_TILE + lane * 16;
+        uint32_t mask = window_pass(S, i0, lane, is_main || lane < (SCAN_LOOKAHEAD + 31) / 32 * 2);
+        if (is_main) {
+            const uint32_t p_lo = S.info.p_lo, p_hi = S.info.p_hi;
             // positions outside [p_lo, p_hi) are not preamble starts of this segment
             const uint32_t lo_cut = p_lo > i0 ? min(p_lo - i0, 16u) : 0u, hi_cut = p_hi > i0 ? min(p_hi - i0, 16u) : 0u;
             mask &= (0xffffu << lo_cut) & ((1u << hi_cut) - 1u);
             const uint32_t both = (mask << (16 * (lane & 1))) | __shfl_xor_sync(FULLMASK, mask << (16 * (lane & 1)), 1);
             if ((lane & 1) == 0) S.pre_bits[i0 >> 5] = both;
-            // look-ahead samples SCAN_TILE .. SCAN_NMAG-1: ticks only (whole warp: the pass shuffles)
-            if (tid < 32) window_pass(S, SCAN_TILE + i0, lane, tid < (SCAN_LOOKAHEAD + 31) / 32 * 2);
+        } else {
+            mask = 0;
+            if (lane == 0 && nxt < P.n_tiles) { const Segment sg = P.segs[nxt_seg]; S.seg_next = sg; S.info_next = make_tile_info(sg, nxt); }
         }
-        if (tid == 0 && nxt < P.n_tiles) S.seg_next = P.segs[nxt_seg];
 
         // ---- warp-local discovery: pre-check passers -> thresholds (magnitudes only, no tick needed yet) ----------------
         uint32_t n_wpass = 0;
         bool wover = false;
-        {
+        if (is_main) {
             uint16_t *wq1 = S.wq.q1[wid];
             uint32_t n_wq1;
             uint32_t off = warp_excl_scan(__popc(mask), lane, &n_wq1);
@@ -552,7 +568,7 @@ __global__ void __maxnreg__(56) scan_kernel(const ScanParams P, const DeviceTabl
 
         // ---- warp-local DF gate over the warp's own passers ------------------------------------------------------------------
         uint32_t n_wfull = 0;
-        if (!__any_sync(FULLMASK, wover)) {
+        if (is_main && !__any_sync(FULLMASK, wover)) {
             for (uint32_t r0 = 0; r0 < 5 * n_wpass; r0 += 32) {
                 const uint32_t i = r0 + lane, r = i / 5, ph = i - 5 * r;
                 uint32_t g = 0;
@@ -564,20 +580,20 @@ __global__ void __maxnreg__(56) scan_kernel(const ScanParams P, const DeviceTabl
             }
         }
         wover = __any_sync(FULLMASK, wover);
-        if (lane == 0) S.wcnt[wid] = wover ? 0xffffffffu : (n_wpass | (n_wfull << 16));
+        if (lane == 0 && is_main) S.wcnt[wid] = wover ? 0xffffffffu : (n_wpass | (n_wfull << 16));
         __syncthreads();                                                   // D: per-warp counts published
 
         // ---- publish to the ordered block lists -----------------------------------------------------------------------------------
         uint32_t n_pass, n_full;
         bool dense;
         {
-            const uint32_t c = lane < SCAN_WARPS ? S.wcnt[lane] : 0u;
+            const uint32_t c = lane < MAIN_WARPS ? S.wcnt[lane] : 0u;
             dense = __any_sync(FULLMASK, c == 0xffffffffu);
             uint32_t tot;
             const uint32_t ex = warp_excl_scan(dense ? 0u : c, lane, &tot);   // both 16-bit counters in one add: no carry (<= 8192 each)
             n_pass = tot & 0xffffu; n_full = tot >> 16;
             dense = dense || n_pass > SCAN_PASS_CAP || n_full > SCAN_FULL_CAP;
-            if (!dense) {
+            if (!dense && is_main) {
                 const uint32_t mine = __shfl_sync(FULLMASK, ex, wid), base_p = mine & 0xffffu, base_f = mine >> 16;
                 for (uint32_t e = lane; e < n_wpass; e += 32) {
                     S.pass_pos[base_p + e] = S.wq.pass_pos[wid][e]; S.pass_tried[base_p + e] = S.wq.pass_tried[wid][e]; S.pass_live[base_p + e] = 0;
