@@ -76,6 +76,14 @@ typedef struct b200_frame {
 
 #define B200_FRAME_ICAO_ADDED 0x01 /* this frame caused icaoFilterAdd(addr) (mode_s.c:766-779) */
 
+/* One Mode A/C reply found by demodulate2400AC() (demod_2400.c:575-761): what it hands to decodeModeAMessage(). */
+typedef struct b200_modeac {
+    int64_t  timestamp;     /* 12 MHz: sampleTimestamp + f2_clock/5, i.e. at the F2 framing pulse (demod_2400.c:745) */
+    uint32_t f1_sample;     /* index into mag_buf.data of the F1 pulse */
+    uint16_t modeac;        /* 00 A4 A2 A1 00 B4 B2 B1 SPI C4 C2 C1 00 D4 D2 D1 (demod_2400.c:716-731) */
+    uint16_t buffer_idx;    /* which buffer of the run (index into b200_demod_buffer_results) */
+} b200_modeac;
+
 /* Per (stream, buffer) scalars: what convert_uc8_nodc() returns (convert.c:100-107) and what
  * demodulate2400() folds into noise stats (demod_2400.c:474-479), kept as exact integers. */
 typedef struct b200_buffer_result {
@@ -102,7 +110,7 @@ typedef struct b200_demod_stats {
     uint64_t sum_signal_power;        /* sum of sigpow_sum (integer form of signal_power_sum) */
     uint64_t strong_signal_count;     /* signalLevel > 0.50119 */
     double   peak_signal_power;       /* highest signalLevel seen (stats.h peak_signal_power) */
-    uint64_t reserved_;
+    uint64_t demod_modeac;            /* Mode A/C replies (stats.h demod_modeac) */
     uint64_t buffers;
     uint64_t icao_flips;
 } b200_demod_stats;
@@ -117,8 +125,10 @@ typedef struct b200_demod_config {
     int32_t  nfix_crc;              /* 0 or 1 (--fix / --no-fix, readsb.c:1460-1464) */
     int32_t  fix_df;                /* 0 or 1 (--no-fix-df, readsb.c:1467) */
     int32_t  icao_ttl_ms;           /* automatic filter flip period in stream time, <0 = never, 0 -> 60000 */
-    uint32_t flags;                 /* reserved, 0 */
+    uint32_t flags;                 /* B200_CFG_* */
 } b200_demod_config;
+
+#define B200_CFG_MODE_AC 0x1u   /* also run the Mode A/C demodulator on every buffer (--modeac, readsb.c:872-874) */
 
 typedef struct b200_demod_ctx b200_demod_ctx;
 
@@ -181,6 +191,8 @@ int b200_demod_fetch(b200_demod_ctx *ctx, uint32_t stream, b200_frame *out, uint
 int b200_demod_buffer_results(b200_demod_ctx *ctx, uint32_t stream, b200_buffer_result *out,
                               uint32_t cap, uint32_t *n);
 int b200_demod_total_frames(b200_demod_ctx *ctx, uint64_t *n); /* all streams, last run */
+/* Mode A/C replies of the last run (contexts created with B200_CFG_MODE_AC), in order */
+int b200_demod_fetch_modeac(b200_demod_ctx *ctx, uint32_t stream, b200_modeac *out, uint32_t cap, uint32_t *n);
 int b200_demod_get_stats(b200_demod_ctx *ctx, uint32_t stream, b200_demod_stats *out);
 
 /* ICAO address filter (icao_filter.h) — per stream, lives next to the resolver on the device */

@@ -18,6 +18,9 @@
 #include <string.h>
 
 #define TRAIL B200_TRAILING_SAMPLES
+#ifndef M_SQRT2
+#define M_SQRT2 1.41421356237309504880 /* math.h value (hidden by -std=c11) */
+#endif
 
 /* ------------------------------------------------------------------ convert.c:35-62 */
 static uint16_t g_lut[65536];
@@ -413,6 +416,62 @@ int oracle_demodulate2400(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64
         res->buffer_seq = o->buffer_seq; res->icao_flipped = (uint32_t)flipped;
     }
     o->buffer_seq++;
+    return overflow ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------ demod_2400.c:575-761
+ * Mode A/C: F1/F2 framing pulse pair 14 bit periods apart on a virtual 60 MHz clock (87 cycles per bit, 25 per sample),
+ * 20 bit cells sliced against thresholds 3 dB either side of the geometric mean of noise and pulse level.
+ * The float / double mix below is the reference's (float products, double for the +0.5 and the sqrt(2) factors). */
+int oracle_demodulate2400AC(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64_t sample_ts,
+                            uint64_t sum_level, uint64_t sum_power, b200_modeac *out, unsigned cap, unsigned *n_out) {
+    int overflow = 0;
+    if (mlen == 0) return 0;
+    const double mean_level = sum_level / 65536.0 / mlen;                 /* convert.c:100-102 */
+    const double mean_power = sum_power / 65535.0 / 65535.0 / mlen;       /* convert.c:104-106 */
+    const double noise_stddev = sqrt(mean_power - mean_level * mean_level);
+    const unsigned noise_level = (unsigned)((mean_power + noise_stddev) * 65535 + 0.5);
+    for (unsigned f1 = 1; f1 < mlen; ++f1) {
+        if (!(m[f1 - 1] < m[f1])) continue;                               /* rising edge */
+        if (m[f1 + 2] > m[f1] || m[f1 + 2] > m[f1 + 1]) continue;         /* quiet part quiet enough */
+        const unsigned f1_level = (m[f1] + m[f1 + 1]) / 2;
+        if (noise_level * 2 > f1_level) continue;                         /* 6 dB above noise */
+        const float f1a = (float)m[f1] * m[f1], f1b = (float)m[f1 + 1] * m[f1 + 1];
+        const float fraction = f1b / (f1a + f1b);
+        const unsigned f1_clock = (unsigned)(25 * (f1 + fraction * fraction) + 0.5);
+        const unsigned f2_clock = f1_clock + 87 * 14, f2 = f2_clock / 25;
+        if (!(m[f2 - 1] < m[f2])) continue;
+        if (m[f2 + 2] > m[f2] || m[f2 + 2] > m[f2 + 1]) continue;
+        const unsigned f2_level = (m[f2] + m[f2 + 1]) / 2;
+        if (noise_level * 2 > f2_level) continue;
+        const unsigned f1f2 = f1_level > f2_level ? f1_level : f2_level;
+        const float midpoint = sqrtf(noise_level * f1f2);                 /* unsigned product, may wrap like the reference's */
+        const unsigned signal_threshold = (unsigned)(midpoint * M_SQRT2 + 0.5);
+        const unsigned noise_threshold = (unsigned)(midpoint / M_SQRT2 + 0.5);
+        unsigned bits = 0, noisy = 0, uncertain = 0, clock = f1_clock;
+        for (unsigned bit = 0; bit < 20; ++bit, clock += 87) {
+            const unsigned s = clock / 25;
+            bits <<= 1; noisy <<= 1; uncertain <<= 1;
+            if (m[s + 2] >= signal_threshold) noisy |= 1;
+            if (m[s] >= signal_threshold || m[s + 1] >= signal_threshold) bits |= 1;
+            else if (m[s] > noise_threshold && m[s + 1] > noise_threshold) uncertain |= 1;
+        }
+        if ((bits & 0x80020) != 0x80020) continue;                        /* F1, F2 on */
+        if ((bits & 0x0101B) != 0) continue;                              /* quiet cells off */
+        if (noisy || uncertain) continue;
+        const unsigned modeac =
+            ((bits & 0x40000) ? 0x0010 : 0) | ((bits & 0x20000) ? 0x1000 : 0) | ((bits & 0x10000) ? 0x0020 : 0) |
+            ((bits & 0x08000) ? 0x2000 : 0) | ((bits & 0x04000) ? 0x0040 : 0) | ((bits & 0x02000) ? 0x4000 : 0) |
+            ((bits & 0x00800) ? 0x0100 : 0) | ((bits & 0x00400) ? 0x0001 : 0) | ((bits & 0x00200) ? 0x0200 : 0) |
+            ((bits & 0x00100) ? 0x0002 : 0) | ((bits & 0x00080) ? 0x0400 : 0) | ((bits & 0x00040) ? 0x0004 : 0) |
+            ((bits & 0x00004) ? 0x0080 : 0);
+        if (*n_out < cap) {
+            b200_modeac *a = &out[(*n_out)++];
+            a->timestamp = sample_ts + f2_clock / 5; a->f1_sample = f1; a->modeac = (uint16_t)modeac; a->buffer_idx = 0;
+        } else overflow = 1;
+        f1 += 20 * 87 / 25;                                               /* skip the reply (the loop adds 1) */
+        o->st.demod_modeac++;
+    }
     return overflow ? -1 : 0;
 }
 

@@ -37,6 +37,8 @@ static unsigned g_cap, g_n, g_overflow;
 static int64_t g_cur_sample_ts;
 static uint32_t g_buffer_seq;
 static unsigned g_buf_frames;
+static b200_modeac *g_ac_out;            /* Mode A/C capture (decodeModeAMessage marks mm->msgtype DFTYPE_MODEAC) */
+static unsigned g_ac_cap, g_ac_n, g_ac_overflow;
 
 struct modesMessage *netGetMM(struct messageBuffer *buf) {
     memset(&g_mm, 0, sizeof g_mm);
@@ -45,6 +47,13 @@ struct modesMessage *netGetMM(struct messageBuffer *buf) {
 }
 
 void netUseMessage(struct modesMessage *mm) {
+    if (mm->msgtype == DFTYPE_MODEAC) {
+        if (g_ac_n >= g_ac_cap) { g_ac_overflow = 1; return; }
+        b200_modeac *a = &g_ac_out[g_ac_n++];
+        a->timestamp = mm->timestamp; a->f1_sample = 0; a->buffer_idx = 0;
+        a->modeac = (uint16_t)((mm->msg[0] << 8) | mm->msg[1]);           /* mode_ac.c:171-173 */
+        return;
+    }
     g_buf_frames++;
     if (g_n >= g_cap) { g_overflow = 1; return; }
     b200_frame *f = &g_out[g_n];
@@ -173,6 +182,23 @@ int ref_demodulate2400(uint16_t *data, unsigned length, int64_t sample_ts, doubl
     g_buffer_seq++;
     return g_overflow ? -1 : 0;
 }
+
+/* The real demodulate2400AC() on one mag_buf (readsb.c:872-874). */
+int ref_demodulate2400AC(uint16_t *data, unsigned length, int64_t sample_ts, double mean_level, double mean_power,
+                         b200_modeac *out, unsigned cap, unsigned *n_out) {
+    struct mag_buf mb;
+    memset(&mb, 0, sizeof mb);
+    mb.sampleTimestamp = sample_ts;
+    mb.sysTimestamp = sample_ts / 12000U + Modes.startup_time;
+    mb.mean_level = mean_level; mb.mean_power = mean_power;
+    mb.length = length; mb.data = data;
+    g_ac_out = out; g_ac_cap = cap; g_ac_n = *n_out; g_ac_overflow = 0;
+    demodulate2400AC(&mb);
+    *n_out = g_ac_n;
+    return g_ac_overflow ? -1 : 0;
+}
+
+uint64_t ref_modeac_count(void) { return Modes.stats_current.demod_modeac; }
 
 /* The ifile replay loop (sdr_ifile.c:169-259) around the real converter and demodulator.
  * mean_levels/mean_powers (optional) receive the converter's two doubles per buffer. */

@@ -28,7 +28,7 @@ class Stats(C.Structure):
                 ("demod_accepted", C.c_uint64 * 2), ("demod_preamblePhase", C.c_uint64 * 5),
                 ("demod_bestPhase", C.c_uint64 * 5), ("signal_power_count", C.c_uint64),
                 ("sum_signal_power", C.c_uint64), ("strong_signal_count", C.c_uint64),
-                ("peak_signal_power", C.c_double), ("reserved_", C.c_uint64), ("buffers", C.c_uint64),
+                ("peak_signal_power", C.c_double), ("demod_modeac", C.c_uint64), ("buffers", C.c_uint64),
                 ("icao_flips", C.c_uint64)]
 
     def as_dict(self):
@@ -46,7 +46,10 @@ class Config(C.Structure):
                 ("icao_ttl_ms", C.c_int32), ("flags", C.c_uint32)]
 
 
-assert C.sizeof(Frame) == 64 and C.sizeof(BufferResult) == 48
+MODEAC_DTYPE = np.dtype([("timestamp", "<i8"), ("f1_sample", "<u4"), ("modeac", "<u2"), ("buffer_idx", "<u2")])
+CFG_MODE_AC = 0x1
+
+assert C.sizeof(Frame) == 64 and C.sizeof(BufferResult) == 48 and MODEAC_DTYPE.itemsize == 16
 
 FRAME_DTYPE = np.dtype([("timestamp", "<i8"), ("sigpow_sum", "<u8"), ("j", "<u4"), ("crc", "<u4"), ("addr", "<u4"),
                         ("score", "<i4"), ("buffer_seq", "<u4"), ("signal_len", "<u2"), ("phase", "u1"),

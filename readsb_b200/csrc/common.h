@@ -118,7 +118,8 @@ struct RunCtl {
     uint32_t rec_alloc;      // atomic bump pointer into rec_pool
     uint32_t rec_cap;
     uint32_t overflow;       // bit0: rec_pool exhausted, bit1: per-tile queue capacity exceeded, bit2: frame capacity,
-                             // bit3: ICAO filter full, bit4: stage B skipped because the step ahead has to be repeated
+                             // bit3: ICAO filter full, bit4: stage B skipped because the step ahead has to be repeated,
+                             // bit5: Mode A/C candidate / output capacity exceeded
     uint32_t tile_counter;   // dynamic tile scheduler
     uint32_t total_frames;
     uint32_t pad_[3];
@@ -174,6 +175,35 @@ struct FinalizeParams {
     const uint16_t *lut_full;         // 65536-entry UC8 table in global memory
 };
 
+// ---- Mode A/C (modeac_kernel.cu) -------------------------------------------------------------------
+struct DeviceTables;
+struct AcScanParams {
+    const Segment *segs;
+    uint32_t n_segs;
+    const uint32_t *tile_seg;
+    uint32_t n_tiles;
+    const BufAcc *buf_acc;            // the scan kernel's exact per-buffer sums: noise floor of demodulate2400AC
+    const DeviceTables *tables;
+    uint32_t *noise;                  // [buffer] noise_level (demod_2400.c:581)
+    uint32_t *bitmap;                 // [tile][SCAN_TILE/32]: bit p = a well-formed reply's F1 pulse starts at position p of the tile
+    RunCtl *ctl;
+};
+
+struct AcWalkParams {
+    const Segment *segs;
+    uint32_t n_segs;
+    const uint32_t *stream_seg_begin;
+    uint32_t n_streams;
+    const uint32_t *bitmap;
+    const uint32_t *noise;
+    const uint16_t *lut_full;
+    b200_modeac *ac_out;              // [buffer][per_buf_cap]
+    uint32_t *ac_count;               // [buffer]
+    uint32_t per_buf_cap;             // buf_samples / 70 + 2: an accepted reply hides the next 69 positions
+    StreamState *state;
+    RunCtl *ctl;
+};
+
 // ---- host-built constant tables, uploaded once ---------------------------------------------------
 struct DeviceTables {
     uint16_t lut_fold[128 * 128];  // folded + bank-swizzled UC8 magnitude table (see modes_tables.h)
@@ -192,6 +222,9 @@ int b200_scan_grid(int n_sm);   // CTAs the scan kernel is launched with (persis
 int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream);
 int b200_launch_resolve(const ResolveParams *p, void *stream);
 int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream);
+int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp, int n_sm, void *stream);
+int b200_launch_modeac_stats(const AcWalkParams *wp, const uint32_t *prefix, void *stream);
+int b200_launch_ac_pack(const b200_modeac *ac_out, const uint32_t *count, uint32_t *prefix, b200_modeac *packed, uint32_t n_units, uint32_t cap, RunCtl *ctl, void *stream);
 int b200_launch_icao_op(StreamState *state, uint32_t stream, int op, uint32_t addr, int *d_result, void *cstream);
 #ifdef __cplusplus
 }

@@ -53,12 +53,17 @@ struct Slot {
     b200_buffer_result *d_buf_out = nullptr, *h_buf_out = nullptr;
     b200_frame *d_frames = nullptr, *d_packed = nullptr, *h_packed = nullptr;
     uint32_t *d_frame_count = nullptr, *d_frame_prefix = nullptr, *h_frame_prefix = nullptr;
+    // Mode A/C (contexts created with B200_CFG_MODE_AC)
+    uint32_t *d_ac_bitmap = nullptr, *d_ac_noise = nullptr;
+    uint32_t *d_ac_count = nullptr, *d_ac_prefix = nullptr, *h_ac_prefix = nullptr;   // per reference buffer of the run
+    b200_modeac *d_ac_out = nullptr, *d_ac_packed = nullptr, *h_ac_packed = nullptr;
     // the run this slot holds
     uint32_t nseg = 0, ntile = 0, nbuf = 0, run_frames = 0;
     bool upload_tiles = true, is_device = false;
     DeviceArgs dargs = {};
     std::vector<uint32_t> stream_buf_begin;   // [n_streams+1] into h_buf_out
-    cudaEvent_t ev[6] = {};                   // 0 scan begin, 1 scan end, 2 resolve end, 3 finalize end, 4 results on host, 5 spare
+    cudaEvent_t ev[7] = {};                   // 0 scan begin, 1 scan end, 2 resolve end, 3 finalize end, 4 results on host,
+                                              // 5 result copies done, 6 Mode A/C scan + walk done
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t launches = 0;
 };
@@ -80,7 +85,7 @@ struct b200_demod_ctx {
     std::vector<uint8_t> halo_valid;  // iq streams: saved 326-sample tail is valid
     std::vector<size_t> cursor;       // append offset in the stream's arena region
 
-    uint32_t seg_cap = 0, tile_cap = 0, buf_cap = 0, frame_cap = 0;
+    uint32_t seg_cap = 0, tile_cap = 0, buf_cap = 0, frame_cap = 0, ac_cap = 0;
     Slot slot[2];
     int cur = 0;                      // slot whose results fetch / buffer_results / timing report
     int next_async = 0;               // slot the next asynchronous step takes
@@ -147,6 +152,8 @@ static void free_slot(Slot &s) {
     cudaFree(s.d_segs); cudaFree(s.d_tile_seg); cudaFree(s.d_stream_seg_begin); cudaFree(s.d_ctl); cudaFree(s.d_pos_pool);
     cudaFree(s.d_rec_pool); cudaFree(s.d_key_pool); cudaFree(s.d_tile_out); cudaFree(s.d_buf_acc); cudaFree(s.d_buf_out);
     cudaFree(s.d_frames); cudaFree(s.d_packed); cudaFree(s.d_frame_count); cudaFree(s.d_frame_prefix);
+    cudaFree(s.d_ac_bitmap); cudaFree(s.d_ac_noise); cudaFree(s.d_ac_count); cudaFree(s.d_ac_prefix); cudaFree(s.d_ac_out); cudaFree(s.d_ac_packed);
+    cudaFreeHost(s.h_ac_prefix); cudaFreeHost(s.h_ac_packed);
     cudaFreeHost(s.h_segs); cudaFreeHost(s.h_tile_seg); cudaFreeHost(s.h_stream_seg_begin); cudaFreeHost(s.h_ctl);
     cudaFreeHost(s.h_buf_acc); cudaFreeHost(s.h_buf_out); cudaFreeHost(s.h_packed); cudaFreeHost(s.h_frame_prefix);
     for (auto &e : s.ev) if (e) cudaEventDestroy(e);
@@ -172,6 +179,15 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
     A(dev_alloc(&s.d_frame_count, S)); A(cudaMemset(s.d_frame_count, 0, S * 4));
     A(dev_alloc(&s.d_frame_prefix, S + 1)); A(pin_alloc(&s.h_frame_prefix, S + 1));
     A(cudaMemset(s.d_ctl, 0, sizeof(RunCtl)));
+    if (c->cfg.flags & B200_CFG_MODE_AC) {
+        // one bit per position, and room for every reply a buffer can hold: nothing here depends on the input
+        const size_t ac_total = (size_t)c->buf_cap * c->ac_cap;
+        A(dev_alloc(&s.d_ac_bitmap, (size_t)c->tile_cap * (SCAN_TILE / 32)));
+        A(dev_alloc(&s.d_ac_noise, c->buf_cap)); A(dev_alloc(&s.d_ac_count, c->buf_cap));
+        A(dev_alloc(&s.d_ac_out, ac_total)); A(dev_alloc(&s.d_ac_packed, ac_total)); A(pin_alloc(&s.h_ac_packed, ac_total));
+        A(dev_alloc(&s.d_ac_prefix, c->buf_cap + 1)); A(pin_alloc(&s.h_ac_prefix, c->buf_cap + 1));
+        memset(s.h_ac_prefix, 0, (S + 1) * 4);
+    }
 #undef A
     memset(s.h_frame_prefix, 0, (S + 1) * 4);
     memset(s.h_ctl, 0, sizeof(RunCtl));
@@ -249,6 +265,7 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     c->tile_cap = S * K * tiles_per_buf;
     c->buf_cap = S * K;
     c->frame_cap = K * (BUF / 113 + 2);
+    c->ac_cap = BUF / 70 + 2;                       // per reference buffer: a Mode A/C reply hides the next 69 positions
     const size_t positions = (size_t)S * K * BUF;
     CUC(alloc_slot(c, c->slot[0], (uint32_t)std::max<size_t>(65536, positions / 16)));
     CUC(dev_alloc(&c->d_carry_src, S)); CUC(pin_alloc(&c->h_carry_src, S));
@@ -368,6 +385,21 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     CU(c, cudaEventRecord(sl.ev[1], scan));
     if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[1], 0));
 
+    // demodulate2400AC on the same buffers (readsb.c:872-874).  Its scan and walk are stateless, so they stay on the
+    // scan stream, where they overlap stage B of this step when the two streams differ.
+    const bool mode_ac = (c->cfg.flags & B200_CFG_MODE_AC) != 0;
+    AcWalkParams aw = {};
+    if (mode_ac) {
+        AcScanParams as;
+        as.segs = sl.d_segs; as.n_segs = sl.nseg; as.tile_seg = sl.d_tile_seg; as.n_tiles = sl.ntile; as.buf_acc = sl.d_buf_acc;
+        as.tables = c->d_tables; as.noise = sl.d_ac_noise; as.bitmap = sl.d_ac_bitmap; as.ctl = sl.d_ctl;
+        aw.segs = sl.d_segs; aw.n_segs = sl.nseg; aw.stream_seg_begin = sl.d_stream_seg_begin; aw.n_streams = S; aw.bitmap = sl.d_ac_bitmap;
+        aw.noise = sl.d_ac_noise; aw.lut_full = c->d_lut_full; aw.ac_out = sl.d_ac_out; aw.ac_count = sl.d_ac_count; aw.per_buf_cap = c->ac_cap;
+        aw.state = c->d_state; aw.ctl = sl.d_ctl;
+        { int r = b200_launch_modeac(&as, &aw, c->n_sm, scan); if (r) return fail(c, B200_E_CUDA, "mode a/c launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 3; }
+        CU(c, cudaEventRecord(sl.ev[6], scan));
+    }
+
     ResolveParams rp;
     rp.segs = sl.d_segs; rp.stream_seg_begin = sl.d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = sl.d_pos_pool;
     rp.rec_pool = sl.d_rec_pool; rp.key_pool = sl.d_key_pool; rp.tile_out = sl.d_tile_out; rp.buf_acc = sl.d_buf_acc; rp.buf_out = sl.d_buf_out;
@@ -382,6 +414,13 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     fp.buf_acc = sl.d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = sl.d_rec_pool;
     { int r = b200_launch_finalize(&fp, sl.d_frame_prefix, sl.d_ctl, res); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
     CU(c, cudaEventRecord(sl.ev[3], res));
+
+    if (mode_ac) {      // per-buffer reply lists -> one packed array in buffer order, receiver statistics
+        if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[6], 0));
+        { int r = b200_launch_ac_pack(sl.d_ac_out, sl.d_ac_count, sl.d_ac_prefix, sl.d_ac_packed, sl.nbuf, c->ac_cap, sl.d_ctl, res); if (r) return fail(c, B200_E_CUDA, "mode a/c pack launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
+        { int r = b200_launch_modeac_stats(&aw, sl.d_ac_prefix, res); if (r) return fail(c, B200_E_CUDA, "mode a/c stats launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
+        CU(c, cudaMemcpyAsync(sl.h_ac_prefix, sl.d_ac_prefix, ((size_t)sl.nbuf + 1) * 4, cudaMemcpyDeviceToHost, res));
+    }
 
     CU(c, cudaMemcpyAsync(sl.h_ctl, sl.d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, res));
     CU(c, cudaMemcpyAsync(sl.h_frame_prefix, sl.d_frame_prefix, (S + 1) * 4, cudaMemcpyDeviceToHost, res));
@@ -406,8 +445,15 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     if (ov & 2u) return fail(c, B200_E_OVERFLOW, "a tile exceeded the in-kernel candidate capacity even with the scratch arena");
     if (ov & 4u) return fail(c, B200_E_OVERFLOW, "per-stream frame capacity exceeded");
     if (ov & 8u) return fail(c, B200_E_OVERFLOW, "a receiver's ICAO filter generation is full (%u addresses)", ICAO_CAP / 2);
+    if (ov & 32u) return fail(c, B200_E_OVERFLOW, "Mode A/C candidate capacity exceeded");
+    const bool mode_ac = (c->cfg.flags & B200_CFG_MODE_AC) != 0;
+    const uint32_t total_ac = mode_ac ? sl.h_ac_prefix[sl.nbuf] : 0;
+    sl.ms[3] = 0;
+    if (mode_ac) cudaEventElapsedTime(&sl.ms[3], sl.ev[1], sl.ev[6]);       // Mode A/C noise + scan + walk kernels
+    if (total_ac) CU(c, cudaMemcpyAsync(sl.h_ac_packed, sl.d_ac_packed, (size_t)total_ac * sizeof(b200_modeac), cudaMemcpyDeviceToHost, c->copy_stream));
     const uint32_t total = sl.h_frame_prefix[S];
     sl.run_frames = total;
+    if (total_ac && !total) { CU(c, cudaEventRecord(sl.ev[5], c->copy_stream)); CU(c, cudaEventSynchronize(sl.ev[5])); }
     if (total) {
         // The frame copy must not queue behind the NEXT step's stage B on the resolve stream: its own stream,
         // ordered after this slot's finalize only (ev[4] already completed: finalize is done).
@@ -425,7 +471,6 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     cudaEventElapsedTime(&sl.ms[2], sl.ev[1], sl.ev[2]);
     cudaEventElapsedTime(&sl.ms[0], sl.ev[0], total ? sl.ev[5] : sl.ev[4]);
     cudaEventElapsedTime(&sl.ms[4], sl.ev[3], total ? sl.ev[5] : sl.ev[4]);
-    sl.ms[3] = 0;
     return B200_OK;
 }
 
@@ -619,6 +664,17 @@ API int b200_demod_fetch(b200_demod_ctx *c, uint32_t s, b200_frame *out, uint32_
     *n = cnt;
     if (cnt > cap) return fail(c, B200_E_OVERFLOW, "stream %u has %u frames, output holds %u", s, cnt, cap);
     if (cnt) memcpy(out, sl.h_packed + sl.h_frame_prefix[s], (size_t)cnt * sizeof(b200_frame));
+    return B200_OK;
+}
+
+API int b200_demod_fetch_modeac(b200_demod_ctx *c, uint32_t s, b200_modeac *out, uint32_t cap, uint32_t *n) {
+    if (!c || !n || s >= c->cfg.n_streams) return B200_E_INVAL;
+    if (!(c->cfg.flags & B200_CFG_MODE_AC)) return fail(c, B200_E_STATE, "context was created without B200_CFG_MODE_AC");
+    const Slot &sl = c->slot[c->cur];
+    const uint32_t first = sl.h_ac_prefix[sl.stream_buf_begin[s]], cnt = sl.h_ac_prefix[sl.stream_buf_begin[s + 1]] - first;
+    *n = cnt;
+    if (cnt > cap) return fail(c, B200_E_OVERFLOW, "stream %u has %u Mode A/C replies, output holds %u", s, cnt, cap);
+    if (cnt) memcpy(out, sl.h_ac_packed + first, (size_t)cnt * sizeof(b200_modeac));
     return B200_OK;
 }
 

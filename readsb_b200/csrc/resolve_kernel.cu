@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
 // ------------------------------------------------------------------------------------------------
 // finalize: prefix of per-stream frame counts, then one warp per frame
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *count, uint32_t *prefix, uint32_t n, RunCtl *ctl) {
+__global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *count, uint32_t *prefix, uint32_t n, RunCtl *ctl, bool set_total = true) {
     const uint32_t n_all = n;
     __shared__ uint32_t scratch[40];
     uint32_t base = 0;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *coun
         base += total;
     }
     for (uint32_t i = n + threadIdx.x; i < n_all; i += blockDim.x) prefix[i] = base;
-    if (threadIdx.x == 0) { prefix[n_all] = base; ctl->total_frames = base; }
+    if (threadIdx.x == 0) { prefix[n_all] = base; if (set_total) ctl->total_frames = base; }
 }
 
 __device__ __forceinline__ unsigned long long dmax_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
@@ -409,6 +409,20 @@ extern "C" int b200_launch_resolve(const ResolveParams *p, void *stream) {
 extern "C" int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream) {
     frame_prefix_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->frame_count, d_frame_prefix, p->n_streams, ctl);
     finalize_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+// Mode A/C: pack the per-buffer reply lists in buffer order (prefix by the frame prefix kernel, then one block per buffer).
+__global__ void ac_pack_kernel(const b200_modeac *ac_out, const uint32_t *count, const uint32_t *prefix, b200_modeac *packed, uint32_t cap) {
+    const uint32_t s = blockIdx.x;
+    const uint32_t n = count[s], base = prefix[s];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) packed[base + i] = ac_out[(size_t)s * cap + i];
+}
+
+extern "C" int b200_launch_ac_pack(const b200_modeac *ac_out, const uint32_t *count, uint32_t *prefix, b200_modeac *packed, uint32_t n_units,
+                                   uint32_t cap, RunCtl *ctl, void *stream) {
+    frame_prefix_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(count, prefix, n_units, ctl, false);
+    if (n_units) ac_pack_kernel<<<n_units, 32, 0, (cudaStream_t)stream>>>(ac_out, count, prefix, packed, cap);
     return (int)cudaGetLastError();
 }
 

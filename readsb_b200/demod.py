@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .abi import BUFRES_DTYPE, FRAME_DTYPE, Config, Stats
+from .abi import BUFRES_DTYPE, CFG_MODE_AC, FRAME_DTYPE, MODEAC_DTYPE, Config, Stats
 
 _LIB = None
 LIB_PATH = Path(__file__).resolve().parent / "libb200demod.so"
@@ -50,6 +50,7 @@ def lib():
         L.b200_demod_wait.argtypes = [vp]
         L.b200_demod_frame_count.argtypes = [vp, u32, C.POINTER(u32)]
         L.b200_demod_fetch.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+        L.b200_demod_fetch_modeac.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_buffer_results.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_total_frames.argtypes = [vp, C.POINTER(u64)]
         L.b200_demod_get_stats.argtypes = [vp, u32, C.POINTER(Stats)]
@@ -71,7 +72,7 @@ EXPORTED_SYMBOLS = [
     "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
     "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
     "b200_demod_uc8_lut", "b200_demod_debug_counters", "b200_demod_submit_iq_uc8_strided", "b200_demod_set_stream",
-    "b200_demod_run_device_uc8_async", "b200_demod_wait",
+    "b200_demod_run_device_uc8_async", "b200_demod_wait", "b200_demod_fetch_modeac",
 ]
 
 
@@ -101,10 +102,10 @@ class PinnedBuffer:
 class Demodulator:
     def __init__(self, n_streams: int = 1, buf_samples: int = 131072, max_buffers_per_run: int = 1,
                  preamble_threshold: int = 58, nfix_crc: int = 1, fix_df: int = 1, icao_ttl_ms: int = 60000,
-                 device: int = -1):
+                 device: int = -1, mode_ac: bool = False):
         self.L = lib()
         self.cfg = Config(C.sizeof(Config), device, n_streams, buf_samples, max_buffers_per_run,
-                          preamble_threshold, nfix_crc, fix_df, icao_ttl_ms, 0)
+                          preamble_threshold, nfix_crc, fix_df, icao_ttl_ms, CFG_MODE_AC if mode_ac else 0)
         self.n_streams, self.buf_samples, self.max_buffers_per_run = n_streams, buf_samples, max_buffers_per_run
         h = C.c_void_p()
         rc = self.L.b200_demod_create(C.byref(self.cfg), C.byref(h))
@@ -174,6 +175,13 @@ class Demodulator:
         self._check(self.L.b200_demod_fetch(self.h, stream, out.ctypes.data, n.value, C.byref(n)))
         return out
 
+    def modeac(self, stream: int) -> np.ndarray:
+        """Mode A/C replies of the last run (needs mode_ac=True), in order."""
+        out = np.zeros(self.max_buffers_per_run * (self.buf_samples // 70 + 2), dtype=MODEAC_DTYPE)
+        n = C.c_uint32()
+        self._check(self.L.b200_demod_fetch_modeac(self.h, stream, out.ctypes.data, out.size, C.byref(n)))
+        return out[: n.value].copy()
+
     def total_frames(self) -> int:
         n = C.c_uint64()
         self._check(self.L.b200_demod_total_frames(self.h, C.byref(n)))
@@ -194,7 +202,7 @@ class Demodulator:
         ms = (C.c_float * 5)()
         n = C.c_uint32()
         self._check(self.L.b200_demod_last_timing(self.h, C.byref(ms), C.byref(n)))
-        return {"run_ms": ms[0], "scan_ms": ms[1], "resolve_ms": ms[2], "h2d_ms": ms[3], "d2h_ms": ms[4], "launches": n.value}
+        return {"run_ms": ms[0], "scan_ms": ms[1], "resolve_ms": ms[2], "modeac_ms": ms[3], "d2h_ms": ms[4], "launches": n.value}
 
     def debug_counters(self) -> dict:
         out = (C.c_uint64 * 8)()
@@ -217,11 +225,12 @@ class Demodulator:
         self._check(self.L.b200_demod_icao_reset(self.h, stream))
 
     # -- convenience: replay a whole capture like `--device-type ifile` --------------------------------
-    def replay(self, iq: np.ndarray, first_ts: int = 0, stream: int = 0):
+    def replay(self, iq: np.ndarray, first_ts: int = 0, stream: int = 0, want_modeac: bool = False):
         """Feeds a uc8 capture as consecutive buffers of buf_samples (last one partial), max_buffers_per_run
-        at a time; returns (frames, buffer_results) concatenated in order."""
+        at a time; returns (frames, buffer_results[, modeac]) concatenated in order."""
         nsamples = iq.size // 2
-        frames, bufres = [], []
+        frames, bufres, acs = [], [], []
+        nbuf_done = 0
         off = 0
         while off < nsamples:
             for _ in range(self.max_buffers_per_run):
@@ -233,8 +242,16 @@ class Demodulator:
             self.run()
             frames.append(self.frames(stream))
             bufres.append(self.buffer_results(stream))
-        return np.concatenate(frames) if frames else np.zeros(0, FRAME_DTYPE), \
-            np.concatenate(bufres) if bufres else np.zeros(0, BUFRES_DTYPE)
+            if want_modeac:
+                a = self.modeac(stream)
+                a["buffer_idx"] += nbuf_done          # make the per-run buffer index a running one
+                acs.append(a)
+            nbuf_done += len(bufres[-1])
+        f = np.concatenate(frames) if frames else np.zeros(0, FRAME_DTYPE)
+        b = np.concatenate(bufres) if bufres else np.zeros(0, BUFRES_DTYPE)
+        if want_modeac:
+            return f, b, (np.concatenate(acs) if acs else np.zeros(0, MODEAC_DTYPE))
+        return f, b
 
 
 def uc8_lut() -> np.ndarray:

@@ -6,7 +6,7 @@ from pathlib import Path
 
 import numpy as np
 
-DF17, DF11, AP, DF18, DF11_IID = 0x01, 0x02, 0x04, 0x08, 0x10
+DF17, DF11, AP, DF18, DF11_IID, MODEAC = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 _LIB = None
 
 
@@ -60,6 +60,12 @@ def config2_stream(seed: int, nsamples: int, out=None):
 def config5_stream(seed: int, nsamples: int, out=None):
     """dense-preamble stress: 10k DF11+DF17 per second with overlaps (BASELINE configs[4])."""
     return generate(nsamples, seed=seed, frames_per_sec=10000.0, df_mask=DF17 | DF11, n_icao=64, out=out)
+
+
+def modeac_stream(seed: int, nsamples: int, frames_per_sec: float = 3000.0, out=None):
+    """Mode A/C replies mixed with Mode S traffic (for the --modeac path, demod_2400.c:575-761)."""
+    return generate(nsamples, seed=seed, frames_per_sec=frames_per_sec, df_mask=MODEAC | DF17 | DF11, n_icao=16,
+                    amp=(0.15, 0.9), out=out)
 
 
 def mixed_stream(seed: int, nsamples: int, frames_per_sec: float = 2000.0, out=None):

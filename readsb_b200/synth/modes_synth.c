@@ -74,8 +74,8 @@ long synth_generate_uc8(const synth_params *p, uint64_t nsamples, uint8_t *iq,
     float *acc = calloc((size_t)nsamples * 2 + 16, sizeof(float));
     if (!acc) return -1;
 
-    uint32_t kinds[5]; int nk = 0;
-    for (uint32_t k = 1; k <= SYNTH_DF11_IID; k <<= 1) if (p->df_mask & k) kinds[nk++] = k;
+    uint32_t kinds[6]; int nk = 0;
+    for (uint32_t k = 1; k <= SYNTH_MODEAC; k <<= 1) if (p->df_mask & k) kinds[nk++] = k;
     uint64_t nframes = nk ? (uint64_t)(p->frames_per_sec * (double)nsamples / 2.4e6 + 0.5) : 0;
     int64_t total_ticks = (int64_t)nsamples * 5;
     uint32_t n_icao = p->n_icao ? p->n_icao : 1;
@@ -84,6 +84,33 @@ long synth_generate_uc8(const synth_params *p, uint64_t nsamples, uint8_t *iq,
     for (uint64_t f = 0; f < nframes; f++) {
         uint8_t msg[14];
         uint32_t kind = kinds[f % (uint64_t)nk];
+        if (kind == SYNTH_MODEAC) {
+            /* 20 bit cells of 87 cycles at 60 MHz (one sample = 25 cycles): F1 C1 A1 C2 A2 C4 A4 X B1 D1 B2 D2 B4 D4 F2 X X SPI X X,
+             * each "on" cell = 27 cycles high.  Start uniformly random at 60 MHz resolution. */
+            uint64_t r = sm64(&rng);
+            uint32_t cells = 0x80020u | ((uint32_t)(r & 0x3f) << 13) | ((uint32_t)((r >> 6) & 0x3f) << 6) | (((r >> 12) & 7) == 0 ? 0x4u : 0u);
+            double us = u01(&rng), ua = u01(&rng), uph = u01(&rng);
+            int64_t total_cyc = (int64_t)nsamples * 25;
+            if (total_cyc <= 20 * 87 + 100) break;
+            int64_t c0 = (int64_t)(us * (double)(total_cyc - 20 * 87 - 100));
+            double amp = (p->amp_min + (p->amp_max - p->amp_min) * ua) * 127.5;
+            float ci = (float)(amp * cos(6.283185307179586 * uph)), cq = (float)(amp * sin(6.283185307179586 * uph));
+            for (int b = 0; b < 20; b++) {
+                if (!((cells >> (19 - b)) & 1u)) continue;
+                int64_t a0 = c0 + 87 * b, a1 = a0 + 27;                 /* high during [a0, a1) cycles */
+                for (int64_t n = a0 / 25; n <= (a1 - 1) / 25 && n < (int64_t)nsamples; n++) {
+                    int64_t lo = n * 25 > a0 ? n * 25 : a0, hi = (n + 1) * 25 < a1 ? (n + 1) * 25 : a1;
+                    if (hi > lo) { float w = (float)(hi - lo) * 0.04f; acc[2 * n] += w * ci; acc[2 * n + 1] += w * cq; }
+                }
+            }
+            if (truth && (uint64_t)injected < truth_cap) {
+                synth_truth *t = &truth[injected];
+                t->start_tick = c0 / 5; memset(t->msg, 0, 14); t->msg[0] = (uint8_t)(cells >> 16); t->msg[1] = (uint8_t)(cells >> 8); t->msg[2] = (uint8_t)cells;
+                t->nbits = 24; t->errors = 0;
+            }
+            injected++;
+            continue;
+        }
         uint32_t addr = icao_of(p->seed, (uint32_t)(sm64(&rng) % n_icao));
         int nbits = build_frame(kind, &rng, addr, msg);
         int errors = 0;

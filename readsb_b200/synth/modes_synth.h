@@ -21,6 +21,7 @@ extern "C" {
 #define SYNTH_AP     0x04u  /* DF0/4/5/16/20/21 with address/parity */
 #define SYNTH_DF18   0x08u
 #define SYNTH_DF11_IID 0x10u /* DF11 with a non-zero interrogator id in the parity */
+#define SYNTH_MODEAC 0x20u  /* Mode A/C reply: F1, 12 code pulses, F2 (+SPI sometimes), 0.45 us pulses every 1.45 us */
 
 typedef struct synth_params {
     uint64_t seed;

@@ -23,6 +23,8 @@ CASES = {
     "dense_df11_df17": (dict(seed=42, frames_per_sec=10000.0, df_mask=synth.DF17 | synth.DF11, n_icao=16), 70000, 32768, dict()),
     "mixed_biterrors": (dict(seed=43, frames_per_sec=6000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.DF18 | synth.DF11_IID,
                              n_icao=6, p_bit_error=0.4, p_two_bit_error=0.1), 70000, 32768, dict()),
+    "modeac_mix": (dict(seed=46, frames_per_sec=3000.0, df_mask=synth.MODEAC | synth.DF17, n_icao=8, amp=(0.4, 0.9)),
+                   120000, 32768, dict()),
     "mixed_nofix": (dict(seed=44, frames_per_sec=6000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP, n_icao=6, p_bit_error=0.4),
                     50000, 65536, dict(nfix_crc=0)),
     "mixed_thr40_nofixdf": (dict(seed=45, frames_per_sec=6000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP, n_icao=6, p_bit_error=0.4),
@@ -36,7 +38,8 @@ def main():
         ref = Reference(**opts)
         frames, levels, bufres, ml, mp = ref.run_stream(iq, buf)
         stats, dstats = ref.stats()
-        np.savez_compressed(HERE / f"{name}.npz", iq=iq, frames=frames, signal_level=levels, bufres=bufres, mean_level=ml,
+        modeac = Reference(**opts).run_stream_ac(iq, buf)      # demodulate2400AC of the same reference build, same buffers
+        np.savez_compressed(HERE / f"{name}.npz", iq=iq, modeac=modeac, frames=frames, signal_level=levels, bufres=bufres, mean_level=ml,
                             mean_power=mp, meta=np.frombuffer(json.dumps(dict(buf_samples=buf, options=opts, stats=stats, dstats=dstats,
                                                                              generator=gen_kw)).encode(), dtype=np.uint8))
         print(name, len(frames), "frames", stats["demod_preambles"], "preambles")

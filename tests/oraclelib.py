@@ -11,7 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
-from readsb_b200.abi import BUFRES_DTYPE, FRAME_DTYPE, BufferResult, Stats
+from readsb_b200.abi import BUFRES_DTYPE, FRAME_DTYPE, MODEAC_DTYPE, BufferResult, Stats
 
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_SO = ROOT / "oracle" / "libmodes_oracle.so"
@@ -55,6 +55,7 @@ class Oracle:
             L.oracle_run_stream_uc8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int64, C.c_void_p,
                                                 C.c_uint, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
             L.oracle_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+            L.oracle_demodulate2400AC.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
             L.oracle_icao_add.argtypes = [C.c_void_p, C.c_uint32]
             L.oracle_icao_test.argtypes = [C.c_void_p, C.c_uint32]
             L.oracle_icao_expire.argtypes = [C.c_void_p]
@@ -115,6 +116,28 @@ class Oracle:
         assert n >= 0, "oracle frame capacity exceeded"
         return frames[:n].copy(), bufres[: nb.value].copy()
 
+    def demodulate_ac(self, data: np.ndarray, length: int, sample_ts: int, sum_level: int, sum_power: int, cap=4096):
+        out = np.zeros(cap, dtype=MODEAC_DTYPE)
+        n = C.c_uint(0)
+        rc = self.L.oracle_demodulate2400AC(self.h, data.ctypes.data, length, sample_ts, sum_level, sum_power, out.ctypes.data, cap, C.byref(n))
+        assert rc == 0
+        return out[: n.value].copy()
+
+    def run_stream_ac(self, iq: np.ndarray, buf_samples: int, first_ts: int = 0):
+        """Mode A/C over a capture, buffer by buffer like the ifile loop (halo carried)."""
+        nsamples = iq.size // 2
+        halo = np.zeros(326, dtype=np.uint16)
+        outs = []
+        for b, off in enumerate(range(0, nsamples, buf_samples)):
+            ln = min(buf_samples, nsamples - off)
+            mag, sl, sp = Oracle.convert(iq[2 * off: 2 * (off + ln)])
+            data = np.concatenate([halo, mag]).astype(np.uint16)
+            a = self.demodulate_ac(data, ln, first_ts + off * 5, sl, sp)
+            a["buffer_idx"] = b
+            outs.append(a)
+            halo = data[ln: ln + 326].copy() if ln >= 326 else np.zeros(326, dtype=np.uint16)
+        return np.concatenate(outs) if outs else np.zeros(0, MODEAC_DTYPE)
+
     def stats(self) -> dict:
         s = Stats()
         self.L.oracle_get_stats(self.h, C.byref(s))
@@ -156,6 +179,8 @@ class Reference:
         L.ref_run_stream_uc8.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
         L.ref_get_stats.argtypes = [C.POINTER(Stats), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_demodulate2400AC.argtypes = [C.c_void_p, C.c_uint, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
+        L.ref_modeac_count.restype = C.c_uint64
         L.ref_time_stream_uc8.restype = C.c_double
         L.ref_time_stream_uc8.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.POINTER(C.c_uint)]
         assert L.ref_init(preamble_threshold, nfix_crc, fix_df, icao_ttl_ms) == 0
@@ -209,6 +234,25 @@ class Reference:
         assert n >= 0
         k = nb.value
         return frames[:n].copy(), levels[:n].copy(), bufres[:k].copy(), ml[:k].copy(), mp[:k].copy()
+
+    def run_stream_ac(self, iq: np.ndarray, buf_samples: int, first_ts: int = 0):
+        nsamples = iq.size // 2
+        halo = np.zeros(326, dtype=np.uint16)
+        outs = []
+        for b, off in enumerate(range(0, nsamples, buf_samples)):
+            ln = min(buf_samples, nsamples - off)
+            mag, ml, mp = self.convert(iq[2 * off: 2 * (off + ln)])
+            data = np.concatenate([halo, mag]).astype(np.uint16)
+            out = np.zeros(4096, dtype=MODEAC_DTYPE)
+            n = C.c_uint(0)
+            assert self.L.ref_demodulate2400AC(data.ctypes.data, ln, first_ts + off * 5, ml, mp, out.ctypes.data, 4096, C.byref(n)) == 0
+            a = out[: n.value].copy(); a["buffer_idx"] = b
+            outs.append(a)
+            halo = data[ln: ln + 326].copy() if ln >= 326 else np.zeros(326, dtype=np.uint16)
+        return np.concatenate(outs) if outs else np.zeros(0, MODEAC_DTYPE)
+
+    def modeac_count(self) -> int:
+        return int(self.L.ref_modeac_count())
 
     def stats(self):
         s = Stats()

@@ -20,8 +20,10 @@ def test_cuda_matches_reference_golden(cuda, path):
     from readsb_b200.demod import Demodulator
     z = np.load(path)
     meta = json.loads(bytes(z["meta"]).decode())
-    d = Demodulator(n_streams=1, buf_samples=meta["buf_samples"], max_buffers_per_run=2, **meta["options"])
-    frames, bufres = d.replay(np.ascontiguousarray(z["iq"]))
+    d = Demodulator(n_streams=1, buf_samples=meta["buf_samples"], max_buffers_per_run=2, mode_ac=True, **meta["options"])
+    frames, bufres, modeac = d.replay(np.ascontiguousarray(z["iq"]), want_modeac=True)
+    assert len(modeac) == len(z["modeac"]) and np.array_equal(modeac["timestamp"], z["modeac"]["timestamp"])
+    assert np.array_equal(modeac["modeac"], z["modeac"]["modeac"]) and np.array_equal(modeac["buffer_idx"], z["modeac"]["buffer_idx"])
     problems = diff_frames(frames, z["frames"], fields=("timestamp", "j", "crc", "addr", "score", "buffer_seq", "signal_len",
                                                         "phase", "msgtype", "msgbits", "correctedbits", "fix_bit", "msg"))
     assert not problems, "\n".join(problems)
@@ -30,7 +32,7 @@ def test_cuda_matches_reference_golden(cuda, path):
     assert np.array_equal(bufres["sum_power"] / 65535.0 / 65535.0 / bufres["length"], z["mean_power"])
     st = d.stats(0)
     for k, v in meta["stats"].items():
-        if k not in ("sum_signal_power", "reserved_", "peak_signal_power"):
+        if k not in ("sum_signal_power", "reserved_", "demod_modeac", "peak_signal_power"):
             assert st[k] == v, k
     assert st["peak_signal_power"] == meta["dstats"]["peak_signal_power"]
     d.close()

@@ -211,12 +211,94 @@ def test_async_pipeline_repeats_steps_exactly_after_a_pool_failure(cuda):
                            amp=(0.3, 0.9), p_bit_error=0.3)
     dev, stride, pad = _device_streams([storm], total)
     o = Oracle(40); fo, bo = o.run_stream(storm, buf)
-    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=nb, preamble_threshold=40)
-    got, gotb = [], []
+    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=nb, preamble_threshold=40, mode_ac=True)
+    got, gotb, gota = [], [], []
     for c in range(calls):
         d.run_device_async(dev.data_ptr() + pad + c * nb * buf * 2, stride, nb, buf, continues=c > 0, first_sample_timestamp=c * nb * buf * 5)
         if c >= 1:
-            d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0))
-    d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0))
+            d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0)); gota.append(d.modeac(0))
+    d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0)); gota.append(d.modeac(0))
     _check(d, o, np.concatenate(got), np.concatenate(gotb), fo, bo)
+    ao = Oracle(40).run_stream_ac(storm, buf)          # the repeated steps must not count their Mode A/C replies twice
+    ag = np.concatenate(gota)
+    assert len(ag) == len(ao) and np.array_equal(ag["timestamp"], ao["timestamp"]) and d.stats(0)["demod_modeac"] == len(ao)
+    d.close()
+
+
+def _diff_modeac(a, b):
+    if len(a) != len(b):
+        return [f"modeac count {len(a)} vs {len(b)}"]
+    return [f"modeac {f} differs at {np.nonzero(a[f] != b[f])[0][:3]}" for f in ("timestamp", "f1_sample", "modeac", "buffer_idx") if not np.array_equal(a[f], b[f])]
+
+
+@pytest.mark.parametrize("buf,K", [(65536, 1), (65536, 3), (20000, 4), (1000, 16), (8191, 5)])
+def test_modeac_matches_oracle(cuda, buf, K):
+    """--modeac: demodulate2400AC (demod_2400.c:575-761) on the GPU next to the Mode S path, same buffers."""
+    from readsb_b200.demod import Demodulator
+    iq = synth.modeac_stream(17, 900_000)
+    o = Oracle(); fo, bo = o.run_stream(iq, buf); ao = o.run_stream_ac(iq, buf)
+    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=K, mode_ac=True)
+    fg, bg, ag = d.replay(iq, want_modeac=True)
+    assert len(ao) > 50
+    problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + _diff_modeac(ag, ao)
+    st = d.stats(0)
+    assert st["demod_modeac"] == len(ao)
+    assert not problems, "\n".join(problems)
+    d.close()
+
+
+def test_modeac_on_magnitude_handoff_and_many_streams(cuda):
+    from readsb_b200.demod import Demodulator
+    S, buf = 3, 32768
+    iqs = [synth.generate(3 * buf, seed=60 + s, frames_per_sec=3000.0, df_mask=synth.MODEAC, amp=(0.5, 0.95)) for s in range(S)]
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=3, mode_ac=True)
+    halos = [np.zeros(326, np.uint16) for _ in range(S)]
+    for b in range(3):
+        for s in range(S):
+            mag, _, _ = Oracle.convert(iqs[s][2 * b * buf: 2 * (b + 1) * buf])
+            data = np.concatenate([halos[s], mag]).astype(np.uint16)
+            d.submit_mag(s, data, buf, b * buf * 5)
+            halos[s] = data[buf: buf + 326].copy()
+    d.run()
+    for s in range(S):
+        ao = Oracle().run_stream_ac(iqs[s], buf)
+        assert len(ao) > 5
+        assert not _diff_modeac(d.modeac(s), ao), f"stream {s}"
+    d.close()
+
+
+def test_modeac_device_path_async_pipeline(cuda):
+    """Mode A/C through run_device_uc8_async: two steps in flight, replies and demod_modeac identical to the oracle."""
+    import torch
+    from readsb_b200.demod import Demodulator
+    S, B, BUF, steps = 4, 2, 32768, 3
+    n = B * BUF * steps
+    iqs = [synth.generate(n, seed=80 + s, frames_per_sec=2500.0, df_mask=synth.MODEAC | synth.DF17, n_icao=4, amp=(0.4, 0.95)) for s in range(S)]
+    pad, stride = 1024, 2 * n + 4096
+    dev = torch.zeros(pad + S * stride, dtype=torch.uint8, device="cuda")
+    for s in range(S):
+        dev[pad + s * stride: pad + s * stride + 2 * n] = torch.from_numpy(iqs[s]).cuda()
+    torch.cuda.synchronize()
+    d = Demodulator(n_streams=S, buf_samples=BUF, max_buffers_per_run=B, mode_ac=True)
+    got_f = [[] for _ in range(S)]; got_a = [[] for _ in range(S)]
+
+    def harvest(k):
+        d.wait()
+        for s in range(S):
+            got_f[s].append(d.frames(s))
+            a = d.modeac(s); a["buffer_idx"] += k * B; got_a[s].append(a)
+
+    for k in range(steps):
+        d.run_device_async(dev.data_ptr() + pad + k * B * BUF * 2, stride, B, BUF, continues=k > 0, first_sample_timestamp=k * B * BUF * 5)
+        if k >= 1:
+            harvest(k - 1)
+    harvest(steps - 1)
+    for s in range(S):
+        o = Oracle()
+        fo, _ = o.run_stream(iqs[s], BUF)
+        ao = o.run_stream_ac(iqs[s], BUF) if False else Oracle().run_stream_ac(iqs[s], BUF)
+        assert len(ao) > 10
+        problems = diff_frames(np.concatenate(got_f[s]), fo) + _diff_modeac(np.concatenate(got_a[s]), ao)
+        assert not problems, f"stream {s}: " + "\n".join(problems)
+        assert d.stats(s)["demod_modeac"] == len(ao)
     d.close()

@@ -39,7 +39,7 @@ def test_oracle_matches_golden(path):
     assert np.array_equal(bufres["icao_flipped"], z["bufres"]["icao_flipped"])
     st = o.stats()
     for k, v in meta["stats"].items():
-        if k in ("sum_signal_power", "reserved_", "peak_signal_power"):
+        if k in ("sum_signal_power", "reserved_", "demod_modeac", "peak_signal_power"):
             continue
         assert st[k] == v, k
     assert st["peak_signal_power"] == meta["dstats"]["peak_signal_power"]
@@ -48,6 +48,19 @@ def test_oracle_matches_golden(path):
     for b in bufres:
         noise += (b["sum_power"] / 65535.0 / 65535.0 / b["length"]) * b["length"] - b["sum_signal_power"] / 65535.0 / 65535.0
     assert noise == meta["dstats"]["noise_power_sum"]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_oracle_modeac_matches_golden(path):
+    """demodulate2400AC (demod_2400.c:575-761): the reference's replies on every fixture (most hold none, modeac_mix many)."""
+    z, meta = load_golden(path)
+    got = Oracle(**meta["options"]).run_stream_ac(np.ascontiguousarray(z["iq"]), meta["buf_samples"])
+    want = z["modeac"]
+    assert len(got) == len(want)
+    assert np.array_equal(got["timestamp"], want["timestamp"]) and np.array_equal(got["modeac"], want["modeac"])
+    assert np.array_equal(got["buffer_idx"], want["buffer_idx"])
+    if path.stem == "modeac_mix":
+        assert len(want) > 15
 
 
 def test_lut_known_answer():
@@ -140,6 +153,17 @@ def test_oracle_matches_reference_options(thr, nfix, fixdf):
     fo = o.run_stream(iq, 65536)[0]
     problems = diff_frames(fo, fr, fields=("timestamp", "crc", "score", "msgtype", "correctedbits", "fix_bit", "msg"))
     assert len(fr) > 50 and not problems, "\n".join(problems)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,buf", [(1, 65536), (2, 131072), (3, 20000)])
+def test_oracle_modeac_matches_reference_live(seed, buf):
+    iq = synth.modeac_stream(seed, 1_500_000)
+    ref, o = Reference(), Oracle()
+    ar, ao = ref.run_stream_ac(iq, buf), o.run_stream_ac(iq, buf)
+    assert len(ar) > 80 and len(ar) == len(ao)
+    assert np.array_equal(ar["timestamp"], ao["timestamp"]) and np.array_equal(ar["modeac"], ao["modeac"])
+    assert ref.modeac_count() == o.stats()["demod_modeac"] == len(ar)
 
 
 @needs_ref
