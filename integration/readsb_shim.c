@@ -5,11 +5,15 @@
  * compiled against readsb's own headers.  Link an UNMODIFIED readsb with
  *
  *     gcc -c -I<readsb> -I<this repo>/include readsb_shim.c
- *     ... readsb objects ... readsb_shim.o -Wl,--wrap=demodulate2400 -Wl,--wrap=icaoFilterAdd \
- *         -Wl,--wrap=icaoFilterExpire -L<this repo>/readsb_b200 -lb200demod
+ *     ... readsb objects ... readsb_shim.o -Wl,--wrap=demodulate2400 -Wl,--wrap=demodulate2400AC \
+ *         -Wl,--wrap=icaoFilterAdd -Wl,--wrap=icaoFilterExpire -L<this repo>/readsb_b200 -lb200demod
  *
- * readsb.o's call `demodulate2400(buf)` (readsb.c:871) then resolves to __wrap_demodulate2400 below;
- * demodulate2400AC and every other symbol of demod_2400.o stay as they are, and __real_demodulate2400
+ * (`make -C oracle readsb-pair` does exactly that where the reference tree is present and leaves
+ * oracle/_ref/readsb_cpu — the stock build — and oracle/_ref/readsb_b200 side by side; tests/test_gpu_shim.py
+ * replays the same capture through both and diffs every frame line and every demodulator counter.)
+ *
+ * readsb.o's calls `demodulate2400(buf)` / `demodulate2400AC(buf)` (readsb.c:871-874) then resolve to the
+ * __wrap_ functions below; every other symbol of demod_2400.o stays as it is, and __real_demodulate2400
  * remains available (it is never used as a fallback here: if the GPU path fails the shim calls setExit(2),
  * readsb.h:406-409 style).
  *
@@ -26,6 +30,8 @@ static b200_demod_ctx *g_ctx;
 static b200_demod_stats g_prev;      /* cumulative counters at the previous buffer */
 static int g_in_shim;                /* adds that come from our own decodeModesMessage calls are already on the device */
 static b200_frame g_frames[2048];
+static b200_modeac *g_ac;            /* replies of the buffer demodulate2400 just handed to the library */
+static uint32_t g_ac_cap;
 
 void __real_icaoFilterAdd(uint32_t addr);
 void __real_icaoFilterExpire(void);
@@ -52,6 +58,12 @@ static int shim_open(void) {
     cfg.nfix_crc = Modes.nfix_crc ? 1 : 0;
     cfg.fix_df = Modes.fixDF;
     cfg.icao_ttl_ms = -1;                                /* flips are driven by backgroundTasks through the wrap above */
+    if (Modes.mode_ac || Modes.mode_ac_auto) {           /* readsb.c:872: Mode A/C runs on the same buffers */
+        cfg.flags |= B200_CFG_MODE_AC;
+        g_ac_cap = cfg.buf_samples / 70 + 2;
+        g_ac = malloc(g_ac_cap * sizeof *g_ac);
+        if (!g_ac) return -1;
+    }
     if (b200_demod_create(&cfg, &g_ctx) != B200_OK) {
         fprintf(stderr, "b200 demodulator: %s\n", b200_demod_last_error(NULL));
         return -1;
@@ -118,4 +130,23 @@ void __wrap_demodulate2400(struct mag_buf *mag) {
     Modes.stats_current.noise_power_count += mag->length;
 
     netDrainMessageBuffers();                                                    /* :481 */
+}
+
+/* demod_2400.c:575-761: the replies were found by the run __wrap_demodulate2400 started for this same buffer. */
+void __wrap_demodulate2400AC(struct mag_buf *mag) {
+    uint32_t n = 0;
+    if (!g_ctx || !g_ac || b200_demod_fetch_modeac(g_ctx, 0, g_ac, g_ac_cap, &n) != B200_OK) {
+        fprintf(stderr, "b200 demodulator (Mode A/C): %s\n", b200_demod_last_error(g_ctx));
+        setExit(2);
+        return;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        struct modesMessage *mm = netGetMM(&Modes.netMessageBuffer[0]);          /* :736 */
+        mm->timestamp = g_ac[i].timestamp;                                       /* :740, at the F2 pulse */
+        mm->sysTimestamp = mag->sysTimestamp + receiveclock_ms_elapsed(mag->sampleTimestamp, mm->timestamp);
+        decodeModeAMessage(mm, g_ac[i].modeac);                                  /* :745 */
+        netUseMessage(mm);
+        Modes.stats_current.demod_modeac++;
+    }
+    netDrainMessageBuffers();
 }

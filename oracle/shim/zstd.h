@@ -1,7 +1,8 @@
-/* Declaration-only stand-in for <zstd.h> (the image has no zstd headers).
- * Only the opaque types that readsb's headers mention are declared so that the
- * reference's hot-path translation units parse; nothing here is ever called by
- * the demodulator path and no zstd symbol is linked. */
+/* Declaration-only stand-in for <zstd.h> (the image has libzstd.so.1 but no zstd headers).
+ * Declares the part of zstd's stable public API that readsb's sources mention, so that the reference's
+ * translation units compile: the hot-path library (_ref/libreadsb_ref.so) never calls or links any of it; the full
+ * `readsb` binaries built by `make readsb-pair` link the system's libzstd.so.1 for their (unused here) JSON / state
+ * compression. */
 #ifndef B200_ORACLE_ZSTD_SHIM_H
 #define B200_ORACLE_ZSTD_SHIM_H
 #include <stddef.h>
@@ -10,4 +11,24 @@ typedef struct ZSTD_DCtx_s ZSTD_DCtx;
 typedef ZSTD_CCtx ZSTD_CStream;
 typedef struct ZSTD_inBuffer_s { const void *src; size_t size; size_t pos; } ZSTD_inBuffer;
 typedef struct ZSTD_outBuffer_s { void *dst; size_t size; size_t pos; } ZSTD_outBuffer;
+typedef enum { ZSTD_e_continue = 0, ZSTD_e_flush = 1, ZSTD_e_end = 2 } ZSTD_EndDirective;
+typedef enum { ZSTD_reset_session_only = 1, ZSTD_reset_parameters = 2, ZSTD_reset_session_and_parameters = 3 } ZSTD_ResetDirective;
+typedef enum { ZSTD_c_compressionLevel = 100 } ZSTD_cParameter;
+ZSTD_CCtx *ZSTD_createCCtx(void);
+size_t ZSTD_freeCCtx(ZSTD_CCtx *cctx);
+ZSTD_DCtx *ZSTD_createDCtx(void);
+size_t ZSTD_freeDCtx(ZSTD_DCtx *dctx);
+ZSTD_CStream *ZSTD_createCStream(void);
+size_t ZSTD_freeCStream(ZSTD_CStream *zcs);
+size_t ZSTD_compressBound(size_t srcSize);
+unsigned ZSTD_isError(size_t code);
+const char *ZSTD_getErrorName(size_t code);
+size_t ZSTD_compressCCtx(ZSTD_CCtx *cctx, void *dst, size_t dstCapacity, const void *src, size_t srcSize, int compressionLevel);
+size_t ZSTD_decompressDCtx(ZSTD_DCtx *dctx, void *dst, size_t dstCapacity, const void *src, size_t srcSize);
+size_t ZSTD_CCtx_reset(ZSTD_CCtx *cctx, ZSTD_ResetDirective reset);
+size_t ZSTD_CCtx_setParameter(ZSTD_CCtx *cctx, ZSTD_cParameter param, int value);
+size_t ZSTD_initCStream(ZSTD_CStream *zcs, int compressionLevel);
+size_t ZSTD_compressStream(ZSTD_CStream *zcs, ZSTD_outBuffer *output, ZSTD_inBuffer *input);
+size_t ZSTD_flushStream(ZSTD_CStream *zcs, ZSTD_outBuffer *output);
+size_t ZSTD_endStream(ZSTD_CStream *zcs, ZSTD_outBuffer *output);
 #endif

@@ -77,8 +77,20 @@ def build_oracle() -> None:
         raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
 
 
+def build_readsb_pair() -> None:
+    """Where the reference tree is present: the whole reference program, stock (oracle/_ref/readsb_cpu) and linked with
+    integration/readsb_shim.c against libb200demod.so (oracle/_ref/readsb_b200), for tests/test_gpu_shim.py.  Needs
+    build_demod() first.  Test infrastructure, like the rest of oracle/."""
+    if not Path("/root/reference/readsb.c").exists() or not LIB_DEMOD.exists():
+        return
+    res = subprocess.run(["make", "-C", str(ROOT / "oracle"), "CC=gcc", "readsb-pair"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("readsb-pair build failed:\n" + res.stdout + res.stderr)
+
+
 if __name__ == "__main__":
     import sys
     build_synth(force=True)
     build_oracle()
     print(build_demod(force=True, verbose="-v" in sys.argv))
+    build_readsb_pair()
