@@ -195,6 +195,18 @@ int b200_demod_total_frames(b200_demod_ctx *ctx, uint64_t *n); /* all streams, l
 int b200_demod_fetch_modeac(b200_demod_ctx *ctx, uint32_t stream, b200_modeac *out, uint32_t cap, uint32_t *n);
 int b200_demod_get_stats(b200_demod_ctx *ctx, uint32_t stream, b200_demod_stats *out);
 
+/* Beast binary records of the last run's accepted frames of one stream, encoded on the device, byte-identical to what
+ * modesSendBeastOutput (net_io.c:1655-1714, netTimestamp :1617-1648) writes to a beast_out client for the same frames:
+ * 0x1a, '2' | '3' | '1', 6-byte big-endian 12 MHz timestamp, signal byte, frame bytes, 0x1a doubled.  Order as the
+ * reference emits them: per buffer the Mode S frames, then (B200_CFG_MODE_AC) the Mode A/C replies (readsb.c:871-874).
+ * flags: B200_BEAST_VERBATIM = bytes as received (Modes.net_verbatim / mm->verbatim) instead of the corrected frame.
+ * The forwarding policy of outputMessage (net_io.c:5820-5880: first message of an aircraft suppressed unless CRC-clean,
+ * --net-verbatim, ...) belongs to the tracker and is not applied: every accepted frame is encoded.
+ * *nbytes = size of the stream's records; B200_E_OVERFLOW if cap is smaller (nothing copied). */
+#define B200_BEAST_VERBATIM 0x1u
+#define B200_BEAST_MAX_RECORD 44
+int b200_demod_fetch_beast(b200_demod_ctx *ctx, uint32_t stream, uint32_t flags, uint8_t *out, uint32_t cap, uint32_t *nbytes);
+
 /* ICAO address filter (icao_filter.h) — per stream, lives next to the resolver on the device */
 int b200_demod_icao_add(b200_demod_ctx *ctx, uint32_t stream, uint32_t addr);
 int b200_demod_icao_test(b200_demod_ctx *ctx, uint32_t stream, uint32_t addr, int *present);

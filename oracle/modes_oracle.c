@@ -498,3 +498,39 @@ long oracle_run_stream_uc8(oracle_ctx *o, const uint8_t *iq, uint64_t nsamples, 
     if (n_bufres) *n_bufres = nb;
     return bad ? -1 : (long)nf;
 }
+
+/* ------------------------------------------------------------------ net_io.c:1617-1648, 1655-1714
+ * Beast binary record of one accepted frame, as modesSendBeastOutput writes it for a net_writer without receiverId:
+ * 0x1a, type ('2' 56-bit, '3' 112-bit, '1' Mode A/C), 6-byte big-endian 12 MHz timestamp, one signal byte, the frame;
+ * every 0x1a after the type byte is doubled.  verbatim = Modes.net_verbatim: the bytes as received (mm->verbatim) instead
+ * of the corrected frame. */
+static uint8_t *beast_put(uint8_t *p, uint8_t ch) { *p++ = ch; if (ch == 0x1a) *p++ = ch; return p; }
+
+static uint8_t *beast_head(uint8_t *p, char type, int64_t timestamp, double signal_level) {
+    *p++ = 0x1a; *p++ = (uint8_t)type;
+    for (int sh = 40; sh >= 0; sh -= 8) p = beast_put(p, (uint8_t)(timestamp >> sh));
+    int sig = (int)nearbyint(sqrt(signal_level) * 255);
+    if (signal_level > 0 && sig < 1) sig = 1;
+    if (sig > 255) sig = 255;
+    return beast_put(p, (uint8_t)sig);
+}
+
+unsigned oracle_beast_frame(const b200_frame *f, int verbatim, uint8_t *out) {
+    uint8_t msg[14];
+    memcpy(msg, f->msg, 14);
+    if (verbatim && f->fix_bit >= 0) msg[f->fix_bit >> 3] ^= (uint8_t)(1u << (7 - (f->fix_bit & 7)));
+    const int len = f->msgbits / 8;
+    /* demod_2400.c:448-457: signalLevel = sum / 65535 / 65535 / signal_len */
+    const double signal_level = (double)f->sigpow_sum / 65535.0 / 65535.0 / f->signal_len;
+    uint8_t *p = beast_head(out, len == 7 ? '2' : '3', f->timestamp, signal_level);
+    for (int i = 0; i < len; i++) p = beast_put(p, msg[i]);
+    return (unsigned)(p - out);
+}
+
+unsigned oracle_beast_modeac(const b200_modeac *a, uint8_t *out) {
+    /* mode_ac.c:171-173: two bytes, Mode A word big-endian; signalLevel is never set for Mode A/C (netGetMM zeroes it) */
+    uint8_t *p = beast_head(out, '1', a->timestamp, 0.0);
+    p = beast_put(p, (uint8_t)(a->modeac >> 8));
+    p = beast_put(p, (uint8_t)a->modeac);
+    return (unsigned)(p - out);
+}

@@ -56,6 +56,10 @@ long oracle_run_stream_uc8(oracle_ctx *o, const uint8_t *iq, uint64_t nsamples, 
 int oracle_demodulate2400AC(oracle_ctx *o, const uint16_t *data, unsigned length, int64_t sample_timestamp,
                             uint64_t sum_level, uint64_t sum_power, b200_modeac *out, unsigned cap, unsigned *n_out);
 
+/* net_io.c:1655-1714 modesSendBeastOutput (+ netTimestamp :1617-1648): one Beast record, at most 44 bytes; returns its length */
+unsigned oracle_beast_frame(const b200_frame *f, int verbatim, uint8_t *out);
+unsigned oracle_beast_modeac(const b200_modeac *a, uint8_t *out);
+
 void oracle_get_stats(const oracle_ctx *o, b200_demod_stats *out);
 void oracle_icao_add(oracle_ctx *o, uint32_t addr);
 int  oracle_icao_test(const oracle_ctx *o, uint32_t addr);

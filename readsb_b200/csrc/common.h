@@ -204,6 +204,21 @@ struct AcWalkParams {
     RunCtl *ctl;
 };
 
+struct BeastParams {                 // beast_kernel.cu
+    const Segment *segs;
+    const uint32_t *stream_seg_begin;
+    const b200_frame *frames;         // packed stream-major
+    const uint32_t *frame_prefix;
+    const b200_buffer_result *buf_out;
+    const b200_modeac *ac;            // packed in buffer order, or null
+    const uint32_t *ac_prefix;        // [buffer + 1], or null
+    uint8_t *out;
+    uint32_t *stream_off, *stream_len;
+    uint32_t *total;
+    uint32_t cap;
+    uint32_t verbatim;
+};
+
 // ---- host-built constant tables, uploaded once ---------------------------------------------------
 struct DeviceTables {
     uint16_t lut_fold[128 * 128];  // folded + bank-swizzled UC8 magnitude table (see modes_tables.h)
@@ -223,6 +238,7 @@ int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm
 int b200_launch_resolve(const ResolveParams *p, void *stream);
 int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream);
 int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp, int n_sm, void *stream);
+int b200_launch_beast(const BeastParams *p, uint32_t n_streams, void *stream);
 int b200_launch_modeac_stats(const AcWalkParams *wp, const uint32_t *prefix, void *stream);
 int b200_launch_ac_pack(const b200_modeac *ac_out, const uint32_t *count, uint32_t *prefix, b200_modeac *packed, uint32_t n_units, uint32_t cap, RunCtl *ctl, void *stream);
 int b200_launch_icao_op(StreamState *state, uint32_t stream, int op, uint32_t addr, int *d_result, void *cstream);

@@ -91,6 +91,11 @@ struct b200_demod_ctx {
     int next_async = 0;               // slot the next asynchronous step takes
     uint32_t *d_carry_src = nullptr, *h_carry_src = nullptr;
     uint8_t *d_scratch = nullptr;     // dense-input slow path arena, allocated on first need
+    // Beast encoding (on demand, b200_demod_fetch_beast): packed records of every stream of one run
+    uint8_t *d_beast = nullptr, *h_beast = nullptr;
+    uint32_t *d_beast_meta = nullptr, *h_beast_meta = nullptr;   // [S] offsets, [S] lengths, [1] total
+    uint32_t beast_cap = 0;
+    int beast_slot = -1; uint32_t beast_flags = 0;               // which run the buffers hold
     int *d_result = nullptr;
 };
 
@@ -203,6 +208,7 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     cudaFree(c->d_tables); cudaFree(c->d_lut_full); cudaFree(c->d_state); cudaFree(c->d_arena);
     cudaFree(c->d_carry_src); cudaFree(c->d_result); cudaFree(c->d_scratch);
     cudaFreeHost(c->h_carry_src);
+    cudaFree(c->d_beast); cudaFree(c->d_beast_meta); cudaFreeHost(c->h_beast); cudaFreeHost(c->h_beast_meta);
     free_slot(c->slot[0]); free_slot(c->slot[1]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->res_stream) cudaStreamDestroy(c->res_stream);
@@ -368,6 +374,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     CU(c, cudaMemcpyAsync(sl.d_stream_seg_begin, sl.h_stream_seg_begin, (S + 1) * 4, cudaMemcpyHostToDevice, scan));
     memset(sl.h_ctl, 0, sizeof(RunCtl));
     sl.h_ctl->rec_cap = sl.rec_cap;
+    if (c->beast_slot == (int)(&sl - c->slot)) c->beast_slot = -1;      // the encoded records belong to the run being replaced
     CU(c, cudaMemcpyAsync(sl.d_ctl, sl.h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, scan));
     CU(c, cudaMemsetAsync(sl.d_buf_acc, 0, (size_t)sl.nbuf * sizeof(BufAcc), scan));
     sl.launches = 0;
@@ -675,6 +682,54 @@ API int b200_demod_fetch_modeac(b200_demod_ctx *c, uint32_t s, b200_modeac *out,
     *n = cnt;
     if (cnt > cap) return fail(c, B200_E_OVERFLOW, "stream %u has %u Mode A/C replies, output holds %u", s, cnt, cap);
     if (cnt) memcpy(out, sl.h_ac_packed + first, (size_t)cnt * sizeof(b200_modeac));
+    return B200_OK;
+}
+
+API int b200_demod_fetch_beast(b200_demod_ctx *c, uint32_t s, uint32_t flags, uint8_t *out, uint32_t cap, uint32_t *nbytes) {
+    if (!c || !nbytes || s >= c->cfg.n_streams || (flags & ~B200_BEAST_VERBATIM)) return B200_E_INVAL;
+    // A later asynchronous step may be in flight: it works in the other slot, and this call only reads the completed one.
+    const uint32_t S = c->cfg.n_streams;
+    Slot &sl = c->slot[c->cur];
+    if (c->beast_slot != c->cur || c->beast_flags != flags) {        // encode every stream of this run once
+        CU(c, cudaSetDevice(c->device));
+        const bool mode_ac = (c->cfg.flags & B200_CFG_MODE_AC) != 0;
+        const uint64_t records = (uint64_t)sl.run_frames + (mode_ac ? sl.h_ac_prefix[sl.nbuf] : 0);
+        const uint64_t need = records * B200_BEAST_MAX_RECORD + 64;
+        if (need > 0xffffffffull) return fail(c, B200_E_OVERFLOW, "Beast output of one run exceeds 4 GiB");
+        if (!c->d_beast_meta) {
+            CU(c, dev_alloc(&c->d_beast_meta, 2 * S + 1));
+            CU(c, pin_alloc(&c->h_beast_meta, 2 * S + 1));
+        }
+        if (need > c->beast_cap) {
+            cudaFree(c->d_beast); cudaFreeHost(c->h_beast); c->d_beast = nullptr; c->h_beast = nullptr; c->beast_cap = 0;
+            const uint32_t cap2 = (uint32_t)std::min<uint64_t>(0xffffffffull, need + need / 2);
+            if (dev_alloc(&c->d_beast, cap2) != cudaSuccess || pin_alloc(&c->h_beast, cap2) != cudaSuccess)
+                return fail(c, B200_E_NOMEM, "cannot allocate %u bytes for the Beast output", cap2);
+            c->beast_cap = cap2;
+        }
+        c->beast_slot = -1;
+        cudaStream_t st = c->copy_stream;
+        CU(c, cudaMemsetAsync(c->d_beast_meta, 0, (2 * (size_t)S + 1) * 4, st));
+        BeastParams bp;
+        bp.segs = sl.d_segs; bp.stream_seg_begin = sl.d_stream_seg_begin; bp.frames = sl.d_packed; bp.frame_prefix = sl.d_frame_prefix;
+        bp.buf_out = sl.d_buf_out; bp.ac = mode_ac ? sl.d_ac_packed : nullptr; bp.ac_prefix = mode_ac ? sl.d_ac_prefix : nullptr;
+        bp.out = c->d_beast; bp.stream_off = c->d_beast_meta; bp.stream_len = c->d_beast_meta + S; bp.total = c->d_beast_meta + 2 * S;
+        bp.cap = c->beast_cap; bp.verbatim = (flags & B200_BEAST_VERBATIM) ? 1u : 0u;
+        { int r = b200_launch_beast(&bp, S, st); if (r) return fail(c, B200_E_CUDA, "beast launch: %s", cudaGetErrorString((cudaError_t)r)); }
+        CU(c, cudaMemcpyAsync(c->h_beast_meta, c->d_beast_meta, (2 * (size_t)S + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        const uint32_t total = c->h_beast_meta[2 * S];
+        if (total > c->beast_cap) return fail(c, B200_E_OVERFLOW, "Beast output larger than its worst case (%u > %u)", total, c->beast_cap);
+        if (total) {
+            CU(c, cudaMemcpyAsync(c->h_beast, c->d_beast, total, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaStreamSynchronize(st));
+        }
+        c->beast_slot = c->cur; c->beast_flags = flags;
+    }
+    const uint32_t off = c->h_beast_meta[s], len = c->h_beast_meta[S + s];
+    *nbytes = len;
+    if (len > cap) return fail(c, B200_E_OVERFLOW, "stream %u has %u bytes of Beast output, buffer holds %u", s, len, cap);
+    if (len) memcpy(out, c->h_beast + off, len);
     return B200_OK;
 }
 

@@ -51,6 +51,7 @@ def lib():
         L.b200_demod_frame_count.argtypes = [vp, u32, C.POINTER(u32)]
         L.b200_demod_fetch.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_fetch_modeac.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+        L.b200_demod_fetch_beast.argtypes = [vp, u32, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_buffer_results.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_total_frames.argtypes = [vp, C.POINTER(u64)]
         L.b200_demod_get_stats.argtypes = [vp, u32, C.POINTER(Stats)]
@@ -70,7 +71,7 @@ EXPORTED_SYMBOLS = [
     "b200_demod_host_alloc", "b200_demod_host_free", "b200_demod_submit_iq_uc8", "b200_demod_submit_mag_u16",
     "b200_demod_run", "b200_demod_run_device_uc8", "b200_demod_frame_count", "b200_demod_fetch",
     "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
-    "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
+    "b200_demod_fetch_beast", "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
     "b200_demod_uc8_lut", "b200_demod_debug_counters", "b200_demod_submit_iq_uc8_strided", "b200_demod_set_stream",
     "b200_demod_run_device_uc8_async", "b200_demod_wait", "b200_demod_fetch_modeac",
 ]
@@ -192,6 +193,18 @@ class Demodulator:
         n = C.c_uint32()
         self._check(self.L.b200_demod_buffer_results(self.h, stream, out.ctypes.data, out.size, C.byref(n)))
         return out[: n.value].copy()
+
+    def beast(self, stream: int, verbatim: bool = False) -> bytes:
+        """Beast binary records of the last run's frames (+ Mode A/C replies) of one stream (net_io.c:1655-1714)."""
+        n = C.c_uint32()
+        flags = 1 if verbatim else 0
+        rc = self.L.b200_demod_fetch_beast(self.h, stream, flags, None, 0, C.byref(n))
+        if n.value == 0:
+            self._check(rc)
+            return b""
+        buf = (C.c_uint8 * n.value)()
+        self._check(self.L.b200_demod_fetch_beast(self.h, stream, flags, buf, n.value, C.byref(n)))
+        return bytes(buf)
 
     def stats(self, stream: int) -> dict:
         s = Stats()

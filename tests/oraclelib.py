@@ -138,6 +138,35 @@ class Oracle:
             halo = data[ln: ln + 326].copy() if ln >= 326 else np.zeros(326, dtype=np.uint16)
         return np.concatenate(outs) if outs else np.zeros(0, MODEAC_DTYPE)
 
+    @classmethod
+    def beast(cls, frames: np.ndarray, modeac: np.ndarray = None, verbatim: bool = False) -> bytes:
+        """Beast records (net_io.c:1655-1714) in the reference's output order: per buffer the Mode S frames, then the
+        Mode A/C replies.  frames["buffer_seq"] and modeac["buffer_idx"] must count buffers from the same origin."""
+        L = cls.lib()
+        L.oracle_beast_frame.restype = C.c_uint
+        L.oracle_beast_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_beast_modeac.restype = C.c_uint
+        L.oracle_beast_modeac.argtypes = [C.c_void_p, C.c_void_p]
+        out = bytearray()
+        tmp = (C.c_uint8 * 48)()
+        frames = np.ascontiguousarray(frames)
+        na = 0 if modeac is None else len(modeac)
+        if na:
+            modeac = np.ascontiguousarray(modeac)
+        fi = ai = 0
+        while fi < len(frames) or ai < na:
+            # next buffer that still has records
+            b = int(frames["buffer_seq"][fi]) if fi < len(frames) else 1 << 62
+            if ai < na:
+                b = min(b, int(modeac["buffer_idx"][ai]))
+            while fi < len(frames) and int(frames["buffer_seq"][fi]) == b:
+                n = L.oracle_beast_frame(frames[fi:fi + 1].ctypes.data, 1 if verbatim else 0, tmp)
+                out += bytes(tmp[:n]); fi += 1
+            while ai < na and int(modeac["buffer_idx"][ai]) == b:
+                n = L.oracle_beast_modeac(modeac[ai:ai + 1].ctypes.data, tmp)
+                out += bytes(tmp[:n]); ai += 1
+        return bytes(out)
+
     def stats(self) -> dict:
         s = Stats()
         self.L.oracle_get_stats(self.h, C.byref(s))

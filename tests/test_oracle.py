@@ -11,7 +11,7 @@ from oraclelib import Oracle, Reference, have_ref
 from paritylib import diff_frames, diff_stats
 from readsb_b200 import synth
 
-GOLDEN = sorted((Path(__file__).parent / "golden").glob("*.npz"))
+GOLDEN = sorted(p for p in (Path(__file__).parent / "golden").glob("*.npz") if p.stem != "beast_stream")
 
 
 def load_golden(path):
@@ -61,6 +61,37 @@ def test_oracle_modeac_matches_golden(path):
     assert np.array_equal(got["buffer_idx"], want["buffer_idx"])
     if path.stem == "modeac_mix":
         assert len(want) > 15
+
+
+def test_oracle_beast_matches_reference_network_output():
+    """the bytes the reference program itself sent to a beast_out TCP client (--net-verbatim --modeac,
+    tests/golden/make_beast_golden.py) == oracle frames + Mode A/C replies through the oracle's Beast encoder."""
+    z = np.load(Path(__file__).parent / "golden" / "beast_stream.npz")
+    meta = json.loads(bytes(z["meta"]).decode())
+    iq = np.concatenate([np.full(2 * meta["silence_samples"], 127, np.uint8), z["traffic"]])
+    buf = 131072                                               # the reference's default --sdr-buffer-size
+    frames, _ = Oracle().run_stream(iq, buf)
+    modeac = Oracle().run_stream_ac(iq, buf)
+    got = Oracle.beast(frames, modeac, verbatim=True)
+    assert meta["n_records"] == len(frames) + len(modeac) > 100
+    assert got == bytes(z["beast"])
+    assert Oracle.beast(frames, modeac, verbatim=False) != got   # the fixture holds repaired frames: corrected bytes differ
+
+
+def test_beast_escaping_and_signal_byte():
+    from readsb_b200.abi import FRAME_DTYPE, MODEAC_DTYPE
+    f = np.zeros(1, FRAME_DTYPE)
+    f["timestamp"] = 0x1A001A1A00FF; f["msgbits"] = 56; f["signal_len"] = 134; f["fix_bit"] = -1
+    f["msg"][0, :7] = [0x1A, 0x5D, 0x1A, 0, 0, 0, 0x1A]
+    f["sigpow_sum"] = int(0.25 * 65535 * 65535 * 134)          # signalLevel 0.25 -> sqrt 0.5 -> 127.5 -> nearbyint: 128 (half to even)
+    rec = Oracle.beast(f)
+    assert rec[:2] == b"\x1a2" and rec[2:].count(b"\x1a\x1a") == 6
+    body = rec[2:].replace(b"\x1a\x1a", b"\x1a")
+    assert body[:6] == bytes([0x1A, 0x00, 0x1A, 0x1A, 0x00, 0xFF]) and body[6] in (127, 128) and body[7:] == bytes([0x1A, 0x5D, 0x1A, 0, 0, 0, 0x1A])
+    f["sigpow_sum"] = 1                                         # tiny but non-zero power: the byte is clamped up to 1
+    assert Oracle.beast(f)[2:].replace(b"\x1a\x1a", b"\x1a")[6] == 1
+    a = np.zeros(1, MODEAC_DTYPE); a["timestamp"] = 5; a["modeac"] = 0x1A7F
+    assert Oracle.beast(np.zeros(0, FRAME_DTYPE), a) == bytes([0x1A, 0x31, 0, 0, 0, 0, 0, 5, 0, 0x1A, 0x1A, 0x7F])
 
 
 def test_lut_known_answer():
