@@ -20,16 +20,7 @@
 #define B200_TRAIL 326
 
 // ---- stage A tiling ----------------------------------------------------------------------------
-#define SCAN_TILE      8192          // preamble start positions per tile
-#define SCAN_MAIN_THREADS 512        // 16 warps: convert + window pass + candidate discovery, 16 positions per lane
-#define SCAN_THREADS   (SCAN_MAIN_THREADS + 32)   // + one helper warp: look-ahead samples, tile prefetch
-#define SCAN_LOOKAHEAD 328           // samples kept after the last position of a tile: >= 291 for the slicer, >= 326 so the last tile of a segment sees (and sums) the tail; multiple of 8
-#define SCAN_NMAG      (SCAN_TILE + SCAN_LOOKAHEAD)
-#define SCAN_Q1_CAP    (SCAN_TILE / 4)   // positions passing the pre-check, per tile
-#define SCAN_PASS_CAP  (SCAN_TILE / 8)   // positions reaching a preamble threshold, per tile
-#define SCAN_FULL_CAP  768             // live records per tile staged in shared memory
-// worst-case candidate queues of one tile in global memory (dense-input slow path), see process_candidates<true>
-#define SCAN_SCRATCH_BYTES (204u * SCAN_TILE)
+#define SCAN_TILE      2048          // preamble start positions per tile (the unit of stage A output and of stage B's walk)
 
 // ---- segment descriptor ------------------------------------------------------------------------
 #define SEG_MAG        0x1u   // input samples are uint16 magnitudes (demodulate2400 hand-off), not uc8 IQ
@@ -122,7 +113,8 @@ struct RunCtl {
                              // bit5: Mode A/C candidate / output capacity exceeded
     uint32_t tile_counter;   // dynamic tile scheduler
     uint32_t total_frames;
-    uint32_t pad_[3];
+    uint32_t stage_need;     // with overflow bit1: the largest number of live records one tile produced (staging areas too small)
+    uint32_t pad_[2];
 };
 
 struct ScanParams {
@@ -138,7 +130,12 @@ struct ScanParams {
     int32_t thr;                 // Modes.preambleThreshold
     uint32_t long_set, short_set; // valid DF bitsets (demod_2400.c:98-128)
     int32_t nfix, fixdf;
-    uint8_t *scratch;            // nullptr, or SCAN_SCRATCH_BYTES per CTA of the scan grid
+    // per-warp private areas in global memory
+    Rec *stage_rec;              // [warp][stage_cap] live records of the tile in progress
+    uint32_t *stage_key;
+    uint32_t stage_cap;
+    uint16_t *q1_over;           // [warp][512] pre-check passers beyond the shared-memory queue (dense input)
+    uint32_t *tick_scratch;      // [warp][b200_scan_tick_words()] the ticks of the run in progress (deferred, pooled slicing)
 };
 
 struct ResolveParams {
@@ -233,7 +230,8 @@ struct DeviceTables {
 extern "C" {
 #endif
 // kernel launch wrappers implemented in demod_kernels.cu (stream is a cudaStream_t)
-int b200_scan_grid(int n_sm);   // CTAs the scan kernel is launched with (persistent, occupancy-sized)
+int b200_scan_warps(int n_sm);      // warps of the (persistent) scan kernel's grid
+int b200_scan_tick_words(void);     // words of tick scratch per warp
 int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream);
 int b200_launch_resolve(const ResolveParams *p, void *stream);
 int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream);

@@ -90,7 +90,9 @@ struct b200_demod_ctx {
     int cur = 0;                      // slot whose results fetch / buffer_results / timing report
     int next_async = 0;               // slot the next asynchronous step takes
     uint32_t *d_carry_src = nullptr, *h_carry_src = nullptr;
-    uint8_t *d_scratch = nullptr;     // dense-input slow path arena, allocated on first need
+    // scan kernel: per-warp staging of a run's live records, spill of the pre-check queue, ticks of the run in progress
+    Rec *d_stage_rec = nullptr; uint32_t *d_stage_key = nullptr; uint16_t *d_q1_over = nullptr; uint32_t *d_tick_scratch = nullptr;
+    uint32_t stage_cap = 0;
     // Beast encoding (on demand, b200_demod_fetch_beast): packed records of every stream of one run
     uint8_t *d_beast = nullptr, *h_beast = nullptr;
     uint32_t *d_beast_meta = nullptr, *h_beast_meta = nullptr;   // [S] offsets, [S] lengths, [1] total
@@ -206,7 +208,8 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     cudaFree(c->d_tables); cudaFree(c->d_lut_full); cudaFree(c->d_state); cudaFree(c->d_arena);
-    cudaFree(c->d_carry_src); cudaFree(c->d_result); cudaFree(c->d_scratch);
+    cudaFree(c->d_carry_src); cudaFree(c->d_result);
+    cudaFree(c->d_stage_rec); cudaFree(c->d_stage_key); cudaFree(c->d_q1_over); cudaFree(c->d_tick_scratch);
     cudaFreeHost(c->h_carry_src);
     cudaFree(c->d_beast); cudaFree(c->d_beast_meta); cudaFreeHost(c->h_beast); cudaFreeHost(c->h_beast_meta);
     free_slot(c->slot[0]); free_slot(c->slot[1]);
@@ -272,6 +275,13 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     c->buf_cap = S * K;
     c->frame_cap = K * (BUF / 113 + 2);
     c->ac_cap = BUF / 70 + 2;                       // per reference buffer: a Mode A/C reply hides the next 69 positions
+    {
+        const size_t warps = (size_t)b200_scan_warps(c->n_sm);
+        c->stage_cap = 1024;
+        CUC(dev_alloc(&c->d_stage_rec, warps * c->stage_cap)); CUC(dev_alloc(&c->d_stage_key, warps * c->stage_cap));
+        CUC(dev_alloc(&c->d_q1_over, warps * 512));
+        CUC(dev_alloc(&c->d_tick_scratch, warps * (size_t)b200_scan_tick_words()));
+    }
     const size_t positions = (size_t)S * K * BUF;
     CUC(alloc_slot(c, c->slot[0], (uint32_t)std::max<size_t>(65536, positions / 16)));
     CUC(dev_alloc(&c->d_carry_src, S)); CUC(pin_alloc(&c->h_carry_src, S));
@@ -382,7 +392,8 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     ScanParams sp;
     sp.segs = sl.d_segs; sp.tile_seg = sl.d_tile_seg; sp.n_tiles = sl.ntile; sp.pos_pool = sl.d_pos_pool; sp.rec_pool = sl.d_rec_pool;
     sp.key_pool = sl.d_key_pool; sp.tile_out = sl.d_tile_out; sp.buf_acc = sl.d_buf_acc; sp.ctl = sl.d_ctl; sp.thr = c->cfg.preamble_threshold;
-    sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df; sp.scratch = c->d_scratch;
+    sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df;
+    sp.stage_rec = c->d_stage_rec; sp.stage_key = c->d_stage_key; sp.stage_cap = c->stage_cap; sp.q1_over = c->d_q1_over; sp.tick_scratch = c->d_tick_scratch;
     // demod_2400.c:112-127
     sp.short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
     sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
@@ -447,9 +458,9 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     CU(c, cudaEventSynchronize(sl.ev[4]));
     const uint32_t ov = sl.h_ctl->overflow;
     if (ov & 1u) return 1;
-    if ((ov & 2u) && !c->d_scratch) return 2;
+    if ((ov & 2u) && sl.h_ctl->stage_need > c->stage_cap) return 2;
     if (ov & 16u) return 3;
-    if (ov & 2u) return fail(c, B200_E_OVERFLOW, "a tile exceeded the in-kernel candidate capacity even with the scratch arena");
+    if (ov & 2u) return fail(c, B200_E_OVERFLOW, "a run of tiles exceeded the record staging capacity even after regrowth");
     if (ov & 4u) return fail(c, B200_E_OVERFLOW, "per-stream frame capacity exceeded");
     if (ov & 8u) return fail(c, B200_E_OVERFLOW, "a receiver's ICAO filter generation is full (%u addresses)", ICAO_CAP / 2);
     if (ov & 32u) return fail(c, B200_E_OVERFLOW, "Mode A/C candidate capacity exceeded");
@@ -493,10 +504,13 @@ static int regrow(b200_demod_ctx *c, Slot &sl, int why) {
             if (dev_alloc(&s.d_rec_pool, s.rec_cap) != cudaSuccess || dev_alloc(&s.d_key_pool, s.rec_cap) != cudaSuccess)
                 return fail(c, B200_E_NOMEM, "cannot grow the record pool to %u records", need);
         }
-    } else if (why == 2 && !c->d_scratch) {   // a tile denser than the shared-memory queues: give the kernel its slow-path arena
-        const int grid = b200_scan_grid(c->n_sm);
-        if (grid <= 0 || cudaMalloc((void **)&c->d_scratch, (size_t)grid * SCAN_SCRATCH_BYTES) != cudaSuccess)
-            return fail(c, B200_E_NOMEM, "cannot allocate the dense-input scratch arena");
+    } else if (why == 2) {       // a run of tiles with more live records than the per-warp staging areas hold: grow them to what it needs
+        const uint32_t need = sl.h_ctl->stage_need + sl.h_ctl->stage_need / 8 + 64;
+        cudaFree(c->d_stage_rec); cudaFree(c->d_stage_key); c->d_stage_rec = nullptr; c->d_stage_key = nullptr; c->stage_cap = 0;
+        const size_t warps = (size_t)b200_scan_warps(c->n_sm);
+        if (dev_alloc(&c->d_stage_rec, warps * need) != cudaSuccess || dev_alloc(&c->d_stage_key, warps * need) != cudaSuccess)
+            return fail(c, B200_E_NOMEM, "cannot grow the record staging areas to %u records per warp", need);
+        c->stage_cap = need;
     }
     return B200_OK;
 }

@@ -24,14 +24,15 @@
 #define AC_WARPS (AC_THREADS / 32)
 #define AC_BEHIND 8            // magnitudes kept before the tile origin (1 needed, 8 keeps 16-byte alignment)
 #define AC_AHEAD 80            // after the last position (<= f1 + 69 is read)
-#define AC_NMAG (AC_BEHIND + SCAN_TILE + AC_AHEAD)
+#define AC_TILE 8192           // positions per block iteration = AC_TILE / SCAN_TILE consecutive scan tiles of one segment
+#define AC_NMAG (AC_BEHIND + AC_TILE + AC_AHEAD)
 #define AC_SKIP (20 * 87 / 25 + 1)   // positions hidden by an accepted reply (demod_2400.c:753 + the loop increment)
 
 struct AcSmem {
     uint16_t lut[128 * 128];                 // folded + swizzled uc8 table, as in the scan kernel
     alignas(16) uint16_t mag[AC_NMAG + 8];
-    uint16_t q1[SCAN_TILE];                  // positions that passed the F1 tests (at most 2 of 3 can), then in place: F2 survivors
-    uint32_t bitmap[SCAN_TILE / 32];
+    uint16_t q1[AC_TILE];                    // positions that passed the F1 tests (at most 2 of 3 can), then in place: F2 survivors
+    uint32_t bitmap[AC_TILE / 32];
     uint32_t q1n;
 };
 
@@ -134,13 +135,15 @@ __global__ void __launch_bounds__(AC_THREADS, 2) modeac_scan_kernel(const AcScan
     }
     for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         const Segment seg = P.segs[P.tile_seg[tile]];
+        if ((tile - seg.tile_begin) % (AC_TILE / SCAN_TILE)) continue;      // this block iteration covers the scan tiles [tile, tile + 4) of the segment
         const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;
         const uint32_t x_data_end = seg.lead + seg.npos + B200_TRAIL;
         const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;
         const bool is_mag = seg.flags & SEG_MAG;
-        if (tid < SCAN_TILE / 32) S.bitmap[tid] = 0;
+        __syncthreads();                                                   // the previous iteration's bitmap has been written out
+        if (tid < AC_TILE / 32) S.bitmap[tid] = 0;
         if (tid == 0) S.q1n = 0;
-        // magnitudes of tile coordinates [x0 - AC_BEHIND, x0 + SCAN_TILE + AC_AHEAD): shared index = x - x0 + AC_BEHIND
+        // magnitudes of tile coordinates [x0 - AC_BEHIND, x0 + AC_TILE + AC_AHEAD): shared index = x - x0 + AC_BEHIND
         for (uint32_t c = tid; c < AC_NMAG / 8; c += AC_THREADS) {
             const int64_t xc = (int64_t)x0 - AC_BEHIND + (int64_t)c * 8;
             uint32_t m[8];
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(AC_THREADS, 2) modeac_scan_kernel(const AcScan
 
         // ---- phase A: F1 edge / quiet / level for 8 consecutive positions per thread, two passes ------------------
 #pragma unroll 1
-        for (uint32_t pass = 0; pass < SCAN_TILE / (8 * AC_THREADS); pass++) {
+        for (uint32_t pass = 0; pass < AC_TILE / (8 * AC_THREADS); pass++) {
             const uint32_t p = 8 * (pass * AC_THREADS + tid);
             const uint16_t *mp = &S.mag[p + AC_BEHIND];
             uint32_t v[11];
@@ -261,7 +264,10 @@ __global__ void __launch_bounds__(AC_THREADS, 2) modeac_scan_kernel(const AcScan
             }
         }
         __syncthreads();
-        if (tid < SCAN_TILE / 32) P.bitmap[(size_t)tile * (SCAN_TILE / 32) + tid] = S.bitmap[tid];
+        {   // one bit per position; only the words of this segment's own scan tiles
+            const uint32_t words = min((uint32_t)(AC_TILE / 32), (seg.tile_begin + seg.n_tiles - tile) * (SCAN_TILE / 32));
+            if (tid < words) P.bitmap[(size_t)tile * (SCAN_TILE / 32) + tid] = S.bitmap[tid];
+        }
     }
 }
 
@@ -340,7 +346,8 @@ extern "C" int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp
     }
     if (sp->n_tiles && sp->n_segs) {
         modeac_noise_kernel<<<min(sp->n_segs, 1024u), 32, 0, (cudaStream_t)stream>>>(*sp);
-        uint32_t grid = (uint32_t)n_sm * 2;
+        // three of four scan tiles are skipped (AC_TILE = 4 scan tiles): an odd grid gives every block the same share of the fourth
+        uint32_t grid = ((uint32_t)n_sm * 2) | 1u;
         if (grid > sp->n_tiles) grid = sp->n_tiles;
         modeac_scan_kernel<<<grid, AC_THREADS, sizeof(AcSmem), (cudaStream_t)stream>>>(*sp);
         modeac_walk_kernel<<<wp->n_segs, 256, 0, (cudaStream_t)stream>>>(*wp);

@@ -1,68 +1,81 @@
-// scan_kernel.cu — stage A of the Mode-S demodulator: the stateless, data-parallel part of
-// demodulate2400() as one persistent sm_100a kernel.
+// scan_kernel.cu — stage A of the Mode-S demodulator, warp-autonomous version: the stateless, data-parallel part of
+// demodulate2400() as one persistent sm_100a kernel in which EVERY WARP owns whole tiles and never meets a block barrier.
 //
-//   per tile of SCAN_TILE preamble start positions (+ SCAN_LOOKAHEAD samples of look-ahead):
-//     1. coalesced 16-byte HBM loads of uc8 IQ, magnitude through a folded, bank-swizzled
-//        lookup table in shared memory (convert.c:35-108), exact per-buffer level/power sums;
-//        magnitudes staged in shared memory as uint16
-//     2. one pass over the magnitudes, 16 consecutive samples per thread in a register window:
-//          - pre-check of every position (demod_2400.c:311-320) -> ordered bitmap
-//          - the TICK MAP: for every sample s and every correlator row r (demod_2400.c:74-93) the sign
-//            bit [row r applied at s > 0], stored at tick U = 5*s + r.  PPM bit k of a frame that starts
-//            at sample j with try_phase t is the single tick 5*(j+19) + t + 12*k (the closed form of
-//            slice_byte, demod_2400.c:133-213), so slicing any (position, phase) later is a stride-12
-//            bit gather and its cost no longer depends on how dense the candidates are.
-//     3. noise-relative thresholds of the three preamble correlations (demod_2400.c:330-378)
-//     4. DF gate: five ticks per (position, phase) (demod_2400.c:215-239)
-//     5. full slice: one thread per surviving (position, phase) gathers 8 message bits per 96 ticks with
-//        three multiply-gathers, CRC-24 by table (crc.c:67-82), then DF17 repair / single-bit-fix
-//        classification (crc.c:383-418, mode_s.c:276-419)
-//     6. ordered emission of PosEntry + Rec lists for the per-receiver resolver (stage B)
+// One CTA per SM shares the read-only tables (folded uc8 magnitude table 32 KB, CRC table, single-bit syndromes); each of
+// its warps pulls tiles of SCAN_TILE positions from an atomic counter and walks them in chunks of 512 positions
+// (16 per lane) through a private shared-memory pipeline:
+//
+//     iteration k:   window(k)        pre-check of the chunk's 512 positions + the TICK MAP of its 512 samples
+//                    load(k+2)        16-byte HBM loads into registers, in flight during ...
+//                    candidates(k-1)  thresholds -> DF gate -> full slice + CRC + classification -> ordered emission
+//                    convert(k+2)     magnitudes through the folded table into the ring, exact per-buffer sums
+//
+// window(k) needs the first samples of chunk k+1, candidates(k-1) need ticks up to 310 samples ahead (chunk k) and
+// magnitudes 18 ahead: a ring of three magnitude chunks and two tick chunks per warp (4.8 KB) holds exactly that.  The
+// warps of an SM drift apart, so table lookups (LSU), tick arithmetic (ALU / IDP) and candidate work of different
+// warps overlap instead of marching through block-wide phases; nothing waits for the slowest warp of a CTA.
+//
+// A warp takes RUNS of consecutive tiles (guided self-scheduling: long runs first, single tiles at the end, so the last
+// warps finish together) and keeps its pipeline going across tile boundaries: the look-ahead chunk is paid once per run.
+// Full slices are rare (1-2 per 512 positions) and expensive, so they are deferred and pooled over the run: DF-gate
+// survivors queue up until 32 lanes have work; the ticks they need are kept in a per-warp global copy (L2 resident).
+//
+// Output per tile is unchanged (PosEntry list in pos_pool, live records contiguous in rec_pool, TileOut): a warp stages
+// the live records of its run in a small private global area and copies them to one reservation at the end of the run.
 //
 // No tensor cores: integer scan/correlate work bounded by HBM reads and instruction issue.
 #include "common.h"
 #include "device_utils.cuh"
 
-#define SCAN_WARPS (SCAN_THREADS / 32)
-#define MAIN_WARPS (SCAN_MAIN_THREADS / 32)
-#define TICK_WORDS ((5 * (SCAN_NMAG + 24) + 31) / 32 + 8)
-#define MAG_PAD 40                      // the register-window pass may read this far past SCAN_NMAG
+#define SC_WARPS 28
+#define SC_THREADS (SC_WARPS * 32)
+#define CHUNK 512
+#define TILE_CHUNKS (SCAN_TILE / CHUNK)       // 4 chunks of positions per tile
+#define RUN_MAX 8                             // a warp takes runs of up to 8 consecutive tiles of one segment (guided self-scheduling)
+#define RUN_CHUNKS_MAX (RUN_MAX * TILE_CHUNKS)
+#define MAG_RING (3 * CHUNK)
+#define MAG_MIRROR 64                         // first samples of slot 0 again behind slot 2: reads never wrap
+#define TICK_CW (5 * CHUNK / 32)              // 80 words of ticks per chunk
+#define TICK_BITS (5 * CHUNK)
+#define TICK_RING (2 * TICK_CW)
+#define TICK_MIRROR 12
+#define Q1_SMEM 256                           // pre-check passers of a chunk kept in shared memory; the rest (dense input) spills
+#define SURV_CAP 64
+#define TICKG_WORDS ((RUN_CHUNKS_MAX + 1) * TICK_CW + 8)   // per-warp global copy of a whole run's ticks (slicing is deferred and pooled)
 
-#define WQ1_CAP   448                   // pre-check passers per warp range kept in shared memory (of 512 positions)
-#define WPASS_CAP 64                    // threshold passers per warp range kept in shared memory
-#define WFULL_CAP 96                    // DF-gate survivors per warp range kept in shared memory
+// Per-run scalars, identical in every lane; kept in shared memory so that the register budget goes to the window pass.
+struct RunCtx {
+    const uint8_t *tile_base;      // byte address of run coordinate 0 (= tile coordinate x0 of the segment)
+    long long n_first;             // new-sample index of run coordinate 0
+    long long bound;               // first new sample of the reference buffer after buffer nb
+    uint32_t x0, x_zero_end, x_data_end;
+    uint32_t p_lo, p_hi;           // run-relative positions that are preamble starts of the segment
+    uint32_t buf_len, first_buf, npos;
+    uint32_t n_chunks;             // chunks of positions; chunk n_chunks is look-ahead only
+    uint32_t nb;                   // reference buffer of the chunk being converted, tracked incrementally
+    uint32_t is_mag, last_tile;
+    uint32_t tile0, n_tiles;
+};
 
-struct TileInfo { uint32_t x0, interior, p_lo, p_hi; };
-
-struct WarpQueues {                     // candidate discovery is warp-local: warp w owns positions [512w, 512w+512)
-    uint16_t q1[MAIN_WARPS][WQ1_CAP];
-    uint16_t pass_pos[MAIN_WARPS][WPASS_CAP];
-    uint8_t  pass_tried[MAIN_WARPS][WPASS_CAP];
-    uint32_t full[MAIN_WARPS][WFULL_CAP];
+struct WarpSmem {
+    alignas(16) uint16_t mag[MAG_RING + MAG_MIRROR];
+    uint32_t tick[TICK_RING + TICK_MIRROR];   // tick of sample s (chunk-local) and row r at bit 5 s + r of the chunk's slot
+    uint16_t q1[Q1_SMEM];                     // pre-check passers of the previous chunk (tile-relative positions, ascending)
+    uint32_t pass[32];                        // current batch of threshold passers, PosEntry format
+    uint32_t surv[SURV_CAP];                  // DF-gate survivors waiting for a full slice: run position | ph << 14 | long << 17 | PosEntry index << 18
+    uint32_t seg[16];                         // the run's Segment
+    uint32_t n_pos[RUN_MAX], n_rec[RUN_MAX];  // per tile of the run
+    RunCtx ctx;
 };
 
 struct ScanSmem {
-    uint16_t lut[128 * 128];            // folded, bank-swizzled UC8 magnitude table
-    uint16_t mag[SCAN_NMAG + MAG_PAD];  // magnitudes of the tile, index = tile coordinate x - x0
-    uint32_t tick[TICK_WORDS];          // tick U = 5*(x - x0) + row at word U >> 5, bit U & 31
+    uint16_t lut[128 * 128];                  // folded, bank-swizzled UC8 magnitude table
     uint32_t crc_tab[256];
     uint32_t bit_syn[112];
     uint32_t syn_hash[512];
-    uint32_t pre_bits[SCAN_TILE / 32];  // pre-check result, one bit per position (input of the dense-tile slow path)
-    uint16_t pass_pos[SCAN_PASS_CAP];   // positions that reached a preamble threshold, ascending
-    uint8_t  pass_tried[SCAN_PASS_CAP]; // phases tried
-    uint8_t  pass_live[SCAN_PASS_CAP];  // phases with a filter-dependent score (a Rec exists)
-    uint32_t full[SCAN_FULL_CAP];       // pass index << 4 | phase << 1 | long, for the phases that passed the DF gate (ascending)
-    union {                             // the warp queues are dead once published to the block lists; the records reuse them
-        WarpQueues wq;
-        Rec recs[SCAN_FULL_CAP];        // one record per fully sliced phase (kind 0 = score -2 regardless of the filter)
-    };
-    Segment seg, seg_next;              // descriptor of the current / prefetched tile's segment
-    TileInfo info, info_next;           // per-tile scalars, computed once by the helper warp
-    uint32_t wcnt[MAIN_WARPS];          // per warp: passers | survivors << 16
-    uint32_t scratch[40];
     uint32_t syn_mul;
-    uint32_t rec_off, tile_next, overflow;
+    uint32_t pad_[3];
+    WarpSmem w[SC_WARPS];
 };
 
 // mixed-sign two-way dot products: a = two unsigned 16-bit magnitudes, b = four signed 8-bit coefficients
@@ -75,19 +88,6 @@ __device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c) {
     int d;
     asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
-}
-
-// Exclusive rank of a 0/1 flag over the block plus the block total (all threads must call).
-__device__ __forceinline__ uint32_t block_flag_scan(bool flag, uint32_t *scratch, uint32_t *total) {
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t bal = __ballot_sync(FULLMASK, flag);
-    __syncthreads();
-    if (lane == 0) scratch[wid] = __popc(bal);
-    __syncthreads();
-    uint32_t tot;
-    const uint32_t ex = warp_excl_scan(lane < SCAN_WARPS ? scratch[lane] : 0u, lane, &tot);
-    *total = tot;
-    return __shfl_sync(FULLMASK, ex, wid) + __popc(bal & ((1u << lane) - 1u));
 }
 
 // crc.c:383-406 for nfix_crc = 1: message bit (>= 5) whose single-bit syndrome equals `syn`, or -2.
@@ -142,13 +142,6 @@ __device__ __forceinline__ uint32_t classify(const ScanSmem &S, const ScanParams
     return K_AP;
 }
 
-// 64 ticks starting at tick B as two words (lo = ticks B..B+31).
-__device__ __forceinline__ void ticks64(const ScanSmem &S, uint32_t B, uint32_t &lo, uint32_t &hi) {
-    const uint32_t *t = &S.tick[B >> 5];
-    const uint32_t sh = B & 31u, a = t[0], b = t[1], c = t[2];
-    lo = __funnelshift_r(a, b, sh); hi = __funnelshift_r(b, c, sh);
-}
-
 // Ticks at stride 12 -> adjacent bits, earliest tick in the most significant position.
 __device__ __forceinline__ uint32_t gather3(uint32_t x) {   // ticks 0, 12, 24 of x -> 3 bits
     return (((x & 0x01001001u) * 0x04002001u) >> 24) & 7u;
@@ -157,11 +150,10 @@ __device__ __forceinline__ uint32_t gather2(uint32_t x) {   // ticks 0, 12 of x 
     return (((x & 0x00001001u) * 0x00002001u) >> 12) & 3u;
 }
 
-// Thresholds of the three preamble correlations at position p (demod_2400.c:330-378): phases to try.
-__device__ __forceinline__ uint32_t threshold_phases(const ScanSmem &S, const ScanParams &P, uint32_t p) {
-    const uint16_t *pa = &S.mag[p];
+// Thresholds of the three preamble correlations at pa = &mag[position] (demod_2400.c:330-378): phases to try.
+__device__ __forceinline__ uint32_t threshold_phases(const uint16_t *pa, int thr) {
     const int base_noise = pa[5] + pa[8] + pa[16] + pa[17] + pa[18];
-    const int ref_level = (base_noise * P.thr) >> 5;
+    const int ref_level = (base_noise * thr) >> 5;
     const int d23 = (int)pa[2] - (int)pa[3], s14 = pa[1] + pa[4], d1011 = (int)pa[10] - (int)pa[11];
     const int common = s14 - d23 + pa[9] + pa[12];
     uint32_t tried = 0;
@@ -171,245 +163,52 @@ __device__ __forceinline__ uint32_t threshold_phases(const ScanSmem &S, const Sc
     return tried;
 }
 
-// DF gate (demod_2400.c:222-239): the five DF ticks of try_phase 4+ph at position p -> keep | long << 1.
-__device__ __forceinline__ uint32_t df_gate(const ScanSmem &S, const ScanParams &P, uint32_t p, uint32_t ph) {
-    uint32_t lo, hi;
-    ticks64(S, 5u * (p + 19u) + 4u + ph, lo, hi);          // bit k at tick 12k: 0, 12, 24, 36, 48
+// Ring bit index of the first message tick of (chunk-local position pl, try_phase 4 + ph) for a chunk whose ticks sit in
+// slot `tslot`: the closed form of slice_byte (demod_2400.c:133-213): PPM bit k is the tick 5 (p + 19) + 4 + ph + 12 k.
+__device__ __forceinline__ uint32_t first_tick(uint32_t tslot, uint32_t pl, uint32_t ph) {
+    uint32_t B = tslot * TICK_BITS + 5u * (pl + 19u) + 4u + ph;
+    if (B >= 2 * TICK_BITS) B -= 2 * TICK_BITS;
+    return B;
+}
+
+// DF gate (demod_2400.c:222-239): the five DF ticks starting at ring bit B -> keep | long << 1.
+__device__ __forceinline__ uint32_t df_gate(const WarpSmem &W, const ScanParams &P, uint32_t B) {
+    const uint32_t *t = &W.tick[B >> 5];
+    const uint32_t sh = B & 31u, a = t[0], b = t[1], c = t[2];
+    const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);     // bit k at tick 12k: 0, 12, 24, 36, 48
     const uint32_t df = (gather3(lo) << 2) | gather2(hi >> 4);
     const uint32_t is_long = (P.long_set >> df) & 1u;
     return (is_long | ((P.short_set >> df) & 1u)) | (is_long << 1);
 }
 
-// Full slice of one (position, phase): 8 message bits per 96 ticks, CRC by table, classification; writes *rec.
+// Full slice of one (position, phase) from the warp's global tick copy (bit B = first message tick, linear over the run):
+// 8 message bits per 96 ticks, CRC by table, classification; fills rw[0..7] (a Rec).
 // Returns the RecKind (0 = score -2 regardless of the filter).
-__device__ __forceinline__ uint32_t slice_and_classify(const ScanSmem &S, const ScanParams &P, uint32_t p, uint32_t ph, bool is_long, Rec *rec) {
+__device__ __forceinline__ uint32_t slice_and_classify(const ScanSmem &S, const uint32_t *tickg, const ScanParams &P, uint32_t B, bool is_long, uint32_t rw[8]) {
     const int nbytes = is_long ? 14 : 7;
-    uint32_t B = 5u * (p + 19u) + 4u + ph;
     uint32_t w[4] = {0, 0, 0, 0}, rem = 0, tail = 0;
 #pragma unroll
-    for (int by = 0; by < 14; by++, B += 96) {
+    for (int by = 0; by < 14; by++) {
         if (by >= nbytes) break;
-        const uint32_t *t = &S.tick[B >> 5];
-        const uint32_t sh = B & 31u, a = t[0], b = t[1], c = t[2], d = t[3];
+        const uint32_t *t = &tickg[B >> 5];
+        const uint32_t sh = B & 31u, a = __ldcg(t), b = __ldcg(t + 1), c = __ldcg(t + 2), d = __ldcg(t + 3);
         const uint32_t x0 = __funnelshift_r(a, b, sh), x1 = __funnelshift_r(b, c, sh), x2 = __funnelshift_r(c, d, sh);
         // message bits at ticks 0,12,24 | 36,48,60 | 72,84 of this 96-tick group, MSB first
         const uint32_t byte = (gather3(x0) << 5) | (gather3(x1 >> 4) << 2) | gather2(x2 >> 8);
         w[by >> 2] |= byte << (24 - 8 * (by & 3));
         if (by < nbytes - 3) rem = ((rem << 8) ^ S.crc_tab[byte ^ ((rem >> 16) & 0xffu)]) & 0xffffffu;   // crc.c:74-77
         else tail = (tail << 8) | byte;
+        B += 96;
     }
     const uint32_t syn = rem ^ tail;                                                                  // crc.c:79-80
     const int df = (int)(w[0] >> 27);
     uint32_t addr; int fixbit;
     const uint32_t kind = classify(S, P, w, df, is_long, syn, &addr, &fixbit);
-    uint32_t *rw = reinterpret_cast<uint32_t *>(rec);
     // bytes 0..13 = message, byte 14 = kind, byte 15 = fixbit (little-endian words, big-endian message)
     rw[0] = __byte_perm(w[0], 0, 0x0123); rw[1] = __byte_perm(w[1], 0, 0x0123); rw[2] = __byte_perm(w[2], 0, 0x0123);
     rw[3] = (__byte_perm(w[3], 0, 0x0123) & 0xffffu) | (kind << 16) | ((uint32_t)(fixbit & 0xff) << 24);
     rw[4] = syn; rw[5] = addr; rw[6] = 0; rw[7] = 0;
     return kind;
-}
-
-// Ordered emission of one tile's lists (block-wide): PosEntry per passer, live records packed at the front of a
-// record-pool chunk sized for every sliced phase.
-__device__ __forceinline__ void emit_tile(ScanSmem &S, const ScanParams &P, uint32_t tile, const uint16_t *pass_pos, const uint8_t *pass_tried,
-                                          const uint8_t *pass_live, const Rec *recs, uint32_t n_pass, uint32_t n_full,
-                                          bool have_chunk, uint32_t chunk_off) {
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) {   // the fast path issued this atomic before slicing so that nobody waits for its round trip here
-        const uint32_t off = have_chunk ? chunk_off : (n_full ? atomicAdd(&P.ctl->rec_alloc, n_full) : 0);
-        S.overflow = 0;
-        if (off + n_full > P.ctl->rec_cap) { atomicOr(&P.ctl->overflow, 1u); S.overflow = 1; }   // host regrows the pool and reruns
-        S.rec_off = off;
-    }
-    PosEntry *pos_out = P.pos_pool + (size_t)tile * SCAN_TILE;
-    for (uint32_t r = tid; r < n_pass; r += SCAN_THREADS)
-        pos_out[r] = (uint32_t)pass_pos[r] | ((uint32_t)pass_tried[r] << 16) | ((uint32_t)pass_live[r] << 21);
-    __syncthreads();   // S.rec_off / S.overflow visible
-    const bool pool_ok = !S.overflow;
-    uint32_t n_recs = 0;
-    for (uint32_t r0 = 0; r0 < n_full; r0 += SCAN_THREADS) {
-        const uint32_t q = r0 + tid;
-        uint4 a = {0, 0, 0, 0}, b = {0, 0, 0, 0};
-        bool live = false;
-        if (q < n_full) {
-            a = reinterpret_cast<const uint4 *>(&recs[q])[0]; b = reinterpret_cast<const uint4 *>(&recs[q])[1];
-            live = (a.w >> 16) & 0xffu;
-        }
-        uint32_t total;
-        const uint32_t r = n_recs + block_flag_scan(live, S.scratch, &total);
-        if (live && pool_ok) {
-            uint4 *dst = reinterpret_cast<uint4 *>(P.rec_pool + S.rec_off + r);
-            dst[0] = a; dst[1] = b;
-            const uint32_t kind = (a.w >> 16) & 0xffu;
-            const int fixbit = (int)(int8_t)(a.w >> 24);
-            const uint32_t aa_changed = (kind == K_ES_FIX && fixbit >= 8 && fixbit <= 31) ? 1u : 0u;   // mode_s.c:560
-            const uint32_t df = (a.x & 0xffu) >> 3;                     // byte 0 of the frame as sliced
-            P.key_pool[S.rec_off + r] = (aa_changed ? KEY_AA_CHANGED : 0u) | (df == 17 ? KEY_DF17 : 0u) | ((df & 0x10u) ? KEY_LONG : 0u) |
-                                        (kind << 24) | (b.y & 0xffffffu);
-        }
-        n_recs += total;
-    }
-    if (tid == 0) { TileOut t; t.n_pos = n_pass; t.n_rec = pool_ok ? n_recs : 0; t.rec_off = S.rec_off; t.pad_ = n_full; P.tile_out[tile] = t; }
-}
-
-// Dense-tile slow path: the same steps block-wide with every queue in this CTA's slice of a global scratch arena
-// sized for the worst case (every position a candidate in all five phases) — never a dropped candidate.
-__device__ __noinline__ void process_candidates_slow(ScanSmem &S, const ScanParams &P, uint32_t tile, uint8_t *scratch) {
-    const uint32_t tid = threadIdx.x;
-    uint16_t *q1 = reinterpret_cast<uint16_t *>(scratch);
-    uint16_t *pass_pos = reinterpret_cast<uint16_t *>(scratch + 2 * SCAN_TILE);
-    uint8_t *pass_tried = scratch + 4 * SCAN_TILE;
-    uint8_t *pass_live = scratch + 5 * SCAN_TILE;
-    uint32_t *full = reinterpret_cast<uint32_t *>(scratch + 6 * SCAN_TILE);
-    Rec *recs = reinterpret_cast<Rec *>(scratch + 26 * SCAN_TILE);
-
-    uint32_t n_q1;
-    {   // ordered compaction of the pre-check bitmap into q1
-        const uint32_t word = tid < SCAN_TILE / 32 ? S.pre_bits[tid] : 0;
-        uint32_t off = block_excl_scan(__popc(word), S.scratch, &n_q1);
-        uint32_t wbits = word;
-        while (wbits) { const uint32_t b = __ffs(wbits) - 1; wbits &= wbits - 1; q1[off++] = (uint16_t)(tid * 32 + b); }
-    }
-    __syncthreads();
-    uint32_t n_pass = 0;
-    for (uint32_t r0 = 0; r0 < n_q1; r0 += SCAN_THREADS) {
-        const uint32_t e = r0 + tid;
-        const uint32_t p = e < n_q1 ? q1[e] : 0;
-        const uint32_t tried = e < n_q1 ? threshold_phases(S, P, p) : 0;
-        uint32_t total;
-        const uint32_t r = n_pass + block_flag_scan(tried != 0, S.scratch, &total);
-        if (tried) { pass_pos[r] = (uint16_t)p; pass_tried[r] = (uint8_t)tried; pass_live[r] = 0; }
-        n_pass += total;
-    }
-    __syncthreads();
-    uint32_t n_full = 0;
-    for (uint32_t r0 = 0; r0 < 5 * n_pass; r0 += SCAN_THREADS) {
-        const uint32_t i = r0 + tid, r = i / 5, ph = i - 5 * r;
-        uint32_t g = 0;
-        if (r < n_pass && ((pass_tried[r] >> ph) & 1u)) g = df_gate(S, P, pass_pos[r], ph);
-        uint32_t total;
-        const uint32_t off = n_full + block_flag_scan(g & 1u, S.scratch, &total);
-        if (g & 1u) full[off] = (r << 4) | (ph << 1) | (g >> 1);
-        n_full += total;
-    }
-    __syncthreads();
-    for (uint32_t q = tid; q < n_full; q += SCAN_THREADS) {
-        const uint32_t fe = full[q], r = fe >> 4, ph = (fe >> 1) & 7u;
-        if (slice_and_classify(S, P, pass_pos[r], ph, fe & 1u, &recs[q]))
-            atomicOr(reinterpret_cast<uint32_t *>(&pass_live[r & ~3u]), (1u << ph) << (8 * (r & 3)));
-    }
-    __syncthreads();
-    emit_tile(S, P, tile, pass_pos, pass_tried, pass_live, recs, n_pass, n_full, false, 0);
-}
-
-// Phase 1: 16-byte HBM loads -> magnitudes in shared memory + per-buffer sums.  INTERIOR tiles (all samples are data,
-// all owned samples belong to one reference buffer) skip every per-chunk boundary test.
-template <bool INTERIOR>
-__device__ __forceinline__ void load_convert(ScanSmem &S, const ScanParams &P, const Segment &seg, uint32_t tile, uint32_t x0) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    // byte address of tile coordinate x: seg.base + 2*(x - lead); x0 multiple of 8 => 16B aligned
-    const uint8_t *tile_base = seg.base + 2 * ((int64_t)x0 - (int64_t)seg.lead);
-    const uint32_t x_data_end = seg.lead + seg.npos + B200_TRAIL;    // first x without data
-    const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead; // x below: magnitude 0, memory not read
-    const bool is_mag = seg.flags & SEG_MAG;
-    const bool last_tile = tile + 1 == seg.tile_begin + seg.n_tiles;
-    // Power statistics (convert.c:75-79) are per reference buffer: new sample n = x - lead - 326 belongs to
-    // buffer n / buf_len and is counted by the tile whose position range holds x (the last tile also owns the tail).
-    const int64_t n_first = (int64_t)x0 - seg.lead - B200_TRAIL;    // new-sample index of tile coordinate x0
-    const uint32_t nb0 = n_first > 0 ? (uint32_t)n_first / seg.buf_len : 0;
-    const int64_t bound1 = (int64_t)(nb0 + 1) * seg.buf_len;         // first new sample of buffer nb0 + 1
-    const int64_t bound2 = bound1 + seg.buf_len;
-
-    unsigned long long acc_level = 0, acc_power = 0;
-    uint32_t acc_buf = INTERIOR ? seg.first_buf + nb0 : 0xffffffffu;
-    // 16 main warps: chunks [0, SCAN_TILE/8) in two rounds; helper warp: the look-ahead chunks — two rounds each, balanced
-    const bool helper = tid >= SCAN_MAIN_THREADS;
-#pragma unroll 1
-    for (uint32_t k = 0; k < 2; k++) {
-        const uint32_t c = helper ? SCAN_TILE / 8 + k * 32 + lane : k * SCAN_MAIN_THREADS + tid;
-        if (c >= SCAN_NMAG / 8) continue;
-        const uint32_t xc = x0 + c * 8;
-        uint32_t m[8];
-        if (!INTERIOR && (xc + 8 <= x_zero_end || xc >= x_data_end)) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) m[i] = 0;
-        } else {
-            const uint4 raw = ldg_stream_u4(tile_base + (size_t)c * 16);
-            const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
-            if (is_mag) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) { m[2 * i] = wv[i] & 0xffffu; m[2 * i + 1] = wv[i] >> 16; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t w = wv[i];                               // bytes I0 Q0 I1 Q1
-                    const uint32_t sgn = prmt(w, 0, 0xba98);                // 0xff where the byte is >= 128
-                    const uint32_t f = (w ^ ~sgn) & 0x7f7f7f7fu;            // fold: v>=128 ? v-128 : 127-v
-                    uint32_t off = f + (f & 0x007f007fu);                   // per half: fq*256 + 2*fi
-                    off ^= (f >> 5) & 0x00780078u;                          // bank swizzle (see modes_tables.h)
-                    m[2 * i] = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(S.lut) + (off & 0xffffu));
-                    m[2 * i + 1] = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(S.lut) + (off >> 16));
-                }
-            }
-            if (INTERIOR) {
-                if (c < SCAN_TILE / 8) {
-                    acc_level += (m[0] + m[1]) + (m[2] + m[3]) + (m[4] + m[5]) + (m[6] + m[7]);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) mad_wide(acc_power, m[i], m[i]);
-                }
-            } else {
-                if (xc < x_zero_end || xc + 8 > x_data_end) {   // boundary chunk: mask the samples that are not data
-#pragma unroll
-                    for (int i = 0; i < 8; i++) if (xc + i < x_zero_end || xc + i >= x_data_end) m[i] = 0;
-                }
-                if (c < SCAN_TILE / 8 || last_tile) {
-                    const int64_t n0 = n_first + (int64_t)c * 8;
-                    uint32_t b = 0xffffffffu;
-                    if (n0 >= 0 && n0 + 8 <= (int64_t)seg.npos) {
-                        if (n0 + 8 <= bound1) b = nb0; else if (n0 >= bound1 && n0 + 8 <= bound2) b = nb0 + 1;
-                    }
-                    if (b != 0xffffffffu) {           // all eight samples belong to buffer b
-                        b += seg.first_buf;
-                        if (b != acc_buf) {
-                            if (acc_buf != 0xffffffffu) { atomicAdd(&P.buf_acc[acc_buf].sum_level, acc_level); atomicAdd(&P.buf_acc[acc_buf].sum_power, acc_power); }
-                            acc_buf = b; acc_level = 0; acc_power = 0;
-                        }
-                        acc_level += (m[0] + m[1]) + (m[2] + m[3]) + (m[4] + m[5]) + (m[6] + m[7]);
-#pragma unroll
-                        for (int i = 0; i < 8; i++) mad_wide(acc_power, m[i], m[i]);
-                    } else if (n0 + 8 > 0 && n0 < (int64_t)seg.npos) {   // chunk straddles a boundary: per sample
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int64_t n = n0 + i;
-                            if (n >= 0 && n < (int64_t)seg.npos) {
-                                const uint32_t bb = seg.first_buf + (uint32_t)n / seg.buf_len;
-                                if (bb != acc_buf) {
-                                    if (acc_buf != 0xffffffffu) { atomicAdd(&P.buf_acc[acc_buf].sum_level, acc_level); atomicAdd(&P.buf_acc[acc_buf].sum_power, acc_power); }
-                                    acc_buf = bb; acc_level = 0; acc_power = 0;
-                                }
-                                acc_level += m[i];
-                                mad_wide(acc_power, m[i], m[i]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        uint4 packed;
-        packed.x = m[0] | (m[1] << 16); packed.y = m[2] | (m[3] << 16);
-        packed.z = m[4] | (m[5] << 16); packed.w = m[6] | (m[7] << 16);
-        *reinterpret_cast<uint4 *>(&S.mag[c * 8]) = packed;
-    }
-    // flush the statistics: one atomic pair per warp when the whole warp fed the same buffer
-    const uint32_t b0 = __shfl_sync(FULLMASK, acc_buf, 0);
-    if (INTERIOR || __all_sync(FULLMASK, acc_buf == b0)) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { acc_level += __shfl_xor_sync(FULLMASK, acc_level, o); acc_power += __shfl_xor_sync(FULLMASK, acc_power, o); }
-        if (lane == 0 && b0 != 0xffffffffu) { atomicAdd(&P.buf_acc[b0].sum_level, acc_level); atomicAdd(&P.buf_acc[b0].sum_power, acc_power); }
-    } else if (acc_buf != 0xffffffffu) {
-        atomicAdd(&P.buf_acc[acc_buf].sum_level, acc_level); atomicAdd(&P.buf_acc[acc_buf].sum_power, acc_power);
-    }
 }
 
 // Correlator rows (demod_2400.c:74-93) NEGATED and packed as four signed bytes (c0, c1, c2, c3):
@@ -420,10 +219,10 @@ __device__ __forceinline__ void load_convert(ScanSmem &S, const ScanParams &P, c
 #define NEG_ROW3 0x0012f5f9u   //  -7, -11,  18,  0
 #define NEG_ROW4 0xff14f1fcu   //  -4, -15,  20, -1
 
-// Phase 2: thread = 16 consecutive samples/positions starting at i0 (window of 32 magnitudes in registers).
-// Returns the 16-bit pre-check mask; writes the 80 ticks of its samples (two lanes share five words).
-__device__ __forceinline__ uint32_t window_pass(ScanSmem &S, uint32_t i0, uint32_t lane, bool store) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(&S.mag[i0]);
+// One lane = 16 consecutive samples / positions starting at ring index mi0 (window of 32 magnitudes in registers).
+// Returns the 16-bit pre-check mask; writes the 80 ticks of its samples (two lanes share five words) at tick word tw0.
+__device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint32_t tw0, uint32_t lane, bool mirror, uint32_t *tickg_chunk) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&W.mag[mi0]);
     const uint4 q0 = src[0], q1v = src[1], q2 = src[2], q3 = src[3];
     const uint32_t wv[16] = {q0.x, q0.y, q0.z, q0.w, q1v.x, q1v.y, q1v.z, q1v.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
     uint32_t mask = 0;
@@ -448,199 +247,382 @@ __device__ __forceinline__ uint32_t window_pass(ScanSmem &S, uint32_t i0, uint32
 #pragma unroll
         for (int r = 0; r < 5; r++) {
             const int nv = dp2a_hi(Bp, rows[r], dp2a_lo(A, rows[r], 0));
-            const int g = 5 * i + r;                                           // tick within this thread's 80
+            const int g = 5 * i + r;                                           // tick within this lane's 80
             acc[g >> 5] = __funnelshift_l((uint32_t)nv, acc[g >> 5], 1);       // shift the sign bit in, earliest tick ends up highest
         }
     }
     // acc[0], acc[1] hold 32 ticks each, earliest in bit 31 -> bit-reverse; acc[2] holds 16 ticks in its low half
     const uint32_t t0 = __brev(acc[0]), t1 = __brev(acc[1]), t2 = __brev(acc[2]) >> 16;
-    // lanes 2j, 2j+1 own ticks [160j', 160j'+160): five words
-    uint32_t *dst = &S.tick[(i0 >> 5) * 5];
+    // lanes 2j, 2j+1 own 160 ticks: five words
+    uint32_t *dst = &W.tick[tw0 + (lane >> 1) * 5];
+    uint32_t *dg = tickg_chunk + (lane >> 1) * 5;
     const uint32_t other_t0 = __shfl_down_sync(FULLMASK, t0, 1);
-    if (store) {
-        if ((lane & 1) == 0) { dst[0] = t0; dst[1] = t1; dst[2] = t2 | (other_t0 << 16); }
-        else { dst[3] = __funnelshift_r(t0, t1, 16); dst[4] = __funnelshift_r(t1, t2, 16); }
+    if ((lane & 1) == 0) {
+        const uint32_t w2 = t2 | (other_t0 << 16);
+        dst[0] = t0; dst[1] = t1; dst[2] = w2;
+        dg[0] = t0; dg[1] = t1; dg[2] = w2;
+        if (mirror && lane < 4) { uint32_t *m = &W.tick[TICK_RING + (lane >> 1) * 5]; m[0] = t0; m[1] = t1; m[2] = w2; }
+    } else {
+        const uint32_t w3 = __funnelshift_r(t0, t1, 16), w4 = __funnelshift_r(t1, t2, 16);
+        dst[3] = w3; dst[4] = w4;
+        dg[3] = w3; dg[4] = w4;
+        if (mirror && lane < 4) { uint32_t *m = &W.tick[TICK_RING + (lane >> 1) * 5]; m[3] = w3; m[4] = w4; }
     }
     return mask;
 }
 
-// Per-tile scalars every thread needs, computed by one lane while the previous tile is being processed.
-__device__ __forceinline__ TileInfo make_tile_info(const Segment &seg, uint32_t tile) {
-    TileInfo t;
-    t.x0 = (tile - seg.tile_begin) * SCAN_TILE;                           // tile origin in tile coordinates
-    const int64_t n_first = (int64_t)t.x0 - seg.lead - B200_TRAIL;
-    const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;
-    bool interior = t.x0 >= x_zero_end && t.x0 + SCAN_NMAG <= seg.lead + seg.npos + B200_TRAIL && n_first >= 0 &&
-                    tile + 1 != seg.tile_begin + seg.n_tiles;
-    if (interior) {   // all owned samples in one reference buffer?
-        const uint32_t nb0 = (uint32_t)n_first / seg.buf_len;
-        interior = (uint64_t)n_first + SCAN_TILE <= (uint64_t)(nb0 + 1) * seg.buf_len;
+// One chunk's samples, two 16-byte pieces per lane (samples 256 r + 8 lane .. + 8), only where the segment has data.
+// Holding the loaded words in registers across the candidate work costs more registers than the kernel has (they spill, and
+// the spill store waits for the load), so the chunk is PREFETCHED into L1 two iterations ahead and loaded when it is converted.
+__device__ __forceinline__ void prefetch_raw(const RunCtx &T, uint32_t c, uint32_t lane, bool all_data) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t xo = c * CHUNK + r * 256 + lane * 8, xc = T.x0 + xo;
+        if (all_data || !(xc + 8 <= T.x_zero_end || xc >= T.x_data_end))
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(T.tile_base + (size_t)xo * 2));
     }
-    t.interior = interior;
-    t.p_lo = seg.lead > t.x0 ? seg.lead - t.x0 : 0;                        // first real position
-    t.p_hi = min((uint32_t)SCAN_TILE, seg.lead + seg.npos > t.x0 ? seg.lead + seg.npos - t.x0 : 0u);
-    return t;
 }
 
-__global__ void __maxnreg__(56) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
+__device__ __forceinline__ void store_mags(WarpSmem &W, uint32_t slot, int r, uint32_t lane, const uint32_t m[8]) {
+    uint4 packed;
+    packed.x = m[0] | (m[1] << 16); packed.y = m[2] | (m[3] << 16);
+    packed.z = m[4] | (m[5] << 16); packed.w = m[6] | (m[7] << 16);
+    *reinterpret_cast<uint4 *>(&W.mag[slot * CHUNK + r * 256 + lane * 8]) = packed;
+    if (slot == 0 && r == 0 && lane < MAG_MIRROR / 8) *reinterpret_cast<uint4 *>(&W.mag[MAG_RING + lane * 8]) = packed;
+}
+
+__device__ __forceinline__ void to_mags(const ScanSmem &S, bool is_mag, const uint4 &raw, uint32_t m[8]) {
+    const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
+    if (is_mag) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { m[2 * i] = wv[i] & 0xffffu; m[2 * i + 1] = wv[i] >> 16; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) uc8_pair_to_mag(S.lut, wv[i], m[2 * i], m[2 * i + 1]);
+    }
+}
+
+// Magnitudes of one chunk into ring slot `slot` + exact statistics (convert.c:64-108), chunk entirely data; if count_buf is a
+// reference buffer the whole chunk lies in it and is counted: lane partials -> warp sum -> one pair of atomics.
+__device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &W, const ScanParams &P, const uint8_t *src, bool is_mag, uint32_t slot,
+                                                   uint32_t lane, uint32_t count_buf) {
+    const uint4 raw0 = *reinterpret_cast<const uint4 *>(src + lane * 16), raw1 = *reinterpret_cast<const uint4 *>(src + 512 + lane * 16);
+    uint32_t level = 0;
+    unsigned long long power = 0;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        uint32_t m[8];
+        to_mags(S, is_mag, r ? raw1 : raw0, m);
+        level += (m[0] + m[1]) + (m[2] + m[3]) + (m[4] + m[5]) + (m[6] + m[7]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) mad_wide(power, m[i], m[i]);
+        store_mags(W, slot, r, lane, m);
+    }
+    if (count_buf != 0xffffffffu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { level += __shfl_xor_sync(FULLMASK, level, o); power += __shfl_xor_sync(FULLMASK, power, o); }
+        if (lane == 0) { atomicAdd(&P.buf_acc[count_buf].sum_level, (unsigned long long)level); atomicAdd(&P.buf_acc[count_buf].sum_power, power); }
+    }
+}
+
+// The same for a chunk at the edge of the data or across a buffer boundary.  Power statistics are per reference buffer:
+// new sample n = x - lead - 326 belongs to buffer n / buf_len and is counted by the run whose position range holds x
+// (the last tile of a segment also owns the tail).
+__device__ __noinline__ void convert_chunk_edge(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t c, uint32_t slot, uint32_t lane) {
+    const RunCtx &T = W.ctx;
+    const bool owned = c < T.n_chunks || T.last_tile;
+    unsigned long long level = 0, power = 0;
+    uint32_t buf = 0xffffffffu;
+    for (int r = 0; r < 2; r++) {
+        const uint32_t xo = c * CHUNK + r * 256 + lane * 8, xc = T.x0 + xo;
+        uint32_t m[8];
+        if (xc + 8 <= T.x_zero_end || xc >= T.x_data_end) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) m[i] = 0;
+        } else {
+            to_mags(S, T.is_mag, *reinterpret_cast<const uint4 *>(T.tile_base + (size_t)xo * 2), m);
+            if (xc < T.x_zero_end || xc + 8 > T.x_data_end) {   // boundary group: mask the samples that are not data
+#pragma unroll
+                for (int i = 0; i < 8; i++) if (xc + i < T.x_zero_end || xc + i >= T.x_data_end) m[i] = 0;
+            }
+            if (owned) {
+                const long long n0 = T.n_first + (long long)xo;
+                for (int i = 0; i < 8; i++) {
+                    const long long n = n0 + i;
+                    if (n >= 0 && n < (long long)T.npos) {
+                        const uint32_t bb = T.first_buf + (uint32_t)n / T.buf_len;
+                        if (bb != buf) {
+                            if (buf != 0xffffffffu) { atomicAdd(&P.buf_acc[buf].sum_level, level); atomicAdd(&P.buf_acc[buf].sum_power, power); }
+                            buf = bb; level = 0; power = 0;
+                        }
+                        level += m[i];
+                        mad_wide(power, m[i], m[i]);
+                    }
+                }
+            }
+        }
+        store_mags(W, slot, r, lane, m);
+    }
+    if (buf != 0xffffffffu) { atomicAdd(&P.buf_acc[buf].sum_level, level); atomicAdd(&P.buf_acc[buf].sum_power, power); }
+}
+
+// One round of full slices: the first `cnt` (<= 32) queued survivors, one per lane; live records go to the warp's staging area.
+__device__ __forceinline__ void slice_round(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t cnt, const uint32_t *tickg, PosEntry *run_pos,
+                                            uint32_t lane, uint32_t &n_stage, Rec *stage, uint32_t *stage_key) {
+    uint32_t rw[8];
+    uint32_t kind = 0;
+    if (lane < cnt) {
+        const uint32_t e = W.surv[lane];
+        const uint32_t p = e & 0x3fffu, ph = (e >> 14) & 7u;
+        kind = slice_and_classify(S, tickg, P, 5u * (p + 19u) + 4u + ph, (e >> 17) & 1u, rw);
+        if (kind) {
+            const uint32_t m = p / SCAN_TILE;
+            atomicOr(&run_pos[(size_t)m * SCAN_TILE + (e >> 18)], 1u << (21 + ph));      // this phase has a record
+            atomicAdd(&W.n_rec[m], 1u);
+        }
+    }
+    const uint32_t bal = __ballot_sync(FULLMASK, kind != 0);
+    if (kind) {
+        const uint32_t at = n_stage + __popc(bal & ((1u << lane) - 1u));
+        if (at < P.stage_cap) {
+            uint4 *dst = reinterpret_cast<uint4 *>(stage + at);
+            dst[0] = make_uint4(rw[0], rw[1], rw[2], rw[3]); dst[1] = make_uint4(rw[4], rw[5], rw[6], rw[7]);
+            const int fixbit = (int)(int8_t)(rw[3] >> 24);
+            const uint32_t aa_changed = (kind == K_ES_FIX && fixbit >= 8 && fixbit <= 31) ? 1u : 0u;   // mode_s.c:560
+            const uint32_t df = (rw[0] & 0xffu) >> 3;                     // byte 0 of the frame as sliced
+            stage_key[at] = (aa_changed ? KEY_AA_CHANGED : 0u) | (df == 17 ? KEY_DF17 : 0u) | ((df & 0x10u) ? KEY_LONG : 0u) | (kind << 24) | (rw[5] & 0xffffffu);
+        }
+    }
+    n_stage += __popc(bal);
+}
+
+// Candidates of one chunk: its pre-check passers (q1, ascending) -> thresholds -> PosEntries; DF gate -> survivor queue,
+// sliced 32 at a time whenever the queue fills (the rest waits for later chunks of the run).
+__device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t n_q1, uint32_t warp_global,
+                                                   uint32_t chunk_p0, uint32_t mslot, uint32_t tslot, uint32_t lane,
+                                                   uint32_t &n_surv, uint32_t &n_stage) {
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t m = chunk_p0 / SCAN_TILE;                     // tile of the run this chunk belongs to
+    const uint16_t *q1_over = P.q1_over + (size_t)warp_global * CHUNK;
+    const uint32_t *tickg = P.tick_scratch + (size_t)warp_global * TICKG_WORDS;
+    Rec *stage = P.stage_rec + (size_t)warp_global * P.stage_cap;
+    uint32_t *stage_key = P.stage_key + (size_t)warp_global * P.stage_cap;
+    PosEntry *run_pos = P.pos_pool + (size_t)W.ctx.tile0 * SCAN_TILE;
+    PosEntry *pos_out = run_pos + (size_t)m * SCAN_TILE;
+    for (uint32_t b0 = 0; b0 < n_q1; b0 += 32) {
+        const uint32_t e = b0 + lane;
+        uint32_t p = 0, tried = 0;
+        if (e < n_q1) {
+            p = e < Q1_SMEM ? W.q1[e] : q1_over[e - Q1_SMEM];    // run-relative position
+            tried = threshold_phases(&W.mag[mslot * CHUNK + (p - chunk_p0)], P.thr);
+        }
+        const uint32_t bal = __ballot_sync(FULLMASK, tried != 0);
+        if (!bal) continue;
+        const uint32_t n_b = __popc(bal), n_pos = W.n_pos[m];
+        if (tried) {
+            const uint32_t r = __popc(bal & lt);
+            W.pass[r] = p | (tried << 16);
+            pos_out[n_pos + r] = (p & (SCAN_TILE - 1)) | (tried << 16);       // live bits are OR-ed in when its phases are sliced
+        }
+        __syncwarp();
+        if (lane == 0) W.n_pos[m] = n_pos + n_b;
+        for (uint32_t i0 = 0; i0 < 5 * n_b; i0 += 32) {
+            const uint32_t i = i0 + lane, r = i / 5, ph = i - 5 * r;
+            uint32_t g = 0, pe = 0;
+            if (r < n_b) {
+                pe = W.pass[r];
+                if ((pe >> (16 + ph)) & 1u) g = df_gate(W, P, first_tick(tslot, (pe & 0x3fffu) - chunk_p0, ph));
+            }
+            const uint32_t bal2 = __ballot_sync(FULLMASK, g & 1u);
+            if (g & 1u) W.surv[n_surv + __popc(bal2 & lt)] = (pe & 0x3fffu) | (ph << 14) | ((g >> 1) << 17) | ((n_pos + r) << 18);
+            n_surv += __popc(bal2);
+            __syncwarp();
+            if (n_surv >= 32) {
+                slice_round(S, W, P, 32, tickg, run_pos, lane, n_stage, stage, stage_key);
+                const uint32_t moved = lane + 32 < n_surv ? W.surv[lane + 32] : 0;
+                __syncwarp();
+                W.surv[lane] = moved;
+                n_surv -= 32;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
     extern __shared__ uint4 smem_raw[];
     ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    // one-time table staging (persistent CTA) and the first tile
-    {
+    {   // one-time table staging (persistent CTA)
         const uint4 *src = reinterpret_cast<const uint4 *>(tables->lut_fold);
         uint4 *dst = reinterpret_cast<uint4 *>(S.lut);
-        for (uint32_t i = tid; i < sizeof(S.lut) / 16; i += SCAN_THREADS) dst[i] = src[i];
-        for (uint32_t i = tid; i < 256; i += SCAN_THREADS) S.crc_tab[i] = tables->crc_tab[i];
-        for (uint32_t i = tid; i < 112; i += SCAN_THREADS) S.bit_syn[i] = tables->bit_syn[i];
-        for (uint32_t i = tid; i < 512; i += SCAN_THREADS) S.syn_hash[i] = tables->syn_hash[i];
-        for (uint32_t i = tid; i < MAG_PAD; i += SCAN_THREADS) S.mag[SCAN_NMAG + i] = 0;
-        if (tid == 0) {
-            S.syn_mul = tables->syn_hash_mul;
-            const uint32_t t = atomicAdd(&P.ctl->tile_counter, 1u);
-            S.tile_next = t;
-            if (t < P.n_tiles) { const Segment sg = P.segs[P.tile_seg[t]]; S.seg_next = sg; S.info_next = make_tile_info(sg, t); }
-        }
+        for (uint32_t i = tid; i < sizeof(S.lut) / 16; i += SC_THREADS) dst[i] = src[i];
+        for (uint32_t i = tid; i < 256; i += SC_THREADS) S.crc_tab[i] = tables->crc_tab[i];
+        for (uint32_t i = tid; i < 112; i += SC_THREADS) S.bit_syn[i] = tables->bit_syn[i];
+        for (uint32_t i = tid; i < 512; i += SC_THREADS) S.syn_hash[i] = tables->syn_hash[i];
+        if (tid == 0) S.syn_mul = tables->syn_hash_mul;
     }
-    const bool helper_lane0 = tid == SCAN_MAIN_THREADS;
+    __syncthreads();      // the only block barrier: from here on every warp is on its own
 
+    WarpSmem &W = S.w[wid];
+    RunCtx &T = W.ctx;
+    const uint32_t warp_global = blockIdx.x * SC_WARPS + wid;
+
+    uint32_t pend_tile = 0, pend_n = 0;       // tiles already claimed but not processed yet (a claim that crossed a segment boundary)
     for (;;) {
-        __syncthreads();
-        const uint32_t tile = S.tile_next;
-        if (tile >= P.n_tiles) break;
-        if (tid < sizeof(Segment) / 4) reinterpret_cast<uint32_t *>(&S.seg)[tid] = reinterpret_cast<const uint32_t *>(&S.seg_next)[tid];
-        if (tid >= 32 && tid < 32 + sizeof(TileInfo) / 4) reinterpret_cast<uint32_t *>(&S.info)[tid - 32] = reinterpret_cast<const uint32_t *>(&S.info_next)[tid - 32];
-        __syncthreads();
-        // Software-pipelined tile fetch (lane 0 of the helper warp only): the atomic is issued here, its result is first
-        // used after phase 1, the segment it names is loaded after phase 2 — three round trips hidden behind this tile's work.
-        uint32_t nxt = 0;
-        if (helper_lane0) nxt = atomicAdd(&P.ctl->tile_counter, 1u);
-
-        const Segment &seg = S.seg;
-        const uint32_t x0 = S.info.x0;
-
-        // ---- phase 1: load + convert ----------------------------------------------------------------
-        if (S.info.interior) load_convert<true>(S, P, seg, tile, x0); else load_convert<false>(S, P, seg, tile, x0);
-        uint32_t nxt_seg = 0;
-        if (helper_lane0) { S.tile_next = nxt; if (nxt < P.n_tiles) nxt_seg = P.tile_seg[nxt]; }
-        __syncthreads();                                                   // B: magnitudes complete
-
-        // ---- phase 2: pre-check masks + tick map, 16 positions per lane; main warp w owns positions [512w, 512w+512),
-        //      the helper warp the look-ahead samples SCAN_TILE .. SCAN_NMAG-1 (ticks only) ------------------------------
-        const bool is_main = tid < SCAN_MAIN_THREADS;
-        const uint32_t i0 = is_main ? tid * 16 : SCAN_TILE + lane * 16;
-        uint32_t mask = window_pass(S, i0, lane, is_main || lane < (SCAN_LOOKAHEAD + 31) / 32 * 2);
-        if (is_main) {
-            const uint32_t p_lo = S.info.p_lo, p_hi = S.info.p_hi;
-            // positions outside [p_lo, p_hi) are not preamble starts of this segment
-            const uint32_t lo_cut = p_lo > i0 ? min(p_lo - i0, 16u) : 0u, hi_cut = p_hi > i0 ? min(p_hi - i0, 16u) : 0u;
-            mask &= (0xffffu << lo_cut) & ((1u << hi_cut) - 1u);
-            const uint32_t both = (mask << (16 * (lane & 1))) | __shfl_xor_sync(FULLMASK, mask << (16 * (lane & 1)), 1);
-            if ((lane & 1) == 0) S.pre_bits[i0 >> 5] = both;
-        } else {
-            mask = 0;
-            if (lane == 0 && nxt < P.n_tiles) { const Segment sg = P.segs[nxt_seg]; S.seg_next = sg; S.info_next = make_tile_info(sg, nxt); }
-        }
-
-        // ---- warp-local discovery: pre-check passers -> thresholds (magnitudes only, no tick needed yet) ----------------
-        uint32_t n_wpass = 0;
-        bool wover = false;
-        if (is_main) {
-            uint16_t *wq1 = S.wq.q1[wid];
-            uint32_t n_wq1;
-            uint32_t off = warp_excl_scan(__popc(mask), lane, &n_wq1);
-            uint32_t mb = mask;
-            if (n_wq1 > WQ1_CAP) { wover = true; n_wq1 = 0; mb = 0; }
-            while (mb) { const uint32_t b = __ffs(mb) - 1; mb &= mb - 1; wq1[off++] = (uint16_t)(i0 + b); }
-            __syncwarp();
-            for (uint32_t r0 = 0; r0 < n_wq1; r0 += 32) {
-                const uint32_t e = r0 + lane;
-                const uint32_t p = e < n_wq1 ? wq1[e] : 0;
-                const uint32_t tried = e < n_wq1 ? threshold_phases(S, P, p) : 0;
-                const uint32_t bal = __ballot_sync(FULLMASK, tried != 0);
-                const uint32_t r = n_wpass + __popc(bal & ((1u << lane) - 1u));
-                if (tried) { if (r < WPASS_CAP) { S.wq.pass_pos[wid][r] = (uint16_t)p; S.wq.pass_tried[wid][r] = (uint8_t)tried; } else wover = true; }
-                n_wpass += __popc(bal);
-            }
-        }
-        __syncthreads();                                                   // C: tick map complete
-
-        // ---- warp-local DF gate over the warp's own passers ------------------------------------------------------------------
-        uint32_t n_wfull = 0;
-        if (is_main && !__any_sync(FULLMASK, wover)) {
-            for (uint32_t r0 = 0; r0 < 5 * n_wpass; r0 += 32) {
-                const uint32_t i = r0 + lane, r = i / 5, ph = i - 5 * r;
-                uint32_t g = 0;
-                if (r < n_wpass && ((S.wq.pass_tried[wid][r] >> ph) & 1u)) g = df_gate(S, P, S.wq.pass_pos[wid][r], ph);
-                const uint32_t bal = __ballot_sync(FULLMASK, g & 1u);
-                const uint32_t q = n_wfull + __popc(bal & ((1u << lane) - 1u));
-                if (g & 1u) { if (q < WFULL_CAP) S.wq.full[wid][q] = (r << 4) | (ph << 1) | (g >> 1); else wover = true; }
-                n_wfull += __popc(bal);
-            }
-        }
-        wover = __any_sync(FULLMASK, wover);
-        if (lane == 0 && is_main) S.wcnt[wid] = wover ? 0xffffffffu : (n_wpass | (n_wfull << 16));
-        __syncthreads();                                                   // D: per-warp counts published
-
-        // ---- publish to the ordered block lists -----------------------------------------------------------------------------------
-        uint32_t n_pass, n_full;
-        bool dense;
-        {
-            const uint32_t c = lane < MAIN_WARPS ? S.wcnt[lane] : 0u;
-            dense = __any_sync(FULLMASK, c == 0xffffffffu);
-            uint32_t tot;
-            const uint32_t ex = warp_excl_scan(dense ? 0u : c, lane, &tot);   // both 16-bit counters in one add: no carry (<= 8192 each)
-            n_pass = tot & 0xffffu; n_full = tot >> 16;
-            dense = dense || n_pass > SCAN_PASS_CAP || n_full > SCAN_FULL_CAP;
-            if (!dense && is_main) {
-                const uint32_t mine = __shfl_sync(FULLMASK, ex, wid), base_p = mine & 0xffffu, base_f = mine >> 16;
-                for (uint32_t e = lane; e < n_wpass; e += 32) {
-                    S.pass_pos[base_p + e] = S.wq.pass_pos[wid][e]; S.pass_tried[base_p + e] = S.wq.pass_tried[wid][e]; S.pass_live[base_p + e] = 0;
+        // ---- claim a run: guided self-scheduling, then cut at the segment boundary --------------------------------------
+        if (!pend_n) {
+            uint32_t start = 0, n = 0;
+            if (lane == 0) {
+                const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&P.ctl->tile_counter);
+                if (cur < P.n_tiles) {
+                    n = min(max((P.n_tiles - cur) / (2u * gridDim.x * SC_WARPS), 1u), (uint32_t)RUN_MAX);
+                    start = atomicAdd(&P.ctl->tile_counter, n);
+                    if (start >= P.n_tiles) n = 0; else n = min(n, P.n_tiles - start);
                 }
-                for (uint32_t e = lane; e < n_wfull; e += 32) S.full[base_f + e] = S.wq.full[wid][e] + (base_p << 4);
+            }
+            pend_tile = __shfl_sync(FULLMASK, start, 0); pend_n = __shfl_sync(FULLMASK, n, 0);
+            if (!pend_n) break;
+        }
+        __syncwarp();
+        if (lane < 16) W.seg[lane] = reinterpret_cast<const uint32_t *>(&P.segs[P.tile_seg[pend_tile]])[lane];
+        if (lane < RUN_MAX) { W.n_pos[lane] = 0; W.n_rec[lane] = 0; }
+        __syncwarp();
+        uint32_t n_chunks;
+        {
+            const Segment &seg = *reinterpret_cast<const Segment *>(W.seg);
+            const uint32_t tile0 = pend_tile, n_tiles_run = min(pend_n, seg.tile_begin + seg.n_tiles - tile0);
+            pend_tile += n_tiles_run; pend_n -= n_tiles_run;
+            n_chunks = n_tiles_run * TILE_CHUNKS;
+            if (lane == 0) {
+                const uint32_t x0 = (tile0 - seg.tile_begin) * SCAN_TILE;             // run origin in tile coordinates (x = data index + lead)
+                T.x0 = x0; T.tile0 = tile0; T.n_tiles = n_tiles_run; T.n_chunks = n_chunks;
+                T.tile_base = seg.base + 2 * ((long long)x0 - (long long)seg.lead);
+                T.x_data_end = seg.lead + seg.npos + B200_TRAIL;                      // first x without data
+                T.x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;   // x below: magnitude 0, memory not read
+                T.is_mag = (seg.flags & SEG_MAG) ? 1u : 0u;
+                T.last_tile = tile0 + n_tiles_run == seg.tile_begin + seg.n_tiles;
+                const long long n_first = (long long)x0 - seg.lead - B200_TRAIL;
+                T.n_first = n_first;
+                T.buf_len = seg.buf_len; T.first_buf = seg.first_buf; T.npos = seg.npos;
+                T.p_lo = seg.lead > x0 ? seg.lead - x0 : 0;                           // first real position
+                T.p_hi = min(n_chunks * CHUNK, seg.lead + seg.npos > x0 ? seg.lead + seg.npos - x0 : 0u);
+                const uint32_t nb = n_first > 0 ? (uint32_t)n_first / seg.buf_len : 0;
+                T.nb = nb; T.bound = (long long)(nb + 1) * seg.buf_len;
             }
         }
-        __syncthreads();                                                   // E: block lists complete, warp queues dead
+        __syncwarp();
 
-        if (dense) {      // denser than the shared-memory queues: redo the candidate steps on the global scratch arena
-            if (P.scratch) {
-                process_candidates_slow(S, P, tile, P.scratch + (size_t)blockIdx.x * SCAN_SCRATCH_BYTES);
-            } else if (tid == 0) {      // no scratch arena yet: tell the host, which allocates one and reruns
-                atomicOr(&P.ctl->overflow, 2u);
-                TileOut t = {0, 0, 0, 0};
-                P.tile_out[tile] = t;
+        uint32_t n_q1 = 0, n_surv = 0, n_stage = 0;
+        uint32_t ms = 0;          // ring slot of chunk k's magnitudes; ticks of chunk k sit in slot k & 1
+
+#pragma unroll 1
+        for (int k = -2; k <= (int)n_chunks; k++) {
+            uint32_t mask = 0;
+            if (k >= 0) {
+                // ---- window(k): pre-check + tick map -----------------------------------------------------------------
+                mask = window_pass(W, ms * CHUNK + lane * 16, (k & 1) * TICK_CW, lane, (k & 1) == 0,
+                                   P.tick_scratch + (size_t)warp_global * TICKG_WORDS + k * TICK_CW);
+                const uint32_t i0 = k * CHUNK + lane * 16;       // run-relative; positions outside [p_lo, p_hi) are not preamble starts
+                const uint32_t p_lo = T.p_lo, p_hi = T.p_hi;
+                const uint32_t lo_cut = p_lo > i0 ? min(p_lo - i0, 16u) : 0u, hi_cut = p_hi > i0 ? min(p_hi - i0, 16u) : 0u;
+                mask &= (0xffffu << lo_cut) & ((1u << hi_cut) - 1u);
             }
-            continue;
+            // ---- prefetch(k+2) --------------------------------------------------------------------------------------
+            const uint32_t cn = (uint32_t)(k + 2);
+            const bool more = cn <= n_chunks;
+            bool all_data = false;
+            if (more) {
+                const uint32_t xs = T.x0 + cn * CHUNK;
+                all_data = xs >= T.x_zero_end && xs + CHUNK <= T.x_data_end;
+                prefetch_raw(T, cn, lane, all_data);
+            }
+            __syncwarp();                                        // ticks of chunk k visible to the warp
+            // ---- candidates(k-1) --------------------------------------------------------------------------------------
+            if (n_q1) process_candidates(S, W, P, n_q1, warp_global, (uint32_t)(k - 1) * CHUNK, ms == 0 ? 2 : ms - 1, (uint32_t)(k - 1) & 1u, lane, n_surv, n_stage);
+            __syncwarp();                                        // chunk k-1's magnitudes are dead now
+            // ---- convert(k+2) into the slot chunk k-1 occupied ------------------------------------------------------
+            if (more) {
+                const uint32_t msn = k < 0 ? cn : (ms == 0 ? 2 : ms - 1);       // (ms + 2) % 3; the first two chunks fill slots 0 and 1
+                const bool owned = cn < n_chunks || T.last_tile;
+                const long long n0 = T.n_first + (long long)cn * CHUNK;
+                uint32_t nb = T.nb;
+                long long bound = T.bound;
+                if (n0 >= bound) {
+                    while (n0 >= bound) { nb++; bound += T.buf_len; }
+                    __syncwarp();
+                    if (lane == 0) { T.nb = nb; T.bound = bound; }
+                }
+                const bool one_buf = n0 >= 0 && n0 + CHUNK <= bound && n0 + CHUNK <= (long long)T.npos;    // every sample counted, all in buffer nb
+                if (all_data && (one_buf || !owned || n0 >= (long long)T.npos))
+                    convert_chunk_fast(S, W, P, T.tile_base + (size_t)cn * CHUNK * 2, T.is_mag, msn, lane, owned && one_buf ? T.first_buf + nb : 0xffffffffu);
+                else
+                    convert_chunk_edge(S, W, P, cn, msn, lane);
+            }
+            // ---- q1 <- pre-check passers of chunk k -------------------------------------------------------------------
+            if (k >= 0) {
+                uint16_t *q1_over = P.q1_over + (size_t)warp_global * CHUNK;
+                uint32_t off = warp_excl_scan(__popc(mask), lane, &n_q1);
+                const uint32_t i0 = k * CHUNK + lane * 16;
+                uint32_t mb = mask;
+                while (mb) {
+                    const uint32_t b = __ffs(mb) - 1; mb &= mb - 1;
+                    if (off < Q1_SMEM) W.q1[off] = (uint16_t)(i0 + b); else q1_over[off - Q1_SMEM] = (uint16_t)(i0 + b);
+                    off++;
+                }
+                ms = ms == 2 ? 0 : ms + 1;
+            }
+            __syncwarp();
         }
 
-        // ---- full slice, one thread per (position, phase) ---------------------------------------------------------------------------
-        uint32_t chunk_off = 0;
-        if (tid == 0 && n_full) chunk_off = atomicAdd(&P.ctl->rec_alloc, n_full);   // record-pool chunk: used only after the slicing below
-        for (uint32_t q = tid; q < n_full; q += SCAN_THREADS) {
-            const uint32_t fe = S.full[q], r = fe >> 4, ph = (fe >> 1) & 7u;
-            if (slice_and_classify(S, P, S.pass_pos[r], ph, fe & 1u, &S.recs[q]))
-                atomicOr(reinterpret_cast<uint32_t *>(&S.pass_live[r & ~3u]), (1u << ph) << (8 * (r & 3)));
+        // ---- end of run: remaining slices, one record-pool reservation, copy of the staged records ------------------------
+        Rec *stage = P.stage_rec + (size_t)warp_global * P.stage_cap;
+        uint32_t *stage_key = P.stage_key + (size_t)warp_global * P.stage_cap;
+        const uint32_t tile0 = T.tile0, n_tiles_run = T.n_tiles;
+        if (n_surv) slice_round(S, W, P, n_surv, P.tick_scratch + (size_t)warp_global * TICKG_WORDS, P.pos_pool + (size_t)tile0 * SCAN_TILE, lane, n_stage, stage, stage_key);
+        __syncwarp();
+        uint32_t off = 0, ok = 1;
+        if (lane == 0) {
+            if (n_stage > P.stage_cap) { atomicOr(&P.ctl->overflow, 2u); atomicMax(&P.ctl->stage_need, n_stage); ok = 0; }   // host grows the staging areas and reruns
+            else if (n_stage) {
+                off = atomicAdd(&P.ctl->rec_alloc, n_stage);
+                if (off + n_stage > P.ctl->rec_cap) { atomicOr(&P.ctl->overflow, 1u); ok = 0; }                              // host regrows the pool and reruns
+            }
         }
-        __syncthreads();                                                   // F: records staged
-        emit_tile(S, P, tile, S.pass_pos, S.pass_tried, S.pass_live, S.recs, n_pass, n_full, true, chunk_off);
+        off = __shfl_sync(FULLMASK, off, 0); ok = __shfl_sync(FULLMASK, ok, 0);
+        if (ok) {
+            for (uint32_t i = lane; i < n_stage; i += 32) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(stage + i);
+                uint4 *dst = reinterpret_cast<uint4 *>(P.rec_pool + off + i);
+                dst[0] = __ldcg(src); dst[1] = __ldcg(src + 1);
+                P.key_pool[off + i] = __ldcg(stage_key + i);
+            }
+        }
+        {   // TileOut per tile of the run: records of tile m follow those of tile m-1 in the reservation
+            const uint32_t mine = lane < n_tiles_run ? W.n_rec[lane] : 0;
+            uint32_t tot;
+            const uint32_t before = warp_excl_scan(mine, lane, &tot);
+            if (lane < n_tiles_run) { TileOut t; t.n_pos = W.n_pos[lane]; t.n_rec = ok ? mine : 0; t.rec_off = off + before; t.pad_ = mine; P.tile_out[tile0 + lane] = t; }
+        }
     }
 }
 
-extern "C" int b200_scan_grid(int n_sm) {
-    static int per_sm = 0;
-    if (!per_sm) {
-        if (cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)) != cudaSuccess) return -1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, SCAN_THREADS, sizeof(ScanSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
-    }
-    return n_sm * per_sm;
-}
+extern "C" int b200_scan_warps(int n_sm) { return n_sm * SC_WARPS; }
+extern "C" int b200_scan_tick_words(void) { return TICKG_WORDS; }
 
 extern "C" int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream) {
-    int grid = b200_scan_grid(n_sm);
-    if (grid < 0) return (int)cudaGetLastError();
-    if ((uint32_t)grid > p->n_tiles) grid = (int)p->n_tiles;
-    if (grid == 0) return 0;
-    scan_kernel<<<grid, SCAN_THREADS, sizeof(ScanSmem), (cudaStream_t)stream>>>(*p, d_tables);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    if (!p->n_tiles) return 0;
+    uint32_t grid = (uint32_t)n_sm;
+    const uint32_t need = (p->n_tiles + SC_WARPS - 1) / SC_WARPS;
+    if (grid > need) grid = need;
+    scan_kernel<<<grid, SC_THREADS, sizeof(ScanSmem), (cudaStream_t)stream>>>(*p, d_tables);
     return (int)cudaGetLastError();
 }
