@@ -43,7 +43,7 @@ struct Segment {
 };
 
 // One position whose preamble correlation reached the threshold (demod_2400.c:344-378).
-//   bits 0..12  position relative to the tile origin (tile coordinates x = data index + lead)
+//   bits 0..12  position relative to the origin of the tile's QUAD (four consecutive tiles of a segment, the unit stage B walks)
 //   bits 16..20 phases tried  (bit p = try_phase 4+p)
 //   bits 21..25 phases whose score depends on the filter (a Rec follows for each, ascending phase)
 typedef uint32_t PosEntry;

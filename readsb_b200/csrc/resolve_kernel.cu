@@ -46,6 +46,7 @@ __device__ __forceinline__ bool gen_add(uint32_t *g, uint32_t *count, uint32_t a
 
 struct ResolveSmem {
     uint32_t gen[2][ICAO_CAP];
+    uint32_t q_np[4], q_nr[4], q_ro[4];      // the current quad's four TileOuts
     PosEntry pos[RS_RING][RS_STAGE];
     uint32_t key[RS_RING][RS_STAGE];
 };
@@ -96,39 +97,69 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
     for (uint32_t si = P.stream_seg_begin[stream]; si < P.stream_seg_begin[stream + 1]; si++) {
         const Segment seg = P.segs[si];
         const uint32_t tile_end = seg.tile_begin + seg.n_tiles;
-        // Tile cursor with a staging ring: tile t's lists live in ring slot (t - tile_begin) % RS_RING; at any time the
-        // current tile is complete and up to three more are in flight.  TileOut descriptors run one step further ahead
-        // in registers (t1..t4).
-        uint32_t tile = seg.tile_begin, idx = 0, rec_rel = 0;
-        TileOut to = {0, 0, 0, 0}, t1 = to, t2 = to, t3 = to, t4 = to;
+        // Stage B walks QUADS of four consecutive scan tiles (8192 positions; PosEntry positions are quad-relative).  Quad
+        // q's four PosEntry / key lists are staged back to back in ring slot q % RS_RING; at any time the current quad is
+        // complete and up to three more are in flight.  TileOut descriptors run one step further ahead in registers:
+        // lane l < 4 holds the descriptor of the quad's tile l (q1..q4).
+        const uint32_t n_quads = (seg.n_tiles + 3) / 4;
+        uint32_t quad = 0, idx = 0, rec_rel = 0, cur_npos = 0, cur_recbase = 0, sub = 4;
+        bool staged = true;
+        uint4 to = make_uint4(0, 0, 0, 0), q1 = to, q2 = to, q3 = to, q4 = to;
         const PosEntry *pe_ptr = nullptr;
         const uint32_t *key_ptr = nullptr;
-        auto stageable = [](const TileOut &o) { return o.n_pos <= RS_STAGE && o.n_rec <= RS_STAGE; };
-        auto issue_stage = [&](uint32_t t, const TileOut &o) {      // always commits a group, so group counting stays uniform
-            if (t < tile_end && stageable(o)) {
-                const uint32_t buf = (t - seg.tile_begin) % RS_RING;
-                for (uint32_t e = lane; e < o.n_pos; e += 32) cp_async4(&S.pos[buf][e], &P.pos_pool[(size_t)t * SCAN_TILE + e]);
-                for (uint32_t e = lane; e < o.n_rec; e += 32) cp_async4(&S.key[buf][e], &P.key_pool[o.rec_off + e]);
+        auto load_desc = [&](uint32_t q) {           // this lane's piece of quad q's descriptor
+            const uint32_t t = seg.tile_begin + 4 * q + lane;
+            return (lane < 4 && q < n_quads && t < tile_end) ? *reinterpret_cast<const uint4 *>(&P.tile_out[t]) : make_uint4(0, 0, 0, 0);
+        };
+        auto issue_stage = [&](uint32_t q, const uint4 &piece) {      // always commits a group, so group counting stays uniform
+            uint32_t np[4], nr[4], ro[4], tp = 0, tr = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { np[i] = __shfl_sync(FULLMASK, piece.x, i); nr[i] = __shfl_sync(FULLMASK, piece.y, i); ro[i] = __shfl_sync(FULLMASK, piece.z, i); tp += np[i]; tr += nr[i]; }
+            if (q < n_quads && tp <= RS_STAGE && tr <= RS_STAGE) {
+                const uint32_t buf = q % RS_RING;
+                uint32_t bp = 0, br = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const PosEntry *src = P.pos_pool + (size_t)(seg.tile_begin + 4 * q + i) * SCAN_TILE;
+                    for (uint32_t e = lane; e < np[i]; e += 32) cp_async4(&S.pos[buf][bp + e], &src[e]);
+                    for (uint32_t e = lane; e < nr[i]; e += 32) cp_async4(&S.key[buf][br + e], &P.key_pool[ro[i] + e]);
+                    bp += np[i]; br += nr[i];
+                }
             }
             cp_async_commit();
         };
-        auto enter_tile = [&](uint32_t t) {          // make tile t current (t1 describes it)
-            to = t1; t1 = t2; t2 = t3; t3 = t4;
-            if (t + 4 < tile_end) t4 = P.tile_out[t + 4];
-            cp_async_wait_2();                       // everything but the two newest groups has landed: tile t is complete
-            __syncwarp();
-            if (stageable(to)) { const uint32_t buf = (t - seg.tile_begin) % RS_RING; pe_ptr = S.pos[buf]; key_ptr = S.key[buf]; }
-            else { pe_ptr = P.pos_pool + (size_t)t * SCAN_TILE; key_ptr = P.key_pool + to.rec_off; }
-            issue_stage(t + 3, t3);                  // reuses the slot of tile t - 1, which is finished
+        auto set_sublist = [&](uint32_t i) {         // dense quad, read in place: one scan tile at a time
+            sub = i;
+            pe_ptr = P.pos_pool + (size_t)(seg.tile_begin + 4 * quad + i) * SCAN_TILE;
+            cur_npos = S.q_np[i]; cur_recbase = S.q_ro[i]; key_ptr = P.key_pool + cur_recbase;
             idx = 0; rec_rel = 0;
         };
-        if (seg.n_tiles) {
-            t1 = P.tile_out[tile];
-            if (tile + 1 < tile_end) t2 = P.tile_out[tile + 1];
-            if (tile + 2 < tile_end) t3 = P.tile_out[tile + 2];
-            if (tile + 3 < tile_end) t4 = P.tile_out[tile + 3];
-            issue_stage(tile, t1); issue_stage(tile + 1, t2); issue_stage(tile + 2, t3);
-            enter_tile(tile);
+        auto enter_quad = [&](uint32_t q) {          // make quad q current (q1 describes it)
+            to = q1; q1 = q2; q2 = q3; q3 = q4;
+            q4 = load_desc(q + 4);
+            cp_async_wait_2();                       // everything but the two newest groups has landed: quad q is complete
+            __syncwarp();
+            if (lane < 4) { S.q_np[lane] = to.x; S.q_nr[lane] = to.y; S.q_ro[lane] = to.z; }
+            __syncwarp();
+            const uint32_t tp = S.q_np[0] + S.q_np[1] + S.q_np[2] + S.q_np[3], tr = S.q_nr[0] + S.q_nr[1] + S.q_nr[2] + S.q_nr[3];
+            staged = tp <= RS_STAGE && tr <= RS_STAGE;
+            if (staged) { const uint32_t buf = q % RS_RING; pe_ptr = S.pos[buf]; key_ptr = S.key[buf]; cur_npos = tp; cur_recbase = 0; sub = 4; idx = 0; rec_rel = 0; }
+            else set_sublist(0);
+            issue_stage(q + 3, q3);                  // reuses the slot of quad q - 1, which is finished
+        };
+        // next list with entries left: the next scan tile of a dense quad, or the next quad
+        auto advance = [&]() {
+            while (idx >= cur_npos) {
+                if (!staged && sub < 3) set_sublist(sub + 1);
+                else if (quad + 1 < n_quads) { quad++; enter_quad(quad); }
+                else return false;
+            }
+            return true;
+        };
+        if (n_quads) {
+            q1 = load_desc(0); q2 = load_desc(1); q3 = load_desc(2); q4 = load_desc(3);
+            issue_stage(0, q1); issue_stage(1, q2); issue_stage(2, q3);
+            enter_quad(0);
         }
 
         for (uint32_t b = 0; b < seg.n_bufs; b++) {
@@ -140,10 +171,9 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
             uint32_t nfr_buf = 0;
 
             for (;;) {
-                while (idx >= to.n_pos && tile + 1 < tile_end) { tile++; enter_tile(tile); }
-                if (idx >= to.n_pos) break;
-                const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;
-                const bool has = idx + lane < to.n_pos;
+                if (!n_quads || !advance()) break;
+                const uint32_t x0 = quad * (4 * SCAN_TILE);
+                const bool has = idx + lane < cur_npos;
                 const PosEntry pe = has ? pe_ptr[idx + lane] : 0;
                 const uint32_t d = x0 + (pe & 0x1fffu) - seg.lead;          // data index = position in the segment
                 const bool inbuf = has && d < d_end;                        // entries are ascending: a prefix of lanes
@@ -202,7 +232,12 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                         if (nframes < P.frame_cap) {
                             // accept record; finalize_kernel turns it into the full frame from the 32-byte Rec
                             b200_frame fr;
-                            fr.timestamp = ts; fr.sigpow_sum = 0; fr.j = j; fr.crc = to.rec_off + best_rel; fr.addr = 0; fr.score = best;
+                            fr.timestamp = ts; fr.sigpow_sum = 0; fr.j = j; fr.crc = 0;
+                            if (staged) {        // index in the quad's concatenated list -> index in the record pool
+                                uint32_t rel = best_rel;
+#pragma unroll
+                                for (int i = 0; i < 4; i++) { const uint32_t n = S.q_nr[i]; if (rel < n) { fr.crc = S.q_ro[i] + rel; break; } rel -= n; }
+                            } else fr.crc = cur_recbase + best_rel; fr.addr = 0; fr.score = best;
                             fr.buffer_seq = seq; fr.signal_len = (uint16_t)(msglen * 12 / 5); fr.phase = (uint8_t)(4 + best_phase);
                             fr.msgtype = 0; fr.msgbits = 0; fr.correctedbits = 0; fr.fix_bit = -1; fr.flags = add ? B200_FRAME_ICAO_ADDED : 0;
 #pragma unroll

@@ -55,6 +55,7 @@ struct RunCtx {
     uint32_t nb;                   // reference buffer of the chunk being converted, tracked incrementally
     uint32_t is_mag, last_tile;
     uint32_t tile0, n_tiles;
+    uint32_t tile_rel0;            // tile0 - seg.tile_begin: stage B walks quads of tiles, PosEntry positions are quad-relative
 };
 
 struct WarpSmem {
@@ -422,7 +423,7 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
         if (tried) {
             const uint32_t r = __popc(bal & lt);
             W.pass[r] = p | (tried << 16);
-            pos_out[n_pos + r] = (p & (SCAN_TILE - 1)) | (tried << 16);       // live bits are OR-ed in when its phases are sliced
+            pos_out[n_pos + r] = (p & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE) | (tried << 16);   // live bits are OR-ed in when its phases are sliced
         }
         __syncwarp();
         if (lane == 0) W.n_pos[m] = n_pos + n_b;
@@ -498,7 +499,7 @@ __global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTabl
             n_chunks = n_tiles_run * TILE_CHUNKS;
             if (lane == 0) {
                 const uint32_t x0 = (tile0 - seg.tile_begin) * SCAN_TILE;             // run origin in tile coordinates (x = data index + lead)
-                T.x0 = x0; T.tile0 = tile0; T.n_tiles = n_tiles_run; T.n_chunks = n_chunks;
+                T.x0 = x0; T.tile0 = tile0; T.n_tiles = n_tiles_run; T.n_chunks = n_chunks; T.tile_rel0 = tile0 - seg.tile_begin;
                 T.tile_base = seg.base + 2 * ((long long)x0 - (long long)seg.lead);
                 T.x_data_end = seg.lead + seg.npos + B200_TRAIL;                      // first x without data
                 T.x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;   // x below: magnitude 0, memory not read
