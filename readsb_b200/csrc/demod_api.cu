@@ -62,8 +62,8 @@ struct Slot {
     bool upload_tiles = true, is_device = false;
     DeviceArgs dargs = {};
     std::vector<uint32_t> stream_buf_begin;   // [n_streams+1] into h_buf_out
-    cudaEvent_t ev[7] = {};                   // 0 scan begin, 1 scan end, 2 resolve end, 3 finalize end, 4 results on host,
-                                              // 5 result copies done, 6 Mode A/C scan + walk done
+    cudaEvent_t ev[8] = {};                   // 0 scan begin, 1 scan end, 2 resolve end, 3 finalize end, 4 results on host,
+                                              // 5 result copies done, 6 Mode A/C scan + walk done, 7 descriptors uploaded
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t launches = 0;
 };
@@ -239,9 +239,14 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     CUC(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
-    CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    CUC(cudaStreamCreateWithFlags(&c->res_stream, cudaStreamNonBlocking));
-    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    {   // Stage A (persistent, one CTA per SM) is placed first, stage B's small CTAs fill what it leaves free: when both become
+        // ready at the same moment the block scheduler follows stream priority.
+        int prio_lo = 0, prio_hi = 0;
+        CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUC(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_hi));
+        CUC(cudaStreamCreateWithPriority(&c->res_stream, cudaStreamNonBlocking, prio_lo));
+        CUC(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_lo));
+    }
     c->stream = c->own_stream;
 
     const uint32_t S = cfg->n_streams, K = cfg->max_buffers_per_run, BUF = cfg->buf_samples;
@@ -379,14 +384,19 @@ static void add_segment(b200_demod_ctx *c, Slot &sl, uint32_t stream, const uint
 // (the same stream in blocking mode).  `prev_ctl`: control block of the step in flight before this one (async mode).
 static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t res, const RunCtl *prev_ctl) {
     const uint32_t S = c->cfg.n_streams;
-    CU(c, cudaMemcpyAsync(sl.d_segs, sl.h_segs, sl.nseg * sizeof(Segment), cudaMemcpyHostToDevice, scan));
-    if (sl.upload_tiles && sl.ntile) CU(c, cudaMemcpyAsync(sl.d_tile_seg, sl.h_tile_seg, sl.ntile * 4, cudaMemcpyHostToDevice, scan));
-    CU(c, cudaMemcpyAsync(sl.d_stream_seg_begin, sl.h_stream_seg_begin, (S + 1) * 4, cudaMemcpyHostToDevice, scan));
+    // The run's descriptors.  Pipelined: they go up on the copy stream right now, while the step before this one is still
+    // scanning, so that this step's scan kernel is ready the moment that one ends — together with the other step's stage B,
+    // and placed before it (stream priority): one persistent CTA per SM first, stage B's small CTAs into what is left.
+    cudaStream_t pre = scan != res ? c->copy_stream : scan;
+    CU(c, cudaMemcpyAsync(sl.d_segs, sl.h_segs, sl.nseg * sizeof(Segment), cudaMemcpyHostToDevice, pre));
+    if (sl.upload_tiles && sl.ntile) CU(c, cudaMemcpyAsync(sl.d_tile_seg, sl.h_tile_seg, sl.ntile * 4, cudaMemcpyHostToDevice, pre));
+    CU(c, cudaMemcpyAsync(sl.d_stream_seg_begin, sl.h_stream_seg_begin, (S + 1) * 4, cudaMemcpyHostToDevice, pre));
     memset(sl.h_ctl, 0, sizeof(RunCtl));
     sl.h_ctl->rec_cap = sl.rec_cap;
     if (c->beast_slot == (int)(&sl - c->slot)) c->beast_slot = -1;      // the encoded records belong to the run being replaced
-    CU(c, cudaMemcpyAsync(sl.d_ctl, sl.h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, scan));
-    CU(c, cudaMemsetAsync(sl.d_buf_acc, 0, (size_t)sl.nbuf * sizeof(BufAcc), scan));
+    CU(c, cudaMemcpyAsync(sl.d_ctl, sl.h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pre));
+    CU(c, cudaMemsetAsync(sl.d_buf_acc, 0, (size_t)sl.nbuf * sizeof(BufAcc), pre));
+    if (pre != scan) { CU(c, cudaEventRecord(sl.ev[7], pre)); CU(c, cudaStreamWaitEvent(scan, sl.ev[7], 0)); }
     sl.launches = 0;
 
     ScanParams sp;

@@ -44,8 +44,17 @@ __device__ __forceinline__ bool gen_add(uint32_t *g, uint32_t *count, uint32_t a
 #define RS_STAGE 384          // PosEntry / score keys of one tile staged in shared memory (bigger tiles are read in place)
 #define RS_RING  4            // staging buffers: the current tile plus three in flight
 
+#define OLD_BITS 8192         // membership pre-filter of the older generation: one bit per hash value
+
+// The ACTIVE generation (the one adds go to) lives in shared memory as the exact table.  The OLDER generation is only ever
+// read until the next flip: shared memory holds a bit per hash value of its entries, and the exact table in global memory
+// (StreamState) is probed only where that bit is set — same answers, 17 KB instead of 32 KB, so two receivers' resolvers
+// fit on an SM next to the scan kernel.
+__device__ __forceinline__ uint32_t old_bit(uint32_t a) { return (a * 0x85EBCA6Bu) >> (32 - 13); }
+
 struct ResolveSmem {
-    uint32_t gen[2][ICAO_CAP];
+    uint32_t act[ICAO_CAP];
+    uint32_t old_bits[OLD_BITS / 32];
     uint32_t q_np[4], q_nr[4], q_ro[4];      // the current quad's four TileOuts
     PosEntry pos[RS_RING][RS_STAGE];
     uint32_t key[RS_RING][RS_STAGE];
@@ -71,7 +80,7 @@ __device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
     }
 }
 
-__global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
+__global__ void __maxnreg__(128) resolve_kernel(const ResolveParams P) {   // 128 registers: two resolver CTAs fit next to the scan kernel (896 x 64)
     __shared__ ResolveSmem S;
     const uint32_t stream = blockIdx.x, lane = threadIdx.x;
     StreamState *st = &P.state[stream];
@@ -80,12 +89,23 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
     if (P.ctl->overflow & 3u) return;
     if (P.prev_ctl && (P.prev_ctl->overflow & 19u)) { if (lane == 0) atomicOr(&P.ctl->overflow, 16u); return; }
 
-    for (uint32_t i = lane; i < 2 * ICAO_CAP; i += 32) (&S.gen[0][0])[i] = (&st->gen[0][0])[i];
     uint32_t gcount[2] = {st->gen_count[0], st->gen_count[1]};
     uint32_t active = st->active, armed = st->flip_armed, seq = st->buffer_seq, err = st->error;
     int64_t next_flip = st->next_flip_ms;
-    bool dirty[2] = {false, false};
+    bool dirty[2] = {false, false};           // dirty[active]: the shared-memory table differs from the global copy
+    for (uint32_t i = lane; i < OLD_BITS / 32; i += 32) S.old_bits[i] = 0;
     __syncwarp();
+    for (uint32_t i = lane; i < ICAO_CAP; i += 32) {
+        S.act[i] = st->gen[active][i];
+        const uint32_t v = st->gen[active ^ 1u][i];
+        if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
+    }
+    __syncwarp();
+    auto known_addr = [&](uint32_t a) {
+        if (gen_has(S.act, a)) return true;
+        const uint32_t h = old_bit(a);
+        return ((S.old_bits[h >> 5] >> (h & 31)) & 1u) && gen_has(st->gen[active ^ 1u], a);
+    };
 
     // per-lane partial counters, reduced at the end
     uint32_t c_pre = 0, c_bad = 0, c_unk = 0, c_acc0 = 0, c_acc1 = 0, c_tp[5] = {0, 0, 0, 0, 0}, c_bp[5] = {0, 0, 0, 0, 0};
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                     for (uint32_t ph = 0; ph < 5; ph++) {
                         if ((live >> ph) & 1u) {
                             const uint32_t key = key_ptr[k];
-                            const bool known = gen_has(S.gen[0], key & 0xffffffu) || gen_has(S.gen[1], key & 0xffffffu);
+                            const bool known = known_addr(key & 0xffffffu);
                             const int sc = rec_score((key >> 24) & 7u, known);
                             if (sc > best) { best = sc; best_rel = k; best_phase = ph; best_key = key; best_known = known; }
                             k++;
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
                         if (corrected) c_acc1++; else c_acc0++;
                         c_bp[best_phase]++;
                         if (add) {
-                            if (!gen_add(S.gen[active], &gcount[active], best_key & 0xffffffu)) err = 1;
+                            if (!gen_add(S.act, &gcount[active], best_key & 0xffffffu)) err = 1;
                             dirty[active] = true;
                             relearn = best_known ? 0u : 1u;      // membership changed: later scores are stale
                         }
@@ -281,8 +301,18 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
             c_samples += d_end - d_begin; c_bufs++;
             uint32_t flipped = 0;
             if (P.ttl_ms > 0 && (!armed || now_ms >= next_flip)) {
+                // the active generation becomes the older one: its exact table goes to global memory, its hash bits stay here;
+                // the other generation is emptied and becomes active
                 const uint32_t other = active ^ 1u;
-                for (uint32_t i = lane; i < ICAO_CAP; i += 32) S.gen[other][i] = ICAO_EMPTY;
+                for (uint32_t i = lane; i < OLD_BITS / 32; i += 32) S.old_bits[i] = 0;
+                __syncwarp();
+                for (uint32_t i = lane; i < ICAO_CAP; i += 32) {
+                    const uint32_t v = S.act[i];
+                    if (dirty[active]) st->gen[active][i] = v;
+                    if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
+                    S.act[i] = ICAO_EMPTY;
+                }
+                dirty[active] = false;
                 gcount[other] = 0; dirty[other] = true; active = other;
                 next_flip = now_ms + P.ttl_ms; armed = 1; flipped = 1; c_flips++;
                 __syncwarp();
@@ -300,8 +330,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(const ResolveParams P) {
     }
 
     // write back
-    for (int g = 0; g < 2; g++)
-        if (dirty[g]) for (uint32_t i = lane; i < ICAO_CAP; i += 32) st->gen[g][i] = S.gen[g][i];
+    if (dirty[active]) for (uint32_t i = lane; i < ICAO_CAP; i += 32) st->gen[active][i] = S.act[i];
     uint32_t red[15] = {c_pre, c_bad, c_unk, c_acc0, c_acc1, c_tp[0], c_tp[1], c_tp[2], c_tp[3], c_tp[4], c_bp[0], c_bp[1], c_bp[2], c_bp[3], c_bp[4]};
 #pragma unroll
     for (int k = 0; k < 15; k++)
@@ -342,7 +371,8 @@ __global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *coun
 
 __device__ __forceinline__ unsigned long long dmax_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
 
-__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
+// Small CTAs (128 threads x 48 registers): they have to fit into what the persistent scan kernel of the NEXT step leaves free on an SM.
+__global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams P) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -436,14 +466,19 @@ __global__ void icao_op_kernel(StreamState *state, uint32_t stream, int op, uint
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
 extern "C" int b200_launch_resolve(const ResolveParams *p, void *stream) {
+    static bool attr_set = false;
+    if (!attr_set) {   // same carve-out as the scan kernel, so that resolver CTAs can join an SM the scan kernel already occupies
+        cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
     if (p->n_streams == 0) return 0;
     resolve_kernel<<<p->n_streams, 32, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
 }
 
 extern "C" int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream) {
-    frame_prefix_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->frame_count, d_frame_prefix, p->n_streams, ctl);
-    finalize_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(*p);
+    frame_prefix_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p->frame_count, d_frame_prefix, p->n_streams, ctl);
+    finalize_kernel<<<148 * 4, 128, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
 }
 
@@ -456,7 +491,7 @@ __global__ void ac_pack_kernel(const b200_modeac *ac_out, const uint32_t *count,
 
 extern "C" int b200_launch_ac_pack(const b200_modeac *ac_out, const uint32_t *count, uint32_t *prefix, b200_modeac *packed, uint32_t n_units,
                                    uint32_t cap, RunCtl *ctl, void *stream) {
-    frame_prefix_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(count, prefix, n_units, ctl, false);
+    frame_prefix_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(count, prefix, n_units, ctl, false);
     if (n_units) ac_pack_kernel<<<n_units, 32, 0, (cudaStream_t)stream>>>(ac_out, count, prefix, packed, cap);
     return (int)cudaGetLastError();
 }

@@ -39,7 +39,7 @@
 #define TICK_BITS (5 * CHUNK)
 #define TICK_RING (2 * TICK_CW)
 #define TICK_MIRROR 12
-#define Q1_SMEM 256                           // pre-check passers of a chunk kept in shared memory; the rest (dense input) spills
+#define Q1_SMEM 128                           // pre-check passers of a chunk kept in shared memory; the rest (dense input) spills
 #define SURV_CAP 64
 #define TICKG_WORDS ((RUN_CHUNKS_MAX + 1) * TICK_CW + 8)   // per-warp global copy of a whole run's ticks (slicing is deferred and pooled)
 
@@ -274,13 +274,14 @@ __device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint3
 
 // One chunk's samples, two 16-byte pieces per lane (samples 256 r + 8 lane .. + 8), only where the segment has data.
 // Holding the loaded words in registers across the candidate work costs more registers than the kernel has (they spill, and
-// the spill store waits for the load), so the chunk is PREFETCHED into L1 two iterations ahead and loaded when it is converted.
+// the spill store waits for the load), so the chunk is PREFETCHED into L2 two iterations ahead and loaded when it is converted
+// (L1 is down to 28 KB per SM with this kernel's shared memory and stage B's next to it: an L1 prefetch does not survive).
 __device__ __forceinline__ void prefetch_raw(const RunCtx &T, uint32_t c, uint32_t lane, bool all_data) {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const uint32_t xo = c * CHUNK + r * 256 + lane * 8, xc = T.x0 + xo;
         if (all_data || !(xc + 8 <= T.x_zero_end || xc >= T.x_data_end))
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(T.tile_base + (size_t)xo * 2));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(T.tile_base + (size_t)xo * 2));
     }
 }
 
@@ -307,7 +308,7 @@ __device__ __forceinline__ void to_mags(const ScanSmem &S, bool is_mag, const ui
 // reference buffer the whole chunk lies in it and is counted: lane partials -> warp sum -> one pair of atomics.
 __device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &W, const ScanParams &P, const uint8_t *src, bool is_mag, uint32_t slot,
                                                    uint32_t lane, uint32_t count_buf) {
-    const uint4 raw0 = *reinterpret_cast<const uint4 *>(src + lane * 16), raw1 = *reinterpret_cast<const uint4 *>(src + 512 + lane * 16);
+    const uint4 raw0 = ldg_stream_u4(src + lane * 16), raw1 = ldg_stream_u4(src + 512 + lane * 16);
     uint32_t level = 0;
     unsigned long long power = 0;
 #pragma unroll
@@ -341,7 +342,7 @@ __device__ __noinline__ void convert_chunk_edge(const ScanSmem &S, WarpSmem &W, 
 #pragma unroll
             for (int i = 0; i < 8; i++) m[i] = 0;
         } else {
-            to_mags(S, T.is_mag, *reinterpret_cast<const uint4 *>(T.tile_base + (size_t)xo * 2), m);
+            to_mags(S, T.is_mag, ldg_stream_u4(T.tile_base + (size_t)xo * 2), m);
             if (xc < T.x_zero_end || xc + 8 > T.x_data_end) {   // boundary group: mask the samples that are not data
 #pragma unroll
                 for (int i = 0; i < 8; i++) if (xc + i < T.x_zero_end || xc + i >= T.x_data_end) m[i] = 0;
@@ -618,6 +619,8 @@ extern "C" int b200_launch_scan(const ScanParams *p, const DeviceTables *d_table
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem));
         if (e != cudaSuccess) return (int)e;
+        // largest shared-memory carve-out: what this persistent kernel leaves free must be usable by two resolver CTAs per SM
+        cudaFuncSetAttribute(scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     if (!p->n_tiles) return 0;
