@@ -152,6 +152,7 @@ struct ResolveParams {
     b200_frame *frames;               // [n_streams][frame_cap]
     uint32_t *frame_count;            // [n_streams]
     uint32_t frame_cap;
+    uint32_t per_buf_cap;             // frames one reference buffer can hold (buf_samples / 113 + 2); frame_cap = buffers per run x this
     RunCtl *ctl;
     const RunCtl *prev_ctl;           // asynchronous pipeline: control block of the step ahead of this one (or nullptr)
     int32_t ttl_ms;

@@ -431,7 +431,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     ResolveParams rp;
     rp.segs = sl.d_segs; rp.stream_seg_begin = sl.d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = sl.d_pos_pool;
     rp.rec_pool = sl.d_rec_pool; rp.key_pool = sl.d_key_pool; rp.tile_out = sl.d_tile_out; rp.buf_acc = sl.d_buf_acc; rp.buf_out = sl.d_buf_out;
-    rp.state = c->d_state; rp.frames = sl.d_frames; rp.frame_count = sl.d_frame_count; rp.frame_cap = c->frame_cap;
+    rp.state = c->d_state; rp.frames = sl.d_frames; rp.frame_count = sl.d_frame_count; rp.frame_cap = c->frame_cap; rp.per_buf_cap = c->cfg.buf_samples / 113 + 2;
     rp.ctl = sl.d_ctl; rp.prev_ctl = prev_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms;
     { int r = b200_launch_resolve(&rp, res); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
     CU(c, cudaEventRecord(sl.ev[2], res));

@@ -41,32 +41,44 @@ __device__ __forceinline__ bool gen_add(uint32_t *g, uint32_t *count, uint32_t a
     return true;
 }
 
-#define RS_STAGE 384          // PosEntry / score keys of one tile staged in shared memory (bigger tiles are read in place)
-#define RS_RING  4            // staging buffers: the current tile plus three in flight
-
+#define RS_WARPS 8            // warps per receiver: buffers of one receiver are resolved speculatively in parallel, eight at a time
+#define RS_STAGE 384          // PosEntry / score keys of one quad staged in shared memory (denser quads are read in place)
+#define RS_RING  2            // staging buffers per warp: the current quad plus one in flight
+#define NEW_CAP  24           // addresses one buffer may learn in deferred mode before it has to be redone in direct mode
 #define OLD_BITS 8192         // membership pre-filter of the older generation: one bit per hash value
 
 // The ACTIVE generation (the one adds go to) lives in shared memory as the exact table.  The OLDER generation is only ever
 // read until the next flip: shared memory holds a bit per hash value of its entries, and the exact table in global memory
-// (StreamState) is probed only where that bit is set — same answers, 17 KB instead of 32 KB, so two receivers' resolvers
-// fit on an SM next to the scan kernel.
+// (StreamState) is probed only where that bit is set — same answers, 17 KB instead of 32 KB.
 __device__ __forceinline__ uint32_t old_bit(uint32_t a) { return (a * 0x85EBCA6Bu) >> (32 - 13); }
+
+struct WarpRing {
+    PosEntry pos[RS_RING][RS_STAGE];
+    uint32_t key[RS_RING][RS_STAGE];
+    uint32_t q_np[4], q_nr[4], q_ro[4];      // the current quad's four TileOuts
+};
+
+// What resolving one reference buffer produced (everything the commit step needs to apply it, or to throw it away).
+struct BufResult {
+    long long now_ms;          // Modes.synthetic_now at the end of the buffer (demod_2400.c:283-285, 409-414)
+    uint32_t n_frames, n_new, fail, pad_;
+    uint32_t stats[15];        // preambles, bad, unknown, accepted[2], tried phases[5], best phases[5]
+    uint32_t news[NEW_CAP];    // addresses this buffer learned that the filter did not hold (deferred mode)
+};
 
 struct ResolveSmem {
     uint32_t act[ICAO_CAP];
     uint32_t old_bits[OLD_BITS / 32];
-    uint32_t q_np[4], q_nr[4], q_ro[4];      // the current quad's four TileOuts
-    PosEntry pos[RS_RING][RS_STAGE];
-    uint32_t key[RS_RING][RS_STAGE];
+    WarpRing ring[RS_WARPS];
+    BufResult res[RS_WARPS];
 };
 
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Score of one record under the current filter (mode_s.c:309-419).
 __device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
     switch (kind) {
         case K_AP: return known ? 1000 : -1;
@@ -80,275 +92,371 @@ __device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
     }
 }
 
-__global__ void __maxnreg__(128) resolve_kernel(const ResolveParams P) {   // 128 registers: two resolver CTAs fit next to the scan kernel (896 x 64)
-    __shared__ ResolveSmem S;
-    const uint32_t stream = blockIdx.x, lane = threadIdx.x;
-    StreamState *st = &P.state[stream];
-    // Stage A failed (record pool / dense tile), or the step ahead of this one in the asynchronous pipeline has to be
-    // repeated: leave every receiver's state untouched; the host repeats the run(s) in order.
-    if (P.ctl->overflow & 3u) return;
-    if (P.prev_ctl && (P.prev_ctl->overflow & 19u)) { if (lane == 0) atomicOr(&P.ctl->overflow, 16u); return; }
+// One reference buffer of one receiver: the sequential loop of demodulate2400 over the threshold-passing positions stage A
+// listed (demod_2400.c:306-471), one warp, 32 positions at a time.
+//   DEFER = true  (speculation): the filter is read only; addresses the buffer would teach it are kept in R.news and the
+//                 frames carry B200_FRAME_ICAO_ADDED — the commit step applies them if the speculation holds.
+//   DEFER = false (direct): adds go straight into the shared-memory table, exactly as the reference does.
+// Frames are written to fout[0 .. n_frames); `old_gen` is the older generation's exact table in global memory.
+template <bool DEFER>
+__device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSmem &S, WarpRing &R, BufResult &out, const Segment &seg, uint32_t si,
+                                               uint32_t b, uint32_t seq, const uint32_t *old_gen, uint32_t *gcount_active, uint32_t *err,
+                                               b200_frame *fout, uint32_t fcap, uint32_t lane) {
+    const uint32_t tile_end = seg.tile_begin + seg.n_tiles;
+    const uint32_t n_quads = (seg.n_tiles + 3) / 4;
+    const uint32_t d_begin = b * seg.buf_len;
+    const uint32_t d_end = min(d_begin + seg.buf_len, seg.npos);
+    const int64_t buf_ts = seg.first_ts + (int64_t)d_begin * 5;
+    int64_t now_ms = buf_ts / 12000;          // demod_2400.c:283-285
+    uint32_t skip_until = d_begin;            // data-index form of the reference's `pa` skip
+    uint32_t nframes = 0, n_new = 0, fail = 0;
+    uint32_t c_pre = 0, c_bad = 0, c_unk = 0, c_acc0 = 0, c_acc1 = 0, c_tp[5] = {0, 0, 0, 0, 0}, c_bp[5] = {0, 0, 0, 0, 0};
 
-    uint32_t gcount[2] = {st->gen_count[0], st->gen_count[1]};
-    uint32_t active = st->active, armed = st->flip_armed, seq = st->buffer_seq, err = st->error;
-    int64_t next_flip = st->next_flip_ms;
-    bool dirty[2] = {false, false};           // dirty[active]: the shared-memory table differs from the global copy
-    for (uint32_t i = lane; i < OLD_BITS / 32; i += 32) S.old_bits[i] = 0;
-    __syncwarp();
-    for (uint32_t i = lane; i < ICAO_CAP; i += 32) {
-        S.act[i] = st->gen[active][i];
-        const uint32_t v = st->gen[active ^ 1u][i];
-        if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
-    }
-    __syncwarp();
     auto known_addr = [&](uint32_t a) {
         if (gen_has(S.act, a)) return true;
         const uint32_t h = old_bit(a);
-        return ((S.old_bits[h >> 5] >> (h & 31)) & 1u) && gen_has(st->gen[active ^ 1u], a);
+        if (((S.old_bits[h >> 5] >> (h & 31)) & 1u) && gen_has(old_gen, a)) return true;
+        if (DEFER) for (uint32_t i = 0; i < n_new; i++) if (out.news[i] == a) return true;
+        return false;
     };
 
-    // per-lane partial counters, reduced at the end
-    uint32_t c_pre = 0, c_bad = 0, c_unk = 0, c_acc0 = 0, c_acc1 = 0, c_tp[5] = {0, 0, 0, 0, 0}, c_bp[5] = {0, 0, 0, 0, 0};
+    // Quad cursor: stage B walks QUADS of four consecutive scan tiles (8192 positions; PosEntry positions are quad-relative).
+    // The quad's four PosEntry / key lists are staged back to back in ring slot q % RS_RING, one quad ahead; the TileOut
+    // descriptors run one more ahead in registers: lane l < 4 holds the descriptor of the quad's tile l.
+    uint32_t quad = (seg.lead + d_begin) / (4 * SCAN_TILE), idx = 0, rec_rel = 0, cur_npos = 0, cur_recbase = 0, sub = 4;
+    bool staged = true;
+    uint4 to = make_uint4(0, 0, 0, 0), d1 = to, d2 = to;
+    const PosEntry *pe_ptr = nullptr;
+    const uint32_t *key_ptr = nullptr;
+    auto load_desc = [&](uint32_t q) {           // this lane's piece of quad q's descriptor
+        const uint32_t t = seg.tile_begin + 4 * q + lane;
+        return (lane < 4 && q < n_quads && t < tile_end) ? *reinterpret_cast<const uint4 *>(&P.tile_out[t]) : make_uint4(0, 0, 0, 0);
+    };
+    auto issue_stage = [&](uint32_t q, const uint4 &piece) {
+        uint32_t np[4], nr[4], ro[4], tp = 0, tr = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { np[i] = __shfl_sync(FULLMASK, piece.x, i); nr[i] = __shfl_sync(FULLMASK, piece.y, i); ro[i] = __shfl_sync(FULLMASK, piece.z, i); tp += np[i]; tr += nr[i]; }
+        if (q < n_quads && tp <= RS_STAGE && tr <= RS_STAGE) {
+            const uint32_t buf = q % RS_RING;
+            uint32_t bp = 0, br = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const PosEntry *src = P.pos_pool + (size_t)(seg.tile_begin + 4 * q + i) * SCAN_TILE;
+                for (uint32_t e = lane; e < np[i]; e += 32) cp_async4(&R.pos[buf][bp + e], &src[e]);
+                for (uint32_t e = lane; e < nr[i]; e += 32) cp_async4(&R.key[buf][br + e], &P.key_pool[ro[i] + e]);
+                bp += np[i]; br += nr[i];
+            }
+        }
+        cp_async_commit();
+    };
+    auto set_sublist = [&](uint32_t i) {         // dense quad, read in place: one scan tile at a time
+        sub = i;
+        pe_ptr = P.pos_pool + (size_t)(seg.tile_begin + 4 * quad + i) * SCAN_TILE;
+        cur_npos = R.q_np[i]; cur_recbase = R.q_ro[i]; key_ptr = P.key_pool + cur_recbase;
+        idx = 0; rec_rel = 0;
+    };
+    auto enter_quad = [&](uint32_t q) {          // make quad q current (d1 describes it, its lists are in flight)
+        to = d1; d1 = d2; d2 = load_desc(q + 2);
+        cp_async_wait_all();
+        __syncwarp();
+        if (lane < 4) { R.q_np[lane] = to.x; R.q_nr[lane] = to.y; R.q_ro[lane] = to.z; }
+        __syncwarp();
+        const uint32_t tp = R.q_np[0] + R.q_np[1] + R.q_np[2] + R.q_np[3], tr = R.q_nr[0] + R.q_nr[1] + R.q_nr[2] + R.q_nr[3];
+        staged = tp <= RS_STAGE && tr <= RS_STAGE;
+        if (staged) { const uint32_t buf = q % RS_RING; pe_ptr = R.pos[buf]; key_ptr = R.key[buf]; cur_npos = tp; cur_recbase = 0; sub = 4; idx = 0; rec_rel = 0; }
+        else set_sublist(0);
+        issue_stage(q + 1, d1);                  // into the slot quad q - 1 occupied
+    };
+    auto advance = [&]() {                       // next list with entries left: the next scan tile of a dense quad, or the next quad
+        while (idx >= cur_npos) {
+            if (!staged && sub < 3) set_sublist(sub + 1);
+            else if (quad + 1 < n_quads) { quad++; enter_quad(quad); }
+            else return false;
+        }
+        return true;
+    };
+    if (quad < n_quads) {
+        d1 = load_desc(quad); d2 = load_desc(quad + 1);
+        issue_stage(quad, d1);
+        enter_quad(quad);
+    }
+
+    for (;;) {
+        if (quad >= n_quads || !advance()) break;
+        const uint32_t x0 = quad * (4 * SCAN_TILE);
+        const bool has = idx + lane < cur_npos;
+        const PosEntry pe = has ? pe_ptr[idx + lane] : 0;
+        const uint32_t d = x0 + (pe & 0x1fffu) - seg.lead;          // data index = position in the segment
+        const bool inbuf = has && d < d_end;                        // entries are ascending: a prefix of lanes
+        const uint32_t n_in = __popc(__ballot_sync(FULLMASK, inbuf));
+        if (n_in == 0) break;                                       // next entry belongs to the next buffer
+        const uint32_t tried = (pe >> 16) & 31u, live = (pe >> 21) & 31u;
+        const uint32_t nlive = inbuf ? __popc(live) : 0;
+        uint32_t dummy;
+        const uint32_t rprefix = warp_excl_scan(nlive, lane, &dummy);
+        const bool valid = inbuf && d >= skip_until;                // also drops the entries of earlier buffers in the first quad
+
+        // score every tried phase with the current filter; first strictly greatest wins (demod_2400.c:243)
+        int best = -2; uint32_t best_rel = 0, best_phase = 0, best_key = 0; bool best_known = false;
+        if (valid && live) {
+            uint32_t k = rec_rel + rprefix;
+#pragma unroll
+            for (uint32_t ph = 0; ph < 5; ph++) {
+                if ((live >> ph) & 1u) {
+                    const uint32_t key = key_ptr[k];
+                    const bool known = known_addr(key & 0xffffffu);
+                    const int sc = rec_score((key >> 24) & 7u, known);
+                    if (sc > best) { best = sc; best_rel = k; best_phase = ph; best_key = key; best_known = known; }
+                    k++;
+                }
+            }
+        }
+        // accept test of decodeModesMessage (mode_s.c:443-596): only a corrected AA that is unknown rejects
+        const bool decode_ok = best >= 0 && !((best_key & KEY_AA_CHANGED) && !best_known);
+        // Commit the chunk in order.  After an accept the skip-ahead (demod_2400.c:468) silently consumes the
+        // following lanes inside the frame; the lanes beyond keep their scores as long as the accepted frame did
+        // not teach the filter a NEW address, so one loaded chunk can yield several frames.
+        uint32_t pending = __ballot_sync(FULLMASK, inbuf), consumed = n_in;
+        for (;;) {
+            const bool live_lane = ((pending >> lane) & 1u) && d >= skip_until;
+            const uint32_t acc_mask = __ballot_sync(FULLMASK, live_lane && decode_ok);
+            const uint32_t f = acc_mask ? (uint32_t)__ffs(acc_mask) - 1 : 32u;
+            if (live_lane && lane < f) {       // rejected preambles before the next accepted one
+                c_pre++;
+#pragma unroll
+                for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
+                if (best == -2) c_bad++; else c_unk++;       // -1, or decode result -1
+            }
+            if (!acc_mask) break;
+            uint32_t msglen = 0, relearn = 0, newaddr = 0xffffffffu;
+            if (lane == f) {
+                c_pre++;
+#pragma unroll
+                for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
+                const uint32_t kind = (best_key >> 24) & 7u;
+                msglen = (best_key & KEY_LONG) ? 112 : 56;              // demod_2400.c:399 (DF as sliced)
+                const bool corrected = kind == K_DFREPAIR || kind == K_DF11_FIX || kind == K_ES_FIX;
+                // mode_s.c:766-779: clean DF17, or DF11 with IID 0, teaches the filter its address
+                const bool add = kind == K_DF11_IID0 || (kind == K_ES_OK && (best_key & KEY_DF17));
+                const uint32_t j = d - d_begin;
+                const int64_t ts = buf_ts + (int64_t)j * 5 + (8 + 56) * 12 + (4 + best_phase);   // demod_2400.c:406
+                if (nframes < fcap) {
+                    // accept record; finalize_kernel turns it into the full frame from the 32-byte Rec
+                    b200_frame fr;
+                    fr.timestamp = ts; fr.sigpow_sum = 0; fr.j = j; fr.addr = best_key & 0xffffffu; fr.score = best;
+                    fr.crc = 0;
+                    if (staged) {        // index in the quad's concatenated list -> index in the record pool
+                        uint32_t rel = best_rel;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { const uint32_t n = R.q_nr[i]; if (rel < n) { fr.crc = R.q_ro[i] + rel; break; } rel -= n; }
+                    } else fr.crc = cur_recbase + best_rel;
+                    fr.buffer_seq = seq; fr.signal_len = (uint16_t)(msglen * 12 / 5); fr.phase = (uint8_t)(4 + best_phase);
+                    fr.msgtype = 0; fr.msgbits = 0; fr.correctedbits = 0; fr.fix_bit = -1; fr.flags = add ? B200_FRAME_ICAO_ADDED : 0;
+#pragma unroll
+                    for (int i = 0; i < 14; i++) fr.msg[i] = 0;
+                    fr.pad_[0] = 0; fr.pad_[1] = 0;
+                    *reinterpret_cast<uint16_t *>(&fr.pad_[0]) = (uint16_t)(si & 0xffffu);   // segment (low 16 bits) and data index
+                    *reinterpret_cast<uint32_t *>(&fr.pad_[2]) = d;
+                    fout[nframes] = fr;
+                } else atomicOr(&P.ctl->overflow, 4u);
+                if (corrected) c_acc1++; else c_acc0++;
+                c_bp[best_phase]++;
+                if (add) {
+                    if (DEFER) { if (!best_known) newaddr = best_key & 0xffffffu; }
+                    else if (!gen_add(S.act, gcount_active, best_key & 0xffffffu)) *err = 1;
+                    relearn = best_known ? 0u : 1u;      // membership changed: later scores are stale
+                }
+                now_ms = buf_ts / 12000 + (ts - buf_ts) / 12000;      // demod_2400.c:409-414
+            }
+            __syncwarp();
+            // broadcast the state the accepting lane changed
+            msglen = __shfl_sync(FULLMASK, msglen, f);
+            relearn = __shfl_sync(FULLMASK, relearn, f);
+            now_ms = __shfl_sync(FULLMASK, now_ms, f);
+            if (DEFER) {
+                newaddr = __shfl_sync(FULLMASK, newaddr, f);
+                if (newaddr != 0xffffffffu) {
+                    if (n_new < NEW_CAP) { if (lane == 0) out.news[n_new] = newaddr; n_new++; } else fail = 1;
+                    __syncwarp();
+                }
+            }
+            const uint32_t d_f = __shfl_sync(FULLMASK, d, f);
+            skip_until = d_f + msglen * 2 + 1;                          // demod_2400.c:468 + loop increment
+            nframes++;
+            pending &= ~((2u << f) - 1u);                               // lanes up to the accepted one are done
+            if (relearn) { consumed = f + 1; break; }                   // re-score the rest of the chunk with the new filter
+            if (!pending) break;
+        }
+        // advance the cursors past the consumed entries
+        const uint32_t last = consumed - 1;
+        rec_rel += __shfl_sync(FULLMASK, rprefix + nlive, last);
+        idx += consumed;
+    }
+    cp_async_wait_all();      // nothing may land in this warp's ring after the next buffer starts to use it
+    __syncwarp();
+
+    uint32_t red[15] = {c_pre, c_bad, c_unk, c_acc0, c_acc1, c_tp[0], c_tp[1], c_tp[2], c_tp[3], c_tp[4], c_bp[0], c_bp[1], c_bp[2], c_bp[3], c_bp[4]};
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) red[k] += __shfl_xor_sync(FULLMASK, red[k], o);
+        if (lane == 0) out.stats[k] = red[k];
+    }
+    if (lane == 0) { out.now_ms = now_ms; out.n_frames = min(nframes, fcap); out.n_new = n_new; out.fail = fail; }
+    __syncwarp();
+}
+
+// Stage B: one CTA per receiver.  The buffers of a receiver only interact through the address filter (what earlier
+// buffers taught it, and the 60 s flip), so RS_WARPS of them are resolved AT THE SAME TIME against the filter as it stands,
+// in deferred mode; then warp 0 commits them in order.  A buffer's speculation holds if no buffer before it in the round
+// changed the filter's membership: then its adds are applied and its frames moved into place.  Otherwise it is resolved
+// again, directly, with the filter as the reference would have it at that point.  In steady state (aircraft already
+// known, no flip) every speculation holds; the results are the sequential ones by construction either way.
+__global__ void __launch_bounds__(RS_WARPS * 32, 1) resolve_kernel(const ResolveParams P) {
+    extern __shared__ uint4 resolve_smem_raw[];
+    ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
+    __shared__ uint32_t s_active, s_gcount[2], s_err;
+    const uint32_t stream = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    StreamState *st = &P.state[stream];
+    // Stage A failed (record pool / staging), or the step ahead of this one in the asynchronous pipeline has to be
+    // repeated: leave every receiver's state untouched; the host repeats the run(s) in order.
+    if (P.ctl->overflow & 3u) return;
+    if (P.prev_ctl && (P.prev_ctl->overflow & 19u)) { if (tid == 0) atomicOr(&P.ctl->overflow, 16u); return; }
+
+    if (tid == 0) { s_active = st->active; s_gcount[0] = st->gen_count[0]; s_gcount[1] = st->gen_count[1]; s_err = st->error; }
+    for (uint32_t i = tid; i < OLD_BITS / 32; i += blockDim.x) S.old_bits[i] = 0;
+    __syncthreads();
+    {
+        const uint32_t active = s_active;
+        for (uint32_t i = tid; i < ICAO_CAP; i += blockDim.x) {
+            S.act[i] = st->gen[active][i];
+            const uint32_t v = st->gen[active ^ 1u][i];
+            if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
+        }
+    }
+    __syncthreads();
+
+    // state only warp 0 touches (the commit step)
+    uint32_t armed = st->flip_armed, seq = st->buffer_seq;
+    int64_t next_flip = st->next_flip_ms;
+    bool dirty_act = false;                  // the shared-memory table differs from the global copy of the active generation
+    uint32_t tot[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) tot[k] = 0;
     unsigned long long c_samples = 0;
-    uint32_t c_bufs = 0, c_flips = 0;
-    uint32_t nframes = 0;
-    b200_frame *fout = P.frames + (size_t)stream * P.frame_cap;
+    uint32_t c_bufs = 0, c_flips = 0, nframes = 0;
+    b200_frame *fstream = P.frames + (size_t)stream * P.frame_cap;
+    uint32_t jbuf = 0;                       // buffers of this receiver before the current round
 
     for (uint32_t si = P.stream_seg_begin[stream]; si < P.stream_seg_begin[stream + 1]; si++) {
         const Segment seg = P.segs[si];
-        const uint32_t tile_end = seg.tile_begin + seg.n_tiles;
-        // Stage B walks QUADS of four consecutive scan tiles (8192 positions; PosEntry positions are quad-relative).  Quad
-        // q's four PosEntry / key lists are staged back to back in ring slot q % RS_RING; at any time the current quad is
-        // complete and up to three more are in flight.  TileOut descriptors run one step further ahead in registers:
-        // lane l < 4 holds the descriptor of the quad's tile l (q1..q4).
-        const uint32_t n_quads = (seg.n_tiles + 3) / 4;
-        uint32_t quad = 0, idx = 0, rec_rel = 0, cur_npos = 0, cur_recbase = 0, sub = 4;
-        bool staged = true;
-        uint4 to = make_uint4(0, 0, 0, 0), q1 = to, q2 = to, q3 = to, q4 = to;
-        const PosEntry *pe_ptr = nullptr;
-        const uint32_t *key_ptr = nullptr;
-        auto load_desc = [&](uint32_t q) {           // this lane's piece of quad q's descriptor
-            const uint32_t t = seg.tile_begin + 4 * q + lane;
-            return (lane < 4 && q < n_quads && t < tile_end) ? *reinterpret_cast<const uint4 *>(&P.tile_out[t]) : make_uint4(0, 0, 0, 0);
-        };
-        auto issue_stage = [&](uint32_t q, const uint4 &piece) {      // always commits a group, so group counting stays uniform
-            uint32_t np[4], nr[4], ro[4], tp = 0, tr = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) { np[i] = __shfl_sync(FULLMASK, piece.x, i); nr[i] = __shfl_sync(FULLMASK, piece.y, i); ro[i] = __shfl_sync(FULLMASK, piece.z, i); tp += np[i]; tr += nr[i]; }
-            if (q < n_quads && tp <= RS_STAGE && tr <= RS_STAGE) {
-                const uint32_t buf = q % RS_RING;
-                uint32_t bp = 0, br = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const PosEntry *src = P.pos_pool + (size_t)(seg.tile_begin + 4 * q + i) * SCAN_TILE;
-                    for (uint32_t e = lane; e < np[i]; e += 32) cp_async4(&S.pos[buf][bp + e], &src[e]);
-                    for (uint32_t e = lane; e < nr[i]; e += 32) cp_async4(&S.key[buf][br + e], &P.key_pool[ro[i] + e]);
-                    bp += np[i]; br += nr[i];
-                }
+        for (uint32_t b0 = 0; b0 < seg.n_bufs; b0 += RS_WARPS) {
+            const uint32_t n_round = min((uint32_t)RS_WARPS, seg.n_bufs - b0);
+            // ---- speculation: warp w resolves buffer b0 + w against the filter as it stands ---------------------------------
+            if (wid < n_round) {
+                const uint32_t b = b0 + wid;
+                resolve_buffer<true>(P, S, S.ring[wid], S.res[wid], seg, si, b, 0 /* buffer_seq is stamped at commit */, st->gen[s_active ^ 1u], nullptr, nullptr,
+                                     fstream + (size_t)(jbuf + wid) * P.per_buf_cap, P.per_buf_cap, lane);
             }
-            cp_async_commit();
-        };
-        auto set_sublist = [&](uint32_t i) {         // dense quad, read in place: one scan tile at a time
-            sub = i;
-            pe_ptr = P.pos_pool + (size_t)(seg.tile_begin + 4 * quad + i) * SCAN_TILE;
-            cur_npos = S.q_np[i]; cur_recbase = S.q_ro[i]; key_ptr = P.key_pool + cur_recbase;
-            idx = 0; rec_rel = 0;
-        };
-        auto enter_quad = [&](uint32_t q) {          // make quad q current (q1 describes it)
-            to = q1; q1 = q2; q2 = q3; q3 = q4;
-            q4 = load_desc(q + 4);
-            cp_async_wait_2();                       // everything but the two newest groups has landed: quad q is complete
-            __syncwarp();
-            if (lane < 4) { S.q_np[lane] = to.x; S.q_nr[lane] = to.y; S.q_ro[lane] = to.z; }
-            __syncwarp();
-            const uint32_t tp = S.q_np[0] + S.q_np[1] + S.q_np[2] + S.q_np[3], tr = S.q_nr[0] + S.q_nr[1] + S.q_nr[2] + S.q_nr[3];
-            staged = tp <= RS_STAGE && tr <= RS_STAGE;
-            if (staged) { const uint32_t buf = q % RS_RING; pe_ptr = S.pos[buf]; key_ptr = S.key[buf]; cur_npos = tp; cur_recbase = 0; sub = 4; idx = 0; rec_rel = 0; }
-            else set_sublist(0);
-            issue_stage(q + 3, q3);                  // reuses the slot of quad q - 1, which is finished
-        };
-        // next list with entries left: the next scan tile of a dense quad, or the next quad
-        auto advance = [&]() {
-            while (idx >= cur_npos) {
-                if (!staged && sub < 3) set_sublist(sub + 1);
-                else if (quad + 1 < n_quads) { quad++; enter_quad(quad); }
-                else return false;
-            }
-            return true;
-        };
-        if (n_quads) {
-            q1 = load_desc(0); q2 = load_desc(1); q3 = load_desc(2); q4 = load_desc(3);
-            issue_stage(0, q1); issue_stage(1, q2); issue_stage(2, q3);
-            enter_quad(0);
-        }
-
-        for (uint32_t b = 0; b < seg.n_bufs; b++) {
-            const uint32_t d_begin = b * seg.buf_len;
-            const uint32_t d_end = min(d_begin + seg.buf_len, seg.npos);
-            const int64_t buf_ts = seg.first_ts + (int64_t)d_begin * 5;
-            int64_t now_ms = buf_ts / 12000;          // demod_2400.c:283-285
-            uint32_t skip_until = d_begin;            // data-index form of the reference's `pa` skip
-            uint32_t nfr_buf = 0;
-
-            for (;;) {
-                if (!n_quads || !advance()) break;
-                const uint32_t x0 = quad * (4 * SCAN_TILE);
-                const bool has = idx + lane < cur_npos;
-                const PosEntry pe = has ? pe_ptr[idx + lane] : 0;
-                const uint32_t d = x0 + (pe & 0x1fffu) - seg.lead;          // data index = position in the segment
-                const bool inbuf = has && d < d_end;                        // entries are ascending: a prefix of lanes
-                const uint32_t n_in = __popc(__ballot_sync(FULLMASK, inbuf));
-                if (n_in == 0) break;                                       // next entry belongs to the next buffer
-                const uint32_t tried = (pe >> 16) & 31u, live = (pe >> 21) & 31u;
-                const uint32_t nlive = inbuf ? __popc(live) : 0;
-                uint32_t dummy;
-                const uint32_t rprefix = warp_excl_scan(nlive, lane, &dummy);
-                const bool valid = inbuf && d >= skip_until;
-
-                // score every tried phase with the current filter; first strictly greatest wins (demod_2400.c:243)
-                int best = -2; uint32_t best_rel = 0, best_phase = 0, best_key = 0; bool best_known = false;
-                if (valid && live) {
-                    uint32_t k = rec_rel + rprefix;
-#pragma unroll
-                    for (uint32_t ph = 0; ph < 5; ph++) {
-                        if ((live >> ph) & 1u) {
-                            const uint32_t key = key_ptr[k];
-                            const bool known = known_addr(key & 0xffffffu);
-                            const int sc = rec_score((key >> 24) & 7u, known);
-                            if (sc > best) { best = sc; best_rel = k; best_phase = ph; best_key = key; best_known = known; }
-                            k++;
-                        }
-                    }
-                }
-                // accept test of decodeModesMessage (mode_s.c:443-596): only a corrected AA that is unknown rejects
-                const bool decode_ok = best >= 0 && !((best_key & KEY_AA_CHANGED) && !best_known);
-                // Commit the chunk in order.  After an accept the skip-ahead (demod_2400.c:468) silently consumes the
-                // following lanes inside the frame; the lanes beyond keep their scores as long as the accepted frame did
-                // not teach the filter a NEW address, so one loaded chunk can yield several frames.
-                uint32_t pending = __ballot_sync(FULLMASK, inbuf), consumed = n_in;
-                for (;;) {
-                    const bool live_lane = ((pending >> lane) & 1u) && d >= skip_until;
-                    const uint32_t acc_mask = __ballot_sync(FULLMASK, live_lane && decode_ok);
-                    const uint32_t f = acc_mask ? (uint32_t)__ffs(acc_mask) - 1 : 32u;
-                    if (live_lane && lane < f) {       // rejected preambles before the next accepted one
-                        c_pre++;
-#pragma unroll
-                        for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
-                        if (best == -2) c_bad++; else c_unk++;       // -1, or decode result -1
-                    }
-                    if (!acc_mask) break;
-                    uint32_t msglen = 0, relearn = 0;
-                    if (lane == f) {
-                        c_pre++;
-#pragma unroll
-                        for (int p = 0; p < 5; p++) c_tp[p] += (tried >> p) & 1u;
-                        const uint32_t kind = (best_key >> 24) & 7u;
-                        msglen = (best_key & KEY_LONG) ? 112 : 56;              // demod_2400.c:399 (DF as sliced)
-                        const bool corrected = kind == K_DFREPAIR || kind == K_DF11_FIX || kind == K_ES_FIX;
-                        // mode_s.c:766-779: clean DF17, or DF11 with IID 0, teaches the filter its address
-                        const bool add = kind == K_DF11_IID0 || (kind == K_ES_OK && (best_key & KEY_DF17));
-                        const uint32_t j = d - d_begin;
-                        const int64_t ts = buf_ts + (int64_t)j * 5 + (8 + 56) * 12 + (4 + best_phase);   // demod_2400.c:406
-                        if (nframes < P.frame_cap) {
-                            // accept record; finalize_kernel turns it into the full frame from the 32-byte Rec
+            __syncthreads();
+            // ---- commit, in order -----------------------------------------------------------------------------------------------
+            if (wid == 0) {
+                bool spec_ok = true;
+                for (uint32_t i = 0; i < n_round; i++) {
+                    const uint32_t b = b0 + i;
+                    BufResult &r = S.res[i];
+                    const uint32_t d_begin = b * seg.buf_len, d_end = min(d_begin + seg.buf_len, seg.npos);
+                    b200_frame *fdst = fstream + nframes;
+                    if (spec_ok && !r.fail) {
+                        // the speculation holds: teach the filter what this buffer learned, move its frames into place
+                        const b200_frame *fsrc = fstream + (size_t)(jbuf + i) * P.per_buf_cap;
+                        const uint32_t n = r.n_frames;
+                        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+                            const bool has = k0 + lane < n;
                             b200_frame fr;
-                            fr.timestamp = ts; fr.sigpow_sum = 0; fr.j = j; fr.crc = 0;
-                            if (staged) {        // index in the quad's concatenated list -> index in the record pool
-                                uint32_t rel = best_rel;
-#pragma unroll
-                                for (int i = 0; i < 4; i++) { const uint32_t n = S.q_nr[i]; if (rel < n) { fr.crc = S.q_ro[i] + rel; break; } rel -= n; }
-                            } else fr.crc = cur_recbase + best_rel; fr.addr = 0; fr.score = best;
-                            fr.buffer_seq = seq; fr.signal_len = (uint16_t)(msglen * 12 / 5); fr.phase = (uint8_t)(4 + best_phase);
-                            fr.msgtype = 0; fr.msgbits = 0; fr.correctedbits = 0; fr.fix_bit = -1; fr.flags = add ? B200_FRAME_ICAO_ADDED : 0;
-#pragma unroll
-                            for (int i = 0; i < 14; i++) fr.msg[i] = 0;
-                            fr.pad_[0] = 0; fr.pad_[1] = 0;
-                            *reinterpret_cast<uint16_t *>(&fr.pad_[0]) = (uint16_t)(si & 0xffffu);   // segment (low 16 bits) and data index
-                            *reinterpret_cast<uint32_t *>(&fr.pad_[2]) = d;
-                            fout[nframes] = fr;
-                        } else atomicOr(&P.ctl->overflow, 4u);
-                        if (corrected) c_acc1++; else c_acc0++;
-                        c_bp[best_phase]++;
-                        if (add) {
-                            if (!gen_add(S.act, &gcount[active], best_key & 0xffffffu)) err = 1;
-                            dirty[active] = true;
-                            relearn = best_known ? 0u : 1u;      // membership changed: later scores are stale
+                            if (has) fr = fsrc[k0 + lane];
+                            const uint32_t addm = __ballot_sync(FULLMASK, has && (fr.flags & B200_FRAME_ICAO_ADDED));
+                            uint32_t m = addm;
+                            while (m) {                                  // mode_s.c:778, in frame order
+                                const uint32_t l = __ffs(m) - 1; m &= m - 1;
+                                const uint32_t a = __shfl_sync(FULLMASK, fr.addr, l);
+                                if (lane == 0) { if (!gen_add(S.act, &s_gcount[s_active], a)) s_err = 1; }
+                                __syncwarp();
+                            }
+                            if (addm) dirty_act = true;
+                            if (has && fdst != fsrc) { fr.buffer_seq = seq; fdst[k0 + lane] = fr; }
+                            else if (has) { const_cast<b200_frame *>(fsrc)[k0 + lane].buffer_seq = seq; }
+                            __syncwarp();
                         }
-                        now_ms = buf_ts / 12000 + (ts - buf_ts) / 12000;      // demod_2400.c:409-414
+                        if (r.n_new) spec_ok = false;                   // later buffers of the round saw a filter without these addresses
+                    } else {
+                        spec_ok = false;
+                        resolve_buffer<false>(P, S, S.ring[0], r, seg, si, b, seq, st->gen[s_active ^ 1u], &s_gcount[s_active], &s_err, fdst,
+                                              P.frame_cap - nframes, lane);
+                        dirty_act = true;
                     }
                     __syncwarp();
-                    // broadcast the state the accepting lane changed
-                    msglen = __shfl_sync(FULLMASK, msglen, f);
-                    relearn = __shfl_sync(FULLMASK, relearn, f);
-                    now_ms = __shfl_sync(FULLMASK, now_ms, f);
-                    gcount[0] = __shfl_sync(FULLMASK, gcount[0], f); gcount[1] = __shfl_sync(FULLMASK, gcount[1], f);
-                    dirty[0] = __shfl_sync(FULLMASK, (int)dirty[0], f); dirty[1] = __shfl_sync(FULLMASK, (int)dirty[1], f);
-                    err = __shfl_sync(FULLMASK, err, f);
-                    const uint32_t d_f = __shfl_sync(FULLMASK, d, f);
-                    skip_until = d_f + msglen * 2 + 1;                          // demod_2400.c:468 + loop increment
-                    nframes++; nfr_buf++;
-                    pending &= ~((2u << f) - 1u);                               // lanes up to the accepted one are done
-                    if (relearn) { consumed = f + 1; break; }                   // re-score the rest of the chunk with the new filter
-                    if (!pending) break;
+#pragma unroll
+                    for (int k = 0; k < 15; k++) tot[k] += r.stats[k];
+                    const uint32_t nfr_buf = r.n_frames;
+                    nframes += nfr_buf;
+                    // end of buffer: readsb.c:876, then backgroundTasks' filter flip (readsb.c:1227-1231)
+                    c_samples += d_end - d_begin; c_bufs++;
+                    uint32_t flipped = 0;
+                    const int64_t now_ms = r.now_ms;
+                    if (P.ttl_ms > 0 && (!armed || now_ms >= next_flip)) {
+                        // the active generation becomes the older one: its exact table goes to global memory, its hash bits stay
+                        // here; the other generation is emptied and becomes active
+                        const uint32_t active = s_active, other = active ^ 1u;
+                        for (uint32_t q = lane; q < OLD_BITS / 32; q += 32) S.old_bits[q] = 0;
+                        __syncwarp();
+                        for (uint32_t q = lane; q < ICAO_CAP; q += 32) {
+                            const uint32_t v = S.act[q];
+                            if (dirty_act) st->gen[active][q] = v;
+                            if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
+                            S.act[q] = ICAO_EMPTY;
+                        }
+                        __syncwarp();
+                        if (lane == 0) { s_gcount[other] = 0; s_active = other; }
+                        dirty_act = true;
+                        next_flip = now_ms + P.ttl_ms; armed = 1; flipped = 1; c_flips++;
+                        spec_ok = false;                                // the rest of the round saw the filter before the flip
+                        __threadfence_block();
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        b200_buffer_result br;
+                        br.sample_timestamp = seg.first_ts + (int64_t)d_begin * 5; br.sum_level = 0; br.sum_power = 0; br.sum_signal_power = 0;
+                        br.length = d_end - d_begin; br.n_frames = nfr_buf; br.buffer_seq = seq; br.icao_flipped = flipped;
+                        P.buf_out[seg.first_buf + b] = br;
+                    }
+                    seq++;
                 }
-                // advance the cursors past the consumed entries
-                const uint32_t last = consumed - 1;
-                rec_rel += __shfl_sync(FULLMASK, rprefix + nlive, last);
-                idx += consumed;
             }
-
-            // end of buffer: readsb.c:876, then backgroundTasks' filter flip (readsb.c:1227-1231)
-            c_samples += d_end - d_begin; c_bufs++;
-            uint32_t flipped = 0;
-            if (P.ttl_ms > 0 && (!armed || now_ms >= next_flip)) {
-                // the active generation becomes the older one: its exact table goes to global memory, its hash bits stay here;
-                // the other generation is emptied and becomes active
-                const uint32_t other = active ^ 1u;
-                for (uint32_t i = lane; i < OLD_BITS / 32; i += 32) S.old_bits[i] = 0;
-                __syncwarp();
-                for (uint32_t i = lane; i < ICAO_CAP; i += 32) {
-                    const uint32_t v = S.act[i];
-                    if (dirty[active]) st->gen[active][i] = v;
-                    if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
-                    S.act[i] = ICAO_EMPTY;
-                }
-                dirty[active] = false;
-                gcount[other] = 0; dirty[other] = true; active = other;
-                next_flip = now_ms + P.ttl_ms; armed = 1; flipped = 1; c_flips++;
-                __syncwarp();
-            }
-            if (lane == 0) {
-                b200_buffer_result r;
-                r.sample_timestamp = buf_ts; r.sum_level = 0; r.sum_power = 0; r.sum_signal_power = 0;
-                r.length = d_end - d_begin; r.n_frames = nfr_buf; r.buffer_seq = seq; r.icao_flipped = flipped;
-                P.buf_out[seg.first_buf + b] = r;
-            }
-            seq++;
+            jbuf += n_round;
+            __syncthreads();
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing of this segment may land after the ring is reused
-        __syncwarp();
     }
 
     // write back
-    if (dirty[active]) for (uint32_t i = lane; i < ICAO_CAP; i += 32) st->gen[active][i] = S.act[i];
-    uint32_t red[15] = {c_pre, c_bad, c_unk, c_acc0, c_acc1, c_tp[0], c_tp[1], c_tp[2], c_tp[3], c_tp[4], c_bp[0], c_bp[1], c_bp[2], c_bp[3], c_bp[4]};
-#pragma unroll
-    for (int k = 0; k < 15; k++)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) red[k] += __shfl_xor_sync(FULLMASK, red[k], o);
-    if (lane == 0) {
-        st->gen_count[0] = gcount[0]; st->gen_count[1] = gcount[1];
-        st->active = active; st->flip_armed = armed; st->next_flip_ms = next_flip; st->buffer_seq = seq; st->error = err;
-        b200_demod_stats &s = st->stats;
-        s.samples_processed += c_samples; s.demod_preambles += red[0]; s.demod_rejected_bad += red[1];
-        s.demod_rejected_unknown_icao += red[2]; s.demod_accepted[0] += red[3]; s.demod_accepted[1] += red[4];
-        for (int p = 0; p < 5; p++) { s.demod_preamblePhase[p] += red[5 + p]; s.demod_bestPhase[p] += red[10 + p]; }
-        s.buffers += c_bufs; s.icao_flips += c_flips;
-        P.frame_count[stream] = min(nframes, P.frame_cap);
-        if (err) atomicOr(&P.ctl->overflow, 8u);
+    if (wid == 0) {
+        const uint32_t active = s_active;
+        if (dirty_act) for (uint32_t i = lane; i < ICAO_CAP; i += 32) st->gen[active][i] = S.act[i];
+        if (lane == 0) {
+            st->gen_count[0] = s_gcount[0]; st->gen_count[1] = s_gcount[1];
+            st->active = active; st->flip_armed = armed; st->next_flip_ms = next_flip; st->buffer_seq = seq; st->error = s_err;
+            b200_demod_stats &s = st->stats;
+            s.samples_processed += c_samples; s.demod_preambles += tot[0]; s.demod_rejected_bad += tot[1];
+            s.demod_rejected_unknown_icao += tot[2]; s.demod_accepted[0] += tot[3]; s.demod_accepted[1] += tot[4];
+            for (int p = 0; p < 5; p++) { s.demod_preamblePhase[p] += tot[5 + p]; s.demod_bestPhase[p] += tot[10 + p]; }
+            s.buffers += c_bufs; s.icao_flips += c_flips;
+            P.frame_count[stream] = min(nframes, P.frame_cap);
+            if (s_err) atomicOr(&P.ctl->overflow, 8u);
+        }
     }
 }
 
+// ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // finalize: prefix of per-stream frame counts, then one warp per frame
 // ------------------------------------------------------------------------------------------------
@@ -467,12 +575,12 @@ __global__ void icao_op_kernel(StreamState *state, uint32_t stream, int op, uint
 // ------------------------------------------------------------------------------------------------
 extern "C" int b200_launch_resolve(const ResolveParams *p, void *stream) {
     static bool attr_set = false;
-    if (!attr_set) {   // same carve-out as the scan kernel, so that resolver CTAs can join an SM the scan kernel already occupies
-        cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem));
+        if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    if (p->n_streams == 0) return 0;
-    resolve_kernel<<<p->n_streams, 32, 0, (cudaStream_t)stream>>>(*p);
+    resolve_kernel<<<p->n_streams, RS_WARPS * 32, sizeof(ResolveSmem), (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
 }
 
