@@ -20,6 +20,7 @@
 #define B200_TRAIL 326
 
 // ---- stage A tiling ----------------------------------------------------------------------------
+#define TILE_QUAD_START 0x80000000u  // tile_seg flag: first tile of a quad (four consecutive tiles of a segment, counted from its first tile)
 #define SCAN_TILE      2048          // preamble start positions per tile (the unit of stage A output and of stage B's walk)
 
 // ---- segment descriptor ------------------------------------------------------------------------
@@ -119,7 +120,7 @@ struct RunCtl {
 
 struct ScanParams {
     const Segment *segs;
-    const uint32_t *tile_seg;    // tile -> segment index
+    const uint32_t *tile_seg;    // tile -> segment index | TILE_QUAD_START
     uint32_t n_tiles;
     PosEntry *pos_pool;
     Rec *rec_pool;

@@ -376,7 +376,7 @@ static void add_segment(b200_demod_ctx *c, Slot &sl, uint32_t stream, const uint
     g.lead = (uint32_t)(((uintptr_t)base & 15) / 2); g.flags = flags; g.stream = stream;
     g.first_buf = sl.nbuf; g.n_bufs = n_bufs; g.tile_begin = sl.ntile;
     g.n_tiles = npos ? (g.lead + npos + SCAN_TILE - 1) / SCAN_TILE : 0;
-    for (uint32_t t = 0; t < g.n_tiles; t++) sl.h_tile_seg[sl.ntile + t] = sl.nseg;
+    for (uint32_t t = 0; t < g.n_tiles; t++) sl.h_tile_seg[sl.ntile + t] = sl.nseg | ((t & 3u) == 0 ? TILE_QUAD_START : 0u);
     sl.ntile += g.n_tiles; sl.nbuf += n_bufs; sl.nseg++;
 }
 

@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(AC_THREADS, 2) modeac_scan_kernel(const AcScan
         for (uint32_t i = tid; i < 128 * 128 * 2 / 16; i += AC_THREADS) dst[i] = src[i];
     }
     for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const Segment seg = P.segs[P.tile_seg[tile]];
-        if ((tile - seg.tile_begin) % (AC_TILE / SCAN_TILE)) continue;      // this block iteration covers the scan tiles [tile, tile + 4) of the segment
+        const uint32_t ts = P.tile_seg[tile];
+        if (!(ts & TILE_QUAD_START)) continue;                              // a block iteration covers one quad: the scan tiles [tile, tile + 4) of the segment
+        const Segment seg = P.segs[ts & ~TILE_QUAD_START];
         const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;
         const uint32_t x_data_end = seg.lead + seg.npos + B200_TRAIL;
         const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;
@@ -347,7 +348,7 @@ extern "C" int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp
     if (sp->n_tiles && sp->n_segs) {
         modeac_noise_kernel<<<min(sp->n_segs, 1024u), 32, 0, (cudaStream_t)stream>>>(*sp);
         // three of four scan tiles are skipped (AC_TILE = 4 scan tiles): an odd grid gives every block the same share of the fourth
-        uint32_t grid = ((uint32_t)n_sm * 2) | 1u;
+        uint32_t grid = (uint32_t)n_sm * 2 - 1;       // odd and not more than one wave (2 CTAs per SM)
         if (grid > sp->n_tiles) grid = sp->n_tiles;
         modeac_scan_kernel<<<grid, AC_THREADS, sizeof(AcSmem), (cudaStream_t)stream>>>(*sp);
         modeac_walk_kernel<<<wp->n_segs, 256, 0, (cudaStream_t)stream>>>(*wp);

@@ -489,7 +489,7 @@ __global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTabl
             if (!pend_n) break;
         }
         __syncwarp();
-        if (lane < 16) W.seg[lane] = reinterpret_cast<const uint32_t *>(&P.segs[P.tile_seg[pend_tile]])[lane];
+        if (lane < 16) W.seg[lane] = reinterpret_cast<const uint32_t *>(&P.segs[P.tile_seg[pend_tile] & ~TILE_QUAD_START])[lane];
         if (lane < RUN_MAX) { W.n_pos[lane] = 0; W.n_rec[lane] = 0; }
         __syncwarp();
         uint32_t n_chunks;
@@ -619,8 +619,6 @@ extern "C" int b200_launch_scan(const ScanParams *p, const DeviceTables *d_table
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem));
         if (e != cudaSuccess) return (int)e;
-        // largest shared-memory carve-out: what this persistent kernel leaves free must be usable by two resolver CTAs per SM
-        cudaFuncSetAttribute(scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     if (!p->n_tiles) return 0;
