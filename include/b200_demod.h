@@ -163,6 +163,16 @@ int b200_demod_submit_mag_u16(b200_demod_ctx *ctx, uint32_t stream, const uint16
 int b200_demod_submit_iq_uc8_strided(b200_demod_ctx *ctx, uint32_t first_stream, uint32_t n_streams,
                                      const uint8_t *iq, uint64_t host_stride_bytes, uint32_t n_buffers,
                                      uint32_t buf_len, int64_t first_sample_timestamp);
+/* The float-path converters for 16-bit frontends (bladeRF, Pluto, Soapy): replaces iq_convert_fn for INPUT_SC16
+ * (convert_sc16_nodc, convert.c:212-250: I / 32768) and, with q11 != 0, INPUT_SC16Q11 (convert_sc16q11_nodc,
+ * convert.c:329-367: I / 2048; the default build has no table path).  `iq` holds nsamples interleaved little-endian
+ * int16 I,Q pairs; halo handling as for submit_iq_uc8.  Magnitudes are the reference's, bit for bit.  The reference
+ * returns mean_level / mean_power of these formats from float accumulators added to in sample order: for buffers
+ * submitted here b200_buffer_result.sum_level / sum_power hold the IEEE-754 bit patterns of those two float sums
+ * (mean_level = (double)(sum_level_f / (float)length), likewise mean_power).  Not combinable with B200_CFG_MODE_AC yet,
+ * nor with other submit kinds on the same stream in one run. */
+int b200_demod_submit_iq_sc16(b200_demod_ctx *ctx, uint32_t stream, const int16_t *iq, uint32_t nsamples,
+                              int64_t sample_timestamp, int q11);
 /* Process everything submitted since the last run; returns when frames are in host memory. */
 int b200_demod_run(b200_demod_ctx *ctx);
 

@@ -534,3 +534,23 @@ unsigned oracle_beast_modeac(const b200_modeac *a, uint8_t *out) {
     p = beast_put(p, (uint8_t)a->modeac);
     return (unsigned)(p - out);
 }
+
+/* ------------------------------------------------------------------ convert.c:212-250 (sc16) and 329-367 (sc16q11)
+ * The float-path converters.  Magnitude per sample exactly as the reference computes it; the two float accumulators are
+ * added to in sample order (sum_power first, then sum_level) and handed back as floats:
+ * mean_level = sum_level / nsamples, mean_power = sum_power / nsamples (float divisions, then widened to double). */
+void oracle_convert_sc16(const int16_t *iq, uint16_t *mag_out, unsigned nsamples, int q11, float *sum_level_out, float *sum_power_out) {
+    const float scale = q11 ? 2048.0f : 32768.0f;
+    float sum_level = 0, sum_power = 0;
+    for (unsigned i = 0; i < nsamples; i++) {
+        const int16_t I = iq[2 * i], Q = iq[2 * i + 1];
+        const float fI = I / scale, fQ = Q / scale;
+        float magsq = fI * fI + fQ * fQ;
+        if (magsq > 1) magsq = 1;
+        const float mag = sqrtf(magsq);
+        sum_power += magsq;
+        sum_level += mag;
+        mag_out[i] = (uint16_t)(mag * 65535.0f + 0.5f);
+    }
+    *sum_level_out = sum_level; *sum_power_out = sum_power;
+}

@@ -34,6 +34,8 @@ void oracle_uc8_lut(uint16_t *out65536);
 /* convert.c:64-108 (integer sums instead of the final fp64 divides) */
 void oracle_convert_uc8(const uint8_t *iq, uint16_t *mag, unsigned nsamples,
                         uint64_t *sum_level, uint64_t *sum_power);
+/* convert.c:212-250 (q11 = 0) / 329-367 (q11 = 1): magnitudes + the two float accumulators */
+void oracle_convert_sc16(const int16_t *iq, uint16_t *mag, unsigned nsamples, int q11, float *sum_level, float *sum_power);
 /* crc.c:67-82 */
 uint32_t oracle_crc24(const uint8_t *msg, int bits);
 /* crc.c:383-406 with nfix_crc=1 tables: returns corrected bit (5..bits-1), -1 if syndrome==0, -2 if none */

@@ -127,6 +127,16 @@ void ref_uc8_lut(uint16_t *out65536) {
     free(iq);
 }
 
+/* The reference's own float-path converters (static in convert.c, reached through init_converter like a frontend does). */
+int ref_convert_sc16(const int16_t *iq, uint16_t *mag, unsigned n, int q11, double *mean_level, double *mean_power) {
+    static iq_convert_fn fn[2];
+    static struct converter_state *st[2];
+    if (!fn[q11 != 0]) fn[q11 != 0] = init_converter(q11 ? INPUT_SC16Q11 : INPUT_SC16, Modes.sample_rate, 0, &st[q11 != 0]);
+    if (!fn[q11 != 0]) return -1;
+    fn[q11 != 0]((void *)iq, mag, n, st[q11 != 0], mean_level, mean_power);
+    return 0;
+}
+
 void ref_convert_uc8(const uint8_t *iq, uint16_t *mag, unsigned n, double *mean_level, double *mean_power) {
     g_conv((void *)iq, mag, n, g_conv_state, mean_level, mean_power);
 }

@@ -238,6 +238,7 @@ int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm
 int b200_launch_resolve(const ResolveParams *p, void *stream);
 int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream);
 int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp, int n_sm, void *stream);
+int b200_launch_sc16_convert(const void *d_iq, uint16_t *d_mag, uint32_t n, int q11, float2 *d_sums, int n_sm, void *stream);
 int b200_launch_beast(const BeastParams *p, uint32_t n_streams, void *stream);
 int b200_launch_modeac_stats(const AcWalkParams *wp, const uint32_t *prefix, void *stream);
 int b200_launch_ac_pack(const b200_modeac *ac_out, const uint32_t *count, uint32_t *prefix, b200_modeac *packed, uint32_t n_units, uint32_t cap, RunCtl *ctl, void *stream);

@@ -30,6 +30,7 @@ struct Pending {
     uint32_t n;          // new samples
     int64_t ts;
     size_t off;          // byte offset of data index 0 (mag) or of the first new sample (iq) in the stream's arena region
+    int fsum = -1;       // sc16 input: index of the buffer's float sums in d_fsum
 };
 
 struct DeviceArgs {      // what a device-resident step was asked to do (kept for a repeat after a pool regrowth)
@@ -81,7 +82,7 @@ struct b200_demod_ctx {
     uint8_t *d_arena = nullptr;
     size_t stream_stride = 0;
     std::vector<std::vector<Pending>> pending;
-    std::vector<uint8_t> kind;        // per stream this run: 0 none, 1 iq, 2 mag
+    std::vector<uint8_t> kind;        // per stream this run: 0 none, 1 uc8 iq, 2 mag hand-off, 3 sc16 iq (magnitudes made by the library)
     std::vector<uint8_t> halo_valid;  // iq streams: saved 326-sample tail is valid
     std::vector<size_t> cursor;       // append offset in the stream's arena region
 
@@ -98,6 +99,10 @@ struct b200_demod_ctx {
     uint32_t *d_beast_meta = nullptr, *h_beast_meta = nullptr;   // [S] offsets, [S] lengths, [1] total
     uint32_t beast_cap = 0;
     int beast_slot = -1; uint32_t beast_flags = 0;               // which run the buffers hold
+    // sc16 input: staging of one raw buffer, float sums of the buffers queued for the next run
+    uint8_t *d_raw16 = nullptr;
+    float2 *d_fsum = nullptr, *h_fsum = nullptr;
+    uint32_t n_fsum = 0;
     int *d_result = nullptr;
 };
 
@@ -211,6 +216,7 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     cudaFree(c->d_carry_src); cudaFree(c->d_result);
     cudaFree(c->d_stage_rec); cudaFree(c->d_stage_key); cudaFree(c->d_q1_over); cudaFree(c->d_tick_scratch);
     cudaFreeHost(c->h_carry_src);
+    cudaFree(c->d_raw16); cudaFree(c->d_fsum); cudaFreeHost(c->h_fsum);
     cudaFree(c->d_beast); cudaFree(c->d_beast_meta); cudaFreeHost(c->h_beast); cudaFreeHost(c->h_beast_meta);
     free_slot(c->slot[0]); free_slot(c->slot[1]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -306,7 +312,7 @@ static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32
     if (c->pending[s].size() >= c->cfg.max_buffers_per_run) return fail(c, B200_E_STATE, "stream %u already has max_buffers_per_run buffers queued", s);
     if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     const uint8_t want = mag ? 2 : 1;
-    if (c->kind[s] && c->kind[s] != want) return fail(c, B200_E_STATE, "stream %u mixes IQ and magnitude submits in one run", s);
+    if (c->kind[s] && c->kind[s] != want) return fail(c, B200_E_STATE, "stream %u mixes submit kinds in one run", s);
     CU(c, cudaSetDevice(c->device));
     if (!c->kind[s]) { c->kind[s] = want; c->cursor[s] = mag ? 0 : (size_t)B200_TRAIL * 2; }
     uint8_t *region = c->d_arena + (size_t)s * c->stream_stride;
@@ -344,7 +350,7 @@ API int b200_demod_submit_iq_uc8_strided(b200_demod_ctx *c, uint32_t first, uint
     const size_t row = (size_t)n_buffers * buf_len * 2;
     if (host_stride < row) return fail(c, B200_E_INVAL, "host_stride_bytes smaller than one stream's data");
     for (uint32_t s = first; s < first + ns; s++) {
-        if (c->kind[s] == 2) return fail(c, B200_E_STATE, "stream %u mixes IQ and magnitude submits in one run", s);
+        if (c->kind[s] >= 2) return fail(c, B200_E_STATE, "stream %u mixes submit kinds in one run", s);
         if (c->pending[s].size() + n_buffers > c->cfg.max_buffers_per_run) return fail(c, B200_E_STATE, "stream %u would exceed max_buffers_per_run", s);
         if (c->kind[s] && c->cursor[s] != c->cursor[first]) return fail(c, B200_E_STATE, "strided submit needs all streams of the range at the same fill level");
     }
@@ -360,6 +366,33 @@ API int b200_demod_submit_iq_uc8_strided(b200_demod_ctx *c, uint32_t first, uint
         }
         c->cursor[s] = off0 + row;
     }
+    return B200_OK;
+}
+
+API int b200_demod_submit_iq_sc16(b200_demod_ctx *c, uint32_t s, const int16_t *iq, uint32_t n, int64_t ts, int q11) {
+    if (!c) return B200_E_INVAL;
+    if (s >= c->cfg.n_streams || (!iq && n)) return fail(c, B200_E_INVAL, "bad stream or buffer");
+    if (n > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "buffer of %u samples exceeds buf_samples=%u", n, c->cfg.buf_samples);
+    if (c->cfg.flags & B200_CFG_MODE_AC) return fail(c, B200_E_INVAL, "sc16 input is not combinable with B200_CFG_MODE_AC yet");
+    if (c->pending[s].size() >= c->cfg.max_buffers_per_run) return fail(c, B200_E_STATE, "stream %u already has max_buffers_per_run buffers queued", s);
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
+    if (c->kind[s] && c->kind[s] != 3) return fail(c, B200_E_STATE, "stream %u mixes submit kinds in one run", s);
+    CU(c, cudaSetDevice(c->device));
+    const uint32_t S = c->cfg.n_streams, K = c->cfg.max_buffers_per_run;
+    if (!c->d_raw16) {
+        CU(c, cudaMalloc((void **)&c->d_raw16, (size_t)c->cfg.buf_samples * 4 + 16));
+        CU(c, dev_alloc(&c->d_fsum, (size_t)S * K)); CU(c, pin_alloc(&c->h_fsum, (size_t)S * K));
+    }
+    if (!c->kind[s]) { c->kind[s] = 3; c->cursor[s] = (size_t)B200_TRAIL * 2; }
+    uint8_t *region = c->d_arena + (size_t)s * c->stream_stride;
+    Pending p;
+    p.n = n; p.ts = ts; p.off = c->cursor[s]; p.fsum = (int)c->n_fsum++;
+    // one staging buffer: the copy and the two kernels of this submit are ordered on the stream before the next submit's copy
+    if (n) CU(c, cudaMemcpyAsync(c->d_raw16, iq, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    { int r = b200_launch_sc16_convert(c->d_raw16, reinterpret_cast<uint16_t *>(region + p.off), n, q11, c->d_fsum + p.fsum, c->n_sm, c->stream);
+      if (r) return fail(c, B200_E_CUDA, "sc16 convert launch: %s", cudaGetErrorString((cudaError_t)r)); }
+    c->cursor[s] = p.off + (size_t)n * 2;
+    c->pending[s].push_back(p);
     return B200_OK;
 }
 
@@ -547,6 +580,7 @@ API int b200_demod_run(b200_demod_ctx *c) {
     Slot &sl = c->slot[0];
     c->cur = 0;
     sl.nseg = sl.ntile = sl.nbuf = 0; sl.is_device = false; sl.upload_tiles = true; sl.cached_tiles = 0;
+    std::vector<std::pair<uint32_t, int>> fsum_of_buf;      // (buffer of the run, float-sum slot) for sc16 buffers
     for (uint32_t s = 0; s < S; s++) {
         sl.h_stream_seg_begin[s] = sl.nseg;
         sl.stream_buf_begin[s] = sl.nbuf;
@@ -571,7 +605,8 @@ API int b200_demod_run(b200_demod_ctx *c) {
                 }
                 const uint32_t nb = (uint32_t)(j - i + 1);
                 add_segment(c, sl, s, region + pl[i].off - (size_t)B200_TRAIL * 2, npos, nb > 1 ? BUF : pl[i].n, nb,
-                            halo_ok ? 0 : SEG_HALO_ZERO, pl[i].ts);
+                            (halo_ok ? 0 : SEG_HALO_ZERO) | (c->kind[s] == 3 ? SEG_MAG : 0), pl[i].ts);
+                if (c->kind[s] == 3) for (size_t q = i; q <= j; q++) fsum_of_buf.push_back({sl.nbuf - nb + (uint32_t)(q - i), pl[q].fsum});
                 halo_ok = pl[j].n >= B200_TRAIL;      // sdr_ifile.c:209-213
                 i = j + 1;
             }
@@ -582,6 +617,16 @@ API int b200_demod_run(b200_demod_ctx *c) {
     sl.h_stream_seg_begin[S] = sl.nseg;
     sl.stream_buf_begin[S] = sl.nbuf;
     int rc = execute_blocking(c, sl);
+    if (rc == B200_OK && !fsum_of_buf.empty()) {      // sc16 input: the reference's float accumulators instead of the integer sums
+        if (cudaMemcpyAsync(c->h_fsum, c->d_fsum, (size_t)c->n_fsum * sizeof(float2), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, B200_E_CUDA, "sc16 sums copy failed");
+        else for (const auto &bf : fsum_of_buf) {
+            uint32_t lv, pw;
+            memcpy(&lv, &c->h_fsum[bf.second].x, 4); memcpy(&pw, &c->h_fsum[bf.second].y, 4);
+            sl.h_buf_out[bf.first].sum_level = lv; sl.h_buf_out[bf.first].sum_power = pw;
+        }
+    }
+    c->n_fsum = 0;
     // next run: move each IQ stream's tail to the front of its region
     if (rc == B200_OK) {
         cudaMemcpyAsync(c->d_carry_src, c->h_carry_src, S * 4, cudaMemcpyHostToDevice, c->stream);

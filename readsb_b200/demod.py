@@ -51,6 +51,7 @@ def lib():
         L.b200_demod_frame_count.argtypes = [vp, u32, C.POINTER(u32)]
         L.b200_demod_fetch.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_fetch_modeac.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+        L.b200_demod_submit_iq_sc16.argtypes = [vp, u32, vp, u32, C.c_int64, C.c_int]
         L.b200_demod_fetch_beast.argtypes = [vp, u32, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_buffer_results.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
         L.b200_demod_total_frames.argtypes = [vp, C.POINTER(u64)]
@@ -71,7 +72,7 @@ EXPORTED_SYMBOLS = [
     "b200_demod_host_alloc", "b200_demod_host_free", "b200_demod_submit_iq_uc8", "b200_demod_submit_mag_u16",
     "b200_demod_run", "b200_demod_run_device_uc8", "b200_demod_frame_count", "b200_demod_fetch",
     "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
-    "b200_demod_fetch_beast", "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
+    "b200_demod_fetch_beast", "b200_demod_submit_iq_sc16", "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
     "b200_demod_uc8_lut", "b200_demod_debug_counters", "b200_demod_submit_iq_uc8_strided", "b200_demod_set_stream",
     "b200_demod_run_device_uc8_async", "b200_demod_wait", "b200_demod_fetch_modeac",
 ]
@@ -142,6 +143,11 @@ class Demodulator:
         """data: uint16 mag_buf.data = 326 halo magnitudes followed by `length` new ones."""
         assert data.dtype == np.uint16 and data.flags.c_contiguous and data.size >= length + 326
         self._check(self.L.b200_demod_submit_mag_u16(self.h, stream, data.ctypes.data, length, sample_timestamp))
+
+    def submit_iq_sc16(self, stream: int, iq16: np.ndarray, sample_timestamp: int, q11: bool = False):
+        """int16 I,Q pairs (convert_sc16_nodc, or convert_sc16q11_nodc with q11)."""
+        iq16 = np.ascontiguousarray(iq16, dtype=np.int16)
+        self._check(self.L.b200_demod_submit_iq_sc16(self.h, stream, iq16.ctypes.data, iq16.size // 2, sample_timestamp, 1 if q11 else 0))
 
     def submit_iq_strided(self, first_stream: int, n_streams: int, ptr: int, host_stride_bytes: int, n_buffers: int,
                           buf_len: int, first_sample_timestamp: int):

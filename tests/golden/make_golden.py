@@ -45,5 +45,22 @@ def main():
         print(name, len(frames), "frames", stats["demod_preambles"], "preambles")
 
 
+def sc16_vectors():
+    """The reference's float-path converters (convert.c:212-250, 329-367) on a small random block, both formats."""
+    out = {}
+    for q11 in (0, 1):
+        rng = np.random.default_rng(90 + q11)
+        lim = 2048 if q11 else 32768
+        iq = rng.integers(-lim, lim, size=2 * 6001, dtype=np.int32)
+        iq[:32] = [-lim, lim - 1] * 16
+        iq[2000:6000] = rng.integers(-lim // 40, lim // 40, size=4000)
+        iq = iq.astype(np.int16)
+        mag, ml, mp = Reference().convert_sc16(iq, bool(q11))
+        out[f"iq{q11}"] = iq; out[f"mag{q11}"] = mag; out[f"means{q11}"] = np.array([ml, mp], np.float64)
+    np.savez_compressed(HERE / "sc16_converters.npz", **out)
+    print("sc16_converters", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main()
+    sc16_vectors()

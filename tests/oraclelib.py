@@ -139,6 +139,34 @@ class Oracle:
         return np.concatenate(outs) if outs else np.zeros(0, MODEAC_DTYPE)
 
     @classmethod
+    def convert_sc16(cls, iq16: np.ndarray, q11: bool = False):
+        """convert_sc16_nodc / convert_sc16q11_nodc: (magnitudes, float32 sum_level, float32 sum_power)."""
+        L = cls.lib()
+        L.oracle_convert_sc16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        iq16 = np.ascontiguousarray(iq16, dtype=np.int16)
+        n = iq16.size // 2
+        mag = np.zeros(n, np.uint16)
+        sl, sp = C.c_float(), C.c_float()
+        L.oracle_convert_sc16(iq16.ctypes.data, mag.ctypes.data, n, 1 if q11 else 0, C.byref(sl), C.byref(sp))
+        return mag, np.float32(sl.value), np.float32(sp.value)
+
+    def run_stream_sc16(self, iq16: np.ndarray, buf_samples: int, q11: bool = False, first_ts: int = 0):
+        """The ifile loop over an sc16 capture: converter, halo carry, demodulate2400 per buffer.
+        Returns (frames, [(length, float32 sum_level, float32 sum_power) per buffer])."""
+        n = iq16.size // 2
+        halo = np.zeros(326, np.uint16)
+        frames, sums, off = [], [], 0
+        while off < n:
+            m = min(buf_samples, n - off)
+            mag, sl, sp = self.convert_sc16(iq16[2 * off: 2 * (off + m)], q11)
+            data = np.concatenate([halo, mag])
+            f, _ = self.demodulate(data, m, first_ts + off * 5)
+            frames.append(f); sums.append((m, sl, sp))
+            halo = data[m: m + 326].copy() if m >= 326 else np.zeros(326, np.uint16)
+            off += m
+        return (np.concatenate(frames) if frames else np.zeros(0, FRAME_DTYPE)), sums
+
+    @classmethod
     def beast(cls, frames: np.ndarray, modeac: np.ndarray = None, verbatim: bool = False) -> bytes:
         """Beast records (net_io.c:1655-1714) in the reference's output order: per buffer the Mode S frames, then the
         Mode A/C replies.  frames["buffer_seq"] and modeac["buffer_idx"] must count buffers from the same origin."""
@@ -263,6 +291,15 @@ class Reference:
         assert n >= 0
         k = nb.value
         return frames[:n].copy(), levels[:n].copy(), bufres[:k].copy(), ml[:k].copy(), mp[:k].copy()
+
+    def convert_sc16(self, iq16: np.ndarray, q11: bool = False):
+        iq16 = np.ascontiguousarray(iq16, dtype=np.int16)
+        n = iq16.size // 2
+        mag = np.zeros(n, np.uint16)
+        ml, mp = C.c_double(), C.c_double()
+        self.L.ref_convert_sc16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        assert self.L.ref_convert_sc16(iq16.ctypes.data, mag.ctypes.data, n, 1 if q11 else 0, C.byref(ml), C.byref(mp)) == 0
+        return mag, ml.value, mp.value
 
     def run_stream_ac(self, iq: np.ndarray, buf_samples: int, first_ts: int = 0):
         nsamples = iq.size // 2

@@ -372,3 +372,46 @@ def test_beast_without_modeac_and_async(cuda):
         fo, _ = Oracle().run_stream(iqs[s], buf)
         assert len(fo) > 20 and got[s] == Oracle.beast(fo)
     d.close()
+
+
+def _to_sc16(iq8: np.ndarray, q11: bool, seed: int) -> np.ndarray:
+    """The uc8 synthetic capture as a 16-bit frontend would deliver it (plus a little sub-LSB dither)."""
+    rng = np.random.default_rng(seed)
+    scale = 16 if q11 else 256
+    v = (iq8.astype(np.int32) - 128) * scale + rng.integers(0, scale, size=iq8.size)
+    return np.clip(v, -2048 if q11 else -32768, 2047 if q11 else 32767).astype(np.int16)
+
+
+@pytest.mark.parametrize("q11", [False, True])
+def test_sc16_input_matches_oracle(cuda, q11):
+    """b200_demod_submit_iq_sc16: the float-path converters on the GPU (magnitudes bit for bit -> identical frames) and
+    the reference's sequential float accumulators (bit patterns in the buffer results)."""
+    from readsb_b200.demod import Demodulator
+    S, buf, K = 2, 32768, 2
+    n = 3 * buf + 12345
+    iq16 = [_to_sc16(GENS["mixed"](120 + s, n), q11, s) for s in range(S)]
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=K)
+    got_f = [[] for _ in range(S)]; got_b = [[] for _ in range(S)]
+    off = 0
+    while off < n:
+        for _ in range(K):
+            if off >= n:
+                break
+            m = min(buf, n - off)
+            for s in range(S):
+                d.submit_iq_sc16(s, iq16[s][2 * off: 2 * (off + m)], off * 5, q11)
+            off += m
+        d.run()
+        for s in range(S):
+            got_f[s].append(d.frames(s)); got_b[s].append(d.buffer_results(s))
+    for s in range(S):
+        fo, sums = Oracle().run_stream_sc16(iq16[s], buf, q11)
+        fg = np.concatenate(got_f[s]); bg = np.concatenate(got_b[s])
+        assert len(fo) > 30
+        problems = diff_frames(fg, fo)
+        assert not problems, "\n".join(problems)
+        assert len(bg) == len(sums)
+        for r, (m, sl, sp) in zip(bg, sums):
+            assert r["length"] == m
+            assert np.uint32(r["sum_level"]).view(np.float32) == sl and np.uint32(r["sum_power"]).view(np.float32) == sp
+    d.close()

@@ -11,7 +11,7 @@ from oraclelib import Oracle, Reference, have_ref
 from paritylib import diff_frames, diff_stats
 from readsb_b200 import synth
 
-GOLDEN = sorted(p for p in (Path(__file__).parent / "golden").glob("*.npz") if p.stem != "beast_stream")
+GOLDEN = sorted(p for p in (Path(__file__).parent / "golden").glob("*.npz") if p.stem not in ("beast_stream", "sc16_converters"))
 
 
 def load_golden(path):
@@ -92,6 +92,15 @@ def test_beast_escaping_and_signal_byte():
     assert Oracle.beast(f)[2:].replace(b"\x1a\x1a", b"\x1a")[6] == 1
     a = np.zeros(1, MODEAC_DTYPE); a["timestamp"] = 5; a["modeac"] = 0x1A7F
     assert Oracle.beast(np.zeros(0, FRAME_DTYPE), a) == bytes([0x1A, 0x31, 0, 0, 0, 0, 0, 5, 0, 0x1A, 0x1A, 0x7F])
+
+
+@pytest.mark.parametrize("q11", [0, 1])
+def test_oracle_sc16_converters_match_golden(q11):
+    z = np.load(Path(__file__).parent / "golden" / "sc16_converters.npz")
+    iq = z[f"iq{q11}"]; n = iq.size // 2
+    mag, sl, sp = Oracle.convert_sc16(iq, bool(q11))
+    assert np.array_equal(mag, z[f"mag{q11}"])
+    assert float(np.float32(sl) / np.float32(n)) == z[f"means{q11}"][0] and float(np.float32(sp) / np.float32(n)) == z[f"means{q11}"][1]
 
 
 def test_lut_known_answer():
@@ -207,3 +216,22 @@ def test_icao_ttl_two_flips():
     fo, bo = o.run_stream(iq, 131072)
     assert not diff_frames(fo, fr, fields=("timestamp", "msg", "score"))
     assert bo["icao_flipped"].sum() >= 3
+
+
+@needs_ref
+@pytest.mark.parametrize("q11", [False, True])
+def test_oracle_sc16_converters_match_reference(q11):
+    """convert_sc16_nodc (convert.c:212-250) / convert_sc16q11_nodc (:329-367), magnitudes and the two
+    sequential float accumulators, against the reference's own converters reached through init_converter."""
+    rng = np.random.default_rng(5 + q11)
+    n = 70001
+    lim = 2048 if q11 else 32768
+    iq = rng.integers(-lim, lim, size=2 * n, dtype=np.int32)
+    iq[:64] = [-lim, lim - 1] * 32                       # saturating corner: magsq clamps at 1
+    iq[64:128] = 0
+    iq[128:4000] = rng.integers(-lim // 50, lim // 50, size=3872)   # noise floor
+    iq = iq.astype(np.int16)
+    mag_r, ml_r, mp_r = Reference().convert_sc16(iq, q11)
+    mag_o, sl_o, sp_o = Oracle.convert_sc16(iq, q11)
+    assert np.array_equal(mag_r, mag_o) and mag_o.max() == 65535 and mag_o[32:64].min() == 0
+    assert float(np.float32(sl_o) / np.float32(n)) == ml_r and float(np.float32(sp_o) / np.float32(n)) == mp_r
