@@ -195,6 +195,21 @@ int b200_demod_run_device_uc8_async(b200_demod_ctx *ctx, const uint8_t *d_iq, ui
                                     int64_t first_sample_timestamp);
 int b200_demod_wait(b200_demod_ctx *ctx);
 
+/* Pipelined host-buffer step: what readsb's reader thread / decode thread pair does with its ring of mag_bufs
+ * (sdr_ifile.c:194-259 fills the next buffers while readsb.c:871 demodulates the current one), for all receivers of the
+ * context at once.  h_iq is a HOST slab laid out like submit_iq_uc8_strided's (receiver s at h_iq + s*host_stride_bytes,
+ * n_buffers*buf_len uc8 IQ samples, first_sample_timestamp for every receiver); pin it (b200_demod_host_alloc) or the
+ * copy is synchronous.  The call returns once the step is enqueued: the slab goes to one of two library-owned device
+ * buffers on a copy stream of its own, so the copy of step n+1 overlaps the kernels of step n; the slab may be reused
+ * after the b200_demod_wait() that completes this step.  At most two steps in flight, completed in order by
+ * b200_demod_wait(), results fetched as usual.  `continues` != 0: these samples follow the previous run_host_uc8_async
+ * step's without a gap (its last 326 samples become the halo, sdr_ifile.c:209-213; that step must have held >= 326
+ * samples per receiver); 0: receiver start (zero halo).  buf_len must be a multiple of 8.  This path keeps its own halo:
+ * it does not continue receivers fed through submit_* / run. */
+int b200_demod_run_host_uc8_async(b200_demod_ctx *ctx, const uint8_t *h_iq, uint64_t host_stride_bytes,
+                                  uint32_t n_buffers, uint32_t buf_len, int continues,
+                                  int64_t first_sample_timestamp);
+
 /* results of the last run ---------------------------------------------------------------------- */
 int b200_demod_frame_count(b200_demod_ctx *ctx, uint32_t stream, uint32_t *n);
 int b200_demod_fetch(b200_demod_ctx *ctx, uint32_t stream, b200_frame *out, uint32_t cap, uint32_t *n);

@@ -72,7 +72,7 @@ struct Slot {
 struct b200_demod_ctx {
     b200_demod_config cfg;
     int device = 0, n_sm = 148;
-    cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
     std::string err;
 
     DeviceTables *d_tables = nullptr;
@@ -104,6 +104,12 @@ struct b200_demod_ctx {
     float2 *d_fsum = nullptr, *h_fsum = nullptr;
     uint32_t n_fsum = 0;
     int *d_result = nullptr;
+    // pipelined host-buffer path (run_host_uc8_async): two device input buffers, one per pipeline slot, filled on in_stream
+    uint8_t *d_pipe[2] = {nullptr, nullptr};
+    size_t pipe_stride = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};
+    bool pipe_prev_valid = false;     // the buffer of the previous step holds >= 326 samples per receiver
+    int pipe_prev = 0; size_t pipe_prev_row = 0;
 };
 
 static int fail(b200_demod_ctx *c, int code, const char *fmt, ...) {
@@ -222,6 +228,8 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->res_stream) cudaStreamDestroy(c->res_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->in_stream) cudaStreamDestroy(c->in_stream);
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_pipe[i]); if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); }
     delete c;
 }
 
@@ -252,6 +260,7 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
         CUC(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_hi));
         CUC(cudaStreamCreateWithPriority(&c->res_stream, cudaStreamNonBlocking, prio_lo));
         CUC(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_lo));
+        CUC(cudaStreamCreateWithPriority(&c->in_stream, cudaStreamNonBlocking, prio_lo));
     }
     c->stream = c->own_stream;
 
@@ -687,6 +696,58 @@ API int b200_demod_run_device_uc8_async(b200_demod_ctx *c, const uint8_t *d_iq, 
     int rc = build_device_run(c, sl, a);
     if (rc != B200_OK) return rc;
     Slot &other = c->slot[c->next_async ^ 1];
+    rc = enqueue(c, sl, c->stream, c->res_stream, other.in_flight ? other.d_ctl : nullptr);
+    if (rc != B200_OK) return rc;
+    sl.in_flight = true; sl.completed = false;
+    c->next_async ^= 1;
+    return B200_OK;
+}
+
+// ---- asynchronous host-buffer steps: the device-resident pipeline fed from two library-owned input buffers ----------
+#define PIPE_LEAD 1024        // bytes in front of each receiver's samples: the 326-sample halo sits right before them
+
+API int b200_demod_run_host_uc8_async(b200_demod_ctx *c, const uint8_t *h_iq, uint64_t host_stride, uint32_t n_buffers, uint32_t buf_len,
+                                      int continues, int64_t first_ts) {
+    if (!c || !h_iq) return B200_E_INVAL;
+    CU(c, cudaSetDevice(c->device));
+    const uint32_t S = c->cfg.n_streams, K = c->cfg.max_buffers_per_run, BUF = c->cfg.buf_samples;
+    if (n_buffers == 0 || n_buffers > K || buf_len == 0 || buf_len > BUF || (buf_len & 7)) return fail(c, B200_E_INVAL, "n_buffers/buf_len exceed the context's configuration (buf_len must be a multiple of 8)");
+    const size_t row = (size_t)n_buffers * buf_len * 2;
+    if (host_stride < row && S > 1) return fail(c, B200_E_INVAL, "host_stride_bytes smaller than one stream's data");
+    for (uint32_t s = 0; s < S; s++) if (!c->pending[s].empty()) return fail(c, B200_E_STATE, "buffers submitted for b200_demod_run are pending: run them first");
+    const int pi = c->next_async;
+    Slot &sl = c->slot[pi];
+    if (sl.in_flight) return fail(c, B200_E_STATE, "two steps are already in flight: call b200_demod_wait");
+    if (continues && !c->pipe_prev_valid) return fail(c, B200_E_STATE, "continues != 0 but there is no previous run_host_uc8_async step with >= 326 samples per receiver");
+    if (!sl.allocated) {
+        cudaError_t e = alloc_slot(c, sl, c->slot[0].rec_cap);
+        if (e != cudaSuccess) return fail(c, B200_E_NOMEM, "second pipeline slot: %s", cudaGetErrorString(e));
+    }
+    if (!c->d_pipe[0]) {
+        c->pipe_stride = (PIPE_LEAD + (size_t)K * BUF * 2 + 64 + 255) & ~(size_t)255;
+        for (int i = 0; i < 2; i++) {
+            if (cudaMalloc((void **)&c->d_pipe[i], c->pipe_stride * S + 256) != cudaSuccess) {
+                cudaFree(c->d_pipe[0]); c->d_pipe[0] = c->d_pipe[1] = nullptr;
+                return fail(c, B200_E_NOMEM, "pipelined input buffers (2 x %zu bytes)", c->pipe_stride * S);
+            }
+            CU(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        }
+    }
+    // The slot's previous step (two steps ago) has been collected, so nothing reads d_pipe[pi] any more; the copies of
+    // consecutive steps are ordered on in_stream, which also orders the halo copy after the previous step's samples.
+    uint8_t *dst = c->d_pipe[pi] + PIPE_LEAD;
+    CU(c, cudaMemcpy2DAsync(dst, c->pipe_stride, h_iq, host_stride, row, S, cudaMemcpyHostToDevice, c->in_stream));
+    if (continues)      // the mag_buf overlap copy (sdr_ifile.c:209-213): the previous step's last 326 samples in front of this step's
+        CU(c, cudaMemcpy2DAsync(dst - (size_t)B200_TRAIL * 2, c->pipe_stride,
+                                c->d_pipe[c->pipe_prev] + PIPE_LEAD + c->pipe_prev_row - (size_t)B200_TRAIL * 2, c->pipe_stride,
+                                (size_t)B200_TRAIL * 2, S, cudaMemcpyDeviceToDevice, c->in_stream));
+    CU(c, cudaEventRecord(c->ev_in[pi], c->in_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_in[pi], 0));
+    c->pipe_prev = pi; c->pipe_prev_row = row; c->pipe_prev_valid = row >= (size_t)B200_TRAIL * 2;
+    const DeviceArgs a = {dst, c->pipe_stride, n_buffers, buf_len, continues ? 1 : 0, first_ts};
+    int rc = build_device_run(c, sl, a);
+    if (rc != B200_OK) return rc;
+    Slot &other = c->slot[pi ^ 1];
     rc = enqueue(c, sl, c->stream, c->res_stream, other.in_flight ? other.d_ctl : nullptr);
     if (rc != B200_OK) return rc;
     sl.in_flight = true; sl.completed = false;

@@ -47,6 +47,7 @@ def lib():
         L.b200_demod_run.argtypes = [vp]
         L.b200_demod_run_device_uc8.argtypes = [vp, vp, u64, u32, u32, C.c_int, i64]
         L.b200_demod_run_device_uc8_async.argtypes = [vp, vp, u64, u32, u32, C.c_int, i64]
+        L.b200_demod_run_host_uc8_async.argtypes = [vp, vp, u64, u32, u32, C.c_int, i64]
         L.b200_demod_wait.argtypes = [vp]
         L.b200_demod_frame_count.argtypes = [vp, u32, C.POINTER(u32)]
         L.b200_demod_fetch.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
@@ -74,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
     "b200_demod_fetch_beast", "b200_demod_submit_iq_sc16", "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
     "b200_demod_uc8_lut", "b200_demod_debug_counters", "b200_demod_submit_iq_uc8_strided", "b200_demod_set_stream",
-    "b200_demod_run_device_uc8_async", "b200_demod_wait", "b200_demod_fetch_modeac",
+    "b200_demod_run_device_uc8_async", "b200_demod_wait", "b200_demod_fetch_modeac", "b200_demod_run_host_uc8_async",
 ]
 
 
@@ -170,6 +171,13 @@ class Demodulator:
                          first_sample_timestamp: int):
         self._check(self.L.b200_demod_run_device_uc8_async(self.h, d_ptr, stream_stride_bytes, n_buffers, buf_len,
                                                            1 if continues else 0, first_sample_timestamp))
+
+    def run_host_async(self, h_ptr: int, host_stride_bytes: int, n_buffers: int, buf_len: int, continues: bool,
+                       first_sample_timestamp: int):
+        """Pipelined host-buffer step (reader thread / decode thread overlap of the reference, readsb.c:871 +
+        sdr_ifile.c:194-259): the host slab is copied on a stream of its own while the previous step's kernels run."""
+        self._check(self.L.b200_demod_run_host_uc8_async(self.h, h_ptr, host_stride_bytes, n_buffers, buf_len,
+                                                         1 if continues else 0, first_sample_timestamp))
 
     def wait(self):
         self._check(self.L.b200_demod_wait(self.h))

@@ -201,6 +201,55 @@ def test_async_pipeline_matches_oracle(cuda):
     d.close()
 
 
+def test_host_async_pipeline_matches_oracle(cuda):
+    """run_host_uc8_async / wait: pinned host slabs, the copy of step n+1 overlapping the kernels of step n; halo carried
+    between the two library-owned input buffers; unpinned memory and a restart (continues=0) in the middle."""
+    from readsb_b200.demod import DemodError, Demodulator, PinnedBuffer
+    S, buf, nb, calls = 3, 32768, 2, 6
+    total = buf * nb * calls
+    iqs = [GENS[["cfg5", "mixed", "cfg2"][s]](800 + s, total) for s in range(S)]
+    pin = PinnedBuffer(S * 2 * total)
+    host = pin.array.reshape(S, 2 * total)
+    for s in range(S):
+        host[s] = iqs[s]
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=nb)
+    with pytest.raises(DemodError):      # nothing to continue from yet
+        d.run_host_async(pin.ptr, 2 * total, nb, buf, True, 0)
+    got = [[] for _ in range(S)]; gotb = [[] for _ in range(S)]
+
+    def collect():
+        d.wait()
+        for s in range(S):
+            got[s].append(d.frames(s)); gotb[s].append(d.buffer_results(s))
+    for c in range(calls):
+        d.run_host_async(pin.ptr + c * nb * buf * 2, 2 * total, nb, buf, c > 0, c * nb * buf * 5)
+        if c >= 1:
+            collect()
+    collect()
+    for s in range(S):
+        o = Oracle()
+        fo, bo = o.run_stream(iqs[s], buf)
+        _check(d, o, np.concatenate(got[s]), np.concatenate(gotb[s]), fo, bo, stream=s)
+    d.close()
+    # ordinary (pageable) memory, a partial last step, and a receiver restart: three steps, the third starts over
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=nb)
+    plain = np.ascontiguousarray(host.copy())
+    got = [[] for _ in range(S)]; gotb = [[] for _ in range(S)]
+    d.run_host_async(plain.ctypes.data, 2 * total, nb, buf, False, 0)
+    d.run_host_async(plain.ctypes.data + nb * buf * 2, 2 * total, 1, buf - 4096, True, nb * buf * 5)
+    collect(); collect()
+    restart_ts = (nb * buf + buf - 4096) * 5 + 12_000_000     # the receiver comes back a second later
+    d.run_host_async(plain.ctypes.data, 2 * total, nb, buf, False, restart_ts)
+    collect()
+    for s in range(S):
+        o = Oracle()
+        fo1, bo1 = o.run_stream(iqs[s][: 2 * (nb * buf + buf - 4096)], buf)
+        fo2, bo2 = o.run_stream(iqs[s][: 2 * nb * buf], buf, first_ts=restart_ts)
+        _check(d, o, np.concatenate(got[s]), np.concatenate(gotb[s]), np.concatenate([fo1, fo2]), np.concatenate([bo1, bo2]), stream=s)
+    d.close()
+    pin.free()
+
+
 def test_async_pipeline_repeats_steps_exactly_after_a_pool_failure(cuda):
     """A dense capture makes the FIRST pipelined step ask for the scratch arena while the second is already in flight:
     both must be repeated in order and stay bit-exact (stage B of the second must not have run on stale state)."""
