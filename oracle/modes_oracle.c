@@ -476,6 +476,9 @@ int oracle_demodulate2400AC(oracle_ctx *o, const uint16_t *m, unsigned mlen, int
 }
 
 /* ------------------------------------------------------------------ sdr_ifile.c:169-259 */
+/* The receiver starts over (a frontend reopened): the next buffer's halo is zeros, like the first one of a stream. */
+void oracle_stream_restart(oracle_ctx *o) { o->halo_valid = 0; }
+
 long oracle_run_stream_uc8(oracle_ctx *o, const uint8_t *iq, uint64_t nsamples, unsigned buf_samples,
                            int64_t first_ts, b200_frame *frames, unsigned frame_cap,
                            b200_buffer_result *bufres, unsigned bufres_cap, unsigned *n_bufres) {

@@ -54,6 +54,9 @@ long oracle_run_stream_uc8(oracle_ctx *o, const uint8_t *iq, uint64_t nsamples, 
                            int64_t first_ts, b200_frame *frames, unsigned frame_cap,
                            b200_buffer_result *bufres, unsigned bufres_cap, unsigned *n_bufres);
 
+/* The halo kept between oracle_run_stream_uc8 calls is dropped: the next call starts like a fresh stream (zero halo). */
+void oracle_stream_restart(oracle_ctx *o);
+
 /* demod_2400.c:575-761 for one mag_buf (needs the converter's sums for mean_level / mean_power).  Appends to out. */
 int oracle_demodulate2400AC(oracle_ctx *o, const uint16_t *data, unsigned length, int64_t sample_timestamp,
                             uint64_t sum_level, uint64_t sum_power, b200_modeac *out, unsigned cap, unsigned *n_out);

@@ -41,7 +41,8 @@ __device__ __forceinline__ bool gen_add(uint32_t *g, uint32_t *count, uint32_t a
     return true;
 }
 
-#define RS_WARPS 8            // warps per receiver: buffers of one receiver are resolved speculatively in parallel, eight at a time
+#define RS_WARPS 8            // warps per receiver: buffers of one receiver are resolved speculatively in parallel, eight at a time.
+                              // 128 registers per thread: two CTAs per SM, so 256 receivers are one wave on 148 SMs
 #define RS_STAGE 384          // PosEntry / score keys of one quad staged in shared memory (denser quads are read in place)
 #define RS_RING  2            // staging buffers per warp: the current quad plus one in flight
 #define NEW_CAP  24           // addresses one buffer may learn in deferred mode before it has to be redone in direct mode
@@ -312,7 +313,7 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
 // changed the filter's membership: then its adds are applied and its frames moved into place.  Otherwise it is resolved
 // again, directly, with the filter as the reference would have it at that point.  In steady state (aircraft already
 // known, no flip) every speculation holds; the results are the sequential ones by construction either way.
-__global__ void __launch_bounds__(RS_WARPS * 32, 1) resolve_kernel(const ResolveParams P) {
+__global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const ResolveParams P) {
     extern __shared__ uint4 resolve_smem_raw[];
     ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
     __shared__ uint32_t s_active, s_gcount[2], s_err;

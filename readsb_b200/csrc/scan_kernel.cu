@@ -28,7 +28,6 @@
 #include "device_utils.cuh"
 
 #define SC_WARPS 28
-#define SC_THREADS (SC_WARPS * 32)
 #define CHUNK 512
 #define TILE_CHUNKS (SCAN_TILE / CHUNK)       // 4 chunks of positions per tile
 #define RUN_MAX 8                             // a warp takes runs of up to 8 consecutive tiles of one segment (guided self-scheduling)
@@ -69,14 +68,18 @@ struct WarpSmem {
     RunCtx ctx;
 };
 
-struct ScanSmem {
+struct ScanSmem {                             // the read-only tables every warp of the CTA shares
     uint16_t lut[128 * 128];                  // folded, bank-swizzled UC8 magnitude table
     uint32_t crc_tab[256];
     uint32_t bit_syn[112];
     uint32_t syn_hash[512];
     uint32_t syn_mul;
     uint32_t pad_[3];
-    WarpSmem w[SC_WARPS];
+};
+
+template <int NW> struct ScanSmemFull {
+    ScanSmem t;
+    WarpSmem w[NW];
 };
 
 // mixed-sign two-way dot products: a = two unsigned 16-bit magnitudes, b = four signed 8-bit coefficients
@@ -232,7 +235,7 @@ __device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint3
 #pragma unroll
         for (int i = 0; i < 16; i++) { v[2 * i] = wv[i] & 0xffffu; v[2 * i + 1] = wv[i] >> 16; }
 #pragma unroll
-        for (int i = 0; i < 16; i++)
+        for (int i = 0; i < 16; i++)      // (ptxas turns a hand-chained setp / predicated-or version of this into the same 3 ISETP + VIADD + 2 SEL)
             if (v[i + 1] > v[i + 7] && v[i + 12] > v[i + 14] && v[i + 12] > v[i + 15]) mask |= 1u << i;
     }
     // tick map: sample i needs the pairs (m[i], m[i+1]) and (m[i+2], m[i+3]); odd i takes them from the 16-bit-shifted words
@@ -452,9 +455,11 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
     }
 }
 
-__global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
+template <int NW> __global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
+    constexpr uint32_t SC_THREADS = NW * 32;
     extern __shared__ uint4 smem_raw[];
-    ScanSmem &S = *reinterpret_cast<ScanSmem *>(smem_raw);
+    ScanSmemFull<NW> &F = *reinterpret_cast<ScanSmemFull<NW> *>(smem_raw);
+    ScanSmem &S = F.t;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     {   // one-time table staging (persistent CTA)
@@ -468,9 +473,9 @@ __global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTabl
     }
     __syncthreads();      // the only block barrier: from here on every warp is on its own
 
-    WarpSmem &W = S.w[wid];
+    WarpSmem &W = F.w[wid];
     RunCtx &T = W.ctx;
-    const uint32_t warp_global = blockIdx.x * SC_WARPS + wid;
+    const uint32_t warp_global = blockIdx.x * NW + wid;
 
     uint32_t pend_tile = 0, pend_n = 0;       // tiles already claimed but not processed yet (a claim that crossed a segment boundary)
     for (;;) {
@@ -480,7 +485,7 @@ __global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTabl
             if (lane == 0) {
                 const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&P.ctl->tile_counter);
                 if (cur < P.n_tiles) {
-                    n = min(max((P.n_tiles - cur) / (2u * gridDim.x * SC_WARPS), 1u), (uint32_t)RUN_MAX);
+                    n = min(max((P.n_tiles - cur + gridDim.x * NW - 1u) / (gridDim.x * NW), 1u), (uint32_t)RUN_MAX);   // ceil(remaining / warps): single tiles only for the last round
                     start = atomicAdd(&P.ctl->tile_counter, n);
                     if (start >= P.n_tiles) n = 0; else n = min(n, P.n_tiles - start);
                 }
@@ -614,17 +619,21 @@ __global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTabl
 extern "C" int b200_scan_warps(int n_sm) { return n_sm * SC_WARPS; }
 extern "C" int b200_scan_tick_words(void) { return TICKG_WORDS; }
 
-extern "C" int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream) {
+template <int NW> static int launch_scan_t(const ScanParams *p, const DeviceTables *d_tables, int n_sm, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem));
+        cudaError_t e = cudaFuncSetAttribute(scan_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemFull<NW>));
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    if (!p->n_tiles) return 0;
     uint32_t grid = (uint32_t)n_sm;
-    const uint32_t need = (p->n_tiles + SC_WARPS - 1) / SC_WARPS;
+    const uint32_t need = (p->n_tiles + NW - 1) / NW;
     if (grid > need) grid = need;
-    scan_kernel<<<grid, SC_THREADS, sizeof(ScanSmem), (cudaStream_t)stream>>>(*p, d_tables);
+    scan_kernel<NW><<<grid, NW * 32, sizeof(ScanSmemFull<NW>), stream>>>(*p, d_tables);
     return (int)cudaGetLastError();
+}
+
+extern "C" int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream) {
+    if (!p->n_tiles) return 0;
+    return launch_scan_t<SC_WARPS>(p, d_tables, n_sm, (cudaStream_t)stream);
 }

@@ -116,6 +116,11 @@ class Oracle:
         assert n >= 0, "oracle frame capacity exceeded"
         return frames[:n].copy(), bufres[: nb.value].copy()
 
+    def restart_stream(self):
+        """The next run_stream call starts with a zero halo (a receiver that was reopened); filter and statistics stay."""
+        self.L.oracle_stream_restart.argtypes = [C.c_void_p]
+        self.L.oracle_stream_restart(self.h)
+
     def demodulate_ac(self, data: np.ndarray, length: int, sample_ts: int, sum_level: int, sum_power: int, cap=4096):
         out = np.zeros(cap, dtype=MODEAC_DTYPE)
         n = C.c_uint(0)

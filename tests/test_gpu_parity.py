@@ -244,6 +244,7 @@ def test_host_async_pipeline_matches_oracle(cuda):
     for s in range(S):
         o = Oracle()
         fo1, bo1 = o.run_stream(iqs[s][: 2 * (nb * buf + buf - 4096)], buf)
+        o.restart_stream()
         fo2, bo2 = o.run_stream(iqs[s][: 2 * nb * buf], buf, first_ts=restart_ts)
         _check(d, o, np.concatenate(got[s]), np.concatenate(gotb[s]), np.concatenate([fo1, fo2]), np.concatenate([bo1, bo2]), stream=s)
     d.close()
