@@ -36,6 +36,7 @@ sys.path.insert(0, str(ROOT))
 BUF = 65536                      # samples per reference buffer: 128 KiB of uint16 magnitudes
 ALG_BYTES_PER_SAMPLE = 2         # uc8 I + Q, read once
 REF_PASSES = 16                  # reference arm: passes over its bounded sample per step
+PIPE_DEPTH = 3                   # asynchronous steps in flight (the library allows three)
 
 
 def parse_args():
@@ -170,7 +171,7 @@ def workload_config(args, n_gpus):
             "buffers_per_stream_per_step": args.buffers, "buf_samples": BUF, "sample_rate_hz": 2400000,
             "samples_per_step_per_gpu": args.streams * args.buffers * BUF,
             "parallelism": f"{n_gpus} independent GPU(s), streams sharded {args.streams}/GPU, no collective",
-            "pipelining": "value: two steps in flight per GPU (run_device_uc8_async/wait); e2e: two steps in flight (run_host_uc8_async/wait: pinned host slab -> H2D on the library's copy stream, overlapping the previous step's kernels); all results collected on the host inside the timed region",
+            "pipelining": f"value: {PIPE_DEPTH} steps in flight per GPU (run_device_uc8_async/wait); e2e: {PIPE_DEPTH} steps in flight (run_host_uc8_async/wait: pinned host slab -> H2D on the library's copy stream, overlapping the previous steps' kernels); all results collected on the host inside the timed region",
             "l2": f"device inputs cycle through a ring of {args.ring} distinct steps "
                   f"({args.ring * args.streams * args.buffers * BUF * 2 / 2**20:.0f} MiB per GPU, L2 is 126 MB); each step reads bytes not touched for {args.ring - 1} steps"}
 
@@ -334,8 +335,8 @@ def b200_arm(args, rank, world, local):
 
     def timed(fn, steps, k0, pipelined=False):
         """Times `steps` steps with CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
-        pipelined: device-resident steps go through run_device_async/wait with two steps in flight (stage A of step
-        n+1 overlaps stage B of step n); every step's results are still collected inside the timed region."""
+        pipelined: steps go through run_*_async/wait with PIPE_DEPTH steps in flight (the GPU never waits for the host between
+        steps); every step's results are still collected on the host inside the timed region."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = {"scan_ms": 0.0, "launches": 0, "frames": 0}
 
@@ -344,15 +345,17 @@ def b200_arm(args, rank, world, local):
             acc["scan_ms"] += t["scan_ms"]; acc["launches"] += t["launches"]; acc["frames"] += d.total_frames()
         barrier()
         ev0.record()
+        flying = 0
         for k in range(k0, k0 + steps):
             fn(k)
             if pipelined:
-                if k > k0:
-                    d.wait(); harvest()
+                flying += 1
+                if flying == PIPE_DEPTH:
+                    d.wait(); harvest(); flying -= 1
             else:
                 harvest()
-        if pipelined:
-            d.wait(); harvest()
+        while flying:
+            d.wait(); harvest(); flying -= 1
         ev1.record()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)

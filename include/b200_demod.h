@@ -186,9 +186,10 @@ int b200_demod_run_device_uc8(b200_demod_ctx *ctx, const uint8_t *d_iq, uint64_t
                               uint32_t n_buffers, uint32_t buf_len, int continues,
                               int64_t first_sample_timestamp);
 
-/* Asynchronous form of the call above: returns once the step is enqueued; at most two steps may be in flight.
+/* Asynchronous form of the call above: returns once the step is enqueued; at most three steps may be in flight.
  * b200_demod_wait() completes the OLDEST step in flight and makes its results current for the fetch calls below.
- * Stage A of step n+1 overlaps stage B of step n on the GPU; per-receiver state still advances strictly in step order.
+ * The GPU never waits for the host between steps: the scan of step n+1 is queued behind the scan of step n, stage B of
+ * step n runs as soon as its scan ends; per-receiver state still advances strictly in step order.
  * The host-buffer calls, get_stats and the icao_* calls need an empty pipeline. */
 int b200_demod_run_device_uc8_async(b200_demod_ctx *ctx, const uint8_t *d_iq, uint64_t stream_stride_bytes,
                                     uint32_t n_buffers, uint32_t buf_len, int continues,
@@ -199,9 +200,9 @@ int b200_demod_wait(b200_demod_ctx *ctx);
  * (sdr_ifile.c:194-259 fills the next buffers while readsb.c:871 demodulates the current one), for all receivers of the
  * context at once.  h_iq is a HOST slab laid out like submit_iq_uc8_strided's (receiver s at h_iq + s*host_stride_bytes,
  * n_buffers*buf_len uc8 IQ samples, first_sample_timestamp for every receiver); pin it (b200_demod_host_alloc) or the
- * copy is synchronous.  The call returns once the step is enqueued: the slab goes to one of two library-owned device
- * buffers on a copy stream of its own, so the copy of step n+1 overlaps the kernels of step n; the slab may be reused
- * after the b200_demod_wait() that completes this step.  At most two steps in flight, completed in order by
+ * copy is synchronous.  The call returns once the step is enqueued: the slab goes to one of three library-owned device
+ * buffers on a copy stream of its own, so the copies of later steps overlap the kernels of earlier ones; the slab may be reused
+ * after the b200_demod_wait() that completes this step.  At most three steps in flight, completed in order by
  * b200_demod_wait(), results fetched as usual.  `continues` != 0: these samples follow the previous run_host_uc8_async
  * step's without a gap (its last 326 samples become the halo, sdr_ifile.c:209-213; that step must have held >= 326
  * samples per receiver); 0: receiver start (zero halo).  buf_len must be a multiple of 8.  This path keeps its own halo:

@@ -6,9 +6,10 @@
 // demodulate2400(buf) (readsb.c:871, demod_2400.h:38) becomes submit_mag_u16 / run / fetch.
 //
 // A run owns one SLOT (segment tables, candidate pools, result buffers).  The blocking calls use slot 0 on one
-// CUDA stream.  The asynchronous device-resident pair (run_device_uc8_async / wait) alternates two slots: stage A
-// of step n+1 (scan stream) overlaps stage B + finalize + D2H of step n (resolve stream); stage B kernels stay
-// ordered among themselves, which is all the per-receiver state needs.
+// CUDA stream.  The asynchronous calls (run_device_uc8_async / run_host_uc8_async / wait) cycle through NSLOT slots: the
+// scan kernels of consecutive steps run back to back on the scan stream, stage B + finalize + D2H of each step follow
+// on the resolve stream (higher priority) as soon as its scan has ended; stage B kernels stay ordered among themselves,
+// which is all the per-receiver state needs.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -69,6 +70,8 @@ struct Slot {
     uint32_t launches = 0;
 };
 
+#define NSLOT 3      // steps in flight in the asynchronous modes; the blocking calls use slot 0
+
 struct b200_demod_ctx {
     b200_demod_config cfg;
     int device = 0, n_sm = 148;
@@ -87,9 +90,10 @@ struct b200_demod_ctx {
     std::vector<size_t> cursor;       // append offset in the stream's arena region
 
     uint32_t seg_cap = 0, tile_cap = 0, buf_cap = 0, frame_cap = 0, ac_cap = 0;
-    Slot slot[2];
+    Slot slot[NSLOT];
     int cur = 0;                      // slot whose results fetch / buffer_results / timing report
     int next_async = 0;               // slot the next asynchronous step takes
+    int head = 0, n_flight = 0;       // oldest step in flight, number of steps in flight (slots head, head+1, ... mod NSLOT)
     uint32_t *d_carry_src = nullptr, *h_carry_src = nullptr;
     // scan kernel: per-warp staging of a run's live records, spill of the pre-check queue, ticks of the run in progress
     Rec *d_stage_rec = nullptr; uint32_t *d_stage_key = nullptr; uint16_t *d_q1_over = nullptr; uint32_t *d_tick_scratch = nullptr;
@@ -105,9 +109,9 @@ struct b200_demod_ctx {
     uint32_t n_fsum = 0;
     int *d_result = nullptr;
     // pipelined host-buffer path (run_host_uc8_async): two device input buffers, one per pipeline slot, filled on in_stream
-    uint8_t *d_pipe[2] = {nullptr, nullptr};
+    uint8_t *d_pipe[NSLOT] = {};
     size_t pipe_stride = 0;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[NSLOT] = {};
     bool pipe_prev_valid = false;     // the buffer of the previous step holds >= 326 samples per receiver
     int pipe_prev = 0; size_t pipe_prev_row = 0;
 };
@@ -224,12 +228,12 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     cudaFreeHost(c->h_carry_src);
     cudaFree(c->d_raw16); cudaFree(c->d_fsum); cudaFreeHost(c->h_fsum);
     cudaFree(c->d_beast); cudaFree(c->d_beast_meta); cudaFreeHost(c->h_beast); cudaFreeHost(c->h_beast_meta);
-    free_slot(c->slot[0]); free_slot(c->slot[1]);
+    for (Slot &sl : c->slot) free_slot(sl);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->res_stream) cudaStreamDestroy(c->res_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->in_stream) cudaStreamDestroy(c->in_stream);
-    for (int i = 0; i < 2; i++) { cudaFree(c->d_pipe[i]); if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); }
+    for (int i = 0; i < NSLOT; i++) { cudaFree(c->d_pipe[i]); if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); }
     delete c;
 }
 
@@ -253,12 +257,14 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     CUC(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
-    {   // Stage A (persistent, one CTA per SM) is placed first, stage B's small CTAs fill what it leaves free: when both become
-        // ready at the same moment the block scheduler follows stream priority.
+    {   // With several steps in flight the scan kernels of later steps are already queued when a scan ends; stage B of the step
+        // that just finished scanning must not wait behind them (its results gate the host), so its stream has the higher
+        // priority: the block scheduler places stage B's CTAs first, the next scan's persistent CTAs follow as SMs drain, and
+        // the small finalize CTAs fit next to them.
         int prio_lo = 0, prio_hi = 0;
         CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUC(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_hi));
-        CUC(cudaStreamCreateWithPriority(&c->res_stream, cudaStreamNonBlocking, prio_lo));
+        CUC(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_lo));
+        CUC(cudaStreamCreateWithPriority(&c->res_stream, cudaStreamNonBlocking, prio_hi));
         CUC(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_lo));
         CUC(cudaStreamCreateWithPriority(&c->in_stream, cudaStreamNonBlocking, prio_lo));
     }
@@ -311,7 +317,7 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     return B200_OK;
 }
 
-static bool any_in_flight(const b200_demod_ctx *c) { return c->slot[0].in_flight || c->slot[1].in_flight; }
+static bool any_in_flight(const b200_demod_ctx *c) { return c->n_flight > 0; }
 
 // ---- submits ---------------------------------------------------------------------------------
 static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32_t n, int64_t ts, bool mag) {
@@ -681,26 +687,33 @@ API int b200_demod_run_device_uc8(b200_demod_ctx *c, const uint8_t *d_iq, uint64
     return execute_blocking(c, sl);
 }
 
-// ---- asynchronous device-resident steps: at most two in flight ---------------------------------------------------
+// ---- asynchronous steps: at most NSLOT in flight ------------------------------------------------------------------------
+// Enqueues the run built in slot next_async behind the steps already in flight and advances the ring.
+static int launch_async(b200_demod_ctx *c, Slot &sl) {
+    Slot &before = c->slot[(c->next_async + NSLOT - 1) % NSLOT];      // the step enqueued just before this one
+    int rc = enqueue(c, sl, c->stream, c->res_stream, before.in_flight ? before.d_ctl : nullptr);
+    if (rc != B200_OK) return rc;
+    if (c->n_flight == 0) c->head = c->next_async;
+    sl.in_flight = true; sl.completed = false;
+    c->next_async = (c->next_async + 1) % NSLOT;
+    c->n_flight++;
+    return B200_OK;
+}
+
 API int b200_demod_run_device_uc8_async(b200_demod_ctx *c, const uint8_t *d_iq, uint64_t stride, uint32_t n_buffers, uint32_t buf_len,
                                         int continues, int64_t first_ts) {
     if (!c || !d_iq) return B200_E_INVAL;
     CU(c, cudaSetDevice(c->device));
     Slot &sl = c->slot[c->next_async];
-    if (sl.in_flight) return fail(c, B200_E_STATE, "two steps are already in flight: call b200_demod_wait");
+    if (sl.in_flight) return fail(c, B200_E_STATE, "%d steps are already in flight: call b200_demod_wait", NSLOT);
     if (!sl.allocated) {
         cudaError_t e = alloc_slot(c, sl, c->slot[0].rec_cap);
-        if (e != cudaSuccess) return fail(c, B200_E_NOMEM, "second pipeline slot: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail(c, B200_E_NOMEM, "pipeline slot %d: %s", c->next_async, cudaGetErrorString(e));
     }
     const DeviceArgs a = {d_iq, stride, n_buffers, buf_len, continues, first_ts};
     int rc = build_device_run(c, sl, a);
     if (rc != B200_OK) return rc;
-    Slot &other = c->slot[c->next_async ^ 1];
-    rc = enqueue(c, sl, c->stream, c->res_stream, other.in_flight ? other.d_ctl : nullptr);
-    if (rc != B200_OK) return rc;
-    sl.in_flight = true; sl.completed = false;
-    c->next_async ^= 1;
-    return B200_OK;
+    return launch_async(c, sl);
 }
 
 // ---- asynchronous host-buffer steps: the device-resident pipeline fed from two library-owned input buffers ----------
@@ -717,23 +730,23 @@ API int b200_demod_run_host_uc8_async(b200_demod_ctx *c, const uint8_t *h_iq, ui
     for (uint32_t s = 0; s < S; s++) if (!c->pending[s].empty()) return fail(c, B200_E_STATE, "buffers submitted for b200_demod_run are pending: run them first");
     const int pi = c->next_async;
     Slot &sl = c->slot[pi];
-    if (sl.in_flight) return fail(c, B200_E_STATE, "two steps are already in flight: call b200_demod_wait");
+    if (sl.in_flight) return fail(c, B200_E_STATE, "%d steps are already in flight: call b200_demod_wait", NSLOT);
     if (continues && !c->pipe_prev_valid) return fail(c, B200_E_STATE, "continues != 0 but there is no previous run_host_uc8_async step with >= 326 samples per receiver");
     if (!sl.allocated) {
         cudaError_t e = alloc_slot(c, sl, c->slot[0].rec_cap);
-        if (e != cudaSuccess) return fail(c, B200_E_NOMEM, "second pipeline slot: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail(c, B200_E_NOMEM, "pipeline slot %d: %s", pi, cudaGetErrorString(e));
     }
     if (!c->d_pipe[0]) {
         c->pipe_stride = (PIPE_LEAD + (size_t)K * BUF * 2 + 64 + 255) & ~(size_t)255;
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < NSLOT; i++) {
             if (cudaMalloc((void **)&c->d_pipe[i], c->pipe_stride * S + 256) != cudaSuccess) {
-                cudaFree(c->d_pipe[0]); c->d_pipe[0] = c->d_pipe[1] = nullptr;
-                return fail(c, B200_E_NOMEM, "pipelined input buffers (2 x %zu bytes)", c->pipe_stride * S);
+                for (int j = 0; j < i; j++) { cudaFree(c->d_pipe[j]); c->d_pipe[j] = nullptr; }
+                return fail(c, B200_E_NOMEM, "pipelined input buffers (%d x %zu bytes)", NSLOT, c->pipe_stride * S);
             }
             CU(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         }
     }
-    // The slot's previous step (two steps ago) has been collected, so nothing reads d_pipe[pi] any more; the copies of
+    // The slot's previous step (NSLOT steps ago) has been collected, so nothing reads d_pipe[pi] any more; the copies of
     // consecutive steps are ordered on in_stream, which also orders the halo copy after the previous step's samples.
     uint8_t *dst = c->d_pipe[pi] + PIPE_LEAD;
     CU(c, cudaMemcpy2DAsync(dst, c->pipe_stride, h_iq, host_stride, row, S, cudaMemcpyHostToDevice, c->in_stream));
@@ -747,40 +760,37 @@ API int b200_demod_run_host_uc8_async(b200_demod_ctx *c, const uint8_t *h_iq, ui
     const DeviceArgs a = {dst, c->pipe_stride, n_buffers, buf_len, continues ? 1 : 0, first_ts};
     int rc = build_device_run(c, sl, a);
     if (rc != B200_OK) return rc;
-    Slot &other = c->slot[pi ^ 1];
-    rc = enqueue(c, sl, c->stream, c->res_stream, other.in_flight ? other.d_ctl : nullptr);
-    if (rc != B200_OK) return rc;
-    sl.in_flight = true; sl.completed = false;
-    c->next_async ^= 1;
-    return B200_OK;
+    return launch_async(c, sl);
 }
 
 API int b200_demod_wait(b200_demod_ctx *c) {
     if (!c) return B200_E_INVAL;
     CU(c, cudaSetDevice(c->device));
-    // the oldest step in flight is the one in the slot the next submit would NOT take, if both are busy
-    int idx = c->next_async;
-    if (!c->slot[idx].in_flight) idx ^= 1;
+    if (c->n_flight == 0) return fail(c, B200_E_STATE, "no asynchronous step in flight");
+    const int idx = c->head;                 // the oldest step in flight
     Slot &sl = c->slot[idx];
-    if (!sl.in_flight) return fail(c, B200_E_STATE, "no asynchronous step in flight");
     c->cur = idx;
-    if (sl.completed) { sl.in_flight = false; return B200_OK; }     // already repeated synchronously (see below)
-    int rc = collect(c, sl, c->res_stream);
-    if (rc > 0) {
-        // This step (and therefore the one behind it, which saw our failure flag and skipped its stage B) must be
-        // repeated.  Drain the pipeline and redo both, in order, synchronously.
-        Slot &next = c->slot[idx ^ 1];
-        if (next.in_flight) CU(c, cudaEventSynchronize(next.ev[4]));
-        CU(c, cudaStreamSynchronize(c->stream));
-        CU(c, cudaStreamSynchronize(c->res_stream));
-        rc = regrow(c, sl, rc);
-        if (rc == B200_OK) rc = execute_blocking(c, sl);
-        if (rc == B200_OK && next.in_flight) {
-            int rc2 = execute_blocking(c, next);
-            if (rc2 != B200_OK) rc = rc2; else next.completed = true;
+    int rc = B200_OK;
+    if (!sl.completed) {                     // (completed: already repeated synchronously, see below)
+        rc = collect(c, sl, c->res_stream);
+        if (rc > 0) {
+            // This step (and therefore the ones behind it, which saw the failure flag of the step ahead and skipped their
+            // stage B) must be repeated.  Drain the pipeline and redo all of them, in order, synchronously.
+            for (int k = 1; k < c->n_flight; k++) CU(c, cudaEventSynchronize(c->slot[(idx + k) % NSLOT].ev[4]));
+            CU(c, cudaStreamSynchronize(c->stream));
+            CU(c, cudaStreamSynchronize(c->res_stream));
+            rc = regrow(c, sl, rc);
+            if (rc == B200_OK) rc = execute_blocking(c, sl);
+            for (int k = 1; k < c->n_flight && rc == B200_OK; k++) {
+                Slot &next = c->slot[(idx + k) % NSLOT];
+                rc = execute_blocking(c, next);
+                if (rc == B200_OK) next.completed = true;
+            }
         }
     }
     sl.in_flight = false;
+    c->head = (idx + 1) % NSLOT;
+    c->n_flight--;
     return rc;
 }
 

@@ -175,10 +175,12 @@ def _device_streams(iqs, total, pad=1024):
     return dev, stride, pad
 
 
-def test_async_pipeline_matches_oracle(cuda):
-    """run_device_uc8_async / wait: two steps in flight, stage A of step n+1 overlapping stage B of step n."""
-    from readsb_b200.demod import Demodulator
-    S, buf, nb, calls = 4, 65536, 2, 5
+@pytest.mark.parametrize("depth", [2, 3])
+def test_async_pipeline_matches_oracle(cuda, depth):
+    """run_device_uc8_async / wait: two or three steps in flight (scans back to back, stage B of each step behind its scan);
+    a fourth step is refused until the oldest one has been waited for."""
+    from readsb_b200.demod import DemodError, Demodulator
+    S, buf, nb, calls = 4, 65536, 2, 6
     total = buf * nb * calls
     iqs = [GENS[["cfg5", "mixed", "cfg2", "mixed"][s]](700 + s, total) for s in range(S)]
     dev, stride, pad = _device_streams(iqs, total)
@@ -189,11 +191,19 @@ def test_async_pipeline_matches_oracle(cuda):
         d.wait()
         for s in range(S):
             got[s].append(d.frames(s)); gotb[s].append(d.buffer_results(s))
+    flying = 0
     for c in range(calls):
         d.run_device_async(dev.data_ptr() + pad + c * nb * buf * 2, stride, nb, buf, continues=c > 0, first_sample_timestamp=c * nb * buf * 5)
-        if c >= 1:
-            collect()
-    collect()
+        flying += 1
+        if depth == 3 and flying == 3:
+            with pytest.raises(DemodError):
+                d.run_device_async(dev.data_ptr() + pad, stride, nb, buf, continues=False, first_sample_timestamp=0)
+        if flying == depth:
+            collect(); flying -= 1
+    while flying:
+        collect(); flying -= 1
+    with pytest.raises(DemodError):
+        d.wait()
     for s in range(S):
         o = Oracle()
         fo, bo = o.run_stream(iqs[s], buf)
@@ -255,7 +265,7 @@ def test_async_pipeline_repeats_steps_exactly_after_a_pool_failure(cuda):
     """A dense capture makes the FIRST pipelined step ask for the scratch arena while the second is already in flight:
     both must be repeated in order and stay bit-exact (stage B of the second must not have run on stale state)."""
     from readsb_b200.demod import Demodulator
-    buf, nb, calls = 32768, 1, 4
+    buf, nb, calls = 32768, 1, 5
     total = buf * nb * calls
     storm = synth.generate(total, seed=8, frames_per_sec=40000, df_mask=synth.DF17 | synth.DF11 | synth.AP, n_icao=4,
                            amp=(0.3, 0.9), p_bit_error=0.3)
@@ -265,9 +275,10 @@ def test_async_pipeline_repeats_steps_exactly_after_a_pool_failure(cuda):
     got, gotb, gota = [], [], []
     for c in range(calls):
         d.run_device_async(dev.data_ptr() + pad + c * nb * buf * 2, stride, nb, buf, continues=c > 0, first_sample_timestamp=c * nb * buf * 5)
-        if c >= 1:
+        if c >= 2:       # three steps in flight when the first one reports its failure: all three are repeated in order
             d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0)); gota.append(d.modeac(0))
-    d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0)); gota.append(d.modeac(0))
+    for _ in range(2):
+        d.wait(); got.append(d.frames(0)); gotb.append(d.buffer_results(0)); gota.append(d.modeac(0))
     _check(d, o, np.concatenate(got), np.concatenate(gotb), fo, bo)
     ao = Oracle(40).run_stream_ac(storm, buf)          # the repeated steps must not count their Mode A/C replies twice
     ag = np.concatenate(gota)
