@@ -6,9 +6,9 @@
 // (16 per lane) through a private shared-memory pipeline:
 //
 //     iteration k:   window(k)        pre-check of the chunk's 512 positions + the TICK MAP of its 512 samples
-//                    load(k+2)        16-byte HBM loads into registers, in flight during ...
+//                    stage(k+2)       cp.async of the chunk's 1 KB of input into the warp's staging area, in flight during ...
 //                    candidates(k-1)  thresholds -> DF gate -> full slice + CRC + classification -> ordered emission
-//                    convert(k+2)     magnitudes through the folded table into the ring, exact per-buffer sums
+//                    convert(k+2)     staged bytes -> magnitudes through the folded table into the ring, exact per-buffer sums
 //
 // window(k) needs the first samples of chunk k+1, candidates(k-1) need ticks up to 310 samples ahead (chunk k) and
 // magnitudes 18 ahead: a ring of three magnitude chunks and two tick chunks per warp (4.8 KB) holds exactly that.  The
@@ -59,6 +59,7 @@ struct RunCtx {
 
 struct WarpSmem {
     alignas(16) uint16_t mag[MAG_RING + MAG_MIRROR];
+    alignas(16) uint8_t raw[2 * CHUNK];       // the next chunk's input bytes, landed here by cp.async while the candidates are worked on
     uint32_t tick[TICK_RING + TICK_MIRROR];   // tick of sample s (chunk-local) and row r at bit 5 s + r of the chunk's slot
     uint16_t q1[Q1_SMEM];                     // pre-check passers of the previous chunk (tile-relative positions, ascending)
     uint32_t pass[32];                        // current batch of threshold passers, PosEntry format
@@ -275,15 +276,25 @@ __device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint3
     return mask;
 }
 
-// One chunk's samples, two 16-byte pieces per lane (samples 256 r + 8 lane .. + 8), only where the segment has data.
-// Holding the loaded words in registers across the candidate work costs more registers than the kernel has (they spill, and
-// the spill store waits for the load), so the chunk is PREFETCHED into L2 two iterations ahead and loaded when it is converted
-// (L1 is down to 28 KB per SM with this kernel's shared memory and stage B's next to it: an L1 prefetch does not survive).
-__device__ __forceinline__ void prefetch_raw(const RunCtx &T, uint32_t c, uint32_t lane, bool all_data) {
+// One chunk's samples, two 16-byte pieces per lane (samples 256 r + 8 lane .. + 8).  Holding the loaded words in registers
+// across the candidate work costs more registers than the kernel has, and an L2 prefetch leaves the L2 latency of the real
+// load exposed at convert time (12 % of the stall samples): the chunk is copied ASYNCHRONOUSLY into the warp's staging
+// kilobyte (LDGSTS, bypassing L1) before the candidate work and read from there when it is converted.  Every lane reads
+// back exactly the bytes it copied, so its own cp.async.wait_group is all the synchronisation there is.
+__device__ __forceinline__ void stage_raw(WarpSmem &W, const uint8_t *src, uint32_t lane) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(W.raw) + lane * 16;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + lane * 16) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 512), "l"(src + 512 + lane * 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Chunks at the edge of the data are not staged (their loads are masked piece by piece): prefetch them into L2 instead.
+__device__ __forceinline__ void prefetch_raw(const RunCtx &T, uint32_t c, uint32_t lane) {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const uint32_t xo = c * CHUNK + r * 256 + lane * 8, xc = T.x0 + xo;
-        if (all_data || !(xc + 8 <= T.x_zero_end || xc >= T.x_data_end))
+        if (!(xc + 8 <= T.x_zero_end || xc >= T.x_data_end))
             asm volatile("prefetch.global.L2 [%0];" :: "l"(T.tile_base + (size_t)xo * 2));
     }
 }
@@ -309,9 +320,10 @@ __device__ __forceinline__ void to_mags(const ScanSmem &S, bool is_mag, const ui
 
 // Magnitudes of one chunk into ring slot `slot` + exact statistics (convert.c:64-108), chunk entirely data; if count_buf is a
 // reference buffer the whole chunk lies in it and is counted: lane partials -> warp sum -> one pair of atomics.
-__device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &W, const ScanParams &P, const uint8_t *src, bool is_mag, uint32_t slot,
+__device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &W, const ScanParams &P, bool is_mag, uint32_t slot,
                                                    uint32_t lane, uint32_t count_buf) {
-    const uint4 raw0 = ldg_stream_u4(src + lane * 16), raw1 = ldg_stream_u4(src + 512 + lane * 16);
+    stage_wait();
+    const uint4 raw0 = *reinterpret_cast<const uint4 *>(&W.raw[lane * 16]), raw1 = *reinterpret_cast<const uint4 *>(&W.raw[512 + lane * 16]);
     uint32_t level = 0;
     unsigned long long power = 0;
 #pragma unroll
@@ -544,7 +556,7 @@ template <int NW> __global__ void __maxnreg__(64) scan_kernel(const ScanParams P
             if (more) {
                 const uint32_t xs = T.x0 + cn * CHUNK;
                 all_data = xs >= T.x_zero_end && xs + CHUNK <= T.x_data_end;
-                prefetch_raw(T, cn, lane, all_data);
+                if (all_data) stage_raw(W, T.tile_base + (size_t)cn * CHUNK * 2, lane); else prefetch_raw(T, cn, lane);
             }
             __syncwarp();                                        // ticks of chunk k visible to the warp
             // ---- candidates(k-1) --------------------------------------------------------------------------------------
@@ -564,9 +576,11 @@ template <int NW> __global__ void __maxnreg__(64) scan_kernel(const ScanParams P
                 }
                 const bool one_buf = n0 >= 0 && n0 + CHUNK <= bound && n0 + CHUNK <= (long long)T.npos;    // every sample counted, all in buffer nb
                 if (all_data && (one_buf || !owned || n0 >= (long long)T.npos))
-                    convert_chunk_fast(S, W, P, T.tile_base + (size_t)cn * CHUNK * 2, T.is_mag, msn, lane, owned && one_buf ? T.first_buf + nb : 0xffffffffu);
-                else
+                    convert_chunk_fast(S, W, P, T.is_mag, msn, lane, owned && one_buf ? T.first_buf + nb : 0xffffffffu);
+                else {
+                    if (all_data) stage_wait();      // staged, but this chunk straddles a buffer boundary: the edge path loads it itself
                     convert_chunk_edge(S, W, P, cn, msn, lane);
+                }
             }
             // ---- q1 <- pre-check passers of chunk k -------------------------------------------------------------------
             if (k >= 0) {
