@@ -27,10 +27,17 @@
 #include "common.h"
 #include "device_utils.cuh"
 
+#ifndef SC_WARPS
 #define SC_WARPS 28
+#endif
+#ifndef SC_MAXNREG
+#define SC_MAXNREG 72                         // SC_WARPS x 32 x SC_MAXNREG <= 65536 registers per SM (28 warps x 72: measured best of 20..32 warps x 64..96)
+#endif
 #define CHUNK 512
 #define TILE_CHUNKS (SCAN_TILE / CHUNK)       // 4 chunks of positions per tile
+#ifndef RUN_MAX
 #define RUN_MAX 8                             // a warp takes runs of up to 8 consecutive tiles of one segment (guided self-scheduling)
+#endif
 #define RUN_CHUNKS_MAX (RUN_MAX * TILE_CHUNKS)
 #define MAG_RING (3 * CHUNK)
 #define MAG_MIRROR 64                         // first samples of slot 0 again behind slot 2: reads never wrap
@@ -336,9 +343,11 @@ __device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &
         store_mags(W, slot, r, lane, m);
     }
     if (count_buf != 0xffffffffu) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { level += __shfl_xor_sync(FULLMASK, level, o); power += __shfl_xor_sync(FULLMASK, power, o); }
-        if (lane == 0) { atomicAdd(&P.buf_acc[count_buf].sum_level, (unsigned long long)level); atomicAdd(&P.buf_acc[count_buf].sum_power, power); }
+        // hardware warp reductions (REDUX) instead of 15 shuffle steps: a lane's level is < 2^20, its power < 2^36, so the
+        // power goes in two pieces whose warp sums stay below 2^32
+        const uint32_t lv = __reduce_add_sync(FULLMASK, level);
+        const uint32_t plo = __reduce_add_sync(FULLMASK, (uint32_t)power & 0xfffffu), phi = __reduce_add_sync(FULLMASK, (uint32_t)(power >> 20));
+        if (lane == 0) { atomicAdd(&P.buf_acc[count_buf].sum_level, (unsigned long long)lv); atomicAdd(&P.buf_acc[count_buf].sum_power, ((unsigned long long)phi << 20) + plo); }
     }
 }
 
@@ -467,7 +476,7 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
     }
 }
 
-template <int NW> __global__ void __maxnreg__(64) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
+template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const ScanParams P, const DeviceTables *__restrict__ tables) {
     constexpr uint32_t SC_THREADS = NW * 32;
     extern __shared__ uint4 smem_raw[];
     ScanSmemFull<NW> &F = *reinterpret_cast<ScanSmemFull<NW> *>(smem_raw);
@@ -536,6 +545,11 @@ template <int NW> __global__ void __maxnreg__(64) scan_kernel(const ScanParams P
 
         uint32_t n_q1 = 0, n_surv = 0, n_stage = 0;
         uint32_t ms = 0;          // ring slot of chunk k's magnitudes; ticks of chunk k sit in slot k & 1
+        // Chunks in the interior of the data and of a reference buffer need no case analysis: `fast_left` counts how many chunks
+        // after the one just classified are of the same kind (staged, converted by the fast path, counted for buffer `fast_buf`);
+        // the classification below runs at the edges of the data and once per reference buffer.
+        uint32_t fast_left = 0, fast_buf = 0;
+        const uint32_t k_int_lo = (T.p_lo + CHUNK - 1) / CHUNK, k_int_hi = T.p_hi / CHUNK;    // chunks whose 512 positions are all preamble starts
 
 #pragma unroll 1
         for (int k = -2; k <= (int)n_chunks; k++) {
@@ -544,20 +558,48 @@ template <int NW> __global__ void __maxnreg__(64) scan_kernel(const ScanParams P
                 // ---- window(k): pre-check + tick map -----------------------------------------------------------------
                 mask = window_pass(W, ms * CHUNK + lane * 16, (k & 1) * TICK_CW, lane, (k & 1) == 0,
                                    P.tick_scratch + (size_t)warp_global * TICKG_WORDS + k * TICK_CW);
-                const uint32_t i0 = k * CHUNK + lane * 16;       // run-relative; positions outside [p_lo, p_hi) are not preamble starts
-                const uint32_t p_lo = T.p_lo, p_hi = T.p_hi;
-                const uint32_t lo_cut = p_lo > i0 ? min(p_lo - i0, 16u) : 0u, hi_cut = p_hi > i0 ? min(p_hi - i0, 16u) : 0u;
-                mask &= (0xffffu << lo_cut) & ((1u << hi_cut) - 1u);
+                if ((uint32_t)k < k_int_lo || (uint32_t)k >= k_int_hi) {      // positions outside [p_lo, p_hi) are not preamble starts
+                    const uint32_t i0 = k * CHUNK + lane * 16;               // run-relative
+                    const uint32_t p_lo = T.p_lo, p_hi = T.p_hi;
+                    const uint32_t lo_cut = p_lo > i0 ? min(p_lo - i0, 16u) : 0u, hi_cut = p_hi > i0 ? min(p_hi - i0, 16u) : 0u;
+                    mask &= (0xffffu << lo_cut) & ((1u << hi_cut) - 1u);
+                }
             }
-            // ---- prefetch(k+2) --------------------------------------------------------------------------------------
+            // ---- what kind of chunk is k+2 ------------------------------------------------------------------------------
             const uint32_t cn = (uint32_t)(k + 2);
-            const bool more = cn <= n_chunks;
-            bool all_data = false;
-            if (more) {
-                const uint32_t xs = T.x0 + cn * CHUNK;
-                all_data = xs >= T.x_zero_end && xs + CHUNK <= T.x_data_end;
-                if (all_data) stage_raw(W, T.tile_base + (size_t)cn * CHUNK * 2, lane); else prefetch_raw(T, cn, lane);
+            bool more, all_data, fast;
+            uint32_t count_buf;
+            if (fast_left) { fast_left--; more = true; all_data = true; fast = true; count_buf = fast_buf; }
+            else {
+                more = cn <= n_chunks; all_data = false; fast = false; count_buf = 0xffffffffu;
+                if (more) {
+                    const uint32_t xs = T.x0 + cn * CHUNK;
+                    all_data = xs >= T.x_zero_end && xs + CHUNK <= T.x_data_end;
+                    const bool owned = cn < n_chunks || T.last_tile;
+                    const long long n0 = T.n_first + (long long)cn * CHUNK;
+                    uint32_t nb = T.nb;
+                    long long bound = T.bound;
+                    if (n0 >= bound) {
+                        while (n0 >= bound) { nb++; bound += T.buf_len; }
+                        __syncwarp();
+                        if (lane == 0) { T.nb = nb; T.bound = bound; }
+                    }
+                    const long long lim = min(bound, (long long)T.npos);
+                    const bool one_buf = n0 >= 0 && n0 + CHUNK <= lim;                        // every sample counted, all in buffer nb
+                    fast = all_data && (one_buf || !owned || n0 >= (long long)T.npos);
+                    if (owned && one_buf) {
+                        count_buf = T.first_buf + nb;
+                        if (all_data) {         // how many of the following chunks are owned, all data and inside the same buffer
+                            const uint32_t e1 = (T.last_tile ? n_chunks : n_chunks - 1u) - cn;
+                            const uint32_t e2 = (T.x_data_end - xs) / CHUNK - 1u;
+                            const uint32_t e3 = (uint32_t)((lim - n0) / CHUNK) - 1u;
+                            fast_left = min(e1, min(e2, e3)); fast_buf = count_buf;
+                        }
+                    }
+                }
             }
+            // ---- stage(k+2) -------------------------------------------------------------------------------------------
+            if (more) { if (all_data) stage_raw(W, T.tile_base + (size_t)cn * CHUNK * 2, lane); else prefetch_raw(T, cn, lane); }
             __syncwarp();                                        // ticks of chunk k visible to the warp
             // ---- candidates(k-1) --------------------------------------------------------------------------------------
             if (n_q1) process_candidates(S, W, P, n_q1, warp_global, (uint32_t)(k - 1) * CHUNK, ms == 0 ? 2 : ms - 1, (uint32_t)(k - 1) & 1u, lane, n_surv, n_stage);
@@ -565,18 +607,7 @@ template <int NW> __global__ void __maxnreg__(64) scan_kernel(const ScanParams P
             // ---- convert(k+2) into the slot chunk k-1 occupied ------------------------------------------------------
             if (more) {
                 const uint32_t msn = k < 0 ? cn : (ms == 0 ? 2 : ms - 1);       // (ms + 2) % 3; the first two chunks fill slots 0 and 1
-                const bool owned = cn < n_chunks || T.last_tile;
-                const long long n0 = T.n_first + (long long)cn * CHUNK;
-                uint32_t nb = T.nb;
-                long long bound = T.bound;
-                if (n0 >= bound) {
-                    while (n0 >= bound) { nb++; bound += T.buf_len; }
-                    __syncwarp();
-                    if (lane == 0) { T.nb = nb; T.bound = bound; }
-                }
-                const bool one_buf = n0 >= 0 && n0 + CHUNK <= bound && n0 + CHUNK <= (long long)T.npos;    // every sample counted, all in buffer nb
-                if (all_data && (one_buf || !owned || n0 >= (long long)T.npos))
-                    convert_chunk_fast(S, W, P, T.is_mag, msn, lane, owned && one_buf ? T.first_buf + nb : 0xffffffffu);
+                if (fast) convert_chunk_fast(S, W, P, T.is_mag, msn, lane, count_buf);
                 else {
                     if (all_data) stage_wait();      // staged, but this chunk straddles a buffer boundary: the edge path loads it itself
                     convert_chunk_edge(S, W, P, cn, msn, lane);

@@ -27,10 +27,12 @@ def lib():
     """Loads the in-tree CUDA library.  Never builds silently on a GPU box: the .so travels with the tree."""
     global _LIB
     if _LIB is None:
-        if not LIB_PATH.exists():
-            raise DemodError(f"{LIB_PATH} is missing: run `python -m readsb_b200.build` (nvcc, sm_100a). "
+        import os
+        path = Path(os.environ.get("B200_DEMOD_LIB") or LIB_PATH)     # an experimental build variant of the same library (build.py)
+        if not path.exists():
+            raise DemodError(f"{path} is missing: run `python -m readsb_b200.build` (nvcc, sm_100a). "
                              "There is no CPU fallback for the demodulator.")
-        L = C.CDLL(str(LIB_PATH))
+        L = C.CDLL(str(path))
         vp, u32, i64, u64 = C.c_void_p, C.c_uint32, C.c_int64, C.c_uint64
         L.b200_demod_abi_version.restype = C.c_int
         L.b200_demod_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
