@@ -199,6 +199,34 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
 
         // score every tried phase with the current filter; first strictly greatest wins (demod_2400.c:243)
         int best = -2; uint32_t best_rel = 0, best_phase = 0, best_key = 0; bool best_known = false;
+#ifndef RESOLVE_PER_POSITION
+        // The chunk's records (about one for every two positions) are scored ONE PER LANE in a single pass; then every position
+        // picks its own (at most five, consecutive, in phase order) with shuffles.  Scoring per position instead walks the five
+        // phases with two or three lanes active each.  More than 32 records in a chunk: further rounds.
+        if (__ballot_sync(FULLMASK, valid && live)) {
+            uint32_t lm = (valid && live) ? live : 0u;          // this position's phases still to pick, ascending
+            uint32_t jr = rprefix;                                // chunk-relative index of its next record
+            for (uint32_t r0 = 0; r0 < dummy; r0 += 32) {
+                uint32_t rkey = 0, rknown = 0; int rsc = -2;
+                if (r0 + lane < dummy) {
+                    rkey = key_ptr[rec_rel + r0 + lane];
+                    rknown = known_addr(rkey & 0xffffffu) ? 1u : 0u;
+                    rsc = rec_score((rkey >> 24) & 7u, rknown != 0);
+                }
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const uint32_t src = (jr - r0) & 31u;
+                    const uint32_t k_ = __shfl_sync(FULLMASK, rkey, src), kn_ = __shfl_sync(FULLMASK, rknown, src);
+                    const int sc_ = __shfl_sync(FULLMASK, rsc, src);
+                    if (lm && jr - r0 < 32u) {                    // my next record is one of this round's
+                        const uint32_t ph = (uint32_t)__ffs(lm) - 1u; lm &= lm - 1u;
+                        if (sc_ > best) { best = sc_; best_rel = rec_rel + jr; best_phase = ph; best_key = k_; best_known = kn_ != 0; }
+                        jr++;
+                    }
+                }
+            }
+        }
+#else   // the earlier form, kept for A/B timing (tools/gpu_variants.sh): every position walks its own phases
         if (valid && live) {
             uint32_t k = rec_rel + rprefix;
 #pragma unroll
@@ -212,6 +240,7 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
                 }
             }
         }
+#endif
         // accept test of decodeModesMessage (mode_s.c:443-596): only a corrected AA that is unknown rejects
         const bool decode_ok = best >= 0 && !((best_key & KEY_AA_CHANGED) && !best_known);
         // Commit the chunk in order.  After an accept the skip-ahead (demod_2400.c:468) silently consumes the

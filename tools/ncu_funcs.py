@@ -8,6 +8,8 @@ import re
 import sys
 from collections import defaultdict
 
+from sass_util import function_lines
+
 
 def main():
     src_csv, sass, cu = sys.argv[1:4]
@@ -15,7 +17,7 @@ def main():
     insts = [r for r in rows[2:] if len(r) >= len(hdr)]
     stack_re = re.compile(r'//## File "([^"]+)", line (\d+)'); ins_re = re.compile(r'^\s+/\*([0-9a-f]{4,})\*/\s+(.*?);')
     locs, chain, cur = [], False, None
-    for ln in open(sass):
+    for ln in function_lines(sass, len(insts)):
         m = stack_re.search(ln)
         if m:
             loc = (m.group(1).split("/")[-1], int(m.group(2)))

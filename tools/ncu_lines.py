@@ -8,6 +8,8 @@ import re
 import sys
 from collections import defaultdict
 
+from sass_util import function_lines
+
 
 def main():
     src_csv, sass, top = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40
@@ -24,7 +26,7 @@ def main():
     cur = None
     stack_re = re.compile(r'//## File "([^"]+)", line (\d+)')
     ins_re = re.compile(r'^\s+/\*([0-9a-f]{4,})\*/\s+(.*?);')
-    for ln in open(sass):
+    for ln in function_lines(sass, len(insts)):
         m = stack_re.search(ln)
         if m:
             if "inlined at" in ln:
