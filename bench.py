@@ -49,9 +49,35 @@ def parse_args():
     ap.add_argument("--buffers", type=int, default=8, help="reference buffers per receiver per step")
     ap.add_argument("--ring", type=int, default=4, help="distinct steps of input kept resident (ring > L2)")
     ap.add_argument("--workload", choices=["config3_256streams", "config5_dense"], default="config3_256streams")
+    ap.add_argument("--depth", type=int, default=0, help="asynchronous steps in flight (default PIPE_DEPTH; 1 = step by step, the order a profiler's kernel serialisation imposes anyway)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
+
+
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Best effort: run this process (and therefore allocate the pinned input slab) on the host NUMA node the GPU hangs off,
+    so that the H2D copies of the e2e leg do not cross the socket interconnect.  Returns a note for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        mine = cpus & os.sched_getaffinity(0)
+        if not mine:
+            return f"numa: GPU on node {node}, none of its CPUs usable here"
+        os.sched_setaffinity(0, mine)
+        return f"numa: bound to node {node} ({len(mine)} CPUs)"
+    except Exception as e:
+        return f"numa: not bound ({type(e).__name__})"
 
 
 def dist_env():
@@ -171,7 +197,7 @@ def workload_config(args, n_gpus):
             "buffers_per_stream_per_step": args.buffers, "buf_samples": BUF, "sample_rate_hz": 2400000,
             "samples_per_step_per_gpu": args.streams * args.buffers * BUF,
             "parallelism": f"{n_gpus} independent GPU(s), streams sharded {args.streams}/GPU, no collective",
-            "pipelining": f"value: {PIPE_DEPTH} steps in flight per GPU (run_device_uc8_async/wait); e2e: {PIPE_DEPTH} steps in flight (run_host_uc8_async/wait: pinned host slab -> H2D on the library's copy stream, overlapping the previous steps' kernels); all results collected on the host inside the timed region",
+            "pipelining": f"value: {args.depth or PIPE_DEPTH} steps in flight per GPU (run_device_uc8_async/wait); e2e: {args.depth or PIPE_DEPTH} steps in flight (run_host_uc8_async/wait: pinned host slab -> H2D on the library's copy stream, overlapping the previous steps' kernels); all results collected on the host inside the timed region",
             "l2": f"device inputs cycle through a ring of {args.ring} distinct steps "
                   f"({args.ring * args.streams * args.buffers * BUF * 2 / 2**20:.0f} MiB per GPU, L2 is 126 MB); each step reads bytes not touched for {args.ring - 1} steps"}
 
@@ -193,6 +219,7 @@ class NvmlClockSampler:
 
     def __init__(self, gpu_index: int):
         self.idx, self.samples, self.reasons, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], set(), False, None, None
+        self.active = False      # samples are kept only while a timed region is running
 
     def start(self):
         try:
@@ -212,6 +239,9 @@ class NvmlClockSampler:
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake_slowdown": 0x80}
         while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.0005)
+                continue
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
@@ -221,7 +251,7 @@ class NvmlClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def stop(self) -> dict:
         self.stop_flag = True
@@ -299,6 +329,7 @@ def b200_arm(args, rank, world, local):
     step_samples = S * B * BUF
     per_stream = R * B * BUF                       # samples of one receiver resident in the ring
     # --- inputs: pinned host slab [S, 2*per_stream] (for e2e) and a device copy (for value) -------------------
+    numa_note = bind_to_gpu_numa_node(local)
     pin = PinnedBuffer(S * 2 * per_stream)
     host = pin.array.reshape(S, 2 * per_stream)
     generate_streams(S, per_stream, 1 + rank * S, args.workload, host)
@@ -328,12 +359,14 @@ def b200_arm(args, rank, world, local):
         slot = k % R
         d.run_host_async(pin.ptr + slot * B * BUF * 2, stride, B, BUF, slot > 0, k * B * BUF * 5)
 
+    depth = args.depth if args.depth > 0 else PIPE_DEPTH
+
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, k0, pipelined=False):
+    def timed(fn, steps, k0, pipelined=False, sample=False):
         """Times `steps` steps with CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
         pipelined: steps go through run_*_async/wait with PIPE_DEPTH steps in flight (the GPU never waits for the host between
         steps); every step's results are still collected on the host inside the timed region."""
@@ -344,13 +377,14 @@ def b200_arm(args, rank, world, local):
             t = d.timing()
             acc["scan_ms"] += t["scan_ms"]; acc["launches"] += t["launches"]; acc["frames"] += d.total_frames()
         barrier()
+        sampler.active = sample
         ev0.record()
         flying = 0
         for k in range(k0, k0 + steps):
             fn(k)
             if pipelined:
                 flying += 1
-                if flying == PIPE_DEPTH:
+                if flying == depth:
                     d.wait(); harvest(); flying -= 1
             else:
                 harvest()
@@ -358,6 +392,7 @@ def b200_arm(args, rank, world, local):
             d.wait(); harvest(); flying -= 1
         ev1.record()
         torch.cuda.synchronize()
+        sampler.active = False
         ms = ev0.elapsed_time(ev1)
         if dist is not None:
             tmax = torch.tensor([ms], device="cuda")
@@ -367,12 +402,11 @@ def b200_arm(args, rank, world, local):
         return ms, acc["scan_ms"], acc["launches"], acc["frames"]
 
     # --- value: inputs resident in HBM -------------------------------------------------------------------------
-    timed(device_step_async, args.warmup, 0, pipelined=True)      # untimed warm-up through the same pipelined path
-    sampler = NvmlClockSampler(local)
+    sampler = NvmlClockSampler(local)          # SM clock / throttle reasons, recorded inside the two timed regions only
     if rank == 0:
         sampler.start()
-    ms, scan_ms, launches, frames = timed(device_step_async, args.steps, args.warmup, pipelined=True)
-    clocks = sampler.stop() if rank == 0 else {}
+    timed(device_step_async, args.warmup, 0, pipelined=True)      # untimed warm-up through the same pipelined path
+    ms, scan_ms, launches, frames = timed(device_step_async, args.steps, args.warmup, pipelined=True, sample=True)
     value = world * step_samples * args.steps / (ms * 1e-3) / 1e6
 
     # --- e2e: host buffers through the C ABI ----------------------------------------------------------------------
@@ -384,13 +418,14 @@ def b200_arm(args, rank, world, local):
         d2.set_stream(torch.cuda.current_stream().cuda_stream)
         d_dev, d = d, d2
         timed(host_step_async, args.warmup, 0, pipelined=True)
-        ms_e, _, launches_e, frames_e = timed(host_step_async, args.steps, args.warmup, pipelined=True)
+        ms_e, _, launches_e, frames_e = timed(host_step_async, args.steps, args.warmup, pipelined=True, sample=True)
         e2e = {"value": world * step_samples * args.steps / (ms_e * 1e-3) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": step_samples * 2 + S * 64 + 64,           # IQ slab + segment table + control block
                "d2h_bytes_per_step": int(frames_e / args.steps * 64) + S * 4 + S * B * 80 + 32,   # frames + counts + buffer results
-               "ms_per_step": ms_e / args.steps, "frames_per_step": frames_e / args.steps}
+               "ms_per_step": ms_e / args.steps, "frames_per_step": frames_e / args.steps, "host_placement": numa_note}
         d = d_dev
         d2.close()
+    clocks = sampler.stop() if rank == 0 else {}      # sampled during both timed regions (value and e2e)
     # --- roofline leg: blocking device-resident steps, so that the scan kernel runs alone on the GPU ----------------
     timed(device_step, 1, 0)
     _, scan_ms_alone, _, _ = timed(device_step, args.steps, 1)

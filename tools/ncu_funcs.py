@@ -30,7 +30,7 @@ def main():
     print(len(locs), "sass instructions,", len(insts), "ncu rows")
     lines = open(cu).read().splitlines()
     fname = cu.split("/")[-1]
-    funcs = [(i, m.group(1)) for i, l in enumerate(lines, 1) for m in [re.match(r'^(?:__device__|__global__).*?\b(\w+)\(', l)] if m]
+    funcs = [(i, m.group(1)) for i, l in enumerate(lines, 1) for m in [re.match(r'^(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:__device__|__global__).*?\b(\w+)\(', l)] if m]
 
     def fn(line):
         name = "?"
