@@ -1,3 +1,4 @@
+import os
 import sys
 from pathlib import Path
 
@@ -20,8 +21,19 @@ def _cuda_available() -> bool:
         return False
 
 
+def emulated() -> bool:
+    """B200_EMU=1: the gpu-marked tests run against the kernels' source compiled for the CPU under the SIMT emulator
+    (tests/emu/, test infrastructure; see tests/test_emu_kernels.py) instead of the sm_100a library on a GPU."""
+    return os.environ.get("B200_EMU") == "1"
+
+
 @pytest.fixture(scope="session")
 def cuda():
+    if emulated():
+        sys.path.insert(0, str(ROOT / "tests" / "emu"))
+        import build_emu
+        os.environ["B200_DEMOD_LIB"] = str(build_emu.build())
+        return True
     if not _cuda_available():
         pytest.skip("no CUDA device")
     return True

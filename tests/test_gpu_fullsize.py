@@ -54,7 +54,7 @@ def _crc24_numpy(msgs: np.ndarray, nbytes: int) -> np.ndarray:
 @pytest.mark.parametrize("workload", ["config3", "config5"])
 def test_full_size_batch_properties(cuda, workload):
     """256 streams x 2 buffers of 65536 samples per launch (BASELINE configs[2] / configs[4] shapes)."""
-    import torch
+    import devbuf
     from readsb_b200.demod import Demodulator
     S, BUF, NB = 256, 65536, 2
     gen = synth.config2_stream if workload == "config3" else synth.config5_stream
@@ -64,9 +64,9 @@ def test_full_size_batch_properties(cuda, workload):
     for s in range(S):
         host[s] = np.roll(base[s % 32], 2 * 997 * (s // 32))
     pad = 4096
-    dev = torch.zeros(pad + host.size + 256, dtype=torch.uint8, device="cuda")
-    dev[pad:pad + host.size] = torch.from_numpy(host.reshape(-1)).cuda()
-    torch.cuda.synchronize()
+    dev = devbuf.zeros(pad + host.size + 256)
+    dev[pad:pad + host.size] = devbuf.to_dev(host.reshape(-1))
+    devbuf.sync()
 
     d = Demodulator(n_streams=S, buf_samples=BUF, max_buffers_per_run=NB)
     d.run_device(dev.data_ptr() + pad, 2 * NB * BUF, NB, BUF, continues=False, first_sample_timestamp=0)

@@ -106,17 +106,17 @@ def test_magnitude_handoff(cuda):
 
 def test_device_resident_batches(cuda):
     """Inputs already in HBM: streams contiguous in device memory, several buffers per call, continuation."""
-    import torch
+    import devbuf
     from readsb_b200.demod import Demodulator
     S, buf, nb, calls = 5, 65536, 2, 3
     total = buf * nb * calls
     iqs = [GENS[["cfg5", "mixed", "cfg2"][s % 3]](300 + s, total) for s in range(S)]
     pad = 1024  # room for the 326-sample halo in front of stream 0
     stride = total * 2 + 4096
-    dev = torch.zeros(pad + S * stride, dtype=torch.uint8, device="cuda")
+    dev = devbuf.zeros(pad + S * stride)
     for s in range(S):
-        dev[pad + s * stride: pad + s * stride + 2 * total] = torch.from_numpy(iqs[s]).cuda()
-    torch.cuda.synchronize()
+        dev[pad + s * stride: pad + s * stride + 2 * total] = devbuf.to_dev(iqs[s])
+    devbuf.sync()
     d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=nb)
     got = [[] for _ in range(S)]
     gotb = [[] for _ in range(S)]
@@ -166,12 +166,12 @@ def test_seeded_filter_accepts_address_parity_replies(cuda):
 
 
 def _device_streams(iqs, total, pad=1024):
-    import torch
+    import devbuf
     stride = total * 2 + 4096
-    dev = torch.zeros(pad + len(iqs) * stride, dtype=torch.uint8, device="cuda")
+    dev = devbuf.zeros(pad + len(iqs) * stride)
     for s, iq in enumerate(iqs):
-        dev[pad + s * stride: pad + s * stride + 2 * total] = torch.from_numpy(iq).cuda()
-    torch.cuda.synchronize()
+        dev[pad + s * stride: pad + s * stride + 2 * total] = devbuf.to_dev(iq)
+    devbuf.sync()
     return dev, stride, pad
 
 
@@ -330,16 +330,16 @@ def test_modeac_on_magnitude_handoff_and_many_streams(cuda):
 
 def test_modeac_device_path_async_pipeline(cuda):
     """Mode A/C through run_device_uc8_async: two steps in flight, replies and demod_modeac identical to the oracle."""
-    import torch
+    import devbuf
     from readsb_b200.demod import Demodulator
     S, B, BUF, steps = 4, 2, 32768, 3
     n = B * BUF * steps
     iqs = [synth.generate(n, seed=80 + s, frames_per_sec=2500.0, df_mask=synth.MODEAC | synth.DF17, n_icao=4, amp=(0.4, 0.95)) for s in range(S)]
     pad, stride = 1024, 2 * n + 4096
-    dev = torch.zeros(pad + S * stride, dtype=torch.uint8, device="cuda")
+    dev = devbuf.zeros(pad + S * stride)
     for s in range(S):
-        dev[pad + s * stride: pad + s * stride + 2 * n] = torch.from_numpy(iqs[s]).cuda()
-    torch.cuda.synchronize()
+        dev[pad + s * stride: pad + s * stride + 2 * n] = devbuf.to_dev(iqs[s])
+    devbuf.sync()
     d = Demodulator(n_streams=S, buf_samples=BUF, max_buffers_per_run=B, mode_ac=True)
     got_f = [[] for _ in range(S)]; got_a = [[] for _ in range(S)]
 
