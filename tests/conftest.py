@@ -32,7 +32,8 @@ def cuda():
     if emulated():
         sys.path.insert(0, str(ROOT / "tests" / "emu"))
         import build_emu
-        os.environ["B200_DEMOD_LIB"] = str(build_emu.build())
+        # B200_EMU_LIB: an instrumented build of the emulated library (e.g. AddressSanitizer, tests/emu/README.md)
+        os.environ["B200_DEMOD_LIB"] = os.environ.get("B200_EMU_LIB") or str(build_emu.build())
         return True
     if not _cuda_available():
         pytest.skip("no CUDA device")

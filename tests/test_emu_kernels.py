@@ -19,10 +19,21 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _run_gpu_tests_emulated(*modules: str, timeout: int = 900) -> str:
+def _run_gpu_tests_emulated(*modules: str, timeout: int = 900, sanitize: str | None = None, select: str | None = None) -> str:
     env = dict(os.environ, B200_EMU="1")
     env.pop("B200_DEMOD_LIB", None)
+    env.pop("B200_EMU_LIB", None)
     cmd = [sys.executable, "-m", "pytest", *modules, "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+    if select:
+        cmd += ["-k", select]
+    if sanitize:
+        sys.path.insert(0, str(ROOT / "tests" / "emu"))
+        import build_emu
+        env["B200_EMU_LIB"] = str(build_emu.build(sanitize=sanitize))
+        env["LD_PRELOAD"] = build_emu.sanitizer_runtime(sanitize)
+        env["ASAN_OPTIONS"] = "detect_leaks=0:detect_stack_use_after_return=0"      # fibers switch stacks by hand
+        env["UBSAN_OPTIONS"] = "halt_on_error=1:print_stacktrace=0"
+        cmd += ["-s"]                                                                # a sanitizer report must reach our pipe
     res = subprocess.run(cmd, cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=timeout)
     tail = (res.stdout + res.stderr)[-3000:]
     assert res.returncode == 0, "gpu-marked tests failed against the emulated kernels:\n" + tail
@@ -43,6 +54,19 @@ def test_emulated_library_exports_the_whole_abi():
 @pytest.mark.parametrize("module", ["tests/test_gpu_parity.py", "tests/test_gpu_edges.py", "tests/test_gpu_fullsize.py"])
 def test_gpu_parity_suite_on_emulated_kernels(module):
     _run_gpu_tests_emulated(module)
+
+
+def test_edge_cases_under_address_sanitizer():
+    """Ragged / tiny / empty buffers, unequal receivers, fuzzed buffer sizes, the dense slow path and Mode A/C with odd buffer
+    lengths, with redzones around every "device" allocation: no kernel reads or writes past a pool, an arena or a result array."""
+    _run_gpu_tests_emulated("tests/test_gpu_edges.py", "tests/test_gpu_fullsize.py", "tests/test_gpu_parity.py", sanitize="address",
+                            select="edges or dense_tile or golden or modeac_matches or sc16 or beast_output or magnitude_handoff")
+
+
+def test_no_undefined_behaviour_where_cpu_and_gpu_semantics_differ():
+    """UBSan over the parity tests: no shift by >= 32, no signed overflow, no misaligned vector access in the kernels' source —
+    the constructs C++ leaves undefined and PTX defines, i.e. where an emulated run could disagree with the hardware."""
+    _run_gpu_tests_emulated("tests/test_gpu_edges.py", "tests/test_gpu_parity.py", sanitize="undefined")
 
 
 def test_product_never_refers_to_the_emulator():
