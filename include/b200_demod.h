@@ -138,6 +138,11 @@ int  b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out);
 void b200_demod_destroy(b200_demod_ctx *ctx);
 const char *b200_demod_last_error(const b200_demod_ctx *ctx); /* ctx may be NULL: last create error */
 
+/* Modes.preambleThreshold for the runs that follow (create() took the initial value from the config).  The reference
+ * re-reads it for every buffer and raises it to at least 75 while its 15-minute statistics show dropped samples
+ * (demod_2400.c:334-338, PREAMBLE_THRESHOLD_PIZERO): a live-SDR caller applies that rule here, buffer by buffer. */
+int b200_demod_set_preamble_threshold(b200_demod_ctx *ctx, int32_t preamble_threshold);
+
 /* Run all work of this context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the
  * context's own stream).  Lets a caller bracket runs with its own events. */
 int b200_demod_set_stream(b200_demod_ctx *ctx, void *cuda_stream);
@@ -157,6 +162,14 @@ int b200_demod_submit_iq_uc8(b200_demod_ctx *ctx, uint32_t stream, const uint8_t
                              uint32_t nsamples, int64_t sample_timestamp);
 int b200_demod_submit_mag_u16(b200_demod_ctx *ctx, uint32_t stream, const uint16_t *data,
                               uint32_t length, int64_t sample_timestamp);
+/* The same hand-off with mag_buf.mean_level / mean_power (readsb.h:452-453) as the converter that filled the buffer
+ * returned them.  demodulate2400AC derives its noise floor from these two fields (demod_2400.c:580-581); for a uc8
+ * frontend they equal what the library computes itself from the magnitudes (convert.c:100-107), so submit_mag_u16 is
+ * enough there; the sc16 converters return float-accumulated means (convert.c:243-249) and DC-filtered ones differ too —
+ * with B200_CFG_MODE_AC and such a frontend hand the buffer over with this call.  Without B200_CFG_MODE_AC the levels
+ * are not used by the library (demodulate2400 itself only needs mean_power for its noise statistics, on the caller's side). */
+int b200_demod_submit_mag_u16_levels(b200_demod_ctx *ctx, uint32_t stream, const uint16_t *data,
+                                     uint32_t length, int64_t sample_timestamp, double mean_level, double mean_power);
 /* Many receivers in one call (a multi-channel frontend's slab): stream first_stream+i has n_buffers*buf_len
  * samples at iq + i*host_stride_bytes, submitted as n_buffers consecutive buffers with timestamps
  * first_sample_timestamp + b*buf_len*5.  One strided DMA instead of n_streams*n_buffers copies. */
@@ -169,8 +182,9 @@ int b200_demod_submit_iq_uc8_strided(b200_demod_ctx *ctx, uint32_t first_stream,
  * int16 I,Q pairs; halo handling as for submit_iq_uc8.  Magnitudes are the reference's, bit for bit.  The reference
  * returns mean_level / mean_power of these formats from float accumulators added to in sample order: for buffers
  * submitted here b200_buffer_result.sum_level / sum_power hold the IEEE-754 bit patterns of those two float sums
- * (mean_level = (double)(sum_level_f / (float)length), likewise mean_power).  Not combinable with B200_CFG_MODE_AC yet,
- * nor with other submit kinds on the same stream in one run. */
+ * (mean_level = (double)(sum_level_f / (float)length), likewise mean_power); with B200_CFG_MODE_AC the Mode A/C noise
+ * floor of such a buffer is derived from exactly these means, as the reference does.  Not combinable with other submit
+ * kinds on the same stream in one run. */
 int b200_demod_submit_iq_sc16(b200_demod_ctx *ctx, uint32_t stream, const int16_t *iq, uint32_t nsamples,
                               int64_t sample_timestamp, int q11);
 /* Process everything submitted since the last run; returns when frames are in host memory. */

@@ -32,6 +32,7 @@ static int g_in_shim;                /* adds that come from our own decodeModesM
 static b200_frame g_frames[2048];
 static b200_modeac *g_ac;            /* replies of the buffer demodulate2400 just handed to the library */
 static uint32_t g_ac_cap;
+static int32_t g_thr;                /* threshold the library currently uses */
 
 void __real_icaoFilterAdd(uint32_t addr);
 void __real_icaoFilterExpire(void);
@@ -69,6 +70,7 @@ static int shim_open(void) {
         return -1;
     }
     memset(&g_prev, 0, sizeof g_prev);
+    g_thr = cfg.preamble_threshold;
     return 0;
 }
 
@@ -78,8 +80,15 @@ void __wrap_demodulate2400(struct mag_buf *mag) {
     /* demod_2400.c:283-285 */
     if (Modes.sdr_type == SDR_IFILE && Modes.synthetic_now) Modes.synthetic_now = mag->sysTimestamp;
 
+    /* demod_2400.c:334-338: fewer preamble detections while samples were dropped recently (live SDRs) */
+    int32_t thr = (int32_t) Modes.preambleThreshold;
+    if (Modes.stats_15min.samples_dropped && thr < PREAMBLE_THRESHOLD_PIZERO) thr = PREAMBLE_THRESHOLD_PIZERO;
+    if (thr != g_thr && b200_demod_set_preamble_threshold(g_ctx, thr) == B200_OK) g_thr = thr;
+
     uint32_t n = 0;
-    if (b200_demod_submit_mag_u16(g_ctx, 0, mag->data, mag->length, mag->sampleTimestamp) != B200_OK ||
+    /* mean_level / mean_power travel with the buffer: demodulate2400AC's noise floor is made from them (demod_2400.c:580-581),
+     * whatever converter filled the mag_buf */
+    if (b200_demod_submit_mag_u16_levels(g_ctx, 0, mag->data, mag->length, mag->sampleTimestamp, mag->mean_level, mag->mean_power) != B200_OK ||
         b200_demod_run(g_ctx) != B200_OK ||
         b200_demod_fetch(g_ctx, 0, g_frames, sizeof g_frames / sizeof g_frames[0], &n) != B200_OK) {
         fprintf(stderr, "b200 demodulator: %s\n", b200_demod_last_error(g_ctx));

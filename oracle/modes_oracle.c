@@ -154,6 +154,10 @@ void oracle_icao_add(oracle_ctx *o, uint32_t a) { aset_add(&o->gen[o->active], a
 int oracle_icao_test(const oracle_ctx *o, uint32_t a) { return aset_has(&o->gen[0], a) || aset_has(&o->gen[1], a); }
 void oracle_icao_expire(oracle_ctx *o) { o->active ^= 1; aset_clear(&o->gen[o->active]); o->st.icao_flips++; }
 
+/* Modes.preambleThreshold is re-read for every buffer (demod_2400.c:334-338): the caller applies the reference's
+ * "at least PREAMBLE_THRESHOLD_PIZERO (75) while samples were dropped recently" rule between buffers. */
+void oracle_set_preamble_threshold(oracle_ctx *o, int thr) { if (thr > 0) o->thr = thr; }
+
 oracle_ctx *oracle_create(int thr, int nfix, int fixdf, int ttl_ms) {
     build_lut(); build_crc();
     oracle_ctx *o = calloc(1, sizeof *o);
@@ -425,11 +429,19 @@ int oracle_demodulate2400(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64
  * The float / double mix below is the reference's (float products, double for the +0.5 and the sqrt(2) factors). */
 int oracle_demodulate2400AC(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64_t sample_ts,
                             uint64_t sum_level, uint64_t sum_power, b200_modeac *out, unsigned cap, unsigned *n_out) {
-    int overflow = 0;
     if (mlen == 0) return 0;
     const double mean_level = sum_level / 65536.0 / mlen;                 /* convert.c:100-102 */
     const double mean_power = sum_power / 65535.0 / 65535.0 / mlen;       /* convert.c:104-106 */
-    const double noise_stddev = sqrt(mean_power - mean_level * mean_level);
+    return oracle_demodulate2400AC_levels(o, m, mlen, sample_ts, mean_level, mean_power, out, cap, n_out);
+}
+
+/* The same with mag_buf.mean_level / mean_power as the converter that filled the buffer returned them (any converter:
+ * the sc16 ones return float-accumulated means, convert.c:243-249). */
+int oracle_demodulate2400AC_levels(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64_t sample_ts,
+                                   double mean_level, double mean_power, b200_modeac *out, unsigned cap, unsigned *n_out) {
+    int overflow = 0;
+    if (mlen == 0) return 0;
+    const double noise_stddev = sqrt(mean_power - mean_level * mean_level);   /* demod_2400.c:580 */
     const unsigned noise_level = (unsigned)((mean_power + noise_stddev) * 65535 + 0.5);
     for (unsigned f1 = 1; f1 < mlen; ++f1) {
         if (!(m[f1 - 1] < m[f1])) continue;                               /* rising edge */

@@ -28,6 +28,7 @@ typedef struct oracle_ctx oracle_ctx;
 
 oracle_ctx *oracle_create(int preamble_threshold, int nfix_crc, int fix_df, int icao_ttl_ms);
 void oracle_destroy(oracle_ctx *o);
+void oracle_set_preamble_threshold(oracle_ctx *o, int preamble_threshold);
 
 /* convert.c:35-62 */
 void oracle_uc8_lut(uint16_t *out65536);
@@ -60,6 +61,8 @@ void oracle_stream_restart(oracle_ctx *o);
 /* demod_2400.c:575-761 for one mag_buf (needs the converter's sums for mean_level / mean_power).  Appends to out. */
 int oracle_demodulate2400AC(oracle_ctx *o, const uint16_t *data, unsigned length, int64_t sample_timestamp,
                             uint64_t sum_level, uint64_t sum_power, b200_modeac *out, unsigned cap, unsigned *n_out);
+int oracle_demodulate2400AC_levels(oracle_ctx *o, const uint16_t *data, unsigned length, int64_t sample_timestamp,
+                                   double mean_level, double mean_power, b200_modeac *out, unsigned cap, unsigned *n_out);
 
 /* net_io.c:1655-1714 modesSendBeastOutput (+ netTimestamp :1617-1648): one Beast record, at most 44 bytes; returns its length */
 unsigned oracle_beast_frame(const b200_frame *f, int verbatim, uint8_t *out);

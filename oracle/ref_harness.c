@@ -119,6 +119,9 @@ int ref_init(int preamble_threshold, int nfix_crc, int fix_df, int icao_ttl_ms) 
     return g_conv ? 0 : -1;
 }
 
+/* Modes.stats_15min.samples_dropped != 0 makes demodulate2400 use max(75, preambleThreshold) (demod_2400.c:334-338). */
+void ref_set_samples_dropped(unsigned n) { Modes.stats_15min.samples_dropped = n; }
+
 void ref_uc8_lut(uint16_t *out65536) {
     uint8_t *iq = malloc(65536 * 2);
     for (int i = 0; i < 256; i++)

@@ -176,6 +176,16 @@ struct FinalizeParams {
 
 // ---- Mode A/C (modeac_kernel.cu) -------------------------------------------------------------------
 struct DeviceTables;
+// Where a reference buffer's Mode A/C noise floor comes from: demodulate2400AC reads mag_buf.mean_level / mean_power
+// (demod_2400.c:580-581), i.e. whatever the converter that filled the buffer returned.
+#define AC_LEVEL_SUMS   0u   // uc8 input or a plain magnitude hand-off: the scan kernel's exact integer sums (convert.c:100-107)
+#define AC_LEVEL_GIVEN  1u   // the caller's mag_buf.mean_level / mean_power (b200_demod_submit_mag_u16_levels)
+#define AC_LEVEL_FSUM   2u   // sc16 input: the converter's float accumulators at fsum[idx], divided in float (convert.c:243-249)
+struct AcLevel {
+    double mean_level, mean_power;
+    uint32_t mode, idx;
+};
+
 struct AcScanParams {
     const Segment *segs;
     uint32_t n_segs;
@@ -186,6 +196,8 @@ struct AcScanParams {
     uint32_t *noise;                  // [buffer] noise_level (demod_2400.c:581)
     uint32_t *bitmap;                 // [tile][SCAN_TILE/32]: bit p = a well-formed reply's F1 pulse starts at position p of the tile
     RunCtl *ctl;
+    const AcLevel *levels;            // [buffer]
+    const float2 *fsum;               // sc16 float sums (sum_level, sum_power), or null
 };
 
 struct AcWalkParams {

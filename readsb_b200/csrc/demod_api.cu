@@ -32,6 +32,8 @@ struct Pending {
     int64_t ts;
     size_t off;          // byte offset of data index 0 (mag) or of the first new sample (iq) in the stream's arena region
     int fsum = -1;       // sc16 input: index of the buffer's float sums in d_fsum
+    bool has_levels = false;             // magnitude hand-off with the mag_buf's own mean_level / mean_power (Mode A/C noise floor)
+    double mean_level = 0, mean_power = 0;
 };
 
 struct DeviceArgs {      // what a device-resident step was asked to do (kept for a repeat after a pool regrowth)
@@ -59,6 +61,7 @@ struct Slot {
     uint32_t *d_ac_bitmap = nullptr, *d_ac_noise = nullptr;
     uint32_t *d_ac_count = nullptr, *d_ac_prefix = nullptr, *h_ac_prefix = nullptr;   // per reference buffer of the run
     b200_modeac *d_ac_out = nullptr, *d_ac_packed = nullptr, *h_ac_packed = nullptr;
+    AcLevel *d_ac_levels = nullptr, *h_ac_levels = nullptr;                           // per reference buffer of the run: source of the noise floor
     // the run this slot holds
     uint32_t nseg = 0, ntile = 0, nbuf = 0, run_frames = 0;
     bool upload_tiles = true, is_device = false;
@@ -176,6 +179,7 @@ static void free_slot(Slot &s) {
     cudaFree(s.d_frames); cudaFree(s.d_packed); cudaFree(s.d_frame_count); cudaFree(s.d_frame_prefix);
     cudaFree(s.d_ac_bitmap); cudaFree(s.d_ac_noise); cudaFree(s.d_ac_count); cudaFree(s.d_ac_prefix); cudaFree(s.d_ac_out); cudaFree(s.d_ac_packed);
     cudaFreeHost(s.h_ac_prefix); cudaFreeHost(s.h_ac_packed);
+    cudaFree(s.d_ac_levels); cudaFreeHost(s.h_ac_levels);
     cudaFreeHost(s.h_segs); cudaFreeHost(s.h_tile_seg); cudaFreeHost(s.h_stream_seg_begin); cudaFreeHost(s.h_ctl);
     cudaFreeHost(s.h_buf_acc); cudaFreeHost(s.h_buf_out); cudaFreeHost(s.h_packed); cudaFreeHost(s.h_frame_prefix);
     for (auto &e : s.ev) if (e) cudaEventDestroy(e);
@@ -208,6 +212,8 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
         A(dev_alloc(&s.d_ac_noise, c->buf_cap)); A(dev_alloc(&s.d_ac_count, c->buf_cap));
         A(dev_alloc(&s.d_ac_out, ac_total)); A(dev_alloc(&s.d_ac_packed, ac_total)); A(pin_alloc(&s.h_ac_packed, ac_total));
         A(dev_alloc(&s.d_ac_prefix, c->buf_cap + 1)); A(pin_alloc(&s.h_ac_prefix, c->buf_cap + 1));
+        A(dev_alloc(&s.d_ac_levels, c->buf_cap)); A(pin_alloc(&s.h_ac_levels, c->buf_cap));
+        memset(s.h_ac_levels, 0, (size_t)c->buf_cap * sizeof(AcLevel));
         memset(s.h_ac_prefix, 0, (S + 1) * 4);
     }
 #undef A
@@ -320,7 +326,7 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
 static bool any_in_flight(const b200_demod_ctx *c) { return c->n_flight > 0; }
 
 // ---- submits ---------------------------------------------------------------------------------
-static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32_t n, int64_t ts, bool mag) {
+static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32_t n, int64_t ts, bool mag, const double *levels = nullptr) {
     if (!c) return B200_E_INVAL;
     if (s >= c->cfg.n_streams || (!host && n)) return fail(c, B200_E_INVAL, "bad stream or buffer");
     if (n > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "buffer of %u samples exceeds buf_samples=%u", n, c->cfg.buf_samples);
@@ -333,6 +339,7 @@ static int submit_common(b200_demod_ctx *c, uint32_t s, const void *host, uint32
     uint8_t *region = c->d_arena + (size_t)s * c->stream_stride;
     Pending p;
     p.n = n; p.ts = ts;
+    if (levels) { p.has_levels = true; p.mean_level = levels[0]; p.mean_power = levels[1]; }
     if (mag) {
         p.off = (c->cursor[s] + 15) & ~(size_t)15;
         const size_t bytes = ((size_t)n + B200_TRAIL) * 2;
@@ -388,7 +395,6 @@ API int b200_demod_submit_iq_sc16(b200_demod_ctx *c, uint32_t s, const int16_t *
     if (!c) return B200_E_INVAL;
     if (s >= c->cfg.n_streams || (!iq && n)) return fail(c, B200_E_INVAL, "bad stream or buffer");
     if (n > c->cfg.buf_samples) return fail(c, B200_E_INVAL, "buffer of %u samples exceeds buf_samples=%u", n, c->cfg.buf_samples);
-    if (c->cfg.flags & B200_CFG_MODE_AC) return fail(c, B200_E_INVAL, "sc16 input is not combinable with B200_CFG_MODE_AC yet");
     if (c->pending[s].size() >= c->cfg.max_buffers_per_run) return fail(c, B200_E_STATE, "stream %u already has max_buffers_per_run buffers queued", s);
     if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
     if (c->kind[s] && c->kind[s] != 3) return fail(c, B200_E_STATE, "stream %u mixes submit kinds in one run", s);
@@ -413,6 +419,18 @@ API int b200_demod_submit_iq_sc16(b200_demod_ctx *c, uint32_t s, const int16_t *
 
 API int b200_demod_submit_iq_uc8(b200_demod_ctx *c, uint32_t s, const uint8_t *iq, uint32_t n, int64_t ts) { return submit_common(c, s, iq, n, ts, false); }
 API int b200_demod_submit_mag_u16(b200_demod_ctx *c, uint32_t s, const uint16_t *data, uint32_t n, int64_t ts) { return submit_common(c, s, data, n, ts, true); }
+API int b200_demod_submit_mag_u16_levels(b200_demod_ctx *c, uint32_t s, const uint16_t *data, uint32_t n, int64_t ts, double mean_level, double mean_power) {
+    const double lv[2] = {mean_level, mean_power};
+    return submit_common(c, s, data, n, ts, true, lv);
+}
+
+API int b200_demod_set_preamble_threshold(b200_demod_ctx *c, int32_t thr) {
+    if (!c) return B200_E_INVAL;
+    if (thr <= 0) return fail(c, B200_E_INVAL, "preamble threshold must be > 0");
+    if (any_in_flight(c)) return fail(c, B200_E_STATE, "asynchronous steps are in flight: call b200_demod_wait first");
+    c->cfg.preamble_threshold = thr;      // read when the next run is enqueued
+    return B200_OK;
+}
 
 // ---- the pipeline ------------------------------------------------------------------------------
 static void add_segment(b200_demod_ctx *c, Slot &sl, uint32_t stream, const uint8_t *base, uint32_t npos, uint32_t buf_len, uint32_t n_bufs,
@@ -466,7 +484,9 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     const bool mode_ac = (c->cfg.flags & B200_CFG_MODE_AC) != 0;
     AcWalkParams aw = {};
     if (mode_ac) {
+        if (sl.nbuf) CU(c, cudaMemcpyAsync(sl.d_ac_levels, sl.h_ac_levels, (size_t)sl.nbuf * sizeof(AcLevel), cudaMemcpyHostToDevice, scan));
         AcScanParams as;
+        as.levels = sl.d_ac_levels; as.fsum = c->d_fsum;
         as.segs = sl.d_segs; as.n_segs = sl.nseg; as.tile_seg = sl.d_tile_seg; as.n_tiles = sl.ntile; as.buf_acc = sl.d_buf_acc;
         as.tables = c->d_tables; as.noise = sl.d_ac_noise; as.bitmap = sl.d_ac_bitmap; as.ctl = sl.d_ctl;
         aw.segs = sl.d_segs; aw.n_segs = sl.nseg; aw.stream_seg_begin = sl.d_stream_seg_begin; aw.n_streams = S; aw.bitmap = sl.d_ac_bitmap;
@@ -596,6 +616,7 @@ API int b200_demod_run(b200_demod_ctx *c) {
     c->cur = 0;
     sl.nseg = sl.ntile = sl.nbuf = 0; sl.is_device = false; sl.upload_tiles = true; sl.cached_tiles = 0;
     std::vector<std::pair<uint32_t, int>> fsum_of_buf;      // (buffer of the run, float-sum slot) for sc16 buffers
+    std::vector<std::pair<uint32_t, const Pending *>> given_levels;   // (buffer of the run, hand-off that brought its own mean_level / mean_power)
     for (uint32_t s = 0; s < S; s++) {
         sl.h_stream_seg_begin[s] = sl.nseg;
         sl.stream_buf_begin[s] = sl.nbuf;
@@ -604,7 +625,10 @@ API int b200_demod_run(b200_demod_ctx *c) {
         if (pl.empty()) continue;
         const uint8_t *region = c->d_arena + (size_t)s * c->stream_stride;
         if (c->kind[s] == 2) {
-            for (const Pending &p : pl) add_segment(c, sl, s, region + p.off, p.n, p.n, 1, SEG_MAG, p.ts);
+            for (const Pending &p : pl) {
+                if (p.has_levels) given_levels.push_back({sl.nbuf, &p});
+                add_segment(c, sl, s, region + p.off, p.n, p.n, 1, SEG_MAG, p.ts);
+            }
         } else {
             // consecutive full buffers with contiguous timestamps form one segment; a partial buffer ends it
             size_t i = 0;
@@ -631,6 +655,11 @@ API int b200_demod_run(b200_demod_ctx *c) {
     }
     sl.h_stream_seg_begin[S] = sl.nseg;
     sl.stream_buf_begin[S] = sl.nbuf;
+    if (c->cfg.flags & B200_CFG_MODE_AC) {                  // demod_2400.c:580-581: the noise floor comes from the mag_buf's own levels
+        memset(sl.h_ac_levels, 0, (size_t)sl.nbuf * sizeof(AcLevel));
+        for (const auto &g : given_levels) { AcLevel &l = sl.h_ac_levels[g.first]; l.mode = AC_LEVEL_GIVEN; l.mean_level = g.second->mean_level; l.mean_power = g.second->mean_power; }
+        for (const auto &bf : fsum_of_buf) { AcLevel &l = sl.h_ac_levels[bf.first]; l.mode = AC_LEVEL_FSUM; l.idx = (uint32_t)bf.second; }
+    }
     int rc = execute_blocking(c, sl);
     if (rc == B200_OK && !fsum_of_buf.empty()) {      // sc16 input: the reference's float accumulators instead of the integer sums
         if (cudaMemcpyAsync(c->h_fsum, c->d_fsum, (size_t)c->n_fsum * sizeof(float2), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
@@ -667,6 +696,7 @@ static int build_device_run(b200_demod_ctx *c, Slot &sl, const DeviceArgs &a) {
     }
     sl.h_stream_seg_begin[S] = sl.nseg;
     sl.stream_buf_begin[S] = sl.nbuf;
+    if (c->cfg.flags & B200_CFG_MODE_AC) memset(sl.h_ac_levels, 0, (size_t)sl.nbuf * sizeof(AcLevel));      // uc8 input: the exact sums
     // the tile -> segment table only depends on the layout; skip its upload when nothing changed
     const uint64_t key = ((uint64_t)a.n_buffers << 40) ^ ((uint64_t)a.buf_len << 8) ^ (((uintptr_t)a.d_iq >> 4) & 15) ^ (a.stride << 20);
     sl.upload_tiles = !(sl.cached_tiles == sl.ntile && sl.cached_layout_key == key);

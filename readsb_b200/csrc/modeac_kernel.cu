@@ -114,8 +114,16 @@ __global__ void modeac_noise_kernel(const AcScanParams P) {
         for (uint32_t b = threadIdx.x; b < seg.n_bufs; b += blockDim.x) {
             const uint32_t len = min(seg.buf_len, seg.npos - b * seg.buf_len);
             const BufAcc &a = P.buf_acc[seg.first_buf + b];     // sum_signal_power may still be accumulating: not read
-            const double mean_level = (double)a.sum_level / 65536.0 / (double)len;            // convert.c:100-102
-            const double mean_power = (double)a.sum_power / 65535.0 / 65535.0 / (double)len;  // convert.c:104-106
+            const AcLevel lv = P.levels[seg.first_buf + b];
+            double mean_level, mean_power;
+            if (lv.mode == AC_LEVEL_GIVEN) { mean_level = lv.mean_level; mean_power = lv.mean_power; }
+            else if (lv.mode == AC_LEVEL_FSUM) {                // `sum_level / nsamples`: a float division, widened afterwards (convert.c:243-249)
+                const float2 f = P.fsum[lv.idx];
+                mean_level = (double)(f.x / (float)len); mean_power = (double)(f.y / (float)len);
+            } else {
+                mean_level = (double)a.sum_level / 65536.0 / (double)len;            // convert.c:100-102
+                mean_power = (double)a.sum_power / 65535.0 / 65535.0 / (double)len;  // convert.c:104-106
+            }
             const double noise_stddev = sqrt(mean_power - mean_level * mean_level);           // demod_2400.c:580
             P.noise[seg.first_buf + b] = (uint32_t)((mean_power + noise_stddev) * 65535 + 0.5);   // :581
         }

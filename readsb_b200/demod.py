@@ -44,6 +44,8 @@ def lib():
         L.b200_demod_host_free.argtypes = [vp]
         L.b200_demod_submit_iq_uc8.argtypes = [vp, u32, vp, u32, i64]
         L.b200_demod_submit_mag_u16.argtypes = [vp, u32, vp, u32, i64]
+        L.b200_demod_submit_mag_u16_levels.argtypes = [vp, u32, vp, u32, i64, C.c_double, C.c_double]
+        L.b200_demod_set_preamble_threshold.argtypes = [vp, C.c_int32]
         L.b200_demod_submit_iq_uc8_strided.argtypes = [vp, u32, u32, vp, u64, u32, u32, i64]
         L.b200_demod_set_stream.argtypes = [vp, vp]
         L.b200_demod_run.argtypes = [vp]
@@ -78,6 +80,7 @@ EXPORTED_SYMBOLS = [
     "b200_demod_fetch_beast", "b200_demod_submit_iq_sc16", "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",
     "b200_demod_uc8_lut", "b200_demod_debug_counters", "b200_demod_submit_iq_uc8_strided", "b200_demod_set_stream",
     "b200_demod_run_device_uc8_async", "b200_demod_wait", "b200_demod_fetch_modeac", "b200_demod_run_host_uc8_async",
+    "b200_demod_submit_mag_u16_levels", "b200_demod_set_preamble_threshold",
 ]
 
 
@@ -142,10 +145,19 @@ class Demodulator:
     def submit_iq_ptr(self, stream: int, ptr: int, nsamples: int, sample_timestamp: int):
         self._check(self.L.b200_demod_submit_iq_uc8(self.h, stream, ptr, nsamples, sample_timestamp))
 
-    def submit_mag(self, stream: int, data: np.ndarray, length: int, sample_timestamp: int):
-        """data: uint16 mag_buf.data = 326 halo magnitudes followed by `length` new ones."""
+    def submit_mag(self, stream: int, data: np.ndarray, length: int, sample_timestamp: int, mean_level: float | None = None,
+                   mean_power: float | None = None):
+        """data: uint16 mag_buf.data = 326 halo magnitudes followed by `length` new ones; mean_level / mean_power: the
+        mag_buf's own (Mode A/C noise floor for frontends whose converter is not the uc8 one)."""
         assert data.dtype == np.uint16 and data.flags.c_contiguous and data.size >= length + 326
-        self._check(self.L.b200_demod_submit_mag_u16(self.h, stream, data.ctypes.data, length, sample_timestamp))
+        if mean_level is None:
+            self._check(self.L.b200_demod_submit_mag_u16(self.h, stream, data.ctypes.data, length, sample_timestamp))
+        else:
+            self._check(self.L.b200_demod_submit_mag_u16_levels(self.h, stream, data.ctypes.data, length, sample_timestamp, mean_level, mean_power))
+
+    def set_preamble_threshold(self, thr: int):
+        """Modes.preambleThreshold for the runs that follow (demod_2400.c:334-338)."""
+        self._check(self.L.b200_demod_set_preamble_threshold(self.h, thr))
 
     def submit_iq_sc16(self, stream: int, iq16: np.ndarray, sample_timestamp: int, q11: bool = False):
         """int16 I,Q pairs (convert_sc16_nodc, or convert_sc16q11_nodc with q11)."""

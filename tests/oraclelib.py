@@ -116,6 +116,10 @@ class Oracle:
         assert n >= 0, "oracle frame capacity exceeded"
         return frames[:n].copy(), bufres[: nb.value].copy()
 
+    def set_preamble_threshold(self, thr: int):
+        self.L.oracle_set_preamble_threshold.argtypes = [C.c_void_p, C.c_int]
+        self.L.oracle_set_preamble_threshold(self.h, thr)
+
     def restart_stream(self):
         """The next run_stream call starts with a zero halo (a receiver that was reopened); filter and statistics stay."""
         self.L.oracle_stream_restart.argtypes = [C.c_void_p]
@@ -127,6 +131,32 @@ class Oracle:
         rc = self.L.oracle_demodulate2400AC(self.h, data.ctypes.data, length, sample_ts, sum_level, sum_power, out.ctypes.data, cap, C.byref(n))
         assert rc == 0
         return out[: n.value].copy()
+
+    def demodulate_ac_levels(self, data: np.ndarray, length: int, sample_ts: int, mean_level: float, mean_power: float, cap=4096):
+        """demodulate2400AC with the mag_buf's own mean_level / mean_power (whatever converter filled it)."""
+        self.L.oracle_demodulate2400AC_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_uint, C.POINTER(C.c_uint)]
+        out = np.zeros(cap, dtype=MODEAC_DTYPE)
+        n = C.c_uint(0)
+        rc = self.L.oracle_demodulate2400AC_levels(self.h, data.ctypes.data, length, sample_ts, mean_level, mean_power, out.ctypes.data, cap, C.byref(n))
+        assert rc == 0
+        return out[: n.value].copy()
+
+    def run_stream_ac_sc16(self, iq16: np.ndarray, buf_samples: int, q11: bool = False, first_ts: int = 0):
+        """Mode A/C over an sc16 capture: the converter's float-accumulated means feed the noise floor (convert.c:243-249)."""
+        n = iq16.size // 2
+        halo = np.zeros(326, np.uint16)
+        outs, off, b = [], 0, 0
+        while off < n:
+            m = min(buf_samples, n - off)
+            mag, sl, sp = self.convert_sc16(iq16[2 * off: 2 * (off + m)], q11)
+            data = np.concatenate([halo, mag])
+            # `sum_level / nsamples` is a float division whose result is widened to double
+            a = self.demodulate_ac_levels(data, m, first_ts + off * 5, float(np.float32(sl) / np.float32(m)), float(np.float32(sp) / np.float32(m)))
+            a["buffer_idx"] = b
+            outs.append(a)
+            halo = data[m: m + 326].copy() if m >= 326 else np.zeros(326, np.uint16)
+            off += m; b += 1
+        return np.concatenate(outs) if outs else np.zeros(0, MODEAC_DTYPE)
 
     def run_stream_ac(self, iq: np.ndarray, buf_samples: int, first_ts: int = 0):
         """Mode A/C over a capture, buffer by buffer like the ifile loop (halo carried)."""
@@ -321,6 +351,28 @@ class Reference:
             outs.append(a)
             halo = data[ln: ln + 326].copy() if ln >= 326 else np.zeros(326, dtype=np.uint16)
         return np.concatenate(outs) if outs else np.zeros(0, MODEAC_DTYPE)
+
+    def run_stream_ac_sc16(self, iq16: np.ndarray, buf_samples: int, q11: bool = False, first_ts: int = 0):
+        """The reference's own sc16 converter feeding the reference's demodulate2400AC, buffer by buffer."""
+        n = iq16.size // 2
+        halo = np.zeros(326, np.uint16)
+        outs, off, b = [], 0, 0
+        while off < n:
+            m = min(buf_samples, n - off)
+            mag, ml, mp = self.convert_sc16(iq16[2 * off: 2 * (off + m)], q11)
+            data = np.concatenate([halo, mag]).astype(np.uint16)
+            out = np.zeros(4096, dtype=MODEAC_DTYPE)
+            cnt = C.c_uint(0)
+            assert self.L.ref_demodulate2400AC(data.ctypes.data, m, first_ts + off * 5, C.c_double(ml), C.c_double(mp), out.ctypes.data, 4096, C.byref(cnt)) == 0
+            a = out[: cnt.value].copy(); a["buffer_idx"] = b
+            outs.append(a)
+            halo = data[m: m + 326].copy() if m >= 326 else np.zeros(326, np.uint16)
+            off += m; b += 1
+        return np.concatenate(outs) if outs else np.zeros(0, MODEAC_DTYPE)
+
+    def set_samples_dropped(self, n: int):
+        self.L.ref_set_samples_dropped.argtypes = [C.c_uint]
+        self.L.ref_set_samples_dropped(n)
 
     def modeac_count(self) -> int:
         return int(self.L.ref_modeac_count())

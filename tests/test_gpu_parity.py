@@ -476,3 +476,93 @@ def test_sc16_input_matches_oracle(cuda, q11):
             assert r["length"] == m
             assert np.uint32(r["sum_level"]).view(np.float32) == sl and np.uint32(r["sum_power"]).view(np.float32) == sp
     d.close()
+
+
+@pytest.mark.parametrize("q11", [False, True])
+def test_sc16_input_with_modeac(cuda, q11):
+    """An sc16 frontend with --modeac: the Mode A/C noise floor comes from the converter's float-accumulated means
+    (convert.c:243-249 -> demod_2400.c:580-581), the Mode S frames from the same magnitudes."""
+    from readsb_b200.demod import Demodulator
+    buf, K = 32768, 3
+    n = 7 * buf + 4321
+    iq8 = synth.generate(n, seed=91 + q11, frames_per_sec=2500.0, df_mask=synth.MODEAC | synth.DF17 | synth.DF11, n_icao=6, amp=(0.35, 0.95))
+    iq16 = _to_sc16(iq8, q11, 5)
+    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=K, mode_ac=True)
+    got_f, got_a, off, b0 = [], [], 0, 0
+    while off < n:
+        k = 0
+        while k < K and off < n:
+            m = min(buf, n - off)
+            d.submit_iq_sc16(0, iq16[2 * off: 2 * (off + m)], off * 5, q11)
+            off += m; k += 1
+        d.run()
+        got_f.append(d.frames(0))
+        a = d.modeac(0); a["buffer_idx"] += b0; got_a.append(a); b0 += k
+    o = Oracle()
+    fo, _ = o.run_stream_sc16(iq16, buf, q11)
+    ao = Oracle().run_stream_ac_sc16(iq16, buf, q11)
+    assert len(fo) > 30 and len(ao) > 15
+    problems = diff_frames(np.concatenate(got_f), fo) + _diff_modeac(np.concatenate(got_a), ao)
+    assert not problems, "\n".join(problems)
+    assert d.stats(0)["demod_modeac"] == len(ao)
+    d.close()
+
+
+def test_modeac_noise_floor_from_the_mag_bufs_own_levels(cuda):
+    """b200_demod_submit_mag_u16_levels: demodulate2400AC reads mag_buf.mean_level / mean_power (demod_2400.c:580-581).  Stream 0
+    gets the means its (sc16) converter returned, stream 1 deliberately wrong ones (a noise floor far too high: replies vanish),
+    stream 2 none (the library's own exact sums)."""
+    from readsb_b200.demod import Demodulator
+    buf, nb = 20000, 5
+    iq8 = synth.generate(nb * buf, seed=77, frames_per_sec=3000.0, df_mask=synth.MODEAC, amp=(0.3, 0.9))
+    iq16 = _to_sc16(iq8, False, 3)
+    d = Demodulator(n_streams=3, buf_samples=buf, max_buffers_per_run=nb, mode_ac=True)
+    o = [Oracle(), Oracle(), Oracle()]
+    want = [[], [], []]
+    halo = np.zeros(326, np.uint16)
+    for b in range(nb):
+        mag, sl, sp = Oracle.convert_sc16(iq16[2 * b * buf: 2 * (b + 1) * buf])
+        data = np.concatenate([halo, mag]).astype(np.uint16)
+        ml, mp = float(np.float32(sl) / np.float32(buf)), float(np.float32(sp) / np.float32(buf))
+        levels = [(ml, mp), (0.3, 0.2), None]
+        for s in range(3):
+            if levels[s] is None:
+                d.submit_mag(s, data, buf, b * buf * 5)
+                a = o[s].demodulate_ac(data, buf, b * buf * 5, int(mag.astype(np.uint64).sum()), int((mag.astype(np.uint64) ** 2).sum()))
+            else:
+                d.submit_mag(s, data, buf, b * buf * 5, *levels[s])
+                a = o[s].demodulate_ac_levels(data, buf, b * buf * 5, *levels[s])
+            a["buffer_idx"] = b
+            want[s].append(a)
+        halo = data[buf: buf + 326].copy()
+    d.run()
+    n_found = []
+    for s in range(3):
+        w = np.concatenate(want[s])
+        assert not _diff_modeac(d.modeac(s), w), f"stream {s}"
+        n_found.append(len(w))
+    assert n_found[0] > 40 and n_found[2] > 40 and n_found[1] < n_found[0] // 4
+    d.close()
+
+
+def test_preamble_threshold_changes_between_runs(cuda):
+    """b200_demod_set_preamble_threshold: the reference re-reads Modes.preambleThreshold for every buffer and uses at least 75
+    while samples were dropped recently (demod_2400.c:334-338)."""
+    from readsb_b200.demod import Demodulator
+    buf = 65536
+    iq = GENS["mixed"](33, 6 * buf)
+    d = Demodulator(n_streams=1, buf_samples=buf, max_buffers_per_run=2)
+    o = Oracle()
+    halo = np.zeros(326, np.uint16)
+    fg, fo = [], []
+    for step, thr in enumerate([58, 75, 58]):
+        d.set_preamble_threshold(thr)
+        o.set_preamble_threshold(thr)
+        for b in (2 * step, 2 * step + 1):
+            d.submit_iq(0, iq[2 * b * buf: 2 * (b + 1) * buf], b * buf * 5)
+        d.run()
+        fg.append(d.frames(0))
+        fo.append(o.run_stream(iq[2 * 2 * step * buf: 2 * 2 * (step + 1) * buf], buf, first_ts=2 * step * buf * 5)[0])
+    problems = diff_frames(np.concatenate(fg), np.concatenate(fo)) + diff_stats(d.stats(0), o.stats())
+    assert not problems, "\n".join(problems)
+    d.close()

@@ -7,6 +7,7 @@ libb200demod.so.  Both replay the same capture (`--device-type ifile`, the refer
 sdr_ifile.c:169-259); every frame line of `--mlat --raw` (12 MHz timestamp + frame bytes, in order) and every
 demodulator counter of `--stats` (stats.c:82-122) must be identical.
 """
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -23,8 +24,25 @@ GPU = ROOT / "oracle" / "_ref" / "readsb_b200"
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (CPU.exists() and GPU.exists()), reason="oracle/_ref/readsb_{cpu,b200} not built")]
 
 
+_EMU_DIR = None
+
+
+def _env_for(exe):
+    """B200_EMU=1 (tests/emu/): the swapped-demodulator program resolves libb200demod.so to the emulated library — LD_LIBRARY_PATH
+    is searched before the binary's RUNPATH — so the whole unmodified reference program runs against the kernels' source on the CPU."""
+    global _EMU_DIR
+    env = dict(os.environ)
+    if exe == GPU and os.environ.get("B200_EMU") == "1":
+        if _EMU_DIR is None:
+            import tempfile
+            _EMU_DIR = tempfile.mkdtemp(prefix="b200emu_")
+            os.symlink(os.environ["B200_DEMOD_LIB"], os.path.join(_EMU_DIR, "libb200demod.so"))
+        env["LD_LIBRARY_PATH"] = _EMU_DIR + (":" + env["LD_LIBRARY_PATH"] if env.get("LD_LIBRARY_PATH") else "")
+    return env
+
+
 def _run_pair(args, timeout=180):
-    procs = [subprocess.Popen([str(exe)] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for exe in (CPU, GPU)]
+    procs = [subprocess.Popen([str(exe)] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=_env_for(exe)) for exe in (CPU, GPU)]
     outs = []
     for p in procs:
         out, _ = p.communicate(timeout=timeout)
@@ -49,7 +67,7 @@ def _stats_block(text):
      dict(frames_per_sec=6000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.DF18 | synth.DF11_IID, n_icao=48,
           p_bit_error=0.35, p_two_bit_error=0.08)),
 ])
-def test_reference_program_with_swapped_demodulator(tmp_path, name, extra, gen):
+def test_reference_program_with_swapped_demodulator(cuda, tmp_path, name, extra, gen):
     nsamples = 2_400_000 * 3 + 12345                      # 3 s and a partial last buffer
     cap = tmp_path / f"{name}.bin"
     synth.generate(nsamples, seed=2024, **gen).tofile(cap)

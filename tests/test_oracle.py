@@ -235,3 +235,44 @@ def test_oracle_sc16_converters_match_reference(q11):
     mag_o, sl_o, sp_o = Oracle.convert_sc16(iq, q11)
     assert np.array_equal(mag_r, mag_o) and mag_o.max() == 65535 and mag_o[32:64].min() == 0
     assert float(np.float32(sl_o) / np.float32(n)) == ml_r and float(np.float32(sp_o) / np.float32(n)) == mp_r
+
+
+def _to_sc16(iq8: np.ndarray, q11: bool, seed: int) -> np.ndarray:
+    """The uc8 synthetic capture as a 16-bit frontend would deliver it (plus a little sub-LSB dither)."""
+    rng = np.random.default_rng(seed)
+    scale = 16 if q11 else 256
+    v = (iq8.astype(np.int32) - 128) * scale + rng.integers(0, scale, size=iq8.size)
+    return np.clip(v, -2048 if q11 else -32768, 2047 if q11 else 32767).astype(np.int16)
+
+
+@needs_ref
+@pytest.mark.parametrize("q11,buf", [(False, 65536), (True, 20000)])
+def test_oracle_modeac_with_converter_levels_matches_reference(q11, buf):
+    """demodulate2400AC takes its noise floor from mag_buf.mean_level / mean_power (demod_2400.c:580-581); for an sc16 frontend
+    those are float-accumulated means (convert.c:243-249), not the exact integer sums: the reference's converter + the
+    reference's demodulate2400AC against the oracle's converter + oracle_demodulate2400AC_levels."""
+    iq16 = _to_sc16(synth.modeac_stream(31 + q11, 1_200_000), q11, 9)
+    ar = Reference().run_stream_ac_sc16(iq16, buf, q11)
+    o = Oracle()
+    ao = o.run_stream_ac_sc16(iq16, buf, q11)
+    assert len(ar) > 80 and len(ar) == len(ao)
+    for f in ("timestamp", "modeac", "buffer_idx"):      # the reference harness cannot see f1_sample
+        assert np.array_equal(ar[f], ao[f]), f
+    assert o.stats()["demod_modeac"] == len(ar)
+
+
+@needs_ref
+def test_dropped_samples_raise_the_threshold_to_75():
+    """demod_2400.c:334-338: while stats_15min.samples_dropped is set the reference uses max(75, preambleThreshold); the
+    boundary exposes that as a threshold the caller sets between buffers."""
+    iq = synth.mixed_stream(21, 6 * 65536)
+    ref = Reference(preamble_threshold=58)
+    ref.set_samples_dropped(3)
+    fr = ref.run_stream(iq, 65536)[0]
+    o = Oracle(preamble_threshold=58)
+    o.set_preamble_threshold(75)
+    fo, _ = o.run_stream(iq, 65536)
+    o58 = Oracle(preamble_threshold=58)
+    o58.run_stream(iq, 65536)
+    assert len(fr) > 50 and not diff_frames(fo, fr, fields=("timestamp", "msg", "score"))
+    assert ref.stats()[0]["demod_preambles"] == o.stats()["demod_preambles"] < o58.stats()["demod_preambles"]
