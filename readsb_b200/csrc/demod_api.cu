@@ -210,6 +210,7 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
         const size_t ac_total = (size_t)c->buf_cap * c->ac_cap;
         A(dev_alloc(&s.d_ac_bitmap, (size_t)c->tile_cap * (SCAN_TILE / 32)));
         A(dev_alloc(&s.d_ac_noise, c->buf_cap)); A(dev_alloc(&s.d_ac_count, c->buf_cap));
+        A(cudaMemset(s.d_ac_count, 0, (size_t)c->buf_cap * 4)); A(cudaMemset(s.d_ac_noise, 0, (size_t)c->buf_cap * 4));
         A(dev_alloc(&s.d_ac_out, ac_total)); A(dev_alloc(&s.d_ac_packed, ac_total)); A(pin_alloc(&s.h_ac_packed, ac_total));
         A(dev_alloc(&s.d_ac_prefix, c->buf_cap + 1)); A(pin_alloc(&s.h_ac_prefix, c->buf_cap + 1));
         A(dev_alloc(&s.d_ac_levels, c->buf_cap)); A(pin_alloc(&s.h_ac_levels, c->buf_cap));

@@ -56,7 +56,10 @@ static inline uint32_t b200_crc24_bytes(const uint32_t *tab, const uint8_t *msg,
 }
 
 // Returns 0 on success.  syn_hash is a perfect hash of the 112 single-bit syndromes:
-// slot = (syndrome * mul) >> 23 (9 bits); entry = syndrome << 8 | bit, 0xffffffff when empty.
+// slot = (syndrome * mul) >> 23 (9 bits); entry = syndrome << 8 | bit, 0 when empty.  (An empty slot must not look like any
+// syndrome a lookup can ask for: with 0xffffffff as the marker the syndrome 0xffffff "matched" empty slots and came back as a
+// correctable error in bit 255 — found by tools/emu_fuzz.py.  Entry 0 can only match syndrome 0, which reports bit 0: never
+// correctable, crc.c:210-211.)
 static inline int b200_build_tables(DeviceTables *t, uint16_t *lut_full /*65536*/) {
     b200_build_uc8_lut(lut_full);
     b200_build_folded_lut(lut_full, t->lut_fold);
@@ -73,11 +76,11 @@ static inline int b200_build_tables(DeviceTables *t, uint16_t *lut_full /*65536*
     }
     for (uint32_t mul = 0x9E3779B1u, tries = 0; tries < 200000; tries++, mul += 0x61C88646u) {
         uint32_t m = mul | 1u;
-        memset(t->syn_hash, 0xff, sizeof t->syn_hash);
+        memset(t->syn_hash, 0, sizeof t->syn_hash);
         int ok = 1;
         for (int b = 0; b < 112 && ok; b++) {
             uint32_t h = (t->bit_syn[b] * m) >> 23;
-            if (t->syn_hash[h] != 0xffffffffu) ok = 0;
+            if (t->syn_hash[h] != 0u) ok = 0;
             else t->syn_hash[h] = (t->bit_syn[b] << 8) | (uint32_t)b;
         }
         if (ok) { t->syn_hash_mul = m; return 0; }

@@ -623,16 +623,17 @@ extern "C" int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_p
 }
 
 // Mode A/C: pack the per-buffer reply lists in buffer order (prefix by the frame prefix kernel, then one block per buffer).
-__global__ void ac_pack_kernel(const b200_modeac *ac_out, const uint32_t *count, const uint32_t *prefix, b200_modeac *packed, uint32_t cap) {
+__global__ void ac_pack_kernel(const b200_modeac *ac_out, const uint32_t *count, const uint32_t *prefix, b200_modeac *packed, uint32_t cap, const RunCtl *ctl) {
+    if (ctl->overflow & 19u) return;          // the walk did not run (this step is going to be repeated): its counts are not this run's
     const uint32_t s = blockIdx.x;
-    const uint32_t n = count[s], base = prefix[s];
+    const uint32_t n = min(count[s], cap), base = prefix[s];
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) packed[base + i] = ac_out[(size_t)s * cap + i];
 }
 
 extern "C" int b200_launch_ac_pack(const b200_modeac *ac_out, const uint32_t *count, uint32_t *prefix, b200_modeac *packed, uint32_t n_units,
                                    uint32_t cap, RunCtl *ctl, void *stream) {
     frame_prefix_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(count, prefix, n_units, ctl, false);
-    if (n_units) ac_pack_kernel<<<n_units, 32, 0, (cudaStream_t)stream>>>(ac_out, count, prefix, packed, cap);
+    if (n_units) ac_pack_kernel<<<n_units, 32, 0, (cudaStream_t)stream>>>(ac_out, count, prefix, packed, cap, ctl);
     return (int)cudaGetLastError();
 }
 

@@ -64,7 +64,7 @@ def test_edge_cases_under_address_sanitizer():
     """Ragged / tiny / empty buffers, unequal receivers, fuzzed buffer sizes, the dense slow path and Mode A/C with odd buffer
     lengths, with redzones around every "device" allocation: no kernel reads or writes past a pool, an arena or a result array."""
     _run_gpu_tests_emulated("tests/test_gpu_edges.py", "tests/test_gpu_fullsize.py", "tests/test_gpu_parity.py", sanitize="address",
-                            select="edges or dense_tile or golden or modeac_matches or sc16 or beast_output or magnitude_handoff")
+                            select="edges or dense_tile or golden or modeac_matches or sc16 or beast_output or magnitude_handoff or has_to_be_repeated or noise_floor")
 
 
 def test_no_undefined_behaviour_where_cpu_and_gpu_semantics_differ():

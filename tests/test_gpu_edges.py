@@ -1,5 +1,7 @@
 """-m gpu: edge cases of the boundary — ragged / tiny / empty buffers, timestamp discontinuities, receivers with different
 amounts of data in one run, random buffer sizes (seeded fuzz) — always against the oracle, bit for bit."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -140,4 +142,22 @@ def test_filter_flip_on_the_stream_clock(cuda):
     assert bo["icao_flipped"].sum() >= 8
     problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(0), o.stats())
     assert not problems, "\n".join(problems)
+    d.close()
+
+
+def test_syndrome_all_ones_is_not_a_correctable_error(cuda):
+    """A DF17 candidate whose syndrome is exactly 0xFFFFFF (tests/golden/syndrome_ffffff.npz: 2200 samples cut out of a
+    tools/emu_fuzz.py case, loud traffic at --preamble-threshold=33).  The single-bit-error lookup is a perfect hash whose
+    empty slots once held 0xffffffff: this syndrome matched an empty slot, came back as 'bit 255' and the frame was accepted
+    with score 700 (and finalize flipped msg[-1]).  The reference finds no such error (crc.c:383-406) and rejects the phase."""
+    from readsb_b200.demod import Demodulator
+    z = np.load(Path(__file__).resolve().parent / "golden" / "syndrome_ffffff.npz")
+    iq, thr = z["iq"], int(z["preamble_threshold"])
+    o = Oracle(preamble_threshold=thr)
+    fo, bo = o.run_stream(iq, 65536)
+    d = Demodulator(n_streams=1, buf_samples=65536, preamble_threshold=thr)
+    fg, bg = d.replay(iq)
+    problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(0), o.stats())
+    assert not problems, "\n".join(problems)
+    assert o.stats()["demod_preambles"] > 10
     d.close()

@@ -566,3 +566,30 @@ def test_preamble_threshold_changes_between_runs(cuda):
     problems = diff_frames(np.concatenate(fg), np.concatenate(fo)) + diff_stats(d.stats(0), o.stats())
     assert not problems, "\n".join(problems)
     d.close()
+
+
+def test_modeac_when_the_run_has_to_be_repeated(cuda):
+    """A run whose stage A outgrows the record pool is repeated after regrowth; the Mode A/C walk skips the failed attempt, and
+    the pack step must not touch that attempt's (absent) reply counts.  Found by tools/emu_fuzz.py (seed 7, case 12) under
+    AddressSanitizer: loud overlapping traffic at --preamble-threshold=33, five receivers, device-resident path."""
+    import devbuf
+    from readsb_b200.demod import Demodulator
+    S, buf, K = 5, 65536, 4
+    total = K * buf
+    iqs = [synth.generate(total, seed=12000 + s, frames_per_sec=8000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.MODEAC, n_icao=8,
+                          amp=(0.7, 1.0), p_bit_error=0.3) for s in range(S)]
+    pad, stride = 1024, 2 * total + 4096
+    dev = devbuf.zeros(pad + S * stride)
+    for s in range(S):
+        dev[pad + s * stride: pad + s * stride + 2 * total] = devbuf.to_dev(iqs[s])
+    devbuf.sync()
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=K, preamble_threshold=33, mode_ac=True)
+    d.run_device(dev.data_ptr() + pad, stride, K, buf, continues=False, first_sample_timestamp=0)
+    for s in range(S):
+        o = Oracle(preamble_threshold=33)
+        fo, bo = o.run_stream(iqs[s], buf)
+        ao = Oracle().run_stream_ac(iqs[s], buf)
+        problems = diff_frames(d.frames(s), fo) + diff_bufres(d.buffer_results(s), bo) + _diff_modeac(d.modeac(s), ao) + diff_stats(d.stats(s), o.stats())
+        assert not problems, f"stream {s}: " + "\n".join(problems)
+        assert d.stats(s)["demod_modeac"] == len(ao)
+    d.close()

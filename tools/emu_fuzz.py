@@ -1,0 +1,190 @@
+"""Randomised parity runs of the kernels' source on the CPU (tests/emu/) against the oracle.  TEST TOOLING.
+
+    python tools/emu_fuzz.py [--seed S] [--cases N] [--minutes M] [--sanitize address]
+
+Each case draws: receivers, buffer length (odd sizes included), buffers per run, input kind (the synthetic workloads, plus
+saturated / sawtooth / constant / uniformly random bytes), preamble threshold, --no-fix / --no-fix-df, Mode A/C on or off, a
+ragged tail, and one of the entry paths (host submits, magnitude hand-off, device-resident blocking, device-resident
+pipelined, pipelined host slab).  Frames, per-buffer results, counters and Mode A/C replies must equal the oracle's.
+Prints the failing case's parameters (re-run it alone with --only K).  The same script works on a GPU (without B200_EMU).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def make_input(rng, kind: str, n: int, seed: int):
+    import numpy as np
+    from readsb_b200 import synth
+    if kind == "cfg2":
+        return synth.config2_stream(seed, n)
+    if kind == "cfg5":
+        return synth.config5_stream(seed, n)
+    if kind == "mixed":
+        return synth.mixed_stream(seed, n, frames_per_sec=float(rng.choice([500, 2000, 6000])))
+    if kind == "modeac":
+        return synth.modeac_stream(seed, n)
+    if kind == "loud":      # strong overlapping traffic close to clipping
+        return synth.generate(n, seed=seed, frames_per_sec=8000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.MODEAC, n_icao=8,
+                              amp=(0.7, 1.0), p_bit_error=0.3)
+    if kind == "random":
+        return rng.integers(0, 256, size=2 * n, dtype=np.uint8)
+    if kind == "sawtooth":
+        return (np.arange(2 * n, dtype=np.uint32) * int(rng.integers(1, 9)) % 256).astype(np.uint8)
+    if kind == "constant":
+        return np.full(2 * n, int(rng.choice([0, 127, 128, 255])), dtype=np.uint8)
+    if kind == "burst":     # quiet, then a block of saturated samples, then traffic
+        iq = synth.mixed_stream(seed, n)
+        a = int(rng.integers(0, max(1, n - 5000)))
+        iq[2 * a: 2 * (a + int(rng.integers(10, 5000)))] = rng.integers(0, 2, dtype=np.uint8) * 255
+        return iq
+    raise ValueError(kind)
+
+
+def run_case(k: int, seed: int, verbose: bool):
+    import numpy as np
+    import devbuf
+    from oraclelib import Oracle
+    from paritylib import diff_bufres, diff_frames, diff_stats
+    from readsb_b200.demod import Demodulator
+    rng = np.random.default_rng([seed, k])
+    S = int(rng.choice([1, 1, 2, 3, 5]))
+    buf = int(rng.choice([1000, 4096, 8191, 8192, 20000, 32768, 65536, 65536, 131072, int(rng.integers(700, 70000))]))
+    path = str(rng.choice(["host", "host", "mag", "device", "device_async", "host_async"]))
+    if path in ("device", "device_async", "host_async"):
+        buf = max(8, buf & ~7)                                   # those entry points want multiples of 8
+    K = int(rng.choice([1, 2, 3, 4, 8]))
+    steps = int(rng.choice([1, 2, 3, 5]))
+    kind = str(rng.choice(["cfg2", "cfg5", "mixed", "mixed", "modeac", "loud", "random", "sawtooth", "constant", "burst"]))
+    thr = int(rng.choice([58, 58, 58, 40, 75, 120, 33]))
+    nfix, fixdf = int(rng.random() < 0.8), int(rng.random() < 0.8)
+    mode_ac = bool(rng.random() < 0.4)
+    ragged = path in ("host", "mag") and rng.random() < 0.5
+    total = K * steps * buf - (int(rng.integers(1, buf)) if ragged else 0)
+    params = dict(case=k, S=S, buf=buf, K=K, steps=steps, kind=kind, thr=thr, nfix=nfix, fixdf=fixdf, mode_ac=mode_ac, path=path, total=total)
+    if verbose:
+        print(params, flush=True)
+    iqs = [make_input(rng, kind, total, 1000 * k + s) for s in range(S)]
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=K, preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, mode_ac=mode_ac)
+    got_f = [[] for _ in range(S)]; got_b = [[] for _ in range(S)]; got_a = [[] for _ in range(S)]
+    nb_done = [0] * S
+
+    def harvest():
+        for s in range(S):
+            got_f[s].append(d.frames(s)); b = d.buffer_results(s); got_b[s].append(b)
+            if mode_ac:
+                a = d.modeac(s); a["buffer_idx"] += nb_done[s]; got_a[s].append(a)
+            nb_done[s] += len(b)
+
+    if path in ("host", "mag"):
+        halos = [np.zeros(326, np.uint16) for _ in range(S)]
+        off = 0
+        while off < total:
+            for _ in range(K):
+                if off >= total:
+                    break
+                m = min(buf, total - off)
+                for s in range(S):
+                    if path == "host":
+                        d.submit_iq(s, iqs[s][2 * off: 2 * (off + m)], off * 5)
+                    else:
+                        mag, _, _ = Oracle.convert(iqs[s][2 * off: 2 * (off + m)])
+                        data = np.concatenate([halos[s], mag]).astype(np.uint16)
+                        d.submit_mag(s, data, m, off * 5)
+                        halos[s] = data[m: m + 326].copy() if m >= 326 else np.zeros(326, np.uint16)
+                off += m
+            d.run(); harvest()
+    elif path in ("device", "device_async"):
+        pad, stride = 1024, 2 * total + 4096
+        dev = devbuf.zeros(pad + S * stride)
+        for s in range(S):
+            dev[pad + s * stride: pad + s * stride + 2 * total] = devbuf.to_dev(iqs[s])
+        devbuf.sync()
+        flying = 0
+        for c in range(steps):
+            args = (dev.data_ptr() + pad + c * K * buf * 2, stride, K, buf)
+            if path == "device":
+                d.run_device(*args, continues=c > 0, first_sample_timestamp=c * K * buf * 5); harvest()
+            else:
+                d.run_device_async(*args, continues=c > 0, first_sample_timestamp=c * K * buf * 5); flying += 1
+                if flying == 3:
+                    d.wait(); harvest(); flying -= 1
+        while path == "device_async" and flying:
+            d.wait(); harvest(); flying -= 1
+    else:   # host_async
+        from readsb_b200.demod import PinnedBuffer
+        row = 2 * K * buf
+        slabs = [PinnedBuffer(S * row) for _ in range(3)]
+        flying = 0
+        for c in range(steps):
+            sl = slabs[c % 3]
+            for s in range(S):
+                sl.array[s * row: (s + 1) * row] = iqs[s][c * row: (c + 1) * row]
+            d.run_host_async(sl.ptr, row, K, buf, continues=c > 0, first_sample_timestamp=c * K * buf * 5); flying += 1
+            if flying == 3:
+                d.wait(); harvest(); flying -= 1
+        while flying:
+            d.wait(); harvest(); flying -= 1
+        for sl in slabs:
+            sl.free()
+
+    problems = []
+    for s in range(S):
+        o = Oracle(preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf)
+        fo, bo = o.run_stream(iqs[s], buf)
+        problems += [f"stream {s}: {p}" for p in diff_frames(np.concatenate(got_f[s]), fo) + diff_bufres(np.concatenate(got_b[s]), bo)]
+        st = d.stats(s)
+        if mode_ac:
+            ao = Oracle().run_stream_ac(iqs[s], buf)
+            ag = np.concatenate(got_a[s])
+            if len(ag) != len(ao) or any(not np.array_equal(ag[f], ao[f]) for f in ("timestamp", "f1_sample", "modeac", "buffer_idx")):
+                problems.append(f"stream {s}: Mode A/C replies differ ({len(ag)} vs {len(ao)})")
+            if st["demod_modeac"] != len(ao):
+                problems.append(f"stream {s}: demod_modeac {st['demod_modeac']} vs {len(ao)}")
+        problems += [f"stream {s}: {p}" for p in diff_stats(st, o.stats())]
+    nframes = sum(len(np.concatenate(x)) for x in got_f)
+    d.close()
+    return params, problems, nframes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cases", type=int, default=50)
+    ap.add_argument("--minutes", type=float, default=0.0, help="stop after this many minutes (0 = run all cases)")
+    ap.add_argument("--only", type=int, default=-1)
+    ap.add_argument("--emu", type=int, default=1, help="1: the emulated library (default), 0: the sm_100a library on a GPU")
+    ap.add_argument("-v", action="store_true")
+    a = ap.parse_args()
+    if a.emu:
+        os.environ["B200_EMU"] = "1"
+        sys.path.insert(0, str(ROOT / "tests" / "emu"))
+        import build_emu
+        os.environ["B200_DEMOD_LIB"] = os.environ.get("B200_EMU_LIB") or str(build_emu.build())
+    t0, bad, frames = time.time(), 0, 0
+    ks = [a.only] if a.only >= 0 else range(a.cases)
+    for k in ks:
+        params, problems, nf = run_case(k, a.seed, a.v)
+        frames += nf
+        if problems:
+            bad += 1
+            print("FAIL", params)
+            for p in problems[:8]:
+                print("   ", p)
+        if a.minutes and time.time() - t0 > a.minutes * 60:
+            print(f"time limit after case {k}")
+            break
+    print(f"{len(list(ks))} cases requested, {bad} failed, {frames} frames compared, {time.time() - t0:.0f} s")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
