@@ -78,6 +78,7 @@ struct Slot {
 struct b200_demod_ctx {
     b200_demod_config cfg;
     int device = 0, n_sm = 148;
+    int n_sm_scan = 148;              // CTAs of the persistent scan kernel (one per SM); < n_sm leaves SMs to stage B of the step before (B200_SCAN_SMS)
     cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
     std::string err;
 
@@ -264,6 +265,11 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     CUC(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
+    c->n_sm_scan = c->n_sm;
+    if (const char *e = getenv("B200_SCAN_SMS")) {       // experiment knob (tools/): in the pipelined modes the scan of step n+1 and stage B of
+        const int v = atoi(e);                           // step n alternate on the SMs; a scan grid smaller than the chip lets them overlap
+        if (v >= 1 && v <= c->n_sm) c->n_sm_scan = v;
+    }
     {   // With several steps in flight the scan kernels of later steps are already queued when a scan ends; stage B of the step
         // that just finished scanning must not wait behind them (its results gate the host), so its stream has the higher
         // priority: the block scheduler places stage B's CTAs first, the next scan's persistent CTAs follow as SMs drain, and
@@ -476,7 +482,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
     if (sp.nfix && sp.fixdf) for (int b = 0; b < 5; b++) sp.long_set |= 1u << (17 ^ (1 << b));
     CU(c, cudaEventRecord(sl.ev[0], scan));
-    if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, c->n_sm, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
+    if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, c->n_sm_scan, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
     CU(c, cudaEventRecord(sl.ev[1], scan));
     if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[1], 0));
 

@@ -276,3 +276,17 @@ def test_dropped_samples_raise_the_threshold_to_75():
     o58.run_stream(iq, 65536)
     assert len(fr) > 50 and not diff_frames(fo, fr, fields=("timestamp", "msg", "score"))
     assert ref.stats()[0]["demod_preambles"] == o.stats()["demod_preambles"] < o58.stats()["demod_preambles"]
+
+
+@needs_ref
+def test_reference_rejects_the_all_ones_syndrome():
+    """tests/golden/syndrome_ffffff.npz holds a DF17 candidate with syndrome 0xFFFFFF (no single-bit error has it): the
+    reference and the oracle both find nothing to accept in that window (the CUDA path once did, see tests/test_gpu_edges.py)."""
+    z = np.load(Path(__file__).resolve().parent / "golden" / "syndrome_ffffff.npz")
+    iq, thr = z["iq"], int(z["preamble_threshold"])
+    ref, o = Reference(preamble_threshold=thr), Oracle(preamble_threshold=thr)
+    fr = ref.run_stream(iq, 65536)[0]
+    fo, _ = o.run_stream(iq, 65536)
+    assert len(fr) == len(fo) == 0
+    assert ref.stats()[0]["demod_preambles"] == o.stats()["demod_preambles"] > 10
+    assert Oracle.diagnose1(0xFFFFFF, 112) < 0 and Oracle.diagnose1(0xFFFFFF, 56) < 0

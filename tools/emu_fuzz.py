@@ -3,9 +3,10 @@
     python tools/emu_fuzz.py [--seed S] [--cases N] [--minutes M] [--sanitize address]
 
 Each case draws: receivers, buffer length (odd sizes included), buffers per run, input kind (the synthetic workloads, plus
-saturated / sawtooth / constant / uniformly random bytes), preamble threshold, --no-fix / --no-fix-df, Mode A/C on or off, a
-ragged tail, and one of the entry paths (host submits, magnitude hand-off, device-resident blocking, device-resident
-pipelined, pipelined host slab).  Frames, per-buffer results, counters and Mode A/C replies must equal the oracle's.
+saturated / sawtooth / constant / uniformly random bytes), preamble threshold, --no-fix / --no-fix-df, Mode A/C on or off, the
+ICAO filter's flip period (down to a few ms of stream time: flips inside a run), a ragged tail, and one of the entry paths
+(host submits, magnitude hand-off, sc16 / sc16q11 input, device-resident blocking, device-resident pipelined, pipelined host
+slab).  Frames, per-buffer results, counters, Mode A/C replies and (sometimes) the Beast byte stream must equal the oracle's.
 Prints the failing case's parameters (re-run it alone with --only K).  The same script works on a GPU (without B200_EMU).
 """
 from __future__ import annotations
@@ -49,6 +50,15 @@ def make_input(rng, kind: str, n: int, seed: int):
     raise ValueError(kind)
 
 
+def to_sc16(iq8, q11: bool, seed: int):
+    """The uc8 capture as a 16-bit frontend would deliver it (plus sub-LSB dither)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    scale = 16 if q11 else 256
+    v = (iq8.astype(np.int32) - 128) * scale + rng.integers(0, scale, size=iq8.size)
+    return np.clip(v, -2048 if q11 else -32768, 2047 if q11 else 32767).astype(np.int16)
+
+
 def run_case(k: int, seed: int, verbose: bool):
     import numpy as np
     import devbuf
@@ -58,7 +68,7 @@ def run_case(k: int, seed: int, verbose: bool):
     rng = np.random.default_rng([seed, k])
     S = int(rng.choice([1, 1, 2, 3, 5]))
     buf = int(rng.choice([1000, 4096, 8191, 8192, 20000, 32768, 65536, 65536, 131072, int(rng.integers(700, 70000))]))
-    path = str(rng.choice(["host", "host", "mag", "device", "device_async", "host_async"]))
+    path = str(rng.choice(["host", "host", "mag", "device", "device_async", "host_async", "sc16"]))
     if path in ("device", "device_async", "host_async"):
         buf = max(8, buf & ~7)                                   # those entry points want multiples of 8
     K = int(rng.choice([1, 2, 3, 4, 8]))
@@ -67,14 +77,21 @@ def run_case(k: int, seed: int, verbose: bool):
     thr = int(rng.choice([58, 58, 58, 40, 75, 120, 33]))
     nfix, fixdf = int(rng.random() < 0.8), int(rng.random() < 0.8)
     mode_ac = bool(rng.random() < 0.4)
-    ragged = path in ("host", "mag") and rng.random() < 0.5
+    ragged = path in ("host", "mag", "sc16") and rng.random() < 0.5
+    ttl = int(rng.choice([60000, 60000, 60000, 300, 40, 7]))          # ms of stream time between ICAO filter flips
+    q11 = bool(rng.random() < 0.5)
+    beast = bool(rng.random() < 0.35)
+    verbatim = bool(rng.random() < 0.5)
     total = K * steps * buf - (int(rng.integers(1, buf)) if ragged else 0)
-    params = dict(case=k, S=S, buf=buf, K=K, steps=steps, kind=kind, thr=thr, nfix=nfix, fixdf=fixdf, mode_ac=mode_ac, path=path, total=total)
+    params = dict(case=k, S=S, buf=buf, K=K, steps=steps, kind=kind, thr=thr, nfix=nfix, fixdf=fixdf, mode_ac=mode_ac, path=path, total=total, ttl=ttl, q11=q11,
+                  beast=beast, verbatim=verbatim)
     if verbose:
         print(params, flush=True)
     iqs = [make_input(rng, kind, total, 1000 * k + s) for s in range(S)]
-    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=K, preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, mode_ac=mode_ac)
-    got_f = [[] for _ in range(S)]; got_b = [[] for _ in range(S)]; got_a = [[] for _ in range(S)]
+    iq16 = [to_sc16(iqs[s], q11, k + s) for s in range(S)] if path == "sc16" else None
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=K, preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, mode_ac=mode_ac,
+                    icao_ttl_ms=ttl)
+    got_f = [[] for _ in range(S)]; got_b = [[] for _ in range(S)]; got_a = [[] for _ in range(S)]; got_beast = [b"" for _ in range(S)]
     nb_done = [0] * S
 
     def harvest():
@@ -83,8 +100,21 @@ def run_case(k: int, seed: int, verbose: bool):
             if mode_ac:
                 a = d.modeac(s); a["buffer_idx"] += nb_done[s]; got_a[s].append(a)
             nb_done[s] += len(b)
+            if beast:
+                got_beast[s] += d.beast(s, verbatim=verbatim)
 
-    if path in ("host", "mag"):
+    if path == "sc16":
+        off = 0
+        while off < total:
+            for _ in range(K):
+                if off >= total:
+                    break
+                m = min(buf, total - off)
+                for s in range(S):
+                    d.submit_iq_sc16(s, iq16[s][2 * off: 2 * (off + m)], off * 5, q11)
+                off += m
+            d.run(); harvest()
+    elif path in ("host", "mag"):
         halos = [np.zeros(326, np.uint16) for _ in range(S)]
         off = 0
         while off < total:
@@ -138,18 +168,29 @@ def run_case(k: int, seed: int, verbose: bool):
 
     problems = []
     for s in range(S):
-        o = Oracle(preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf)
-        fo, bo = o.run_stream(iqs[s], buf)
-        problems += [f"stream {s}: {p}" for p in diff_frames(np.concatenate(got_f[s]), fo) + diff_bufres(np.concatenate(got_b[s]), bo)]
+        o = Oracle(preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, icao_ttl_ms=ttl)
+        ao = None
+        if path == "sc16":
+            fo, sums = o.run_stream_sc16(iq16[s], buf, q11)
+            bg = np.concatenate(got_b[s])
+            problems += [f"stream {s}: {p}" for p in diff_frames(np.concatenate(got_f[s]), fo)]
+            if len(bg) != len(sums) or any(r["length"] != m or np.uint32(r["sum_level"]).view(np.float32) != sl or np.uint32(r["sum_power"]).view(np.float32) != sp
+                                           for r, (m, sl, sp) in zip(bg, sums)):
+                problems.append(f"stream {s}: sc16 float sums differ")
+        else:
+            fo, bo = o.run_stream(iqs[s], buf)
+            problems += [f"stream {s}: {p}" for p in diff_frames(np.concatenate(got_f[s]), fo) + diff_bufres(np.concatenate(got_b[s]), bo)]
         st = d.stats(s)
         if mode_ac:
-            ao = Oracle().run_stream_ac(iqs[s], buf)
+            ao = Oracle().run_stream_ac_sc16(iq16[s], buf, q11) if path == "sc16" else Oracle().run_stream_ac(iqs[s], buf)
             ag = np.concatenate(got_a[s])
             if len(ag) != len(ao) or any(not np.array_equal(ag[f], ao[f]) for f in ("timestamp", "f1_sample", "modeac", "buffer_idx")):
                 problems.append(f"stream {s}: Mode A/C replies differ ({len(ag)} vs {len(ao)})")
             if st["demod_modeac"] != len(ao):
                 problems.append(f"stream {s}: demod_modeac {st['demod_modeac']} vs {len(ao)}")
         problems += [f"stream {s}: {p}" for p in diff_stats(st, o.stats())]
+        if beast and got_beast[s] != Oracle.beast(fo, ao, verbatim=verbatim):
+            problems.append(f"stream {s}: Beast output differs")
     nframes = sum(len(np.concatenate(x)) for x in got_f)
     d.close()
     return params, problems, nframes
