@@ -27,6 +27,17 @@
 #include "common.h"
 #include "device_utils.cuh"
 
+// Trip counters for the instruction model in profiles/ (tools/scan_model.py): compiled in only with -DB200_SCAN_COUNTERS, which
+// only an analysis build of the test infrastructure passes; nothing of this is in the sm_100a library (its SASS is unchanged).
+#ifdef B200_SCAN_COUNTERS
+extern "C" { __attribute__((visibility("default"))) unsigned long long b200_scan_counters[16]; }
+#define SCAN_COUNT(id, n) do { if ((threadIdx.x & 31) == 0) b200_scan_counters[id] += (n); } while (0)
+#else
+#define SCAN_COUNT(id, n) do { } while (0)
+#endif
+enum { SCN_RUNS, SCN_LOOP_ITERS, SCN_WINDOW_CHUNKS, SCN_FAST_CONVERTS, SCN_EDGE_CONVERTS, SCN_Q1_ENTRIES, SCN_Q1_LOOP_TRIPS, SCN_THR_BATCHES,
+       SCN_PASS_BATCHES, SCN_PASSERS, SCN_GATE_TRIPS, SCN_SURVIVORS, SCN_SLICE_ROUNDS, SCN_SLICE_BYTES };
+
 #ifndef SC_WARPS
 #define SC_WARPS 28
 #endif
@@ -397,6 +408,10 @@ __device__ __forceinline__ void slice_round(const ScanSmem &S, WarpSmem &W, cons
                                             uint32_t lane, uint32_t &n_stage, Rec *stage, uint32_t *stage_key) {
     uint32_t rw[8];
     uint32_t kind = 0;
+    SCAN_COUNT(SCN_SLICE_ROUNDS, 1);
+#ifdef B200_SCAN_COUNTERS
+    { const bool lg = lane < cnt && ((W.surv[lane] >> 17) & 1u); const uint32_t nby = __any_sync(FULLMASK, lg) ? 14 : 7; SCAN_COUNT(SCN_SLICE_BYTES, nby); }
+#endif
     if (lane < cnt) {
         const uint32_t e = W.surv[lane];
         const uint32_t p = e & 0x3fffu, ph = (e >> 14) & 7u;
@@ -436,6 +451,7 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
     PosEntry *run_pos = P.pos_pool + (size_t)W.ctx.tile0 * SCAN_TILE;
     PosEntry *pos_out = run_pos + (size_t)m * SCAN_TILE;
     for (uint32_t b0 = 0; b0 < n_q1; b0 += 32) {
+        SCAN_COUNT(SCN_THR_BATCHES, 1);
         const uint32_t e = b0 + lane;
         uint32_t p = 0, tried = 0;
         if (e < n_q1) {
@@ -445,6 +461,7 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
         const uint32_t bal = __ballot_sync(FULLMASK, tried != 0);
         if (!bal) continue;
         const uint32_t n_b = __popc(bal), n_pos = W.n_pos[m];
+        SCAN_COUNT(SCN_PASS_BATCHES, 1); SCAN_COUNT(SCN_PASSERS, n_b);
         if (tried) {
             const uint32_t r = __popc(bal & lt);
             W.pass[r] = p | (tried << 16);
@@ -453,6 +470,7 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
         __syncwarp();
         if (lane == 0) W.n_pos[m] = n_pos + n_b;
         for (uint32_t i0 = 0; i0 < 5 * n_b; i0 += 32) {
+            SCAN_COUNT(SCN_GATE_TRIPS, 1);
             const uint32_t i = i0 + lane, r = i / 5, ph = i - 5 * r;
             uint32_t g = 0, pe = 0;
             if (r < n_b) {
@@ -462,6 +480,7 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
             const uint32_t bal2 = __ballot_sync(FULLMASK, g & 1u);
             if (g & 1u) W.surv[n_surv + __popc(bal2 & lt)] = (pe & 0x3fffu) | (ph << 14) | ((g >> 1) << 17) | ((n_pos + r) << 18);
             n_surv += __popc(bal2);
+            SCAN_COUNT(SCN_SURVIVORS, __popc(bal2));
             __syncwarp();
             if (n_surv >= 32) {
                 slice_round(S, W, P, 32, tickg, run_pos, lane, n_stage, stage, stage_key);
@@ -544,6 +563,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
         __syncwarp();
 
         uint32_t n_q1 = 0, n_surv = 0, n_stage = 0;
+        SCAN_COUNT(SCN_RUNS, 1);
         uint32_t ms = 0;          // ring slot of chunk k's magnitudes; ticks of chunk k sit in slot k & 1
         // Chunks in the interior of the data and of a reference buffer need no case analysis: `fast_left` counts how many chunks
         // after the one just classified are of the same kind (staged, converted by the fast path, counted for buffer `fast_buf`);
@@ -554,7 +574,9 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
 #pragma unroll 1
         for (int k = -2; k <= (int)n_chunks; k++) {
             uint32_t mask = 0;
+            SCAN_COUNT(SCN_LOOP_ITERS, 1);
             if (k >= 0) {
+                SCAN_COUNT(SCN_WINDOW_CHUNKS, 1);
                 // ---- window(k): pre-check + tick map -----------------------------------------------------------------
                 mask = window_pass(W, ms * CHUNK + lane * 16, (k & 1) * TICK_CW, lane, (k & 1) == 0,
                                    P.tick_scratch + (size_t)warp_global * TICKG_WORDS + k * TICK_CW);
@@ -607,6 +629,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
             // ---- convert(k+2) into the slot chunk k-1 occupied ------------------------------------------------------
             if (more) {
                 const uint32_t msn = k < 0 ? cn : (ms == 0 ? 2 : ms - 1);       // (ms + 2) % 3; the first two chunks fill slots 0 and 1
+                SCAN_COUNT(fast ? SCN_FAST_CONVERTS : SCN_EDGE_CONVERTS, 1);
                 if (fast) convert_chunk_fast(S, W, P, T.is_mag, msn, lane, count_buf);
                 else {
                     if (all_data) stage_wait();      // staged, but this chunk straddles a buffer boundary: the edge path loads it itself
@@ -619,6 +642,9 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
                 uint32_t off = warp_excl_scan(__popc(mask), lane, &n_q1);
                 const uint32_t i0 = k * CHUNK + lane * 16;
                 uint32_t mb = mask;
+#ifdef B200_SCAN_COUNTERS
+                { const uint32_t trips = __reduce_max_sync(FULLMASK, (uint32_t)__popc(mask)); SCAN_COUNT(SCN_Q1_LOOP_TRIPS, trips); SCAN_COUNT(SCN_Q1_ENTRIES, n_q1); }
+#endif
                 while (mb) {
                     const uint32_t b = __ffs(mb) - 1; mb &= mb - 1;
                     if (off < Q1_SMEM) W.q1[off] = (uint16_t)(i0 + b); else q1_over[off - Q1_SMEM] = (uint16_t)(i0 + b);

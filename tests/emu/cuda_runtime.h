@@ -68,7 +68,7 @@ extern unsigned char *emu_smem;      // the CTA's dynamic shared memory (256 KiB
 #define gridDim (emu_cur->gdim)
 
 // rendezvous primitives (emu_rt.cpp)
-uint64_t *emu_warp_exchange(unsigned mask, uint64_t value);   // returns the 32 values of the lanes that took part (lane-indexed)
+uint64_t *emu_warp_exchange(unsigned mask, uint64_t value, int kind);   // returns the 32 values of the lanes that took part (lane-indexed); kind: which collective (all lanes of a rendezvous must agree)
 unsigned emu_warp_arrived_mask();                             // lanes that took part in the exchange just completed
 void emu_block_barrier();
 
@@ -77,27 +77,27 @@ template <class T> static inline uint64_t emu_pack(T v) { static_assert(sizeof(T
 template <class T> static inline T emu_unpack(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
 
 template <class T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
-    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v));
+    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v), 1);
     const unsigned lane = emu_cur->lane, base = lane & ~(unsigned)(width - 1);
     return emu_unpack<T>(x[base + ((unsigned)src & (unsigned)(width - 1))]);
 }
 template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
-    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v));
+    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v), 2);
     const unsigned lane = emu_cur->lane, base = lane & ~(unsigned)(width - 1);
     return (lane - base) >= delta ? emu_unpack<T>(x[lane - delta]) : v;
 }
 template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
-    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v));
+    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v), 3);
     const unsigned lane = emu_cur->lane, base = lane & ~(unsigned)(width - 1);
     return (lane - base) + delta < (unsigned)width ? emu_unpack<T>(x[lane + delta]) : v;
 }
 template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
-    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v));
+    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v), 4);
     const unsigned lane = emu_cur->lane, other = lane ^ (unsigned)lanemask;
     return (other & ~(unsigned)(width - 1)) == (lane & ~(unsigned)(width - 1)) ? emu_unpack<T>(x[other]) : v;
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
-    const uint64_t *x = emu_warp_exchange(mask, pred ? 1u : 0u);
+    const uint64_t *x = emu_warp_exchange(mask, pred ? 1u : 0u, 5);
     const unsigned part = emu_warp_arrived_mask();
     unsigned r = 0;
     for (unsigned l = 0; l < 32; l++) if (((part >> l) & 1u) && x[l]) r |= 1u << l;
@@ -105,12 +105,12 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) { const unsigned b = __ballot_sync(mask, pred); return b == (emu_warp_arrived_mask()); }
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)emu_warp_exchange(mask, 0); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)emu_warp_exchange(mask, 0, 6); }
 static inline void __syncthreads() { emu_block_barrier(); }
 static inline void __threadfence_block() {}
 static inline void __threadfence() {}
 template <class T> static inline T emu_reduce(unsigned mask, T v, int op) {
-    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v));
+    const uint64_t *x = emu_warp_exchange(mask, emu_pack(v), 16 + op);
     const unsigned part = emu_warp_arrived_mask();
     bool first = true; T r = 0;
     for (unsigned l = 0; l < 32; l++) if ((part >> l) & 1u) {

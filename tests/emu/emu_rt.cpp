@@ -36,6 +36,7 @@ emu_switch:
 
 struct EmuWarp {
     unsigned arrived = 0, part = 0, gen = 0, alive = 0, pending_mask = 0;
+    int pending_kind = 0;
     uint64_t xchg[2][32];
     unsigned parts[2] = {0, 0};
 };
@@ -92,13 +93,18 @@ static void fiber_exit_check_warp(EmuWarp *w) {
     if (w->arrived && w->arrived == (w->pending_mask & w->alive)) complete_rendezvous(w);
 }
 
-uint64_t *emu_warp_exchange(unsigned mask, uint64_t value) {
+uint64_t *emu_warp_exchange(unsigned mask, uint64_t value, int kind) {
     EmuThread *me = emu_cur;
     EmuWarp *w = me->warp;
     const unsigned g = w->gen, buf = g & 1u;
     if (!((mask >> me->lane) & 1u)) { g_fault = "a lane called a *_sync collective with a mask that does not name it"; fprintf(stderr, "emu: %s\n", g_fault); abort(); }
     if (w->arrived && w->pending_mask != mask) { g_fault = "lanes of one warp met in *_sync collectives with different masks"; fprintf(stderr, "emu: %s\n", g_fault); abort(); }
-    w->pending_mask = mask;
+    if (w->arrived && w->pending_kind != kind) {
+        g_fault = "lanes of one warp met in DIFFERENT collectives (e.g. a *_sync call that only some lanes execute)";
+        fprintf(stderr, "emu: %s: kinds %d and %d, block %u warp %u lane %u\n", g_fault, w->pending_kind, kind, me->bid.x, me->warp_id, me->lane);
+        abort();
+    }
+    w->pending_mask = mask; w->pending_kind = kind;
     w->xchg[buf][me->lane] = value;
     w->arrived |= 1u << me->lane;
     if (w->arrived == (mask & w->alive)) complete_rendezvous(w);

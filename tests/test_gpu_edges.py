@@ -146,12 +146,12 @@ def test_filter_flip_on_the_stream_clock(cuda):
 
 
 def test_syndrome_all_ones_is_not_a_correctable_error(cuda):
-    """A DF17 candidate whose syndrome is exactly 0xFFFFFF (tests/golden/syndrome_ffffff.npz: 2200 samples cut out of a
+    """A DF17 candidate whose syndrome is exactly 0xFFFFFF (tests/golden/regress/syndrome_ffffff.npz: 2200 samples cut out of a
     tools/emu_fuzz.py case, loud traffic at --preamble-threshold=33).  The single-bit-error lookup is a perfect hash whose
     empty slots once held 0xffffffff: this syndrome matched an empty slot, came back as 'bit 255' and the frame was accepted
     with score 700 (and finalize flipped msg[-1]).  The reference finds no such error (crc.c:383-406) and rejects the phase."""
     from readsb_b200.demod import Demodulator
-    z = np.load(Path(__file__).resolve().parent / "golden" / "syndrome_ffffff.npz")
+    z = np.load(Path(__file__).resolve().parent / "golden" / "regress" / "syndrome_ffffff.npz")
     iq, thr = z["iq"], int(z["preamble_threshold"])
     o = Oracle(preamble_threshold=thr)
     fo, bo = o.run_stream(iq, 65536)

@@ -280,9 +280,9 @@ def test_dropped_samples_raise_the_threshold_to_75():
 
 @needs_ref
 def test_reference_rejects_the_all_ones_syndrome():
-    """tests/golden/syndrome_ffffff.npz holds a DF17 candidate with syndrome 0xFFFFFF (no single-bit error has it): the
+    """tests/golden/regress/syndrome_ffffff.npz holds a DF17 candidate with syndrome 0xFFFFFF (no single-bit error has it): the
     reference and the oracle both find nothing to accept in that window (the CUDA path once did, see tests/test_gpu_edges.py)."""
-    z = np.load(Path(__file__).resolve().parent / "golden" / "syndrome_ffffff.npz")
+    z = np.load(Path(__file__).resolve().parent / "golden" / "regress" / "syndrome_ffffff.npz")
     iq, thr = z["iq"], int(z["preamble_threshold"])
     ref, o = Reference(preamble_threshold=thr), Oracle(preamble_threshold=thr)
     fr = ref.run_stream(iq, 65536)[0]
