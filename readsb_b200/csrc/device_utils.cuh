@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // memory (modes_tables.h; convert.c:35-62 is symmetric about 127.5 in both I and Q).
 __device__ __forceinline__ void uc8_pair_to_mag(const uint16_t *lut_smem, uint32_t w, uint32_t &m0, uint32_t &m1) {
     const uint32_t sgn = prmt(w, 0, 0xba98);                // 0xff where the byte is >= 128
-    const uint32_t f = (w ^ ~sgn) & 0x7f7f7f7fu;            // fold: v>=128 ? v-128 : 127-v
+    const uint32_t f = (w ^ sgn) & 0x7f7f7f7fu;             // fold: v>=128 ? 255-v : v  (127 = centre, 0 = full scale; one LOP3)
     uint32_t off = f + (f & 0x007f007fu);                   // per half: fq*256 + 2*fi
     off ^= (f >> 5) & 0x00780078u;                          // bank swizzle
     m0 = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(lut_smem) + (off & 0xffffu));

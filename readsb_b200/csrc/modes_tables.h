@@ -38,7 +38,8 @@ static inline uint32_t b200_crc32_ieee(const void *data, size_t n) {
 }
 
 // Folded table: the magnitude depends only on |2I-255| and |2Q-255|, so 128 x 128 entries suffice.
-// fold(v) = v >= 128 ? v - 128 : 127 - v.  Entry (fi, fq) is stored at uint16 index
+// fold(v) = v >= 128 ? 255 - v : v  (127 = centre, 0 = full scale: `(v ^ sign) & 0x7f` on the device, a single LOP3 for four
+// bytes).  Entry (fi, fq) is stored at uint16 index
 //   fq*128 + (fi ^ ((fq & 15) << 2))
 // i.e. byte offset fq*256 + 2*fi with bits 3..6 XOR-ed by (fq & 15): rows that differ in their low
 // four bits land in different shared-memory banks, which matters because receiver noise keeps
@@ -46,7 +47,7 @@ static inline uint32_t b200_crc32_ieee(const void *data, size_t n) {
 static inline void b200_build_folded_lut(const uint16_t *lut_full, uint16_t *fold) {
     for (int fq = 0; fq < 128; fq++)
         for (int fi = 0; fi < 128; fi++)
-            fold[fq * 128 + (fi ^ ((fq & 15) << 2))] = lut_full[(128 + fi) * 256 + (128 + fq)];
+            fold[fq * 128 + (fi ^ ((fq & 15) << 2))] = lut_full[fi * 256 + fq];
 }
 
 static inline uint32_t b200_crc24_bytes(const uint32_t *tab, const uint8_t *msg, int nbytes) {

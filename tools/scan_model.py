@@ -18,12 +18,12 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests")); sys.path
 # static warp instructions per trip (fast paths; out-of-line divergence handlers of the collectives not counted)
 STATIC = {
     "window_pass (pre-check 16 positions + 80 ticks per lane)": ("window_chunks", 429),
-    "convert_chunk_fast (8 sample pairs through the table, sums, REDUX)": ("fast_converts", 207),
+    "convert_chunk_fast (8 sample pairs through the table, sums, REDUX)": ("fast_converts", 191),
     "q1 compaction: prefix scan": ("window_chunks", 50),
     "q1 compaction: one pass of the set-bit loop": ("q1_loop_trips", 17),
     "chunk loop control, staging, classification (fast chunk)": ("loop_iters", 60),
     "threshold batch (32 pre-check passers)": ("thr_batches", 66),
-    "batch with threshold passers: PosEntry writes": ("pass_batches", 33),
+    "batch with threshold passers: PosEntry writes": ("pass_batches", 28),
     "DF-gate trip (32 (position, phase) slots)": ("gate_trips", 90),
     "slice round: per message byte": ("slice_bytes", 30),
     "slice round: classification + emission": ("slice_rounds", 170),
