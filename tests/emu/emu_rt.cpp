@@ -4,6 +4,7 @@
 #include <sys/mman.h>
 #include <time.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -162,10 +163,21 @@ void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, const std::fun
             for (int i = 0; i < 6; i++) *--sp = nullptr;
             th.sp = sp;
         }
-        // round-robin until every thread is done
+        // round-robin until every thread is done.  B200_EMU_SCHED_SEED=<n>: a different random order of the fibers in every round
+        // (lanes within a warp and warps within the CTA), to shake out code that only works in the default lane-0-first order
+        static const char *sched_env = getenv("B200_EMU_SCHED_SEED");
+        static uint64_t rng = sched_env ? (uint64_t)strtoull(sched_env, nullptr, 10) * 0x9E3779B97F4A7C15ull + 1 : 0;
+        std::vector<unsigned> order(block);
+        for (unsigned t = 0; t < block; t++) order[t] = t;
         while (g_alive) {
             bool progressed = false;
-            for (unsigned t = 0; t < block; t++) {
+            if (sched_env)
+                for (unsigned i = block - 1; i > 0; i--) {
+                    rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;          // xorshift64
+                    std::swap(order[i], order[rng % (i + 1)]);
+                }
+            for (unsigned oi = 0; oi < block; oi++) {
+                const unsigned t = order[oi];
                 EmuThread &th = g_threads[t];
                 if (th.state != 0) continue;
                 progressed = true;

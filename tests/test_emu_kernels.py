@@ -19,8 +19,11 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _run_gpu_tests_emulated(*modules: str, timeout: int = 900, sanitize: str | None = None, select: str | None = None) -> str:
+def _run_gpu_tests_emulated(*modules: str, timeout: int = 900, sanitize: str | None = None, select: str | None = None,
+                            sched_seed: int | None = None) -> str:
     env = dict(os.environ, B200_EMU="1")
+    if sched_seed is not None:
+        env["B200_EMU_SCHED_SEED"] = str(sched_seed)
     env.pop("B200_DEMOD_LIB", None)
     env.pop("B200_EMU_LIB", None)
     cmd = [sys.executable, "-m", "pytest", *modules, "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
@@ -71,6 +74,13 @@ def test_no_undefined_behaviour_where_cpu_and_gpu_semantics_differ():
     """UBSan over the parity tests: no shift by >= 32, no signed overflow, no misaligned vector access in the kernels' source —
     the constructs C++ leaves undefined and PTX defines, i.e. where an emulated run could disagree with the hardware."""
     _run_gpu_tests_emulated("tests/test_gpu_edges.py", "tests/test_gpu_parity.py", sanitize="undefined")
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_parity_does_not_depend_on_the_order_lanes_and_warps_run_in(seed):
+    """The emulator's default schedule runs lane 0 first and warp 0 first; here every scheduling round uses a fresh random order
+    of the CTA's fibers (lanes within a warp, warps within the CTA) — code that leans on the default order fails."""
+    _run_gpu_tests_emulated("tests/test_gpu_parity.py", "tests/test_gpu_edges.py", sched_seed=seed)
 
 
 def test_product_never_refers_to_the_emulator():
