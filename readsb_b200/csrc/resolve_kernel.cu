@@ -518,9 +518,16 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams P) {
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t total = P.frame_prefix[P.n_streams];
     for (uint32_t fi = warp_global; fi < total; fi += n_warps) {
-        // stream = last s with prefix[s] <= fi
-        uint32_t lo = 0, hi = P.n_streams;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (P.frame_prefix[mid] <= fi) lo = mid; else hi = mid; }
+        // stream = last s with prefix[s] <= fi.  The whole kernel is one dependent-load chain per frame, so the search is done by
+        // the warp, 32 probes per level (two loads deep for 256 receivers instead of eight), ...
+        uint32_t lo = 0, span = P.n_streams;                     // the answer lies in [lo, lo + span)
+        while (span > 1) {
+            const uint32_t step = (span + 31) >> 5, idx = lo + lane * step;
+            const bool le = lane * step < span && P.frame_prefix[idx] <= fi;          // true for lane 0: prefix[lo] <= fi
+            const uint32_t j = __popc(__ballot_sync(FULLMASK, le)) - 1u;              // prefixes ascend: the true lanes are 0..j
+            lo += j * step;
+            span = min(step, span - j * step);
+        }
         const uint32_t stream = lo, k = fi - P.frame_prefix[lo];
         const b200_frame *src = &P.frames[(size_t)stream * P.frame_cap + k];
         const uint32_t d = *reinterpret_cast<const uint32_t *>(&src->pad_[2]);
@@ -531,15 +538,30 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams P) {
             while ((seg_i & 0xffffu) != low) seg_i++;
         }
         const Segment seg = P.segs[seg_i];
-        const uint32_t len = src->signal_len;
+        const uint32_t len = src->signal_len;                    // 134 or 268 samples (demod_2400.c:439): at most 9 per lane
+        // ... and the samples are fetched with all loads of a lane in flight at once (then the table lookups, likewise)
+        constexpr int FIN_PER_LANE = 9;
+        uint32_t raw[FIN_PER_LANE];
+#pragma unroll
+        for (int u = 0; u < FIN_PER_LANE; u++) {
+            const uint32_t i = lane + 32u * u, dd = d + 19 + i;  // data index of the sample (demod_2400.c:443)
+            const bool live = i < len && !((seg.flags & SEG_HALO_ZERO) && dd < B200_TRAIL);
+            raw[u] = live ? (uint32_t)*reinterpret_cast<const uint16_t *>(seg.base + 2 * (size_t)dd) : 0xffffffffu;
+        }
         unsigned long long sum = 0;
-        for (uint32_t i = lane; i < len; i += 32) {
-            const uint32_t dd = d + 19 + i;                      // data index of the sample (demod_2400.c:443)
+#pragma unroll
+        for (int u = 0; u < FIN_PER_LANE; u++) {
+            uint32_t m = 0;
+            if (raw[u] != 0xffffffffu) m = (seg.flags & SEG_MAG) ? raw[u] : P.lut_full[(raw[u] & 0xffu) * 256 + (raw[u] >> 8)];
+            sum += (unsigned long long)(m * m);
+        }
+        for (uint32_t i = lane + 32u * FIN_PER_LANE; i < len; i += 32) {      // (not reached with the reference's frame lengths)
+            const uint32_t dd = d + 19 + i;
             uint32_t m;
             if ((seg.flags & SEG_HALO_ZERO) && dd < B200_TRAIL) m = 0;
             else {
-                const uint16_t raw = *reinterpret_cast<const uint16_t *>(seg.base + 2 * (size_t)dd);
-                m = (seg.flags & SEG_MAG) ? raw : P.lut_full[(raw & 0xffu) * 256 + (raw >> 8)];
+                const uint16_t r16 = *reinterpret_cast<const uint16_t *>(seg.base + 2 * (size_t)dd);
+                m = (seg.flags & SEG_MAG) ? r16 : P.lut_full[(r16 & 0xffu) * 256 + (r16 >> 8)];
             }
             sum += (unsigned long long)(m * m);
         }
