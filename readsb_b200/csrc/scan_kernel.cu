@@ -80,7 +80,7 @@ struct WarpSmem {
     alignas(16) uint8_t raw[2 * CHUNK];       // the next chunk's input bytes, landed here by cp.async while the candidates are worked on
     uint32_t tick[TICK_RING + TICK_MIRROR];   // tick of sample s (chunk-local) and row r at bit 5 s + r of the chunk's slot
     uint16_t q1[Q1_SMEM];                     // pre-check passers of the previous chunk (tile-relative positions, ascending)
-    uint32_t pass[64];                        // threshold passers waiting for their DF gates (up to two batches), PosEntry format
+    uint32_t pass[32];                        // threshold passers waiting for their DF gates, PosEntry format
     uint32_t surv[SURV_CAP];                  // DF-gate survivors waiting for a full slice: run position | ph << 14 | long << 17 | PosEntry index << 18
     uint32_t seg[16];                         // the run's Segment
     uint32_t n_pos[RUN_MAX], n_rec[RUN_MAX];  // per tile of the run
@@ -450,54 +450,60 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
     uint32_t *stage_key = P.stage_key + (size_t)warp_global * P.stage_cap;
     PosEntry *run_pos = P.pos_pool + (size_t)W.ctx.tile0 * SCAN_TILE;
     PosEntry *pos_out = run_pos + (size_t)m * SCAN_TILE;
-    // Threshold passers wait in W.pass until a whole chunk's worth (or more than 32) of them is there: their DF gates are
-    // evaluated five lanes per passer, and a single batch rarely has more than three (one gate trip per batch left most
-    // lanes idle: 1.76 trips per chunk on the bench workload against 1.1 now).
+    // Threshold passers wait in W.pass (32 entries) until the chunk's last batch is through or the next batch's passers would
+    // not fit: their DF gates are evaluated five lanes per passer, and a single batch rarely has more than three (one gate
+    // trip per batch left most lanes idle: 1.76 trips per chunk on the bench workload against 1.1 now).
     uint32_t n_pass = 0, pos_base = W.n_pos[m];                 // passers waiting in W.pass; PosEntry index (in the tile) of W.pass[0]
-    for (uint32_t b0 = 0; b0 < n_q1; b0 += 32) {
-        SCAN_COUNT(SCN_THR_BATCHES, 1);
-        const uint32_t e = b0 + lane;
-        uint32_t p = 0, tried = 0;
-        if (e < n_q1) {
-            p = e < Q1_SMEM ? W.q1[e] : q1_over[e - Q1_SMEM];    // run-relative position
-            tried = threshold_phases(&W.mag[mslot * CHUNK + (p - chunk_p0)], P.thr);
+    for (uint32_t b0 = 0;; b0 += 32) {
+        const bool have_batch = b0 < n_q1;
+        uint32_t p = 0, tried = 0, bal = 0;
+        if (have_batch) {
+            SCAN_COUNT(SCN_THR_BATCHES, 1);
+            const uint32_t e = b0 + lane;
+            if (e < n_q1) {
+                p = e < Q1_SMEM ? W.q1[e] : q1_over[e - Q1_SMEM];    // run-relative position
+                tried = threshold_phases(&W.mag[mslot * CHUNK + (p - chunk_p0)], P.thr);
+            }
+            bal = __ballot_sync(FULLMASK, tried != 0);
         }
-        const uint32_t bal = __ballot_sync(FULLMASK, tried != 0);
+        const uint32_t n_b = __popc(bal);
+        if (n_pass && (!have_batch || n_pass + n_b > 32)) {      // ---- DF gates of the waiting passers
+            __syncwarp();
+            for (uint32_t i0 = 0; i0 < 5 * n_pass; i0 += 32) {
+                SCAN_COUNT(SCN_GATE_TRIPS, 1);
+                const uint32_t i = i0 + lane, r = i / 5, ph = i - 5 * r;
+                uint32_t g = 0, pe = 0;
+                if (r < n_pass) {
+                    pe = W.pass[r];
+                    if ((pe >> (16 + ph)) & 1u) g = df_gate(W, P, first_tick(tslot, (pe & 0x3fffu) - chunk_p0, ph));
+                }
+                const uint32_t bal2 = __ballot_sync(FULLMASK, g & 1u);
+                if (g & 1u) W.surv[n_surv + __popc(bal2 & lt)] = (pe & 0x3fffu) | (ph << 14) | ((g >> 1) << 17) | ((pos_base + r) << 18);
+                n_surv += __popc(bal2);
+                SCAN_COUNT(SCN_SURVIVORS, __popc(bal2));
+                __syncwarp();
+                if (n_surv >= 32) {
+                    slice_round(S, W, P, 32, tickg, run_pos, lane, n_stage, stage, stage_key);
+                    const uint32_t moved = lane + 32 < n_surv ? W.surv[lane + 32] : 0;
+                    __syncwarp();
+                    W.surv[lane] = moved;
+                    n_surv -= 32;
+                    __syncwarp();
+                }
+            }
+            pos_base += n_pass; n_pass = 0;
+            __syncwarp();                                        // W.pass is free again
+        }
+        if (!have_batch) break;
         if (bal) {
-            SCAN_COUNT(SCN_PASS_BATCHES, 1); SCAN_COUNT(SCN_PASSERS, __popc(bal));
+            SCAN_COUNT(SCN_PASS_BATCHES, 1); SCAN_COUNT(SCN_PASSERS, n_b);
             if (tried) {
                 const uint32_t r = n_pass + __popc(bal & lt);
                 W.pass[r] = p | (tried << 16);
                 pos_out[pos_base + r] = (p & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE) | (tried << 16);   // live bits are OR-ed in when its phases are sliced
             }
-            n_pass += __popc(bal);
+            n_pass += n_b;
         }
-        if (n_pass == 0 || (n_pass <= 32 && b0 + 32 < n_q1)) continue;       // nothing waiting, or room for the next batch's passers
-        __syncwarp();
-        for (uint32_t i0 = 0; i0 < 5 * n_pass; i0 += 32) {
-            SCAN_COUNT(SCN_GATE_TRIPS, 1);
-            const uint32_t i = i0 + lane, r = i / 5, ph = i - 5 * r;
-            uint32_t g = 0, pe = 0;
-            if (r < n_pass) {
-                pe = W.pass[r];
-                if ((pe >> (16 + ph)) & 1u) g = df_gate(W, P, first_tick(tslot, (pe & 0x3fffu) - chunk_p0, ph));
-            }
-            const uint32_t bal2 = __ballot_sync(FULLMASK, g & 1u);
-            if (g & 1u) W.surv[n_surv + __popc(bal2 & lt)] = (pe & 0x3fffu) | (ph << 14) | ((g >> 1) << 17) | ((pos_base + r) << 18);
-            n_surv += __popc(bal2);
-            SCAN_COUNT(SCN_SURVIVORS, __popc(bal2));
-            __syncwarp();
-            if (n_surv >= 32) {
-                slice_round(S, W, P, 32, tickg, run_pos, lane, n_stage, stage, stage_key);
-                const uint32_t moved = lane + 32 < n_surv ? W.surv[lane + 32] : 0;
-                __syncwarp();
-                W.surv[lane] = moved;
-                n_surv -= 32;
-                __syncwarp();
-            }
-        }
-        pos_base += n_pass; n_pass = 0;
-        __syncwarp();                                            // W.pass is written again by the next batch
     }
     if (lane == 0) W.n_pos[m] = pos_base;
 }
