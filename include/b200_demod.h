@@ -247,7 +247,11 @@ int b200_demod_get_stats(b200_demod_ctx *ctx, uint32_t stream, b200_demod_stats 
 #define B200_BEAST_MAX_RECORD 44
 int b200_demod_fetch_beast(b200_demod_ctx *ctx, uint32_t stream, uint32_t flags, uint8_t *out, uint32_t cap, uint32_t *nbytes);
 
-/* ICAO address filter (icao_filter.h) — per stream, lives next to the resolver on the device */
+/* ICAO address filter (icao_filter.h) — per stream, lives next to the resolver on the device.
+ * Capacity: 2048 addresses per generation (two generations, entries live for one to two flip periods like the reference's).
+ * The reference's tables grow instead (icao_filter.c:47-90, up to 2^20 buckets): a receiver never comes near the limit here
+ * (a few hundred aircraft in two minutes), but a process that forwards an aggregator's network-input addresses with
+ * b200_demod_icao_add can; B200_E_OVERFLOW from add / run then says so — nothing is dropped silently. */
 int b200_demod_icao_add(b200_demod_ctx *ctx, uint32_t stream, uint32_t addr);
 int b200_demod_icao_test(b200_demod_ctx *ctx, uint32_t stream, uint32_t addr, int *present);
 int b200_demod_icao_expire(b200_demod_ctx *ctx, uint32_t stream);
