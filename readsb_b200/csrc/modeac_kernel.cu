@@ -113,6 +113,7 @@ __global__ void modeac_noise_kernel(const AcScanParams P) {
         const Segment seg = P.segs[si];
         for (uint32_t b = threadIdx.x; b < seg.n_bufs; b += blockDim.x) {
             const uint32_t len = min(seg.buf_len, seg.npos - b * seg.buf_len);
+            if (len == 0) { P.noise[seg.first_buf + b] = 0; continue; }       // empty buffer: nothing will ask for its noise floor
             const BufAcc &a = P.buf_acc[seg.first_buf + b];     // sum_signal_power may still be accumulating: not read
             const AcLevel lv = P.levels[seg.first_buf + b];
             double mean_level, mean_power;
@@ -290,6 +291,10 @@ __global__ void __launch_bounds__(256) modeac_walk_kernel(const AcWalkParams P) 
         const uint32_t *bits = P.bitmap + (size_t)seg.tile_begin * (SCAN_TILE / 32);    // bit x = tile coordinate x of the segment
         for (uint32_t b = wid; b < seg.n_bufs; b += nw) {
             const uint32_t len_b = min(seg.buf_len, seg.npos - b * seg.buf_len);
+            if (len_b == 0) {       // an empty buffer (a frontend that had nothing to deliver): no positions, no tiles, no bit-map words
+                if (lane == 0) P.ac_count[seg.first_buf + b] = 0;
+                continue;
+            }
             const uint32_t xa = seg.lead + b * seg.buf_len, xb = xa + len_b;
             const uint32_t w_first = xa >> 5, w_last = (xb - 1) >> 5;
             b200_modeac *out = P.ac_out + (size_t)(seg.first_buf + b) * P.per_buf_cap;
@@ -353,12 +358,14 @@ extern "C" int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    if (sp->n_tiles && sp->n_segs) {
+    if (sp->n_segs) {       // also for a run of empty buffers only (no tiles): the walk is what sets every buffer's reply count, zero included
         modeac_noise_kernel<<<min(sp->n_segs, 1024u), 32, 0, (cudaStream_t)stream>>>(*sp);
-        // three of four scan tiles are skipped (AC_TILE = 4 scan tiles): an odd grid gives every block the same share of the fourth
-        uint32_t grid = (uint32_t)n_sm * 2 - 1;       // odd and not more than one wave (2 CTAs per SM)
-        if (grid > sp->n_tiles) grid = sp->n_tiles;
-        modeac_scan_kernel<<<grid, AC_THREADS, sizeof(AcSmem), (cudaStream_t)stream>>>(*sp);
+        if (sp->n_tiles) {
+            // three of four scan tiles are skipped (AC_TILE = 4 scan tiles): an odd grid gives every block the same share of the fourth
+            uint32_t grid = (uint32_t)n_sm * 2 - 1;       // odd and not more than one wave (2 CTAs per SM)
+            if (grid > sp->n_tiles) grid = sp->n_tiles;
+            modeac_scan_kernel<<<grid, AC_THREADS, sizeof(AcSmem), (cudaStream_t)stream>>>(*sp);
+        }
         modeac_walk_kernel<<<wp->n_segs, 256, 0, (cudaStream_t)stream>>>(*wp);
     }
     return (int)cudaGetLastError();

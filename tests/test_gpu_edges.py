@@ -161,3 +161,42 @@ def test_syndrome_all_ones_is_not_a_correctable_error(cuda):
     assert not problems, "\n".join(problems)
     assert o.stats()["demod_preambles"] > 10
     d.close()
+
+
+def test_modeac_with_empty_and_tiny_buffers(cuda):
+    """Mode A/C next to buffers a frontend delivered empty or shorter than the halo.  An empty buffer has no tiles and no
+    bit-map words: the walk once computed its last word from `x_end - 1` (wrapping for an empty range) and read the bit map out
+    of bounds — found by tools/emu_fuzz.py under AddressSanitizer (seed 71, case 47)."""
+    from readsb_b200.demod import Demodulator
+    iq = synth.modeac_stream(45, 150_000)
+    sizes = [20000, 0, 1, 7, 20000, 0, 325, 326, 327, 20000, 0, 13000, 20000]
+    cuts, pos = [], 0
+    for n in sizes:
+        cuts.append((pos, pos + n)); pos += n
+    assert pos <= 150_000
+    for per_run in (1, 2, 5):
+        d = Demodulator(n_streams=1, buf_samples=20000, max_buffers_per_run=per_run, mode_ac=True)
+        o, oa = Oracle(), Oracle()
+        fo, bo = _oracle_buffers(o, iq, cuts, lambda b, lo: lo * 5)
+        fg, bg, ag, nb0 = [], [], [], 0
+        for i in range(0, len(cuts), per_run):
+            part = cuts[i:i + per_run]
+            for lo, hi in part:
+                d.submit_iq(0, iq[2 * lo: 2 * hi], lo * 5)
+            d.run()
+            fg.append(d.frames(0)); bg.append(d.buffer_results(0))
+            a = d.modeac(0); a["buffer_idx"] += nb0; ag.append(a); nb0 += len(part)
+        halo, want = np.zeros(326, np.uint16), []
+        for b, (lo, hi) in enumerate(cuts):
+            mag, sl, sp = Oracle.convert(iq[2 * lo: 2 * hi]) if hi > lo else (np.zeros(0, np.uint16), 0, 0)
+            data = np.concatenate([halo, mag]).astype(np.uint16)
+            a = oa.demodulate_ac(data, hi - lo, lo * 5, sl, sp); a["buffer_idx"] = b; want.append(a)
+            halo = data[hi - lo: hi - lo + 326].copy() if hi - lo >= 326 else np.zeros(326, np.uint16)
+        ao, agc = np.concatenate(want), np.concatenate(ag)
+        assert len(ao) > 8 and len(agc) == len(ao), f"per_run={per_run}: {len(agc)} vs {len(ao)} replies"
+        for f in ("timestamp", "f1_sample", "modeac", "buffer_idx"):
+            assert np.array_equal(agc[f], ao[f]), f"per_run={per_run}: {f}"
+        problems = diff_frames(np.concatenate(fg), fo) + diff_bufres(np.concatenate(bg), bo) + diff_stats(d.stats(0), o.stats())
+        assert not problems, f"per_run={per_run}\n" + "\n".join(problems)
+        assert d.stats(0)["demod_modeac"] == len(ao)
+        d.close()

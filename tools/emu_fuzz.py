@@ -68,7 +68,7 @@ def run_case(k: int, seed: int, verbose: bool):
     rng = np.random.default_rng([seed, k])
     S = int(rng.choice([1, 1, 2, 3, 5]))
     buf = int(rng.choice([1000, 4096, 8191, 8192, 20000, 32768, 65536, 65536, 131072, int(rng.integers(700, 70000))]))
-    path = str(rng.choice(["host", "host", "mag", "device", "device_async", "host_async", "sc16"]))
+    path = str(rng.choice(["host", "host", "mag", "device", "device_async", "host_async", "sc16", "host_var"]))
     if path in ("device", "device_async", "host_async"):
         buf = max(8, buf & ~7)                                   # those entry points want multiples of 8
     K = int(rng.choice([1, 2, 3, 4, 8]))
@@ -103,6 +103,41 @@ def run_case(k: int, seed: int, verbose: bool):
             if beast:
                 got_beast[s] += d.beast(s, verbatim=verbatim)
 
+    if path == "host_var":      # buffers of random lengths (empty, shorter than the halo, odd), like a frontend that delivers what it has
+        import test_gpu_edges as E
+        cuts, pos = [], 0
+        while pos < total and len(cuts) < 150:
+            n = int(min(total - pos, rng.integers(0, buf + 1) if rng.random() < 0.5 else buf))
+            if rng.random() < 0.1:
+                n = int(min(total - pos, rng.choice([0, 1, 7, 325, 326, 327])))
+            cuts.append((pos, pos + n)); pos += n
+        problems = []
+        for s_ in range(S):
+            o = Oracle(preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, icao_ttl_ms=ttl)
+            fo, bo = E._oracle_buffers(o, iqs[s_], cuts, lambda b, lo: lo * 5)
+            fgl, bgl, agl, nb0 = [], [], [], 0
+            for i in range(0, len(cuts), K):
+                part = cuts[i:i + K]
+                for lo, hi in part:
+                    d.submit_iq(s_, iqs[s_][2 * lo: 2 * hi], lo * 5)
+                d.run()
+                fgl.append(d.frames(s_)); bgl.append(d.buffer_results(s_))
+                if mode_ac:
+                    a_ = d.modeac(s_); a_["buffer_idx"] += nb0; agl.append(a_)
+                nb0 += len(part)
+            problems += [f"stream {s_}: {p}" for p in diff_frames(np.concatenate(fgl), fo) + diff_bufres(np.concatenate(bgl), bo) + diff_stats(d.stats(s_), o.stats())]
+            if mode_ac:
+                oa, halo, want = Oracle(), np.zeros(326, np.uint16), []
+                for b_, (lo, hi) in enumerate(cuts):
+                    mag, sl, sp = Oracle.convert(iqs[s_][2 * lo: 2 * hi]) if hi > lo else (np.zeros(0, np.uint16), 0, 0)
+                    data = np.concatenate([halo, mag]).astype(np.uint16)
+                    a_ = oa.demodulate_ac(data, hi - lo, lo * 5, sl, sp); a_["buffer_idx"] = b_; want.append(a_)
+                    halo = data[hi - lo: hi - lo + 326].copy() if hi - lo >= 326 else np.zeros(326, np.uint16)
+                ao, ag = np.concatenate(want), np.concatenate(agl)
+                if len(ag) != len(ao) or any(not np.array_equal(ag[f], ao[f]) for f in ("timestamp", "f1_sample", "modeac", "buffer_idx")):
+                    problems.append(f"stream {s_}: Mode A/C replies differ ({len(ag)} vs {len(ao)})")
+        d.close()
+        return params, problems, 0
     if path == "sc16":
         off = 0
         while off < total:
