@@ -68,7 +68,7 @@ def run_case(k: int, seed: int, verbose: bool):
     rng = np.random.default_rng([seed, k])
     S = int(rng.choice([1, 1, 2, 3, 5]))
     buf = int(rng.choice([1000, 4096, 8191, 8192, 20000, 32768, 65536, 65536, 131072, int(rng.integers(700, 70000))]))
-    path = str(rng.choice(["host", "host", "mag", "device", "device_async", "host_async", "sc16", "host_var"]))
+    path = str(rng.choice(["host", "host", "mag", "device", "device_async", "host_async", "sc16", "host_var", "mixed", "host_ops"]))
     if path in ("device", "device_async", "host_async"):
         buf = max(8, buf & ~7)                                   # those entry points want multiples of 8
     K = int(rng.choice([1, 2, 3, 4, 8]))
@@ -77,7 +77,7 @@ def run_case(k: int, seed: int, verbose: bool):
     thr = int(rng.choice([58, 58, 58, 40, 75, 120, 33]))
     nfix, fixdf = int(rng.random() < 0.8), int(rng.random() < 0.8)
     mode_ac = bool(rng.random() < 0.4)
-    ragged = path in ("host", "mag", "sc16") and rng.random() < 0.5
+    ragged = path in ("host", "mag", "sc16", "mixed") and rng.random() < 0.5
     ttl = int(rng.choice([60000, 60000, 60000, 300, 40, 7]))          # ms of stream time between ICAO filter flips
     q11 = bool(rng.random() < 0.5)
     beast = bool(rng.random() < 0.35)
@@ -138,6 +138,92 @@ def run_case(k: int, seed: int, verbose: bool):
                     problems.append(f"stream {s_}: Mode A/C replies differ ({len(ag)} vs {len(ao)})")
         d.close()
         return params, problems, 0
+    if path == "host_ops":      # between runs: addresses added to / expired from the filter through the API, the threshold changed
+        oracles = [Oracle(preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, icao_ttl_ms=ttl) for _ in range(S)]
+        gf = [[] for _ in range(S)]; of = [[] for _ in range(S)]
+        seen = [0x123456]
+        nrun = (total + K * buf - 1) // (K * buf)
+        for r_ in range(nrun):
+            lo, hi = r_ * K * buf, min(total, (r_ + 1) * K * buf)
+            for s_ in range(S):
+                for o_ in range(lo, hi, buf):
+                    d.submit_iq(s_, iqs[s_][2 * o_: 2 * min(hi, o_ + buf)], o_ * 5)
+            d.run()
+            for s_ in range(S):
+                f_ = d.frames(s_); gf[s_].append(f_)
+                of[s_].append(oracles[s_].run_stream(iqs[s_][2 * lo: 2 * hi], buf, first_ts=lo * 5)[0])
+                seen += [int(a) for a in f_["addr"][:4]]
+            for s_ in range(S):
+                op = rng.random()
+                if op < 0.35:
+                    a_ = int(rng.choice(seen)) if rng.random() < 0.7 else int(rng.integers(0, 1 << 24))
+                    d.icao_add(s_, a_); oracles[s_].icao_add(a_)
+                    if d.icao_test(s_, a_) != oracles[s_].icao_test(a_):
+                        return params, [f"stream {s_}: icao_test differs after add"], 0
+                elif op < 0.5:
+                    d.icao_expire(s_); oracles[s_].icao_expire()
+            if rng.random() < 0.3:
+                t2 = int(rng.choice([40, 58, 75, 120, 400]))
+                d.set_preamble_threshold(t2)
+                for o in oracles:
+                    o.set_preamble_threshold(t2)
+        problems = []
+        for s_ in range(S):
+            problems += [f"stream {s_}: {p}" for p in diff_frames(np.concatenate(gf[s_]), np.concatenate(of[s_])) + diff_stats(d.stats(s_), oracles[s_].stats())]
+        d.close()
+        return params, problems, sum(len(np.concatenate(x)) for x in gf)
+    if path == "mixed":         # every receiver its own entry point and its own amount of data, all in the same runs
+        kinds = [str(rng.choice(["host", "mag", "sc16"])) for _ in range(S)]
+        tot = [int(max(1, total * rng.uniform(0.2, 1.0))) for _ in range(S)]
+        tot[int(rng.integers(0, S))] = total
+        iq16m = [to_sc16(iqs[s_], q11, k + s_) if kinds[s_] == "sc16" else None for s_ in range(S)]
+        halos = [np.zeros(326, np.uint16) for _ in range(S)]
+        offs = [0] * S
+        gf = [[] for _ in range(S)]; gb = [[] for _ in range(S)]; ga = [[] for _ in range(S)]; nbd = [0] * S
+        while any(offs[s_] < tot[s_] for s_ in range(S)):
+            for _ in range(K):
+                for s_ in range(S):
+                    if offs[s_] >= tot[s_]:
+                        continue
+                    m = min(buf, tot[s_] - offs[s_]); o_ = offs[s_]
+                    if kinds[s_] == "host":
+                        d.submit_iq(s_, iqs[s_][2 * o_: 2 * (o_ + m)], o_ * 5)
+                    elif kinds[s_] == "sc16":
+                        d.submit_iq_sc16(s_, iq16m[s_][2 * o_: 2 * (o_ + m)], o_ * 5, q11)
+                    else:
+                        mag, _, _ = Oracle.convert(iqs[s_][2 * o_: 2 * (o_ + m)])
+                        data = np.concatenate([halos[s_], mag]).astype(np.uint16)
+                        d.submit_mag(s_, data, m, o_ * 5)
+                        halos[s_] = data[m: m + 326].copy() if m >= 326 else np.zeros(326, np.uint16)
+                    offs[s_] += m
+            d.run()
+            for s_ in range(S):
+                gf[s_].append(d.frames(s_)); b_ = d.buffer_results(s_); gb[s_].append(b_)
+                if mode_ac:
+                    a_ = d.modeac(s_); a_["buffer_idx"] += nbd[s_]; ga[s_].append(a_)
+                nbd[s_] += len(b_)
+        problems = []
+        for s_ in range(S):
+            o = Oracle(preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, icao_ttl_ms=ttl)
+            fgc, bgc = np.concatenate(gf[s_]), np.concatenate(gb[s_])
+            if kinds[s_] == "sc16":
+                fo, sums = o.run_stream_sc16(iq16m[s_][:2 * tot[s_]], buf, q11)
+                problems += [f"stream {s_} ({kinds[s_]}): {p}" for p in diff_frames(fgc, fo)]
+                if len(bgc) != len(sums) or any(r["length"] != m or np.uint32(r["sum_level"]).view(np.float32) != sl or np.uint32(r["sum_power"]).view(np.float32) != sp
+                                                for r, (m, sl, sp) in zip(bgc, sums)):
+                    problems.append(f"stream {s_}: sc16 float sums differ")
+                ao = Oracle().run_stream_ac_sc16(iq16m[s_][:2 * tot[s_]], buf, q11) if mode_ac else None
+            else:
+                fo, bo = o.run_stream(iqs[s_][:2 * tot[s_]], buf)
+                problems += [f"stream {s_} ({kinds[s_]}): {p}" for p in diff_frames(fgc, fo) + diff_bufres(bgc, bo)]
+                ao = Oracle().run_stream_ac(iqs[s_][:2 * tot[s_]], buf) if mode_ac else None
+            problems += [f"stream {s_} ({kinds[s_]}): {p}" for p in diff_stats(d.stats(s_), o.stats())]
+            if mode_ac:
+                ag = np.concatenate(ga[s_])
+                if len(ag) != len(ao) or any(not np.array_equal(ag[f], ao[f]) for f in ("timestamp", "f1_sample", "modeac", "buffer_idx")):
+                    problems.append(f"stream {s_} ({kinds[s_]}): Mode A/C replies differ ({len(ag)} vs {len(ao)})")
+        d.close()
+        return params, problems, sum(len(np.concatenate(x)) for x in gf)
     if path == "sc16":
         off = 0
         while off < total:
