@@ -60,7 +60,8 @@ struct EmuThread {
     unsigned wait_gen;
 };
 extern EmuThread *emu_cur;
-extern unsigned char *emu_smem;      // the CTA's dynamic shared memory (256 KiB, 128-byte aligned)
+extern unsigned char *emu_smem;      // the CTA's dynamic shared memory (16-byte aligned; its end touches an inaccessible page)
+extern size_t emu_smem_bytes;
 
 #define threadIdx (emu_cur->tid)
 #define blockIdx (emu_cur->bid)
@@ -170,7 +171,7 @@ template <class T> static inline T __ldcs(const T *p) { return *p; }
 template <class T> static inline void __stcg(T *p, T v) { *p = v; }
 static inline size_t __cvta_generic_to_shared(const void *p) {
     const ptrdiff_t off = (const unsigned char *)p - emu_smem;
-    if (off < 0 || off >= (256 << 10)) { fprintf(stderr, "emu: __cvta_generic_to_shared of a pointer outside dynamic shared memory\n"); abort(); }
+    if (off < 0 || (size_t)off >= emu_smem_bytes) { fprintf(stderr, "emu: __cvta_generic_to_shared of a pointer outside dynamic shared memory\n"); abort(); }
     return (size_t)off;
 }
 

@@ -43,8 +43,12 @@ struct EmuWarp {
 };
 
 EmuThread *emu_cur = nullptr;
-alignas(128) static unsigned char emu_smem_storage[256 << 10];
-unsigned char *emu_smem = emu_smem_storage;
+// Dynamic shared memory of the CTA being run: the END of what the launch asked for touches an inaccessible page, so a kernel that
+// strays past its shared-memory size faults (to 16 bytes, the alignment the base keeps).
+static const size_t SMEM_MAX = 256 << 10;
+static unsigned char *g_smem_region = nullptr;     // SMEM_MAX usable bytes followed by a PROT_NONE page
+unsigned char *emu_smem = nullptr;
+size_t emu_smem_bytes = 0;
 
 static const size_t STACK_BYTES = 256 << 10;
 static std::vector<void *> g_stacks;              // reused across launches
@@ -142,11 +146,18 @@ static void *new_stack() {
 
 void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()> &body) {
     std::lock_guard<std::mutex> lock(g_launch_mutex);
-    if (block == 0 || block > 1024 || smem_bytes > sizeof(emu_smem_storage)) { fprintf(stderr, "emu: bad launch configuration (%u threads, %zu bytes)\n", block, smem_bytes); abort(); }
+    if (!g_smem_region) {
+        g_smem_region = (unsigned char *)mmap(nullptr, SMEM_MAX + 4096, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (g_smem_region == MAP_FAILED) { perror("emu: mmap"); abort(); }
+        mprotect(g_smem_region + SMEM_MAX, 4096, PROT_NONE);
+    }
+    if (block == 0 || block > 1024 || smem_bytes > SMEM_MAX) { fprintf(stderr, "emu: bad launch configuration (%u threads, %zu bytes)\n", block, smem_bytes); abort(); }
     while (g_stacks.size() < block) g_stacks.push_back(new_stack());
     const unsigned n_warps = (block + 31) / 32;
     for (unsigned b = 0; b < grid; b++) {
-        memset(emu_smem_storage, 0xcd, smem_bytes ? smem_bytes : 1);     // shared memory starts undefined
+        emu_smem_bytes = (smem_bytes + 15) & ~(size_t)15;
+        emu_smem = g_smem_region + SMEM_MAX - emu_smem_bytes;
+        memset(emu_smem, 0xcd, emu_smem_bytes);                           // shared memory starts undefined
         g_threads.assign(block, EmuThread());
         g_warps.assign(n_warps, EmuWarp());
         g_body = &body; g_block_arrived = 0; g_alive = block;
