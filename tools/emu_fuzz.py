@@ -238,7 +238,16 @@ def run_case(k: int, seed: int, verbose: bool):
     elif path in ("host", "mag"):
         halos = [np.zeros(326, np.uint16) for _ in range(S)]
         off = 0
+        use_strided = path == "host" and rng.random() < 0.4
+        slab = np.stack(iqs) if use_strided else None             # [S, 2 * total]: receiver s at slab + s * row stride
         while off < total:
+            if use_strided:                                        # all receivers in one strided DMA: K full buffers, or the partial tail
+                nfull = min(K, (total - off) // buf)
+                nb_, bl_ = (nfull, buf) if nfull else (1, total - off)
+                d.submit_iq_strided(0, S, slab.ctypes.data + 2 * off, slab.strides[0], nb_, bl_, off * 5)
+                off += nb_ * bl_
+                d.run(); harvest()
+                continue
             for _ in range(K):
                 if off >= total:
                     break
