@@ -239,14 +239,20 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = now_ms(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
+// Fault injection for the error paths of the host code: the n-th allocation from now on fails (0 = never).
+static long g_fail_after = 0;
+extern "C" __attribute__((visibility("default"))) void emu_fail_alloc_after(long n) { g_fail_after = n; }
+static bool alloc_should_fail() { return g_fail_after > 0 && --g_fail_after == 0; }
+
 cudaError_t cudaMalloc(void **p, size_t n) {
+    if (alloc_should_fail()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     // 256-byte alignment like the real allocator; contents undefined (0xcd) so that reads of unwritten device memory show up
     if (posix_memalign(p, 256, n ? n : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
     memset(*p, 0xcd, n);
     return cudaSuccess;
 }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { if (posix_memalign(p, 256, n ? n : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; } memset(*p, 0xcd, n); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { if (alloc_should_fail()) { *p = nullptr; return cudaErrorMemoryAllocation; } if (posix_memalign(p, 256, n ? n : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; } memset(*p, 0xcd, n); return cudaSuccess; }
 cudaError_t cudaMallocHost(void **p, size_t n) { return cudaHostAlloc(p, n, 0); }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }

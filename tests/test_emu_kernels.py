@@ -84,6 +84,13 @@ def test_parity_does_not_depend_on_the_order_lanes_and_warps_run_in(seed):
     _run_gpu_tests_emulated("tests/test_gpu_parity.py", "tests/test_gpu_edges.py", sched_seed=seed)
 
 
+def test_every_allocation_failure_is_reported_not_fatal():
+    """tests/emu/fail_alloc_probe.py: the n-th device / pinned allocation fails, for every n the host code reaches."""
+    env = dict(os.environ); env.pop("B200_DEMOD_LIB", None); env.pop("B200_EMU_LIB", None)
+    res = subprocess.run([sys.executable, str(ROOT / "tests" / "emu" / "fail_alloc_probe.py")], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "results equal the oracle's" in res.stdout, (res.stdout + res.stderr)[-2000:]
+
+
 def test_product_never_refers_to_the_emulator():
     for p in list((ROOT / "readsb_b200").rglob("*.py")) + list((ROOT / "readsb_b200" / "csrc").glob("*")) + list((ROOT / "include").glob("*")) \
             + [ROOT / "bench.py", ROOT / "__graft_entry__.py"]:
