@@ -200,3 +200,23 @@ def test_modeac_with_empty_and_tiny_buffers(cuda):
         assert not problems, f"per_run={per_run}\n" + "\n".join(problems)
         assert d.stats(0)["demod_modeac"] == len(ao)
         d.close()
+
+
+@pytest.mark.parametrize("mode_ac", [False, True])
+def test_runs_with_nothing_submitted(cuda, mode_ac):
+    """b200_demod_run with no buffer queued, before and after a run that had data for one of two receivers: no results, and the
+    previous run's frames / replies / Beast bytes do not reappear."""
+    from readsb_b200.demod import Demodulator
+    iq = synth.modeac_stream(5, 40000)
+    d = Demodulator(n_streams=2, buf_samples=20000, max_buffers_per_run=2, mode_ac=mode_ac)
+    d.run()
+    assert len(d.frames(0)) == 0 and len(d.buffer_results(1)) == 0 and d.beast(0) == b"" and (not mode_ac or len(d.modeac(0)) == 0)
+    d.submit_iq(1, iq[:40000], 0)
+    d.submit_iq(1, iq[40000:], 20000 * 5)
+    d.run()
+    fo, _ = Oracle().run_stream(iq, 20000)
+    assert len(fo) > 5 and not diff_frames(d.frames(1), fo) and len(d.frames(0)) == 0 and len(d.beast(1)) > 0
+    d.run()
+    assert len(d.frames(1)) == 0 and d.beast(1) == b"" and (not mode_ac or len(d.modeac(1)) == 0)
+    assert d.stats(1)["demod_accepted"][0] + d.stats(1)["demod_accepted"][1] == len(fo)
+    d.close()
