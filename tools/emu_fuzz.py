@@ -36,6 +36,15 @@ def make_input(rng, kind: str, n: int, seed: int):
     if kind == "loud":      # strong overlapping traffic close to clipping
         return synth.generate(n, seed=seed, frames_per_sec=8000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.MODEAC, n_icao=8,
                               amp=(0.7, 1.0), p_bit_error=0.3)
+    if kind == "synthrand":     # the generator with every knob drawn at random
+        mask = 0
+        for bit in (synth.DF17, synth.DF11, synth.AP, synth.DF18, synth.DF11_IID, synth.MODEAC):
+            if rng.random() < 0.5:
+                mask |= bit
+        lo = float(rng.uniform(0.02, 0.6))
+        return synth.generate(n, seed=seed, frames_per_sec=float(10 ** rng.uniform(1.5, 4.3)), df_mask=mask or synth.DF17, n_icao=int(rng.integers(1, 200)),
+                              amp=(lo, float(rng.uniform(lo, 1.0))), noise_sigma=float(rng.uniform(0.2, 12.0)), p_bit_error=float(rng.uniform(0, 0.6)),
+                              p_two_bit_error=float(rng.uniform(0, 0.2)))
     if kind == "random":
         return rng.integers(0, 256, size=2 * n, dtype=np.uint8)
     if kind == "sawtooth":
@@ -73,8 +82,8 @@ def run_case(k: int, seed: int, verbose: bool):
         buf = max(8, buf & ~7)                                   # those entry points want multiples of 8
     K = int(rng.choice([1, 2, 3, 4, 8]))
     steps = int(rng.choice([1, 2, 3, 5]))
-    kind = str(rng.choice(["cfg2", "cfg5", "mixed", "mixed", "modeac", "loud", "random", "sawtooth", "constant", "burst"]))
-    thr = int(rng.choice([58, 58, 58, 40, 75, 120, 33]))
+    kind = str(rng.choice(["cfg2", "cfg5", "mixed", "mixed", "modeac", "loud", "random", "sawtooth", "constant", "burst", "synthrand", "synthrand"]))
+    thr = int(rng.choice([58, 58, 58, 40, 75, 120, 33, 400]))
     nfix, fixdf = int(rng.random() < 0.8), int(rng.random() < 0.8)
     mode_ac = bool(rng.random() < 0.4)
     ragged = path in ("host", "mag", "sc16", "mixed") and rng.random() < 0.5
