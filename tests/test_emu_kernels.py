@@ -55,7 +55,7 @@ def test_emulated_library_exports_the_whole_abi():
 
 
 @pytest.mark.parametrize("module", ["tests/test_gpu_parity.py", "tests/test_gpu_edges.py", "tests/test_gpu_fullsize.py", "tests/test_gpu_shim.py",
-                                    "tests/test_gpu_fuzz.py"])
+                                    "tests/test_gpu_fuzz.py", "tests/test_gpu_emu_semantics.py"])
 def test_gpu_parity_suite_on_emulated_kernels(module):
     """test_gpu_shim.py: the whole unmodified reference program linked with integration/readsb_shim.c, its libb200demod.so
     resolved to the emulated library (needs oracle/_ref/readsb_{cpu,b200}, i.e. the reference tree at build time)."""
