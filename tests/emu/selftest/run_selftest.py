@@ -70,7 +70,7 @@ def check(inp, ow, ob, cnt):
         assert o[8] == (wide >> (l & 31)) & M, "funnelshift_r"
         assert o[9] == ((wide << (l & 31)) >> 32) & M, "funnelshift_l"
         by = [(x >> (8 * i)) & 0xff for i in range(4)] + [(nx >> (8 * i)) & 0xff for i in range(4)]
-        sel = 0x5410 + (l & 3) + ((l & 4) << 2) + ((l & 24) << 9)
+        sel = 0x5410 + (l & 3) + ((l & 4) << 2) + ((l & 24) << 5)
         assert o[10] == sum(by[(sel >> (4 * i)) & 7] << (8 * i) for i in range(4)), "byte_perm"
         assert o[11] == sum((0xff if by[i] & 0x80 else 0) << (8 * i) for i in range(4)), "prmt sign replication"
         lo, hi = x & 0xffff, x >> 16

@@ -22,7 +22,7 @@ __global__ void st_warp_kernel(const uint32_t *in, uint32_t *out) {
     o[7] = __brev(v);
     o[8] = __funnelshift_r(v, ~v, lane);
     o[9] = __funnelshift_l(v, ~v, lane);
-    o[10] = __byte_perm(v, ~v, 0x5410 + (lane & 3) + ((lane & 4) << 2) + ((lane & 24) << 9));     // selector nibbles stay in 0..7
+    o[10] = __byte_perm(v, ~v, 0x5410 + (lane & 3) + ((lane & 4) << 2) + ((lane & 24) << 5));     // selector nibbles stay in 0..7
     o[11] = st_prmt(v, 0, 0xba98);
     o[12] = (uint32_t)st_dp2a_lo(v, 0x00030feeu, -7);
     o[13] = (uint32_t)st_dp2a_hi(v, 0xff14f1fcu, 11);
