@@ -42,7 +42,9 @@ def build_sm100a() -> Path:
     """The same source as real CUDA (for the gpu-marked test that pins the emulator's definitions against the hardware)."""
     out = build_emu.BUILD / "libemu_selftest_sm100a.so"
     build_emu.BUILD.mkdir(parents=True, exist_ok=True)
-    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
                     str(HERE / "selftest.cu"), "-o", str(out)], check=True)
     return out
 

@@ -25,7 +25,11 @@ def test_emulator_primitives_match_the_hardware(cuda):
         assert L.b200_emu_selftest(inp.ctypes.data, ow.ctypes.data, ob.ctypes.data, cnt.ctypes.data, st.NB, st.NT) == 0
     else:
         import torch
-        L = ctypes.CDLL(str(st.build_sm100a()))
+        try:
+            lib = st.build_sm100a()
+        except (OSError, FileNotFoundError) as e:           # no nvcc on this box: nothing to compare with
+            pytest.skip(f"nvcc not available: {e}")
+        L = ctypes.CDLL(str(lib))
         L.b200_emu_selftest.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32] * 2
         d_in = torch.from_numpy(inp.view(np.int32)).cuda()
         d_ow = torch.zeros(32 * 16, dtype=torch.int32, device="cuda")
