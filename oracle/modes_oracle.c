@@ -108,6 +108,84 @@ int oracle_crc_diagnose1(uint32_t syndrome, int bits) {
     return -2;
 }
 
+/* crc.c:180-378 with max_correct = 2, max_detect = 4 (modesChecksumInit's `default:` case, i.e. --aggressive,
+ * readsb.c:1535-1537).  PREPARATION for a later round: nothing on the demodulator path of this oracle uses it yet (the
+ * library refuses nfix_crc = 2), but the table is the part that has to be exactly the reference's, so it is restated and
+ * pinned now.  The reference enumerates every 1- and 2-bit error pattern over message bits 5..bits-1, sorts by syndrome,
+ * drops every syndrome that occurs more than once, then drops every entry whose syndrome is also the syndrome of some 3- or
+ * 4-bit pattern (flagCollisions).  The same set, built with a bit per syndrome instead of sorting and searching:
+ *   keep(s) <=> exactly one pattern of <= 2 bits has syndrome s, and no pattern of 3 or 4 bits has it. */
+typedef struct { uint32_t syndrome; int8_t b0, b1; } err2;
+static err2 *g_tab2[2]; static int g_ntab2[2];        /* [0] 56-bit, [1] 112-bit, sorted by syndrome */
+
+static int err2_cmp(const void *a, const void *b) { return (int)((const err2 *)a)->syndrome - (int)((const err2 *)b)->syndrome; }
+
+static void build_tab2(int which) {
+    if (g_tab2[which]) return;
+    build_crc();
+    const int bits = which ? 112 : 56, off = 112 - bits, n = bits - 5;
+    const uint32_t *syn = &g_bit_syn[5 + off];                      /* syn[i] = syndrome of message bit 5 + i */
+    uint8_t *seen12 = calloc(1 << 21, 1), *dup12 = calloc(1 << 21, 1), *seen34 = calloc(1 << 21, 1);
+#define BIT(a, x) ((a)[(x) >> 3] >> ((x) & 7) & 1)
+#define SET(a, x) ((a)[(x) >> 3] |= (uint8_t)(1u << ((x) & 7)))
+    for (int i = 0; i < n; i++) {
+        uint32_t s1 = syn[i];
+        if (BIT(seen12, s1)) SET(dup12, s1); else SET(seen12, s1);
+        for (int j = i + 1; j < n; j++) {
+            uint32_t s2 = s1 ^ syn[j];
+            if (BIT(seen12, s2)) SET(dup12, s2); else SET(seen12, s2);
+            for (int k = j + 1; k < n; k++) {
+                uint32_t s3 = s2 ^ syn[k];
+                SET(seen34, s3);
+                for (int l = k + 1; l < n; l++) SET(seen34, s3 ^ syn[l]);
+            }
+        }
+    }
+    err2 *t = malloc(sizeof(err2) * (size_t)(n + n * (n - 1) / 2));
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t s1 = syn[i];
+        if (!BIT(dup12, s1) && !BIT(seen34, s1)) { t[m].syndrome = s1; t[m].b0 = (int8_t)(5 + i); t[m].b1 = -1; m++; }
+        for (int j = i + 1; j < n; j++) {
+            uint32_t s2 = s1 ^ syn[j];
+            if (!BIT(dup12, s2) && !BIT(seen34, s2)) { t[m].syndrome = s2; t[m].b0 = (int8_t)(5 + i); t[m].b1 = (int8_t)(5 + j); m++; }
+        }
+    }
+#undef BIT
+#undef SET
+    free(seen12); free(dup12); free(seen34);
+    qsort(t, (size_t)m, sizeof(err2), err2_cmp);
+    g_tab2[which] = t; g_ntab2[which] = m;
+}
+
+/* modesChecksumDiagnose (crc.c:383-406) for --aggressive: returns the number of errors (0 for syndrome 0, 1 or 2 with the
+ * bit positions in *b0 / *b1, ascending), or -2 when the syndrome is not in the table. */
+int oracle_crc_diagnose2(uint32_t syndrome, int bits, int *b0, int *b1) {
+    *b0 = *b1 = -1;
+    if (syndrome == 0) return 0;
+    const int which = bits == 112;
+    build_tab2(which);
+    err2 key; key.syndrome = syndrome;
+    const err2 *e = bsearch(&key, g_tab2[which], (size_t)g_ntab2[which], sizeof(err2), err2_cmp);
+    if (!e) return -2;
+    *b0 = e->b0; *b1 = e->b1;
+    return e->b1 >= 0 ? 2 : 1;
+}
+
+/* Entries of the table and a digest over (syndrome, errors, bits) of every entry, for pinning against the reference. */
+int oracle_crc_table2_digest(int bits, uint64_t *digest) {
+    const int which = bits == 112;
+    build_tab2(which);
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < g_ntab2[which]; i++) {
+        const err2 *e = &g_tab2[which][i];
+        const uint64_t v = ((uint64_t)e->syndrome << 16) | ((uint64_t)(uint8_t)e->b0 << 8) | (uint8_t)e->b1;
+        h = (h ^ v) * 1099511628211ull;
+    }
+    *digest = h;
+    return g_ntab2[which];
+}
+
 /* ------------------------------------------------------------------ icao_filter.c semantics
  * Two generations; Test looks in both (icao_filter.c:132-154), Add goes to the active one
  * (:112-130), Expire clears the other one and makes it active (:96-110).  The hash layout of

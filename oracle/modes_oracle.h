@@ -41,6 +41,9 @@ void oracle_convert_sc16(const int16_t *iq, uint16_t *mag, unsigned nsamples, in
 uint32_t oracle_crc24(const uint8_t *msg, int bits);
 /* crc.c:383-406 with nfix_crc=1 tables: returns corrected bit (5..bits-1), -1 if syndrome==0, -2 if none */
 int oracle_crc_diagnose1(uint32_t syndrome, int bits);
+/* --aggressive (nfix_crc = 2) error tables, crc.c:180-378 with max_correct 2 / max_detect 4: preparation, not used by the path yet */
+int oracle_crc_diagnose2(uint32_t syndrome, int bits, int *b0, int *b1);
+int oracle_crc_table2_digest(int bits, uint64_t *digest);
 
 /* demod_2400.c:264-482 for one mag_buf: data = 326 halo + length new magnitudes.
  * Appends accepted frames to out[*n_out...] (cap entries); returns 0, or -1 if cap was hit. */

@@ -153,6 +153,24 @@ int ref_crc_diagnose1(uint32_t syndrome, int bits) {
     return ei->bit[0];
 }
 
+/* The reference's own --aggressive tables (modesChecksumInit(2)): number of syndromes modesChecksumDiagnose knows and a digest
+ * over (syndrome, errors, bits) in ascending syndrome order.  Re-initialises the tables: call ref_init again afterwards. */
+int ref_crc_table2_digest(int bits, uint64_t *digest) {
+    modesChecksumInit(2);
+    uint64_t h = 1469598103934665603ull;
+    int n = 0;
+    for (uint32_t syn = 1; syn < (1u << 24); syn++) {
+        struct errorinfo *ei = modesChecksumDiagnose(syn, bits);
+        if (!ei) continue;
+        const int b0 = ei->bit[0], b1 = ei->errors > 1 ? ei->bit[1] : -1;
+        const uint64_t v = ((uint64_t)syn << 16) | ((uint64_t)(uint8_t)b0 << 8) | (uint8_t)b1;
+        h = (h ^ v) * 1099511628211ull;
+        n++;
+    }
+    *digest = h;
+    return n;
+}
+
 int ref_score(const uint8_t *msg14, int validbits) {
     uint8_t tmp[14];
     memcpy(tmp, msg14, 14);

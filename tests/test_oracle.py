@@ -290,3 +290,28 @@ def test_reference_rejects_the_all_ones_syndrome():
     assert len(fr) == len(fo) == 0
     assert ref.stats()[0]["demod_preambles"] == o.stats()["demod_preambles"] > 10
     assert Oracle.diagnose1(0xFFFFFF, 112) < 0 and Oracle.diagnose1(0xFFFFFF, 56) < 0
+
+
+@needs_ref
+def test_aggressive_error_tables_match_reference():
+    """--aggressive (nfix_crc = 2, crc.c:180-378 with max_correct 2 / max_detect 4): the oracle's table — preparation, the
+    demodulator path does not use it yet — holds exactly the syndromes the reference's modesChecksumDiagnose knows, with the same
+    bit positions: 51 + 1275 entries for 56-bit frames, 107 + 3724 (of 5671 two-bit patterns: the rest collide with 3- or 4-bit
+    patterns and are dropped) for 112-bit frames; digest over every entry, reference side taken over all 2^24 syndromes."""
+    import ctypes as C
+    L = Oracle.lib()
+    L.oracle_crc_table2_digest.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
+    L.oracle_crc_diagnose2.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    ref = Reference()
+    ref.L.ref_crc_table2_digest.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
+    for bits, n_expected in ((56, 51 + 1275), (112, 107 + 3724)):
+        do, dr = C.c_uint64(), C.c_uint64()
+        no = L.oracle_crc_table2_digest(bits, C.byref(do))
+        nr = ref.L.ref_crc_table2_digest(bits, C.byref(dr))
+        assert no == nr == n_expected and do.value == dr.value
+    Reference()        # the digest call re-initialised the reference's tables for two-bit correction: put them back
+    b0, b1 = C.c_int(), C.c_int()
+    assert L.oracle_crc_diagnose2(0x3935EA, 112, C.byref(b0), C.byref(b1)) == -2          # bit 0 is a DF bit: never corrected
+    assert L.oracle_crc_diagnose2(0xFFF409, 112, C.byref(b0), C.byref(b1)) == 1 and (b0.value, b1.value) == (87, -1)
+    assert L.oracle_crc_diagnose2(0xFFF409 ^ 0x000001, 112, C.byref(b0), C.byref(b1)) in (2, -2)
+    assert L.oracle_crc_diagnose2(0, 112, C.byref(b0), C.byref(b1)) == 0
