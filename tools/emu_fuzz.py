@@ -248,6 +248,9 @@ def run_case(k: int, seed: int, verbose: bool):
         halos = [np.zeros(326, np.uint16) for _ in range(S)]
         off = 0
         use_strided = path == "host" and rng.random() < 0.4
+        mag_levels = path == "mag" and mode_ac and rng.random() < 0.6
+        level_scale = (float(rng.uniform(0.5, 2.0)), float(rng.uniform(0.5, 3.0)))
+        given = [[] for _ in range(S)]
         slab = np.stack(iqs) if use_strided else None             # [S, 2 * total]: receiver s at slab + s * row stride
         while off < total:
             if use_strided:                                        # all receivers in one strided DMA: K full buffers, or the partial tail
@@ -265,9 +268,17 @@ def run_case(k: int, seed: int, verbose: bool):
                     if path == "host":
                         d.submit_iq(s, iqs[s][2 * off: 2 * (off + m)], off * 5)
                     else:
-                        mag, _, _ = Oracle.convert(iqs[s][2 * off: 2 * (off + m)])
+                        mag, sl_, sp_ = Oracle.convert(iqs[s][2 * off: 2 * (off + m)])
                         data = np.concatenate([halos[s], mag]).astype(np.uint16)
-                        d.submit_mag(s, data, m, off * 5)
+                        if mag_levels and m:        # the mag_buf's own mean_level / mean_power: exact ones, or (receiver 0) distorted ones
+                            ml, mp = sl_ / 65536.0 / m, sp_ / 65535.0 / 65535.0 / m
+                            if s == 0:
+                                ml, mp = ml * level_scale[0], mp * level_scale[1]
+                            d.submit_mag(s, data, m, off * 5, ml, mp)
+                            given[s].append((data.copy(), m, off * 5, ml, mp))
+                        else:
+                            d.submit_mag(s, data, m, off * 5)
+                            given[s].append((data.copy(), m, off * 5, None, None))
                         halos[s] = data[m: m + 326].copy() if m >= 326 else np.zeros(326, np.uint16)
                 off += m
             d.run(); harvest()
@@ -321,7 +332,17 @@ def run_case(k: int, seed: int, verbose: bool):
             problems += [f"stream {s}: {p}" for p in diff_frames(np.concatenate(got_f[s]), fo) + diff_bufres(np.concatenate(got_b[s]), bo)]
         st = d.stats(s)
         if mode_ac:
-            ao = Oracle().run_stream_ac_sc16(iq16[s], buf, q11) if path == "sc16" else Oracle().run_stream_ac(iqs[s], buf)
+            if path == "mag" and mag_levels:
+                oa, parts = Oracle(), []
+                for b_, (data_, m_, ts_, ml_, mp_) in enumerate(given[s]):
+                    if ml_ is None:
+                        a_ = oa.demodulate_ac(data_, m_, ts_, int(data_[326:326 + m_].astype(np.uint64).sum()), int((data_[326:326 + m_].astype(np.uint64) ** 2).sum()))
+                    else:
+                        a_ = oa.demodulate_ac_levels(data_, m_, ts_, ml_, mp_)
+                    a_["buffer_idx"] = b_; parts.append(a_)
+                ao = np.concatenate(parts)
+            else:
+                ao = Oracle().run_stream_ac_sc16(iq16[s], buf, q11) if path == "sc16" else Oracle().run_stream_ac(iqs[s], buf)
             ag = np.concatenate(got_a[s])
             if len(ag) != len(ao) or any(not np.array_equal(ag[f], ao[f]) for f in ("timestamp", "f1_sample", "modeac", "buffer_idx")):
                 problems.append(f"stream {s}: Mode A/C replies differ ({len(ag)} vs {len(ao)})")
