@@ -96,6 +96,9 @@ def run_case(k: int, seed: int, verbose: bool):
                   beast=beast, verbatim=verbatim)
     if verbose:
         print(params, flush=True)
+    # device / pipelined paths: at one step the receivers start over (continues = 0: the samples before are not a halo)
+    restart_at = int(rng.integers(1, steps)) if path in ("device", "device_async", "host_async") and steps > 1 and rng.random() < 0.35 else -1
+    params["restart_at"] = restart_at
     iqs = [make_input(rng, kind, total, 1000 * k + s) for s in range(S)]
     iq16 = [to_sc16(iqs[s], q11, k + s) for s in range(S)] if path == "sc16" else None
     d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=K, preamble_threshold=thr, nfix_crc=nfix, fix_df=fixdf, mode_ac=mode_ac,
@@ -292,9 +295,9 @@ def run_case(k: int, seed: int, verbose: bool):
         for c in range(steps):
             args = (dev.data_ptr() + pad + c * K * buf * 2, stride, K, buf)
             if path == "device":
-                d.run_device(*args, continues=c > 0, first_sample_timestamp=c * K * buf * 5); harvest()
+                d.run_device(*args, continues=c > 0 and c != restart_at, first_sample_timestamp=c * K * buf * 5); harvest()
             else:
-                d.run_device_async(*args, continues=c > 0, first_sample_timestamp=c * K * buf * 5); flying += 1
+                d.run_device_async(*args, continues=c > 0 and c != restart_at, first_sample_timestamp=c * K * buf * 5); flying += 1
                 if flying == 3:
                     d.wait(); harvest(); flying -= 1
         while path == "device_async" and flying:
@@ -308,7 +311,7 @@ def run_case(k: int, seed: int, verbose: bool):
             sl = slabs[c % 3]
             for s in range(S):
                 sl.array[s * row: (s + 1) * row] = iqs[s][c * row: (c + 1) * row]
-            d.run_host_async(sl.ptr, row, K, buf, continues=c > 0, first_sample_timestamp=c * K * buf * 5); flying += 1
+            d.run_host_async(sl.ptr, row, K, buf, continues=c > 0 and c != restart_at, first_sample_timestamp=c * K * buf * 5); flying += 1
             if flying == 3:
                 d.wait(); harvest(); flying -= 1
         while flying:
@@ -327,6 +330,13 @@ def run_case(k: int, seed: int, verbose: bool):
             if len(bg) != len(sums) or any(r["length"] != m or np.uint32(r["sum_level"]).view(np.float32) != sl or np.uint32(r["sum_power"]).view(np.float32) != sp
                                            for r, (m, sl, sp) in zip(bg, sums)):
                 problems.append(f"stream {s}: sc16 float sums differ")
+        elif restart_at > 0:
+            cut = restart_at * K * buf
+            f1, b1 = o.run_stream(iqs[s][:2 * cut], buf)
+            o.restart_stream()
+            f2, b2 = o.run_stream(iqs[s][2 * cut:], buf, first_ts=cut * 5)
+            fo, bo = np.concatenate([f1, f2]), np.concatenate([b1, b2])
+            problems += [f"stream {s}: {p}" for p in diff_frames(np.concatenate(got_f[s]), fo) + diff_bufres(np.concatenate(got_b[s]), bo)]
         else:
             fo, bo = o.run_stream(iqs[s], buf)
             problems += [f"stream {s}: {p}" for p in diff_frames(np.concatenate(got_f[s]), fo) + diff_bufres(np.concatenate(got_b[s]), bo)]
@@ -341,6 +351,11 @@ def run_case(k: int, seed: int, verbose: bool):
                         a_ = oa.demodulate_ac_levels(data_, m_, ts_, ml_, mp_)
                     a_["buffer_idx"] = b_; parts.append(a_)
                 ao = np.concatenate(parts)
+            elif restart_at > 0:
+                cut = restart_at * K * buf
+                a1 = Oracle().run_stream_ac(iqs[s][:2 * cut], buf)
+                a2 = Oracle().run_stream_ac(iqs[s][2 * cut:], buf, first_ts=cut * 5); a2["buffer_idx"] += restart_at * K
+                ao = np.concatenate([a1, a2])
             else:
                 ao = Oracle().run_stream_ac_sc16(iq16[s], buf, q11) if path == "sc16" else Oracle().run_stream_ac(iqs[s], buf)
             ag = np.concatenate(got_a[s])
