@@ -110,7 +110,14 @@ void __wrap_demodulate2400(struct mag_buf *mag) {
         g_in_shim = 1;
         int result = decodeModesMessage(mm);                                     /* :421, field decoding stays on the host */
         g_in_shim = 0;
-        if (result < 0) continue;                      /* cannot happen while the two filters are in step */
+        if (result < 0) {
+            /* The library's filter follows icao_filter.c's semantics (table resize included), so its accept decision is
+             * decodeModesMessage's.  Should the two ever disagree (a host-side filter change that was not forwarded), count
+             * the frame the way demod_2400.c:422-428 counts a rejected message instead of losing it silently. */
+            if (result == -1) Modes.stats_current.demod_rejected_unknown_icao++;
+            else Modes.stats_current.demod_rejected_bad++;
+            continue;
+        }
         Modes.stats_current.demod_accepted[mm->correctedbits]++;
         Modes.stats_current.demod_bestPhase[f->phase - 4]++;
         double signal_power = f->sigpow_sum / 65535.0 / 65535.0;                 /* :448-457 */

@@ -188,8 +188,13 @@ int oracle_crc_table2_digest(int bits, uint64_t *digest) {
 
 /* ------------------------------------------------------------------ icao_filter.c semantics
  * Two generations; Test looks in both (icao_filter.c:132-154), Add goes to the active one
- * (:112-130), Expire clears the other one and makes it active (:96-110).  The hash layout of
- * the reference is unobservable; this is a growable open-addressed set of its own design. */
+ * (:112-130), Expire clears the other one and makes it active (:96-110).  The reference's hash LAYOUT is
+ * unobservable, its table SIZE is not: icaoFilterAdd doubles both tables once the active one holds more than
+ * buckets / 3 addresses (:126-128) and icaoFilterResize re-inserts the active generation only (:66-92) - the older
+ * generation is forgotten at that moment (the 86th, 171st, 342nd ... new address of a generation, starting from
+ * 2^8 buckets); icaoFilterExpire halves the tables first when the active generation holds fewer than buckets / 9
+ * (:97-99).  So the observable state is two sets plus `bits`; the sets themselves are growable open-addressed
+ * sets of this file's own design. */
 typedef struct { uint32_t *slot; uint32_t cap, n; } aset;
 
 static void aset_init(aset *s) { s->cap = 1024; s->n = 0; s->slot = malloc(s->cap * 4); memset(s->slot, 0xff, s->cap * 4); }
@@ -221,6 +226,7 @@ struct oracle_ctx {
     int thr, nfix, fixdf, ttl_ms;
     uint32_t long_set, short_set;     /* demod_2400.c:98-128 */
     aset gen[2]; int active;
+    int filter_bits;                  /* icao_filter.c:30,45-46: log2 of the reference's bucket count, 8..20 */
     int64_t next_flip; int flip_armed;
     /* stream state for oracle_run_stream_uc8 */
     uint16_t halo[TRAIL]; int halo_valid;
@@ -228,9 +234,19 @@ struct oracle_ctx {
     b200_demod_stats st;
 };
 
-void oracle_icao_add(oracle_ctx *o, uint32_t a) { aset_add(&o->gen[o->active], a); }
+void oracle_icao_add(oracle_ctx *o, uint32_t a) {
+    aset *act = &o->gen[o->active];
+    aset_add(act, a);                                                  /* icao_filter.c:112-124 (`occupied` = size of the active set) */
+    if (act->n > (1u << o->filter_bits) / 3 && o->filter_bits < 20) {  /* :126-128 -> icaoFilterResize :66-92 */
+        o->filter_bits++;
+        aset_clear(&o->gen[o->active ^ 1]);                            /* only the active generation is re-inserted */
+    }
+}
 int oracle_icao_test(const oracle_ctx *o, uint32_t a) { return aset_has(&o->gen[0], a) || aset_has(&o->gen[1], a); }
-void oracle_icao_expire(oracle_ctx *o) { o->active ^= 1; aset_clear(&o->gen[o->active]); o->st.icao_flips++; }
+void oracle_icao_expire(oracle_ctx *o) {
+    if (o->gen[o->active].n < (1u << o->filter_bits) / 9 && o->filter_bits > 8) o->filter_bits--;   /* icao_filter.c:97-99 */
+    o->active ^= 1; aset_clear(&o->gen[o->active]); o->st.icao_flips++;
+}
 
 /* Modes.preambleThreshold is re-read for every buffer (demod_2400.c:334-338): the caller applies the reference's
  * "at least PREAMBLE_THRESHOLD_PIZERO (75) while samples were dropped recently" rule between buffers. */
@@ -251,6 +267,7 @@ oracle_ctx *oracle_create(int thr, int nfix, int fixdf, int ttl_ms) {
         for (int b = 0; b < 5; b++) o->long_set |= 1u << (17 ^ (1 << b));
     }
     aset_init(&o->gen[0]); aset_init(&o->gen[1]);
+    o->filter_bits = 8;               /* icao_filter.c:45,50 MINBITS */
     return o;
 }
 

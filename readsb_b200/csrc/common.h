@@ -79,7 +79,7 @@ struct TileOut {
     uint32_t n_pos;    // PosEntry count; entries live at pos_pool[tile * SCAN_TILE ...]
     uint32_t n_rec;
     uint32_t rec_off;  // first Rec in rec_pool
-    uint32_t pad_;
+    uint32_t n_found;  // records the tile produced, also when the run's reservation failed (n_rec is 0 then)
 };
 
 struct BufAcc {        // exact per-buffer sums (convert.c:75-79), zeroed at the start of a run
@@ -90,18 +90,27 @@ struct BufAcc {        // exact per-buffer sums (convert.c:75-79), zeroed at the
 };
 
 // ---- per-receiver persistent state (device) -----------------------------------------------------
+// The address filter (icao_filter.c): two generations of an open-addressed set.  A receiver starts with tables of
+// ICAO_CAP slots (a slab of the context; stage B keeps such a table in shared memory).  The load is kept <= 1/2; a receiver that
+// needs more gets tables of its own, as large as it takes (the reference grows to 2^20 buckets, icao_filter.c:45-46), and stage B
+// then works on them in global memory.  What the reference's own table SIZE makes observable is modelled exactly: `filter_bits`
+// follows icao_filter.c:97-99 and :126-128, and the older generation is dropped when the reference's resize drops it (:66-92).
 #define ICAO_CAP_LOG2 12
-#define ICAO_CAP      (1u << ICAO_CAP_LOG2)   // slots per generation
+#define ICAO_CAP      (1u << ICAO_CAP_LOG2)   // slots per generation of the default tables
 #define ICAO_EMPTY    0xffffffffu
+#define ICAO_MINBITS  8
+#define ICAO_MAXBITS  20
 
 struct StreamState {
-    uint32_t gen[2][ICAO_CAP];   // two generations of the address filter (icao_filter.c)
+    uint32_t *tab[2];            // the two generations
+    uint32_t cap_log2;           // slots per generation = 1 << cap_log2
+    uint32_t grow_log2;          // set by the capacity check when this run could fill a generation beyond 1/2: what the host should grow to
     uint32_t gen_count[2];
     uint32_t active;             // generation that receives adds
+    uint32_t filter_bits;        // the reference's filterBits (8..20)
     uint32_t flip_armed;         // 0 until the first flip (readsb.c:1227: next_flip starts at 0)
-    int64_t  next_flip_ms;
     uint32_t buffer_seq;         // running buffer number
-    uint32_t error;              // sticky: 1 = filter generation full
+    int64_t  next_flip_ms;
     b200_demod_stats stats;
 };
 
@@ -110,13 +119,15 @@ struct RunCtl {
     uint32_t rec_alloc;      // atomic bump pointer into rec_pool
     uint32_t rec_cap;
     uint32_t overflow;       // bit0: rec_pool exhausted, bit1: per-tile queue capacity exceeded, bit2: frame capacity,
-                             // bit3: ICAO filter full, bit4: stage B skipped because the step ahead has to be repeated,
-                             // bit5: Mode A/C candidate / output capacity exceeded
+                             // bit3: a receiver's ICAO tables have to grow before this run (StreamState.grow_log2), bit4: stage B skipped
+                             // because the step ahead has to be repeated, bit5: Mode A/C candidate / output capacity exceeded
     uint32_t tile_counter;   // dynamic tile scheduler
     uint32_t total_frames;
     uint32_t stage_need;     // with overflow bit1: the largest number of live records one tile produced (staging areas too small)
     uint32_t pad_[2];
 };
+
+#define RUN_REPEAT_BITS (1u | 2u | 8u | 16u)   // stage B did not run (or must not): the host repairs and repeats the step
 
 struct ScanParams {
     const Segment *segs;
@@ -137,6 +148,7 @@ struct ScanParams {
     uint32_t stage_cap;
     uint16_t *q1_over;           // [warp][512] pre-check passers beyond the shared-memory queue (dense input)
     uint32_t *tick_scratch;      // [warp][b200_scan_tick_words()] the ticks of the run in progress (deferred, pooled slicing)
+    uint32_t *stream_addable;    // [stream] records of this run that could teach the receiver's filter an address (clean DF17, DF11 with IID 0)
 };
 
 struct ResolveParams {
@@ -157,6 +169,7 @@ struct ResolveParams {
     RunCtl *ctl;
     const RunCtl *prev_ctl;           // asynchronous pipeline: control block of the step ahead of this one (or nullptr)
     int32_t ttl_ms;
+    uint32_t *stream_addable;         // [n_streams] upper bound of the filter adds of this run (scan kernel); read and zeroed by the capacity check
 };
 
 struct FinalizeParams {
@@ -247,8 +260,13 @@ extern "C" {
 int b200_scan_warps(int n_sm);      // warps of the (persistent) scan kernel's grid
 int b200_scan_tick_words(void);     // words of tick scratch per warp
 int b200_launch_scan(const ScanParams *p, const DeviceTables *d_tables, int n_sm, void *stream);
-int b200_launch_resolve(const ResolveParams *p, void *stream);
-int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream);
+int b200_prepare_scan(void);       // per-device kernel attributes (dynamic shared memory opt-in): call with the device current
+int b200_prepare_resolve(void);
+int b200_prepare_modeac(void);
+int b200_launch_resolve(const ResolveParams *p, int any_grown, void *stream);
+int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, int n_sm, void *stream);
+int b200_launch_init_state(StreamState *state, uint32_t n, uint32_t *slab, void *stream);
+int b200_launch_icao_rehash(StreamState *state, uint32_t stream, uint32_t *new0, uint32_t *new1, uint32_t new_log2, void *stream_);
 int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp, int n_sm, void *stream);
 int b200_launch_sc16_convert(const void *d_iq, uint16_t *d_mag, uint32_t n, int q11, float2 *d_sums, int n_sm, void *stream);
 int b200_launch_beast(const BeastParams *p, uint32_t n_streams, void *stream);

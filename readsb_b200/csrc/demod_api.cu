@@ -57,6 +57,7 @@ struct Slot {
     b200_buffer_result *d_buf_out = nullptr, *h_buf_out = nullptr;
     b200_frame *d_frames = nullptr, *d_packed = nullptr, *h_packed = nullptr;
     uint32_t *d_frame_count = nullptr, *d_frame_prefix = nullptr, *h_frame_prefix = nullptr;
+    uint32_t *d_addable = nullptr;    // [S] filter adds this run can make at most (scan kernel -> capacity check, which zeroes it again)
     // Mode A/C (contexts created with B200_CFG_MODE_AC)
     uint32_t *d_ac_bitmap = nullptr, *d_ac_noise = nullptr;
     uint32_t *d_ac_count = nullptr, *d_ac_prefix = nullptr, *h_ac_prefix = nullptr;   // per reference buffer of the run
@@ -85,6 +86,9 @@ struct b200_demod_ctx {
     DeviceTables *d_tables = nullptr;
     uint16_t *d_lut_full = nullptr;
     StreamState *d_state = nullptr;
+    uint32_t *d_icao_slab = nullptr;              // default filter tables of all receivers: [S][2][ICAO_CAP]
+    std::vector<uint32_t *> icao_grown;           // tables of receivers that outgrew them (freed at destroy)
+    std::vector<StreamState> h_state;             // scratch for growing
 
     uint8_t *d_arena = nullptr;
     size_t stream_stride = 0;
@@ -146,17 +150,6 @@ __global__ void carry_halo_kernel(uint8_t *arena, size_t stride, const uint32_t 
     for (uint32_t i = threadIdx.x; i < B200_TRAIL; i += blockDim.x) to[i] = from[i];
 }
 
-__global__ void init_state_kernel(StreamState *st, uint32_t n) {
-    const uint32_t s = blockIdx.x;
-    if (s >= n) return;
-    for (uint32_t i = threadIdx.x; i < 2 * ICAO_CAP; i += blockDim.x) (&st[s].gen[0][0])[i] = ICAO_EMPTY;
-    if (threadIdx.x == 0) {
-        st[s].gen_count[0] = st[s].gen_count[1] = 0; st[s].active = 0; st[s].flip_armed = 0; st[s].next_flip_ms = 0;
-        st[s].buffer_seq = 0; st[s].error = 0;
-        memset(&st[s].stats, 0, sizeof(st[s].stats));
-    }
-}
-
 API int b200_demod_abi_version(void) { return B200_DEMOD_ABI_VERSION; }
 
 API const char *b200_demod_last_error(const b200_demod_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -177,7 +170,7 @@ API int b200_demod_uc8_lut(uint16_t *out) {
 static void free_slot(Slot &s) {
     cudaFree(s.d_segs); cudaFree(s.d_tile_seg); cudaFree(s.d_stream_seg_begin); cudaFree(s.d_ctl); cudaFree(s.d_pos_pool);
     cudaFree(s.d_rec_pool); cudaFree(s.d_key_pool); cudaFree(s.d_tile_out); cudaFree(s.d_buf_acc); cudaFree(s.d_buf_out);
-    cudaFree(s.d_frames); cudaFree(s.d_packed); cudaFree(s.d_frame_count); cudaFree(s.d_frame_prefix);
+    cudaFree(s.d_frames); cudaFree(s.d_packed); cudaFree(s.d_frame_count); cudaFree(s.d_frame_prefix); cudaFree(s.d_addable);
     cudaFree(s.d_ac_bitmap); cudaFree(s.d_ac_noise); cudaFree(s.d_ac_count); cudaFree(s.d_ac_prefix); cudaFree(s.d_ac_out); cudaFree(s.d_ac_packed);
     cudaFreeHost(s.h_ac_prefix); cudaFreeHost(s.h_ac_packed);
     cudaFree(s.d_ac_levels); cudaFreeHost(s.h_ac_levels);
@@ -204,6 +197,7 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
     A(dev_alloc(&s.d_frames, (size_t)S * c->frame_cap));
     A(dev_alloc(&s.d_packed, (size_t)S * c->frame_cap)); A(pin_alloc(&s.h_packed, (size_t)S * c->frame_cap));
     A(dev_alloc(&s.d_frame_count, S)); A(cudaMemset(s.d_frame_count, 0, S * 4));
+    A(dev_alloc(&s.d_addable, S)); A(cudaMemset(s.d_addable, 0, S * 4));
     A(dev_alloc(&s.d_frame_prefix, S + 1)); A(pin_alloc(&s.h_frame_prefix, S + 1));
     A(cudaMemset(s.d_ctl, 0, sizeof(RunCtl)));
     if (c->cfg.flags & B200_CFG_MODE_AC) {
@@ -230,7 +224,8 @@ API void b200_demod_destroy(b200_demod_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->d_tables); cudaFree(c->d_lut_full); cudaFree(c->d_state); cudaFree(c->d_arena);
+    cudaFree(c->d_tables); cudaFree(c->d_lut_full); cudaFree(c->d_state); cudaFree(c->d_arena); cudaFree(c->d_icao_slab);
+    for (uint32_t *t : c->icao_grown) cudaFree(t);
     cudaFree(c->d_carry_src); cudaFree(c->d_result);
     cudaFree(c->d_stage_rec); cudaFree(c->d_stage_key); cudaFree(c->d_q1_over); cudaFree(c->d_tick_scratch);
     cudaFreeHost(c->h_carry_src);
@@ -297,9 +292,11 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
         CUC(cudaMemcpy(c->d_lut_full, lut.data(), 65536 * 2, cudaMemcpyHostToDevice));
         delete t;
     }
+    // kernel attributes (dynamic shared memory opt-in) are per device: set them for this context's device, every time
+    CUC((cudaError_t)b200_prepare_scan()); CUC((cudaError_t)b200_prepare_resolve()); CUC((cudaError_t)b200_prepare_modeac());
     CUC(dev_alloc(&c->d_state, S));
-    init_state_kernel<<<S, 256, 0, c->stream>>>(c->d_state, S);
-    CUC(cudaGetLastError());
+    CUC(dev_alloc(&c->d_icao_slab, (size_t)S * 2 * ICAO_CAP));
+    CUC((cudaError_t)b200_launch_init_state(c->d_state, S, c->d_icao_slab, c->stream));
     CUC(dev_alloc(&c->d_result, 1));
 
     // arena for host submits: [326-sample halo][K buffers, each with room for its own halo when magnitudes are submitted]
@@ -461,6 +458,12 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     // scanning, so that this step's scan kernel is ready the moment that one ends — together with the other step's stage B,
     // and placed before it (stream priority): one persistent CTA per SM first, stage B's small CTAs into what is left.
     cudaStream_t pre = scan != res ? c->copy_stream : scan;
+    if (pre != scan) {
+        // This slot's control block is what the step enqueued after its previous run reads as `prev_ctl`: do not overwrite it before
+        // that step's stage B has looked (it may still be queued behind other work on the resolve stream).
+        Slot &succ = c->slot[((&sl - c->slot) + 1) % NSLOT];
+        if (succ.in_flight) CU(c, cudaStreamWaitEvent(pre, succ.ev[2], 0));
+    }
     CU(c, cudaMemcpyAsync(sl.d_segs, sl.h_segs, sl.nseg * sizeof(Segment), cudaMemcpyHostToDevice, pre));
     if (sl.upload_tiles && sl.ntile) CU(c, cudaMemcpyAsync(sl.d_tile_seg, sl.h_tile_seg, sl.ntile * 4, cudaMemcpyHostToDevice, pre));
     CU(c, cudaMemcpyAsync(sl.d_stream_seg_begin, sl.h_stream_seg_begin, (S + 1) * 4, cudaMemcpyHostToDevice, pre));
@@ -477,6 +480,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     sp.key_pool = sl.d_key_pool; sp.tile_out = sl.d_tile_out; sp.buf_acc = sl.d_buf_acc; sp.ctl = sl.d_ctl; sp.thr = c->cfg.preamble_threshold;
     sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df;
     sp.stage_rec = c->d_stage_rec; sp.stage_key = c->d_stage_key; sp.stage_cap = c->stage_cap; sp.q1_over = c->d_q1_over; sp.tick_scratch = c->d_tick_scratch;
+    sp.stream_addable = sl.d_addable;
     // demod_2400.c:112-127
     sp.short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
     sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
@@ -507,15 +511,16 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     rp.segs = sl.d_segs; rp.stream_seg_begin = sl.d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = sl.d_pos_pool;
     rp.rec_pool = sl.d_rec_pool; rp.key_pool = sl.d_key_pool; rp.tile_out = sl.d_tile_out; rp.buf_acc = sl.d_buf_acc; rp.buf_out = sl.d_buf_out;
     rp.state = c->d_state; rp.frames = sl.d_frames; rp.frame_count = sl.d_frame_count; rp.frame_cap = c->frame_cap; rp.per_buf_cap = c->cfg.buf_samples / 113 + 2;
-    rp.ctl = sl.d_ctl; rp.prev_ctl = prev_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms;
-    { int r = b200_launch_resolve(&rp, res); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
+    rp.ctl = sl.d_ctl; rp.prev_ctl = prev_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms; rp.stream_addable = sl.d_addable;
+    { const int grown = !c->icao_grown.empty();
+      int r = b200_launch_resolve(&rp, grown, res); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2 + grown; }
     CU(c, cudaEventRecord(sl.ev[2], res));
 
     FinalizeParams fp;
     fp.segs = sl.d_segs; fp.stream_seg_begin = sl.d_stream_seg_begin; fp.n_streams = S; fp.frames = sl.d_frames;
     fp.frame_count = sl.d_frame_count; fp.frame_prefix = sl.d_frame_prefix; fp.frame_cap = c->frame_cap; fp.packed = sl.d_packed;
     fp.buf_acc = sl.d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = sl.d_rec_pool;
-    { int r = b200_launch_finalize(&fp, sl.d_frame_prefix, sl.d_ctl, res); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
+    { int r = b200_launch_finalize(&fp, sl.d_frame_prefix, sl.d_ctl, c->n_sm, res); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
     CU(c, cudaEventRecord(sl.ev[3], res));
 
     if (mode_ac) {      // per-buffer reply lists -> one packed array in buffer order, receiver statistics
@@ -537,7 +542,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
 
 // Second half: wait for the first result copy, fetch the frames, derive the timings.  Returns B200_OK, or a positive
 // value when the run has to be repeated: 1 = record pool too small, 2 = dense-tile scratch arena needed, 3 = skipped
-// because the step before it had to be repeated.
+// because the step before it had to be repeated, 4 = a receiver's ICAO filter tables have to grow first.
 static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     const uint32_t S = c->cfg.n_streams;
     CU(c, cudaEventSynchronize(sl.ev[4]));
@@ -545,9 +550,9 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     if (ov & 1u) return 1;
     if ((ov & 2u) && sl.h_ctl->stage_need > c->stage_cap) return 2;
     if (ov & 16u) return 3;
+    if (ov & 8u) return 4;
     if (ov & 2u) return fail(c, B200_E_OVERFLOW, "a run of tiles exceeded the record staging capacity even after regrowth");
     if (ov & 4u) return fail(c, B200_E_OVERFLOW, "per-stream frame capacity exceeded");
-    if (ov & 8u) return fail(c, B200_E_OVERFLOW, "a receiver's ICAO filter generation is full (%u addresses)", ICAO_CAP / 2);
     if (ov & 32u) return fail(c, B200_E_OVERFLOW, "Mode A/C candidate capacity exceeded");
     const bool mode_ac = (c->cfg.flags & B200_CFG_MODE_AC) != 0;
     const uint32_t total_ac = mode_ac ? sl.h_ac_prefix[sl.nbuf] : 0;
@@ -577,8 +582,35 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     return B200_OK;
 }
 
+// Every receiver whose capacity check (or b200_demod_icao_add) asked for larger filter tables gets them: both generations are
+// re-inserted on the device; the default tables stay part of the context's slab, grown ones are freed when replaced.
+static int grow_icao_tables(b200_demod_ctx *c) {
+    const uint32_t S = c->cfg.n_streams;
+    c->h_state.resize(S);
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(c->h_state.data(), c->d_state, (size_t)S * sizeof(StreamState), cudaMemcpyDeviceToHost));
+    for (uint32_t s = 0; s < S; s++) {
+        const StreamState &st = c->h_state[s];
+        if (st.grow_log2 <= st.cap_log2) continue;
+        if (st.grow_log2 > ICAO_MAXBITS + 1) return fail(c, B200_E_OVERFLOW, "receiver %u: ICAO filter beyond 2^%d slots", s, ICAO_MAXBITS + 1);
+        uint32_t *t0 = nullptr, *t1 = nullptr;
+        const size_t n = (size_t)1 << st.grow_log2;
+        if (dev_alloc(&t0, n) != cudaSuccess || dev_alloc(&t1, n) != cudaSuccess) { cudaFree(t0); return fail(c, B200_E_NOMEM, "receiver %u: cannot grow the ICAO filter to 2 x %zu slots", s, n); }
+        int r = b200_launch_icao_rehash(c->d_state, s, t0, t1, st.grow_log2, c->stream);
+        if (r) return fail(c, B200_E_CUDA, "icao rehash launch: %s", cudaGetErrorString((cudaError_t)r));
+        CU(c, cudaStreamSynchronize(c->stream));
+        for (uint32_t *old : {st.tab[0], st.tab[1]}) {
+            auto it = std::find(c->icao_grown.begin(), c->icao_grown.end(), old);
+            if (it != c->icao_grown.end()) { cudaFree(old); c->icao_grown.erase(it); }
+        }
+        c->icao_grown.push_back(t0); c->icao_grown.push_back(t1);
+    }
+    return B200_OK;
+}
+
 // Repairs after collect() asked for a repeat.  Every slot gets the new capacity so that later steps do not trip again.
 static int regrow(b200_demod_ctx *c, Slot &sl, int why) {
+    if (why == 4) return grow_icao_tables(c);
     if (why == 1) {
         const uint32_t need = std::max(sl.h_ctl->rec_alloc + sl.h_ctl->rec_alloc / 4 + 65536, sl.rec_cap);
         for (Slot &s : c->slot) {
@@ -624,6 +656,7 @@ API int b200_demod_run(b200_demod_ctx *c) {
     sl.nseg = sl.ntile = sl.nbuf = 0; sl.is_device = false; sl.upload_tiles = true; sl.cached_tiles = 0;
     std::vector<std::pair<uint32_t, int>> fsum_of_buf;      // (buffer of the run, float-sum slot) for sc16 buffers
     std::vector<std::pair<uint32_t, const Pending *>> given_levels;   // (buffer of the run, hand-off that brought its own mean_level / mean_power)
+    std::vector<uint8_t> halo_after(c->halo_valid);        // committed only when the run succeeded (a failed run leaves no halo behind)
     for (uint32_t s = 0; s < S; s++) {
         sl.h_stream_seg_begin[s] = sl.nseg;
         sl.stream_buf_begin[s] = sl.nbuf;
@@ -656,7 +689,7 @@ API int b200_demod_run(b200_demod_ctx *c) {
                 halo_ok = pl[j].n >= B200_TRAIL;      // sdr_ifile.c:209-213
                 i = j + 1;
             }
-            c->halo_valid[s] = halo_ok;
+            halo_after[s] = halo_ok;
             if (halo_ok) c->h_carry_src[s] = (uint32_t)(c->cursor[s] - (size_t)B200_TRAIL * 2);
         }
     }
@@ -685,7 +718,12 @@ API int b200_demod_run(b200_demod_ctx *c) {
         sl.launches++;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, B200_E_CUDA, "halo carry failed");
     }
-    for (uint32_t s = 0; s < S; s++) { c->pending[s].clear(); c->kind[s] = 0; c->cursor[s] = 0; }
+    for (uint32_t s = 0; s < S; s++) {
+        // after a failed run the tail was not carried: the receiver's next buffer starts like a fresh stream (zero halo) instead of
+        // reading stale arena bytes
+        if (!c->pending[s].empty() && c->kind[s] != 2) c->halo_valid[s] = rc == B200_OK ? halo_after[s] : 0;
+        c->pending[s].clear(); c->kind[s] = 0; c->cursor[s] = 0;
+    }
     return rc;
 }
 
@@ -961,8 +999,16 @@ static int icao_op(b200_demod_ctx *c, uint32_t s, int op, uint32_t addr, int *re
     int host = 0;
     CU(c, cudaMemcpyAsync(&host, c->d_result, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (op == 0 && host < 0) {               // the generation would pass half of its slots: larger tables, then once more
+        int rc = grow_icao_tables(c);
+        if (rc != B200_OK) return rc;
+        r = b200_launch_icao_op(c->d_state, s, op, addr & 0xffffffu, c->d_result, c->stream);
+        if (r) return fail(c, B200_E_CUDA, "icao op launch: %s", cudaGetErrorString((cudaError_t)r));
+        CU(c, cudaMemcpyAsync(&host, c->d_result, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (host < 0) return fail(c, B200_E_OVERFLOW, "ICAO filter could not be grown");
+    }
     if (result) *result = host;
-    if (op == 0 && host < 0) return fail(c, B200_E_OVERFLOW, "ICAO filter generation full");
     return B200_OK;
 }
 API int b200_demod_icao_add(b200_demod_ctx *c, uint32_t s, uint32_t addr) { return icao_op(c, s, 0, addr, nullptr); }

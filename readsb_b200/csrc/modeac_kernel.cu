@@ -344,20 +344,18 @@ __global__ void __launch_bounds__(256) modeac_walk_kernel(const AcWalkParams P) 
 // after the count prefix: receiver statistics (the only state Mode A/C touches; skipped with the rest of stage B on a failed run)
 __global__ void modeac_stats_kernel(const AcWalkParams P, const uint32_t *prefix) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.n_streams || (P.ctl->overflow & (3u | 16u | 32u))) return;
+    if (s >= P.n_streams || (P.ctl->overflow & (RUN_REPEAT_BITS | 32u))) return;
     const uint32_t sb = P.stream_seg_begin[s], se = P.stream_seg_begin[s + 1];
     if (sb == se) return;
     const uint32_t b0 = P.segs[sb].first_buf, b1 = P.segs[se - 1].first_buf + P.segs[se - 1].n_bufs;
     P.state[s].stats.demod_modeac += prefix[b1] - prefix[b0];
 }
 
+extern "C" int b200_prepare_modeac(void) {      // per device, from b200_demod_create
+    return (int)cudaFuncSetAttribute(modeac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcSmem));
+}
+
 extern "C" int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp, int n_sm, void *stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(modeac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcSmem));
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
     if (sp->n_segs) {       // also for a run of empty buffers only (no tiles): the walk is what sets every buffer's reply count, zero included
         modeac_noise_kernel<<<min(sp->n_segs, 1024u), 32, 0, (cudaStream_t)stream>>>(*sp);
         if (sp->n_tiles) {

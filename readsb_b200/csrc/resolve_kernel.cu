@@ -16,30 +16,39 @@
 // ------------------------------------------------------------------------------------------------
 // ICAO address filter: two generations of an open-addressed set (icao_filter.c semantics)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t icao_slot(uint32_t a) { return (a * 0x9E3779B1u) >> (32 - ICAO_CAP_LOG2); }
+__device__ __forceinline__ uint32_t icao_slot(uint32_t a, uint32_t log2) { return (a * 0x9E3779B1u) >> (32 - log2); }
 
-__device__ __forceinline__ bool gen_has(const uint32_t *g, uint32_t a) {
-    uint32_t h = icao_slot(a);
+__device__ __forceinline__ bool gen_has(const uint32_t *g, uint32_t log2, uint32_t a) {
+    const uint32_t mask = (1u << log2) - 1u;
+    uint32_t h = icao_slot(a, log2);
     for (;;) {
         const uint32_t v = g[h];
         if (v == a) return true;
         if (v == ICAO_EMPTY) return false;
-        h = (h + 1) & (ICAO_CAP - 1);
+        h = (h + 1) & mask;
     }
 }
 
-__device__ __forceinline__ bool gen_add(uint32_t *g, uint32_t *count, uint32_t a) {   // false when full
-    uint32_t h = icao_slot(a);
+// Inserts `a` unless it is there; true when it was new to this generation (the caller keeps the generation's count and applies
+// the reference's resize rule).  Room is guaranteed: the capacity check ahead of stage B keeps every generation's load <= 1/2.
+__device__ __forceinline__ bool gen_insert(uint32_t *g, uint32_t log2, uint32_t a) {
+    const uint32_t mask = (1u << log2) - 1u;
+    uint32_t h = icao_slot(a, log2);
     for (;;) {
         const uint32_t v = g[h];
-        if (v == a) return true;
+        if (v == a) return false;
         if (v == ICAO_EMPTY) break;
-        h = (h + 1) & (ICAO_CAP - 1);
+        h = (h + 1) & mask;
     }
-    if (*count >= ICAO_CAP / 2) return false;
-    g[h] = a; (*count)++;
+    g[h] = a;
     return true;
 }
+
+// icao_filter.c:126-128: the insertion that made the active generation `count` addresses large doubles the reference's tables
+// (filterBits + 1) - and icaoFilterResize (:66-92) carries only the ACTIVE generation over: the older one is forgotten.
+__device__ __forceinline__ bool ref_resize_due(uint32_t count, uint32_t bits) { return count > (1u << bits) / 3u && bits < ICAO_MAXBITS; }
+// icao_filter.c:97-99: icaoFilterExpire halves the tables first when the active generation is small
+__device__ __forceinline__ bool ref_shrink_due(uint32_t count, uint32_t bits) { return count < (1u << bits) / 9u && bits > ICAO_MINBITS; }
 
 #define RS_WARPS 8            // warps per receiver: buffers of one receiver are resolved speculatively in parallel, eight at a time.
                               // 128 registers per thread: two CTAs per SM, so 256 receivers are one wave on 148 SMs
@@ -62,9 +71,21 @@ struct WarpRing {
 // What resolving one reference buffer produced (everything the commit step needs to apply it, or to throw it away).
 struct BufResult {
     long long now_ms;          // Modes.synthetic_now at the end of the buffer (demod_2400.c:283-285, 409-414)
-    uint32_t n_frames, n_new, fail, pad_;
+    uint32_t n_frames, n_new, fail;
+    uint32_t n_add;            // frames of this buffer that call icaoFilterAdd (mode_s.c:778): at most so many insertions
     uint32_t stats[15];        // preambles, bad, unknown, accepted[2], tried phases[5], best phases[5]
     uint32_t news[NEW_CAP];    // addresses this buffer learned that the filter did not hold (deferred mode)
+};
+
+// How a buffer's walk reaches the receiver's filter.  Default tables (ICAO_CAP slots): the active generation is S.act (shared
+// memory) and `act` is unused; grown tables (BIG): both generations stay in global memory.
+struct FilterRef {
+    uint32_t *act;             // BIG: the active generation
+    uint32_t *old_gen;         // the older generation's exact table (global memory), probed where its hash bit is set
+    uint32_t log2;             // slots per generation = 1 << log2
+    uint32_t *counts;          // direct mode: sizes of the two generations ...
+    uint32_t *bits;            // ... the reference's filterBits ...
+    uint32_t active;           // ... and which generation is the active one
 };
 
 struct ResolveSmem {
@@ -99,10 +120,10 @@ __device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
 //                 frames carry B200_FRAME_ICAO_ADDED — the commit step applies them if the speculation holds.
 //   DEFER = false (direct): adds go straight into the shared-memory table, exactly as the reference does.
 // Frames are written to fout[0 .. n_frames); `old_gen` is the older generation's exact table in global memory.
-template <bool DEFER>
+template <bool DEFER, bool BIG>
 __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSmem &S, WarpRing &R, BufResult &out, const Segment &seg, uint32_t si,
-                                               uint32_t b, uint32_t seq, const uint32_t *old_gen, uint32_t *gcount_active, uint32_t *err,
-                                               b200_frame *fout, uint32_t fcap, uint32_t lane) {
+                                               uint32_t b, uint32_t seq, const FilterRef &F, b200_frame *fout, uint32_t fcap, uint32_t lane) {
+    const uint32_t LOG2 = BIG ? F.log2 : (uint32_t)ICAO_CAP_LOG2;
     const uint32_t tile_end = seg.tile_begin + seg.n_tiles;
     const uint32_t n_quads = (seg.n_tiles + 3) / 4;
     const uint32_t d_begin = b * seg.buf_len;
@@ -110,13 +131,13 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
     const int64_t buf_ts = seg.first_ts + (int64_t)d_begin * 5;
     int64_t now_ms = buf_ts / 12000;          // demod_2400.c:283-285
     uint32_t skip_until = d_begin;            // data-index form of the reference's `pa` skip
-    uint32_t nframes = 0, n_new = 0, fail = 0;
+    uint32_t nframes = 0, n_new = 0, fail = 0, c_add = 0;
     uint32_t c_pre = 0, c_bad = 0, c_unk = 0, c_acc0 = 0, c_acc1 = 0, c_tp[5] = {0, 0, 0, 0, 0}, c_bp[5] = {0, 0, 0, 0, 0};
 
     auto known_addr = [&](uint32_t a) {
-        if (gen_has(S.act, a)) return true;
+        if (BIG ? gen_has(F.act, LOG2, a) : gen_has(S.act, ICAO_CAP_LOG2, a)) return true;
         const uint32_t h = old_bit(a);
-        if (((S.old_bits[h >> 5] >> (h & 31)) & 1u) && gen_has(old_gen, a)) return true;
+        if (((S.old_bits[h >> 5] >> (h & 31)) & 1u) && gen_has(F.old_gen, LOG2, a)) return true;
         if (DEFER) for (uint32_t i = 0; i < n_new; i++) if (out.news[i] == a) return true;
         return false;
     };
@@ -260,7 +281,7 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
                 if (best == -2) c_bad++; else c_unk++;       // -1, or decode result -1
             }
             if (!acc_mask) break;
-            uint32_t msglen = 0, relearn = 0, newaddr = 0xffffffffu;
+            uint32_t msglen = 0, relearn = 0, newaddr = 0xffffffffu, dropped = 0;
             if (lane == f) {
                 c_pre++;
 #pragma unroll
@@ -294,9 +315,13 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
                 if (corrected) c_acc1++; else c_acc0++;
                 c_bp[best_phase]++;
                 if (add) {
+                    c_add++;
                     if (DEFER) { if (!best_known) newaddr = best_key & 0xffffffu; }
-                    else if (!gen_add(S.act, gcount_active, best_key & 0xffffffu)) *err = 1;
-                    relearn = best_known ? 0u : 1u;      // membership changed: later scores are stale
+                    else if (gen_insert(BIG ? F.act : S.act, LOG2, best_key & 0xffffffu)) {      // icaoFilterAdd, icao_filter.c:112-130
+                        const uint32_t cnt = ++F.counts[F.active];
+                        if (ref_resize_due(cnt, *F.bits)) { (*F.bits)++; dropped = 1; }
+                    }
+                    relearn = (best_known && !dropped) ? 0u : 1u;      // membership changed: later scores are stale
                 }
                 now_ms = buf_ts / 12000 + (ts - buf_ts) / 12000;      // demod_2400.c:409-414
             }
@@ -309,6 +334,15 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
                 newaddr = __shfl_sync(FULLMASK, newaddr, f);
                 if (newaddr != 0xffffffffu) {
                     if (n_new < NEW_CAP) { if (lane == 0) out.news[n_new] = newaddr; n_new++; } else fail = 1;
+                    __syncwarp();
+                }
+            }
+            if (!DEFER) {
+                dropped = __shfl_sync(FULLMASK, dropped, f);
+                if (dropped) {      // the reference's resize carried only the active generation over (icao_filter.c:66-92): forget the older one
+                    for (uint32_t q = lane; q < OLD_BITS / 32; q += 32) S.old_bits[q] = 0;
+                    for (uint32_t q = lane; q < (1u << LOG2); q += 32) F.old_gen[q] = ICAO_EMPTY;
+                    if (lane == 0) F.counts[F.active ^ 1u] = 0;
                     __syncwarp();
                 }
             }
@@ -334,35 +368,29 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
         for (int o = 16; o > 0; o >>= 1) red[k] += __shfl_xor_sync(FULLMASK, red[k], o);
         if (lane == 0) out.stats[k] = red[k];
     }
-    if (lane == 0) { out.now_ms = now_ms; out.n_frames = min(nframes, fcap); out.n_new = n_new; out.fail = fail; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c_add += __shfl_xor_sync(FULLMASK, c_add, o);
+    if (lane == 0) { out.now_ms = now_ms; out.n_frames = min(nframes, fcap); out.n_new = n_new; out.fail = fail; out.n_add = c_add; }
     __syncwarp();
 }
 
-// Stage B: one CTA per receiver.  The buffers of a receiver only interact through the address filter (what earlier
-// buffers taught it, and the 60 s flip), so RS_WARPS of them are resolved AT THE SAME TIME against the filter as it stands,
-// in deferred mode; then warp 0 commits them in order.  A buffer's speculation holds if no buffer before it in the round
-// changed the filter's membership: then its adds are applied and its frames moved into place.  Otherwise it is resolved
-// again, directly, with the filter as the reference would have it at that point.  In steady state (aircraft already
-// known, no flip) every speculation holds; the results are the sequential ones by construction either way.
-__global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const ResolveParams P) {
-    extern __shared__ uint4 resolve_smem_raw[];
-    ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
-    __shared__ uint32_t s_active, s_gcount[2], s_err;
-    const uint32_t stream = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    StreamState *st = &P.state[stream];
-    // Stage A failed (record pool / staging), or the step ahead of this one in the asynchronous pipeline has to be
-    // repeated: leave every receiver's state untouched; the host repeats the run(s) in order.
-    if (P.ctl->overflow & 3u) return;
-    if (P.prev_ctl && (P.prev_ctl->overflow & 19u)) { if (tid == 0) atomicOr(&P.ctl->overflow, 16u); return; }
+template <bool BIG>
+__device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSmem &S, StreamState *st, uint32_t stream) {
+    __shared__ uint32_t s_active, s_gcount[2], s_bits;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t LOG2 = BIG ? st->cap_log2 : (uint32_t)ICAO_CAP_LOG2, CAP = 1u << LOG2;
+    uint32_t *const tab0 = st->tab[0], *const tab1 = st->tab[1];
+    auto tab = [&](uint32_t g) { return g ? tab1 : tab0; };
 
-    if (tid == 0) { s_active = st->active; s_gcount[0] = st->gen_count[0]; s_gcount[1] = st->gen_count[1]; s_err = st->error; }
+    if (tid == 0) { s_active = st->active; s_gcount[0] = st->gen_count[0]; s_gcount[1] = st->gen_count[1]; s_bits = st->filter_bits; }
     for (uint32_t i = tid; i < OLD_BITS / 32; i += blockDim.x) S.old_bits[i] = 0;
     __syncthreads();
     {
         const uint32_t active = s_active;
-        for (uint32_t i = tid; i < ICAO_CAP; i += blockDim.x) {
-            S.act[i] = st->gen[active][i];
-            const uint32_t v = st->gen[active ^ 1u][i];
+        const uint32_t *ta = tab(active), *to = tab(active ^ 1u);
+        for (uint32_t i = tid; i < CAP; i += blockDim.x) {
+            if (!BIG) S.act[i] = ta[i];
+            const uint32_t v = to[i];
             if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
         }
     }
@@ -387,8 +415,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
             // ---- speculation: warp w resolves buffer b0 + w against the filter as it stands ---------------------------------
             if (wid < n_round) {
                 const uint32_t b = b0 + wid;
-                resolve_buffer<true>(P, S, S.ring[wid], S.res[wid], seg, si, b, 0 /* buffer_seq is stamped at commit */, st->gen[s_active ^ 1u], nullptr, nullptr,
-                                     fstream + (size_t)(jbuf + wid) * P.per_buf_cap, P.per_buf_cap, lane);
+                FilterRef F;
+                F.act = tab(s_active); F.old_gen = tab(s_active ^ 1u); F.log2 = LOG2; F.counts = nullptr; F.bits = nullptr; F.active = s_active;
+                resolve_buffer<true, BIG>(P, S, S.ring[wid], S.res[wid], seg, si, b, 0 /* buffer_seq is stamped at commit */, F,
+                                          fstream + (size_t)(jbuf + wid) * P.per_buf_cap, P.per_buf_cap, lane);
             }
             __syncthreads();
             // ---- commit, in order -----------------------------------------------------------------------------------------------
@@ -399,10 +429,14 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
                     BufResult &r = S.res[i];
                     const uint32_t d_begin = b * seg.buf_len, d_end = min(d_begin + seg.buf_len, seg.npos);
                     b200_frame *fdst = fstream + nframes;
-                    if (spec_ok && !r.fail) {
+                    // A speculation cannot know about the reference's table resize (icao_filter.c:126-128), which forgets the older
+                    // generation in the middle of a buffer: if this buffer's adds could reach the resize threshold it is resolved directly.
+                    const bool resize_possible = s_bits < ICAO_MAXBITS && s_gcount[s_active] + r.n_add > (1u << s_bits) / 3u;
+                    if (spec_ok && !r.fail && !resize_possible) {
                         // the speculation holds: teach the filter what this buffer learned, move its frames into place
                         const b200_frame *fsrc = fstream + (size_t)(jbuf + i) * P.per_buf_cap;
                         const uint32_t n = r.n_frames;
+                        uint32_t *act = BIG ? tab(s_active) : S.act;
                         for (uint32_t k0 = 0; k0 < n; k0 += 32) {
                             const bool has = k0 + lane < n;
                             b200_frame fr;
@@ -412,7 +446,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
                             while (m) {                                  // mode_s.c:778, in frame order
                                 const uint32_t l = __ffs(m) - 1; m &= m - 1;
                                 const uint32_t a = __shfl_sync(FULLMASK, fr.addr, l);
-                                if (lane == 0) { if (!gen_add(S.act, &s_gcount[s_active], a)) s_err = 1; }
+                                if (lane == 0) { if (gen_insert(act, LOG2, a)) s_gcount[s_active]++; }
                                 __syncwarp();
                             }
                             if (addm) dirty_act = true;
@@ -423,8 +457,9 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
                         if (r.n_new) spec_ok = false;                   // later buffers of the round saw a filter without these addresses
                     } else {
                         spec_ok = false;
-                        resolve_buffer<false>(P, S, S.ring[0], r, seg, si, b, seq, st->gen[s_active ^ 1u], &s_gcount[s_active], &s_err, fdst,
-                                              P.frame_cap - nframes, lane);
+                        FilterRef F;
+                        F.act = tab(s_active); F.old_gen = tab(s_active ^ 1u); F.log2 = LOG2; F.counts = s_gcount; F.bits = &s_bits; F.active = s_active;
+                        resolve_buffer<false, BIG>(P, S, S.ring[0], r, seg, si, b, seq, F, fdst, P.frame_cap - nframes, lane);
                         dirty_act = true;
                     }
                     __syncwarp();
@@ -437,19 +472,23 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
                     uint32_t flipped = 0;
                     const int64_t now_ms = r.now_ms;
                     if (P.ttl_ms > 0 && (!armed || now_ms >= next_flip)) {
-                        // the active generation becomes the older one: its exact table goes to global memory, its hash bits stay
-                        // here; the other generation is emptied and becomes active
+                        // icaoFilterExpire (icao_filter.c:96-110): the active generation becomes the older one (its exact table in global
+                        // memory, its hash bits here); the other generation is emptied and becomes active
                         const uint32_t active = s_active, other = active ^ 1u;
+                        uint32_t *ta = tab(active), *to = tab(other);
                         for (uint32_t q = lane; q < OLD_BITS / 32; q += 32) S.old_bits[q] = 0;
                         __syncwarp();
-                        for (uint32_t q = lane; q < ICAO_CAP; q += 32) {
-                            const uint32_t v = S.act[q];
-                            if (dirty_act) st->gen[active][q] = v;
+                        for (uint32_t q = lane; q < CAP; q += 32) {
+                            const uint32_t v = BIG ? ta[q] : S.act[q];
+                            if (!BIG && dirty_act) ta[q] = v;
                             if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
-                            S.act[q] = ICAO_EMPTY;
+                            if (BIG) to[q] = ICAO_EMPTY; else S.act[q] = ICAO_EMPTY;
                         }
                         __syncwarp();
-                        if (lane == 0) { s_gcount[other] = 0; s_active = other; }
+                        if (lane == 0) {
+                            if (ref_shrink_due(s_gcount[active], s_bits)) s_bits--;
+                            s_gcount[other] = 0; s_active = other;
+                        }
                         dirty_act = true;
                         next_flip = now_ms + P.ttl_ms; armed = 1; flipped = 1; c_flips++;
                         spec_ok = false;                                // the rest of the round saw the filter before the flip
@@ -473,18 +512,59 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
     // write back
     if (wid == 0) {
         const uint32_t active = s_active;
-        if (dirty_act) for (uint32_t i = lane; i < ICAO_CAP; i += 32) st->gen[active][i] = S.act[i];
+        if (!BIG && dirty_act) { uint32_t *ta = tab(active); for (uint32_t i = lane; i < ICAO_CAP; i += 32) ta[i] = S.act[i]; }
         if (lane == 0) {
             st->gen_count[0] = s_gcount[0]; st->gen_count[1] = s_gcount[1];
-            st->active = active; st->flip_armed = armed; st->next_flip_ms = next_flip; st->buffer_seq = seq; st->error = s_err;
+            st->active = active; st->filter_bits = s_bits; st->flip_armed = armed; st->next_flip_ms = next_flip; st->buffer_seq = seq;
             b200_demod_stats &s = st->stats;
             s.samples_processed += c_samples; s.demod_preambles += tot[0]; s.demod_rejected_bad += tot[1];
             s.demod_rejected_unknown_icao += tot[2]; s.demod_accepted[0] += tot[3]; s.demod_accepted[1] += tot[4];
             for (int p = 0; p < 5; p++) { s.demod_preamblePhase[p] += tot[5 + p]; s.demod_bestPhase[p] += tot[10 + p]; }
             s.buffers += c_bufs; s.icao_flips += c_flips;
             P.frame_count[stream] = min(nframes, P.frame_cap);
-            if (s_err) atomicOr(&P.ctl->overflow, 8u);
         }
+    }
+}
+
+// Stage B: one CTA per receiver.  The buffers of a receiver only interact through the address filter (what earlier
+// buffers taught it, and the 60 s flip), so RS_WARPS of them are resolved AT THE SAME TIME against the filter as it stands,
+// in deferred mode; then warp 0 commits them in order.  A buffer's speculation holds if no buffer before it in the round
+// changed the filter's membership: then its adds are applied and its frames moved into place.  Otherwise it is resolved
+// again, directly, with the filter as the reference would have it at that point.  In steady state (aircraft already
+// known, no flip) every speculation holds; the results are the sequential ones by construction either way.
+// Receivers with grown tables (BIG) are rare: they get an instantiation of their own, launched only when there is one, so that
+// the common case does not share its register allocation; each CTA of either launch leaves the other kind alone.
+template <bool BIG>
+__global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const ResolveParams P) {
+    extern __shared__ uint4 resolve_smem_raw[];
+    ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
+    const uint32_t stream = blockIdx.x;
+    StreamState *st = &P.state[stream];
+    // Stage A failed (record pool / staging), a receiver's filter tables have to grow first (icao_capacity_kernel), or the step
+    // ahead of this one in the asynchronous pipeline has to be repeated: leave every receiver's state untouched; the host
+    // repairs and repeats the run(s) in order.
+    if (P.ctl->overflow & RUN_REPEAT_BITS) return;
+    if ((st->cap_log2 != ICAO_CAP_LOG2) != BIG) return;
+    resolve_stream<BIG>(P, S, st, stream);
+}
+
+// Runs ahead of resolve_kernel on its stream: (1) the asynchronous pipeline's "the step ahead has to be repeated" test, once
+// for the whole grid; (2) the capacity check of the receivers' filter tables.  stream_addable[s] (scan kernel) bounds the
+// insertions of this run; a generation never exceeds (active now + that), so with 2 x that <= slots no table can fill up and
+// stage B needs no overflow path.  A receiver that could exceed it gets grow_log2 set: the host grows its tables and repeats.
+__global__ void icao_capacity_kernel(StreamState *state, uint32_t *stream_addable, uint32_t n_streams, RunCtl *ctl, const RunCtl *prev_ctl) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0 && prev_ctl && (prev_ctl->overflow & RUN_REPEAT_BITS)) atomicOr(&ctl->overflow, 16u);
+    if (s >= n_streams) return;
+    const uint32_t add = stream_addable[s];
+    stream_addable[s] = 0;
+    StreamState *st = &state[s];
+    const uint32_t need = max(st->gen_count[0], st->gen_count[1]) + add;
+    if (2u * need > (1u << st->cap_log2)) {
+        uint32_t lg = st->cap_log2 + 1;
+        while ((1u << lg) < 4u * need && lg < ICAO_MAXBITS + 1) lg++;
+        st->grow_log2 = lg;
+        atomicOr(&ctl->overflow, 8u);
     }
 }
 
@@ -496,7 +576,7 @@ __global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *coun
     const uint32_t n_all = n;
     __shared__ uint32_t scratch[40];
     uint32_t base = 0;
-    if (ctl->overflow & 19u) n = 0;
+    if (ctl->overflow & RUN_REPEAT_BITS) n = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
         const uint32_t v = i < n ? count[i] : 0;
@@ -607,46 +687,110 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams P) {
 // ------------------------------------------------------------------------------------------------
 __global__ void icao_op_kernel(StreamState *state, uint32_t stream, int op, uint32_t addr, int *result) {
     StreamState *st = &state[stream];
-    if (threadIdx.x != 0) return;
+    const uint32_t log2 = st->cap_log2, cap = 1u << log2;
     int r = 0;
     if (op == 0) {            // add (icao_filter.c:112-130)
-        r = gen_add(st->gen[st->active], &st->gen_count[st->active], addr) ? 0 : -1;
+        const uint32_t a = st->active;
+        __shared__ int s_dropped;
+        if (threadIdx.x == 0) {
+            s_dropped = 0;
+            if (!gen_has(st->tab[a], log2, addr)) {
+                if (2u * (st->gen_count[a] + 1u) > cap) { st->grow_log2 = log2 + 1; r = -1; }       // the host grows the tables and asks again
+                else {
+                    gen_insert(st->tab[a], log2, addr);
+                    const uint32_t cnt = ++st->gen_count[a];
+                    if (ref_resize_due(cnt, st->filter_bits)) { st->filter_bits++; st->gen_count[a ^ 1u] = 0; s_dropped = 1; }
+                }
+            }
+        }
+        __syncthreads();
+        if (s_dropped) for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) st->tab[a ^ 1u][i] = ICAO_EMPTY;      // icaoFilterResize, :66-92
     } else if (op == 1) {     // test (icao_filter.c:132-154)
-        r = (gen_has(st->gen[0], addr) || gen_has(st->gen[1], addr)) ? 1 : 0;
+        if (threadIdx.x == 0) r = (gen_has(st->tab[0], log2, addr) || gen_has(st->tab[1], log2, addr)) ? 1 : 0;
     } else if (op == 2) {     // expire (icao_filter.c:96-110)
         const uint32_t other = st->active ^ 1u;
-        for (uint32_t i = 0; i < ICAO_CAP; i++) st->gen[other][i] = ICAO_EMPTY;
-        st->gen_count[other] = 0; st->active = other; st->stats.icao_flips++;
+        for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) st->tab[other][i] = ICAO_EMPTY;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (ref_shrink_due(st->gen_count[other ^ 1u], st->filter_bits)) st->filter_bits--;
+            st->gen_count[other] = 0; st->active = other; st->stats.icao_flips++;
+        }
     } else if (op == 3) {     // reset (icaoFilterInit)
-        for (uint32_t i = 0; i < ICAO_CAP; i++) { st->gen[0][i] = ICAO_EMPTY; st->gen[1][i] = ICAO_EMPTY; }
-        st->gen_count[0] = st->gen_count[1] = 0; st->active = 0; st->flip_armed = 0; st->next_flip_ms = 0;
+        for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) { st->tab[0][i] = ICAO_EMPTY; st->tab[1][i] = ICAO_EMPTY; }
+        if (threadIdx.x == 0) { st->gen_count[0] = st->gen_count[1] = 0; st->active = 0; st->filter_bits = ICAO_MINBITS; st->flip_armed = 0; st->next_flip_ms = 0; }
     }
-    if (result) *result = r;
+    if (result && threadIdx.x == 0) *result = r;
+}
+
+// A receiver's tables move to larger ones (host: b200 grow_icao_tables): both generations are re-inserted.
+__global__ void icao_rehash_kernel(StreamState *state, uint32_t stream, uint32_t *new0, uint32_t *new1, uint32_t new_log2) {
+    StreamState *st = &state[stream];
+    const uint32_t old_cap = 1u << st->cap_log2, new_cap = 1u << new_log2, mask = new_cap - 1u;
+    for (uint32_t i = threadIdx.x; i < new_cap; i += blockDim.x) { new0[i] = ICAO_EMPTY; new1[i] = ICAO_EMPTY; }
+    __syncthreads();
+    for (int g = 0; g < 2; g++) {
+        const uint32_t *from = st->tab[g];
+        uint32_t *to = g ? new1 : new0;
+        for (uint32_t i = threadIdx.x; i < old_cap; i += blockDim.x) {
+            const uint32_t v = from[i];
+            if (v == ICAO_EMPTY) continue;
+            uint32_t h = icao_slot(v, new_log2);
+            while (atomicCAS(&to[h], ICAO_EMPTY, v) != ICAO_EMPTY) h = (h + 1) & mask;       // addresses of one generation are distinct
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { st->tab[0] = new0; st->tab[1] = new1; st->cap_log2 = new_log2; st->grow_log2 = 0; }
+}
+
+__global__ void init_state_kernel(StreamState *st, uint32_t n, uint32_t *slab) {
+    const uint32_t s = blockIdx.x;
+    if (s >= n) return;
+    uint32_t *t0 = slab + (size_t)s * 2 * ICAO_CAP;
+    for (uint32_t i = threadIdx.x; i < 2 * ICAO_CAP; i += blockDim.x) t0[i] = ICAO_EMPTY;
+    if (threadIdx.x == 0) {
+        StreamState z;
+        memset(&z, 0, sizeof z);
+        z.tab[0] = t0; z.tab[1] = t0 + ICAO_CAP; z.cap_log2 = ICAO_CAP_LOG2; z.filter_bits = ICAO_MINBITS;
+        st[s] = z;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
-extern "C" int b200_launch_resolve(const ResolveParams *p, void *stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem));
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    resolve_kernel<<<p->n_streams, RS_WARPS * 32, sizeof(ResolveSmem), (cudaStream_t)stream>>>(*p);
+extern "C" int b200_prepare_resolve(void) {      // per device, from b200_demod_create
+    cudaError_t e = cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem));
+    return (int)e;
+}
+
+// any_grown: some receiver of the context has filter tables of its own (then the second instantiation runs too; returns the launches made)
+extern "C" int b200_launch_resolve(const ResolveParams *p, int any_grown, void *stream) {
+    icao_capacity_kernel<<<(p->n_streams + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->state, p->stream_addable, p->n_streams, p->ctl, p->prev_ctl);
+    resolve_kernel<false><<<p->n_streams, RS_WARPS * 32, sizeof(ResolveSmem), (cudaStream_t)stream>>>(*p);
+    if (any_grown) resolve_kernel<true><<<p->n_streams, RS_WARPS * 32, sizeof(ResolveSmem), (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
 }
 
-extern "C" int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, void *stream) {
+extern "C" int b200_launch_finalize(const FinalizeParams *p, uint32_t *d_frame_prefix, RunCtl *ctl, int n_sm, void *stream) {
     frame_prefix_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p->frame_count, d_frame_prefix, p->n_streams, ctl);
-    finalize_kernel<<<148 * 4, 128, 0, (cudaStream_t)stream>>>(*p);
+    finalize_kernel<<<n_sm * 4, 128, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200_launch_init_state(StreamState *state, uint32_t n, uint32_t *slab, void *stream) {
+    init_state_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(state, n, slab);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200_launch_icao_rehash(StreamState *state, uint32_t stream, uint32_t *new0, uint32_t *new1, uint32_t new_log2, void *cstream) {
+    icao_rehash_kernel<<<1, 1024, 0, (cudaStream_t)cstream>>>(state, stream, new0, new1, new_log2);
     return (int)cudaGetLastError();
 }
 
 // Mode A/C: pack the per-buffer reply lists in buffer order (prefix by the frame prefix kernel, then one block per buffer).
 __global__ void ac_pack_kernel(const b200_modeac *ac_out, const uint32_t *count, const uint32_t *prefix, b200_modeac *packed, uint32_t cap, const RunCtl *ctl) {
-    if (ctl->overflow & 19u) return;          // the walk did not run (this step is going to be repeated): its counts are not this run's
+    if (ctl->overflow & RUN_REPEAT_BITS) return;          // the walk did not run (this step is going to be repeated): its counts are not this run's
     const uint32_t s = blockIdx.x;
     const uint32_t n = min(count[s], cap), base = prefix[s];
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) packed[base + i] = ac_out[(size_t)s * cap + i];
@@ -660,6 +804,6 @@ extern "C" int b200_launch_ac_pack(const b200_modeac *ac_out, const uint32_t *co
 }
 
 extern "C" int b200_launch_icao_op(StreamState *state, uint32_t stream, int op, uint32_t addr, int *d_result, void *cstream) {
-    icao_op_kernel<<<1, 32, 0, (cudaStream_t)cstream>>>(state, stream, op, addr, d_result);
+    icao_op_kernel<<<1, 256, 0, (cudaStream_t)cstream>>>(state, stream, op, addr, d_result);
     return (int)cudaGetLastError();
 }

@@ -432,6 +432,9 @@ __device__ __forceinline__ void slice_round(const ScanSmem &S, WarpSmem &W, cons
             const uint32_t aa_changed = (kind == K_ES_FIX && fixbit >= 8 && fixbit <= 31) ? 1u : 0u;   // mode_s.c:560
             const uint32_t df = (rw[0] & 0xffu) >> 3;                     // byte 0 of the frame as sliced
             stage_key[at] = (aa_changed ? KEY_AA_CHANGED : 0u) | (df == 17 ? KEY_DF17 : 0u) | ((df & 0x10u) ? KEY_LONG : 0u) | (kind << 24) | (rw[5] & 0xffffffu);
+            // mode_s.c:766-779: only these can teach the filter an address; counted so that stage B knows before it starts whether the
+            // receiver's tables are large enough for this run (real frames only: noise does not produce CRC-clean DF11 / DF17)
+            if (kind == K_DF11_IID0 || (kind == K_ES_OK && df == 17)) atomicAdd(&P.stream_addable[reinterpret_cast<const Segment *>(W.seg)->stream], 1u);
         }
     }
     n_stage += __popc(bal);
@@ -695,7 +698,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
             const uint32_t mine = lane < n_tiles_run ? W.n_rec[lane] : 0;
             uint32_t tot;
             const uint32_t before = warp_excl_scan(mine, lane, &tot);
-            if (lane < n_tiles_run) { TileOut t; t.n_pos = W.n_pos[lane]; t.n_rec = ok ? mine : 0; t.rec_off = off + before; t.pad_ = mine; P.tile_out[tile0 + lane] = t; }
+            if (lane < n_tiles_run) { TileOut t; t.n_pos = W.n_pos[lane]; t.n_rec = ok ? mine : 0; t.rec_off = off + before; t.n_found = mine; P.tile_out[tile0 + lane] = t; }
         }
     }
 }
@@ -703,13 +706,12 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
 extern "C" int b200_scan_warps(int n_sm) { return n_sm * SC_WARPS; }
 extern "C" int b200_scan_tick_words(void) { return TICKG_WORDS; }
 
+// Kernel attributes are per device: b200_demod_create calls this for the context's device (current at that point).
+extern "C" int b200_prepare_scan(void) {
+    return (int)cudaFuncSetAttribute(scan_kernel<SC_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemFull<SC_WARPS>));
+}
+
 template <int NW> static int launch_scan_t(const ScanParams *p, const DeviceTables *d_tables, int n_sm, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemFull<NW>));
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
     uint32_t grid = (uint32_t)n_sm;
     const uint32_t need = (p->n_tiles + NW - 1) / NW;
     if (grid > need) grid = need;

@@ -389,6 +389,9 @@ class Reference:
     def icao_test(self, a) -> bool:
         return bool(self.L.ref_icao_test(a))
 
+    def icao_expire(self):
+        self.L.ref_icao_expire()
+
     def time_stream(self, iq: np.ndarray, buf_samples: int):
         nf = C.c_uint(0)
         secs = self.L.ref_time_stream_uc8(iq.ctypes.data, iq.size // 2, buf_samples, C.byref(nf))

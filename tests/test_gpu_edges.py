@@ -145,6 +145,80 @@ def test_filter_flip_on_the_stream_clock(cuda):
     d.close()
 
 
+@pytest.mark.parametrize("n_icao,fps,K,ttl", [(120, 3000.0, 1, 400), (400, 6000.0, 4, 400), (400, 6000.0, 8, 0), (1000, 9000.0, 3, 150)])
+def test_busy_airspace_follows_the_reference_table_resize(cuda, n_icao, fps, K, ttl):
+    """icao_filter.c:126-128 + :66-92: with the 86th, 171st, 342nd ... new address of a generation the reference doubles its tables
+    and keeps the active generation only - address/parity replies of aircraft that only the older generation knew are rejected from
+    that frame on (the oracle is pinned against the reference for this, tests/test_oracle.py).  Buffers resolved speculatively in
+    parallel, in one run, across the resize points; with and without flips (ttl 0 = the reference's 60 s: none in this capture)."""
+    from readsb_b200.demod import Demodulator
+    iq = synth.generate(3_000_000, seed=5, frames_per_sec=fps, df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.DF11_IID, n_icao=n_icao)
+    kw = {"icao_ttl_ms": ttl} if ttl else {}
+    o = Oracle(**kw); fo, bo = o.run_stream(iq, 65536)
+    d = Demodulator(n_streams=1, buf_samples=65536, max_buffers_per_run=K, **kw)
+    fg, bg = d.replay(iq)
+    assert len(fo) > 1000
+    problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(0), o.stats())
+    assert not problems, "\n".join(problems)
+    d.close()
+
+
+def test_filter_api_follows_the_reference_table_resize(cuda):
+    """The same rule through b200_demod_icao_add / _expire (the shim forwards network-input adds and the 60 s flip): an address of the
+    older generation dies with the 86th new address of the next one; a small generation shrinks the tables at the flip (:97-99)."""
+    from readsb_b200.demod import Demodulator
+    d = Demodulator(n_streams=1, buf_samples=4096, max_buffers_per_run=1)
+    o = Oracle()
+    for f in (lambda a: d.icao_add(0, a), o.icao_add):
+        f(0xABCDEF)
+    d.icao_expire(0); o.icao_expire()
+    for a in range(1, 86):
+        d.icao_add(0, a); o.icao_add(a)
+    assert d.icao_test(0, 0xABCDEF) and o.icao_test(0xABCDEF)
+    d.icao_add(0, 86); o.icao_add(86)
+    assert not d.icao_test(0, 0xABCDEF) and not o.icao_test(0xABCDEF) and d.icao_test(0, 1) and d.icao_test(0, 86)
+    rng = np.random.default_rng(3)
+    pool = rng.choice(1 << 24, size=1500, replace=False)
+    for step in range(6):
+        for a in rng.choice(pool, size=int(rng.integers(20, 260))):
+            d.icao_add(0, int(a)); o.icao_add(int(a))
+        probe = rng.choice(pool, size=150)
+        assert [d.icao_test(0, int(a)) for a in probe] == [o.icao_test(int(a)) for a in probe], step
+        d.icao_expire(0); o.icao_expire()
+    d.close()
+
+
+def test_filter_grows_beyond_the_default_tables(cuda):
+    """The default tables hold 2048 addresses per generation (stage B keeps them in shared memory); the reference's grow to 2^20
+    buckets.  Receiver 0: 10 000 addresses forwarded through the API (an aggregator's network input), then a capture.  Receiver 1:
+    its own traffic (thousands of aircraft) pushes it past the default size in the middle of a replay: the capacity check ahead
+    of stage B asks for larger tables, the library grows them (icao_rehash_kernel) and repeats the step.  Receiver 2 stays small.
+    Results are the oracle's for all three."""
+    from readsb_b200.demod import Demodulator
+    S = 3
+    d = Demodulator(n_streams=S, buf_samples=65536, max_buffers_per_run=4)
+    os_ = [Oracle() for _ in range(S)]
+    rng = np.random.default_rng(17)
+    fwd = rng.choice(1 << 24, size=10_000, replace=False)
+    for a in fwd:
+        d.icao_add(0, int(a)); os_[0].icao_add(int(a))
+    probe = list(fwd[::97]) + list(rng.choice(1 << 24, size=100))
+    assert [d.icao_test(0, int(a)) for a in probe] == [os_[0].icao_test(int(a)) for a in probe]
+    iqs = [synth.generate(900_000, seed=40, frames_per_sec=2000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP, n_icao=30),
+           synth.generate(6_000_000, seed=41, frames_per_sec=4000.0, df_mask=synth.DF17 | synth.DF11 | synth.AP, n_icao=9000, amp=(0.5, 0.9)),
+           synth.generate(600_000, seed=42, frames_per_sec=500.0, df_mask=synth.DF17 | synth.AP, n_icao=10)]
+    for s in (1, 0, 2):
+        fo, bo = os_[s].run_stream(iqs[s], 65536)
+        fg, bg = d.replay(iqs[s], stream=s)
+        problems = diff_frames(fg, fo) + diff_bufres(bg, bo) + diff_stats(d.stats(s), os_[s].stats())
+        assert not problems, f"receiver {s}\n" + "\n".join(problems)
+        if s == 1:
+            taught = {int(a) for a, t, c in zip(fo["addr"], fo["msgtype"], fo["correctedbits"]) if t in (11, 17) and c == 0}
+            assert len(taught) > 2600, len(taught)        # more than a default table takes
+            assert all(d.icao_test(1, a) == os_[1].icao_test(a) for a in list(taught)[::40])
+    d.close()
+
+
 def test_syndrome_all_ones_is_not_a_correctable_error(cuda):
     """A DF17 candidate whose syndrome is exactly 0xFFFFFF (tests/golden/regress/syndrome_ffffff.npz: 2200 samples cut out of a
     tools/emu_fuzz.py case, loud traffic at --preamble-threshold=33).  The single-bit-error lookup is a perfect hash whose

@@ -219,6 +219,56 @@ def test_icao_ttl_two_flips():
 
 
 @needs_ref
+def test_icao_filter_resize_forgets_the_older_generation():
+    """icao_filter.c:112-130: once the active generation holds more than buckets / 3 addresses (86, 171, 342 ... from 2^8
+    buckets) icaoFilterResize re-inserts the ACTIVE generation only (:66-92) - whatever the older one held is gone; and
+    icaoFilterExpire halves the tables when the active generation is small (:97-99).  The oracle's sets follow the same
+    state machine: random add / test / expire sequences against the reference's own icao_filter.c."""
+    rng = np.random.default_rng(11)
+    ref, o = Reference(), Oracle()
+    pool = rng.choice(1 << 24, size=6000, replace=False).astype(np.uint32)
+    known = []
+    for step in range(40):
+        for a in rng.choice(pool, size=int(rng.integers(1, 700))):
+            ref.icao_add(int(a)); o.icao_add(int(a)); known.append(int(a))
+        probe = list(rng.choice(pool, size=300)) + known[-200:] + known[:200]
+        got_r = [ref.icao_test(int(a)) for a in probe]
+        got_o = [o.icao_test(int(a)) for a in probe]
+        assert got_r == got_o, f"step {step}"
+        if rng.random() < 0.35:
+            ref.icao_expire(); o.icao_expire()
+    # the advisor's case, spelled out: an address of the older generation dies with the 86th new address of the next one
+    ref, o = Reference(), Oracle()
+    for f in (ref, o):
+        f.icao_add(0xABCDEF); f.icao_expire()
+        for a in range(1, 86):
+            f.icao_add(a)
+        assert f.icao_test(0xABCDEF)
+        f.icao_add(86)
+        assert not f.icao_test(0xABCDEF) and f.icao_test(1) and f.icao_test(86)
+
+
+@needs_ref
+@pytest.mark.parametrize("n_icao,fps", [(120, 3000.0), (400, 6000.0)])
+def test_oracle_matches_reference_in_busy_airspace(n_icao, fps):
+    """More aircraft than the reference's filter keeps without resizing (> 85, > 170, > 341): address/parity replies of
+    aircraft that only the older generation knew are rejected after a resize (score -1), and the scan goes on where the
+    reference's does."""
+    ttl = 400
+    iq = synth.generate(5_000_000, seed=5, frames_per_sec=fps, df_mask=synth.DF17 | synth.DF11 | synth.AP | synth.DF11_IID, n_icao=n_icao)
+    ref, o = Reference(icao_ttl_ms=ttl), Oracle(icao_ttl_ms=ttl)
+    fr = ref.run_stream(iq, 65536)[0]
+    fo, bo = o.run_stream(iq, 65536)
+    problems = diff_frames(fo, fr, fields=("timestamp", "crc", "addr", "score", "msgtype", "correctedbits", "msg"))
+    assert len(fr) > 1000 and not problems, "\n".join(problems)
+    sr = ref.stats()[0]
+    so = o.stats()
+    sr["sum_signal_power"] = so["sum_signal_power"]
+    assert not diff_stats(so, sr)
+    assert bo["icao_flipped"].sum() >= 3
+
+
+@needs_ref
 @pytest.mark.parametrize("q11", [False, True])
 def test_oracle_sc16_converters_match_reference(q11):
     """convert_sc16_nodc (convert.c:212-250) / convert_sc16q11_nodc (:329-367), magnitudes and the two
