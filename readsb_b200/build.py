@@ -72,6 +72,20 @@ def build_synth(force: bool = False) -> Path:
     return LIB_SYNTH
 
 
+def build_probe(force: bool = False) -> Path:
+    """tools/liblatency_probe.so: bench.py's C stopwatch around the public C ABI (per-call latency of the drop-in's call shape)."""
+    src = ROOT / "tools" / "latency_probe.c"
+    out = ROOT / "tools" / "liblatency_probe.so"
+    if not force and _newer(out, [src, ROOT / "include" / "b200_demod.h"]):
+        return out
+    cc = shutil.which("gcc") or "gcc"
+    res = subprocess.run([cc, "-O2", "-std=c11", "-fPIC", "-shared", "-Wall", "-I", str(ROOT / "include"), str(src), "-o", str(out)],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build_oracle() -> None:
     """Builds oracle/libmodes_oracle.so and, if /root/reference exists, oracle/_ref/libreadsb_ref.so.
     (Building the checker is not using it: nothing in this package loads those libraries.)"""

@@ -72,7 +72,8 @@ struct WarpRing {
 struct BufResult {
     long long now_ms;          // Modes.synthetic_now at the end of the buffer (demod_2400.c:283-285, 409-414)
     uint32_t n_frames, n_new, fail;
-    uint32_t n_add;            // frames of this buffer that call icaoFilterAdd (mode_s.c:778): at most so many insertions
+    uint32_t n_add;            // icaoFilterAdd calls of this buffer (mode_s.c:778) whose address the ACTIVE generation did not hold when the
+                               // buffer was speculated: at most so many insertions into it
     uint32_t stats[15];        // preambles, bad, unknown, accepted[2], tried phases[5], best phases[5]
     uint32_t news[NEW_CAP];    // addresses this buffer learned that the filter did not hold (deferred mode)
 };
@@ -315,8 +316,10 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
                 if (corrected) c_acc1++; else c_acc0++;
                 c_bp[best_phase]++;
                 if (add) {
-                    c_add++;
-                    if (DEFER) { if (!best_known) newaddr = best_key & 0xffffffu; }
+                    if (DEFER) {
+                        if (!best_known) newaddr = best_key & 0xffffffu;
+                        if (!(BIG ? gen_has(F.act, LOG2, best_key & 0xffffffu) : gen_has(S.act, ICAO_CAP_LOG2, best_key & 0xffffffu))) c_add++;
+                    }
                     else if (gen_insert(BIG ? F.act : S.act, LOG2, best_key & 0xffffffu)) {      // icaoFilterAdd, icao_filter.c:112-130
                         const uint32_t cnt = ++F.counts[F.active];
                         if (ref_resize_due(cnt, *F.bits)) { (*F.bits)++; dropped = 1; }

@@ -56,7 +56,9 @@ enum { SCN_RUNS, SCN_LOOP_ITERS, SCN_WINDOW_CHUNKS, SCN_FAST_CONVERTS, SCN_EDGE_
 #define TICK_BITS (5 * CHUNK)
 #define TICK_RING (2 * TICK_CW)
 #define TICK_MIRROR 12
-#define Q1_SMEM 128                           // pre-check passers of a chunk kept in shared memory; the rest (dense input) spills
+#ifndef Q1_SMEM
+#define Q1_SMEM 128                           // pre-check passers of a chunk kept in shared memory (58 on receiver noise); the rest (dense input) spills to global memory
+#endif
 #define SURV_CAP 64
 #define TICKG_WORDS ((RUN_CHUNKS_MAX + 1) * TICK_CW + 8)   // per-warp global copy of a whole run's ticks (slicing is deferred and pooled)
 
@@ -79,11 +81,14 @@ struct WarpSmem {
     alignas(16) uint16_t mag[MAG_RING + MAG_MIRROR];
     alignas(16) uint8_t raw[2 * CHUNK];       // the next chunk's input bytes, landed here by cp.async while the candidates are worked on
     uint32_t tick[TICK_RING + TICK_MIRROR];   // tick of sample s (chunk-local) and row r at bit 5 s + r of the chunk's slot
-    uint16_t q1[Q1_SMEM];                     // pre-check passers of the previous chunk (tile-relative positions, ascending)
-    uint32_t pass[32];                        // threshold passers waiting for their DF gates, PosEntry format
+    uint16_t q1[Q1_SMEM];                     // pre-check passers of the previous chunk (chunk-local positions, ascending)
+    uint32_t pass[32];                        // threshold passers waiting for their DF gates: chunk-local position | tried << 16
     uint32_t surv[SURV_CAP];                  // DF-gate survivors waiting for a full slice: run position | ph << 14 | long << 17 | PosEntry index << 18
     uint32_t seg[16];                         // the run's Segment
     uint32_t n_pos[RUN_MAX], n_rec[RUN_MAX];  // per tile of the run
+    // L2 eviction policies: the input is read once (evict first); the warp's tick copy and record staging are rewritten run after
+    // run and should stay in L2 instead of being written back to HBM behind the input stream (evict last)
+    unsigned long long pol_stream, pol_keep;
     RunCtx ctx;
 };
 
@@ -100,6 +105,18 @@ template <int NW> struct ScanSmemFull {
     ScanSmem t;
     WarpSmem w[NW];
 };
+
+__device__ __forceinline__ void stg_keep(uint32_t *p, uint32_t v, unsigned long long policy) {
+#ifndef V_NO_KEEP_HINT
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(policy) : "memory");
+#else
+    *p = v;
+#endif
+}
+
+// packed unsigned 16-bit min / max (VIMNMX.U16x2): two magnitudes per instruction
+__device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { uint32_t d; asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b) { uint32_t d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 
 // mixed-sign two-way dot products: a = two unsigned 16-bit magnitudes, b = four signed 8-bit coefficients
 __device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c) {
@@ -242,53 +259,70 @@ __device__ __forceinline__ uint32_t slice_and_classify(const ScanSmem &S, const 
 #define NEG_ROW3 0x0012f5f9u   //  -7, -11,  18,  0
 #define NEG_ROW4 0xff14f1fcu   //  -4, -15,  20, -1
 
-// One lane = 16 consecutive samples / positions starting at ring index mi0 (window of 32 magnitudes in registers).
-// Returns the 16-bit pre-check mask; writes the 80 ticks of its samples (two lanes share five words) at tick word tw0.
-__device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint32_t tw0, uint32_t lane, bool mirror, uint32_t *tickg_chunk) {
+// Half of a lane's window: 8 consecutive positions / samples starting at W.mag[mi0] (24 magnitudes in registers).
+// Returns the 8-bit pre-check mask; a0 / a1 receive the 40 ticks of the 8 samples (a0: ticks 0..31, a1: ticks 32..39, tick n at bit n).
+__device__ __forceinline__ uint32_t half_window(const WarpSmem &W, uint32_t mi0, uint32_t &a0, uint32_t &a1) {
     const uint4 *src = reinterpret_cast<const uint4 *>(&W.mag[mi0]);
-    const uint4 q0 = src[0], q1v = src[1], q2 = src[2], q3 = src[3];
-    const uint32_t wv[16] = {q0.x, q0.y, q0.z, q0.w, q1v.x, q1v.y, q1v.z, q1v.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-    uint32_t mask = 0;
-    {   // pre-check (demod_2400.c:311-320): pa[1] > pa[7] && pa[12] > pa[14] && pa[12] > pa[15]
-        uint32_t v[32];
+    const uint4 q0 = src[0], q1v = src[1], q2 = src[2];
+    const uint32_t wv[12] = {q0.x, q0.y, q0.z, q0.w, q1v.x, q1v.y, q1v.z, q1v.w, q2.x, q2.y, q2.z, q2.w};
+    // xs[j] = the pair (m[2j+1], m[2j+2]): the 16-bit-shifted view of the window, used by the pre-check and by the odd samples of the tick map
+    uint32_t xs[11];
 #pragma unroll
-        for (int i = 0; i < 16; i++) { v[2 * i] = wv[i] & 0xffffu; v[2 * i + 1] = wv[i] >> 16; }
+    for (int j = 0; j < 11; j++) xs[j] = __funnelshift_r(wv[j], wv[j + 1], 16);
+    // pre-check (demod_2400.c:311-320): pa[1] > pa[7] && pa[12] > pa[14] && pa[12] > pa[15], two positions (2k, 2k+1) per step on
+    // packed halves: a > b  <=>  a - min(a, b) != 0 (no borrow between the halves: min(a, b) <= a in each); both conditions hold
+    // <=> the smaller of the two differences is not zero.
+    uint32_t acc2 = 0;
 #pragma unroll
-        for (int i = 0; i < 16; i++)      // (ptxas turns a hand-chained setp / predicated-or version of this into the same 3 ISETP + VIADD + 2 SEL)
-            if (v[i + 1] > v[i + 7] && v[i + 12] > v[i + 14] && v[i + 12] > v[i + 15]) mask |= 1u << i;
+    for (int k = 3; k >= 0; k--) {
+        const uint32_t mx = vmax2(wv[k + 7], xs[k + 7]);             // max(pa[14], pa[15]) of both positions
+        const uint32_t d2 = wv[k + 6] - vmin2(wv[k + 6], mx);         // pa[12] - min(pa[12], that)
+        const uint32_t d1 = xs[k] - vmin2(xs[k], xs[k + 3]);          // pa[1] - min(pa[1], pa[7])
+        const uint32_t c = vmin2(vmin2(d1, d2), 0x00010001u);         // 1 per half where the position passes
+        acc2 = acc2 * 4u + c;                                         // position 2k at bit 2k, position 2k+1 at bit 16 + 2k
     }
     // tick map: sample i needs the pairs (m[i], m[i+1]) and (m[i+2], m[i+3]); odd i takes them from the 16-bit-shifted words
-    uint32_t xs[10];
+    uint32_t acc[2] = {0, 0};
 #pragma unroll
-    for (int j = 0; j < 10; j++) xs[j] = __funnelshift_r(wv[j], wv[j + 1], 16);
-    uint32_t acc[3] = {0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
+    for (int i = 0; i < 8; i++) {
         const uint32_t A = (i & 1) ? xs[i >> 1] : wv[i >> 1];
         const uint32_t Bp = (i & 1) ? xs[(i >> 1) + 1] : wv[(i >> 1) + 1];
         const uint32_t rows[5] = {NEG_ROW0, NEG_ROW1, NEG_ROW2, NEG_ROW3, NEG_ROW4};
 #pragma unroll
         for (int r = 0; r < 5; r++) {
             const int nv = dp2a_hi(Bp, rows[r], dp2a_lo(A, rows[r], 0));
-            const int g = 5 * i + r;                                           // tick within this lane's 80
+            const int g = 5 * i + r;                                           // tick within these 40
             acc[g >> 5] = __funnelshift_l((uint32_t)nv, acc[g >> 5], 1);       // shift the sign bit in, earliest tick ends up highest
         }
     }
-    // acc[0], acc[1] hold 32 ticks each, earliest in bit 31 -> bit-reverse; acc[2] holds 16 ticks in its low half
-    const uint32_t t0 = __brev(acc[0]), t1 = __brev(acc[1]), t2 = __brev(acc[2]) >> 16;
+    a0 = __brev(acc[0]); a1 = __brev(acc[1]) >> 24;                            // acc[1] holds 8 ticks in its low byte
+    return (acc2 & 0xffu) | ((acc2 >> 15) & 0xffu);
+}
+
+// One lane = 16 consecutive samples / positions starting at ring index mi0, in two halves of 8 (the window of a half is 24
+// magnitudes: half the registers of a 16-position window, which is what lets the kernel run with more warps per SM).
+// Returns the 16-bit pre-check mask; writes the 80 ticks of its samples (two lanes share five words) at tick word tw0.
+__device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint32_t tw0, uint32_t lane, bool mirror, uint32_t *tickg_chunk) {
+    uint32_t h0a, h0b, h1a, h1b;
+    const uint32_t m0 = half_window(W, mi0, h0a, h0b);
+    const uint32_t m1 = half_window(W, mi0 + 8, h1a, h1b);
+    const uint32_t mask = m0 | (m1 << 8);
+    // 80 ticks: t0 = ticks 0..31, t1 = ticks 32..63, t2 = ticks 64..79 (low half)
+    const uint32_t t0 = h0a, t1 = h0b | (h1a << 8), t2 = (h1a >> 24) | (h1b << 8);
     // lanes 2j, 2j+1 own 160 ticks: five words
     uint32_t *dst = &W.tick[tw0 + (lane >> 1) * 5];
     uint32_t *dg = tickg_chunk + (lane >> 1) * 5;
+    const unsigned long long keep = W.pol_keep;
     const uint32_t other_t0 = __shfl_down_sync(FULLMASK, t0, 1);
     if ((lane & 1) == 0) {
         const uint32_t w2 = t2 | (other_t0 << 16);
         dst[0] = t0; dst[1] = t1; dst[2] = w2;
-        dg[0] = t0; dg[1] = t1; dg[2] = w2;
+        stg_keep(dg, t0, keep); stg_keep(dg + 1, t1, keep); stg_keep(dg + 2, w2, keep);
         if (mirror && lane < 4) { uint32_t *m = &W.tick[TICK_RING + (lane >> 1) * 5]; m[0] = t0; m[1] = t1; m[2] = w2; }
     } else {
         const uint32_t w3 = __funnelshift_r(t0, t1, 16), w4 = __funnelshift_r(t1, t2, 16);
         dst[3] = w3; dst[4] = w4;
-        dg[3] = w3; dg[4] = w4;
+        stg_keep(dg + 3, w3, keep); stg_keep(dg + 4, w4, keep);
         if (mirror && lane < 4) { uint32_t *m = &W.tick[TICK_RING + (lane >> 1) * 5]; m[3] = w3; m[4] = w4; }
     }
     return mask;
@@ -301,8 +335,14 @@ __device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint3
 // back exactly the bytes it copied, so its own cp.async.wait_group is all the synchronisation there is.
 __device__ __forceinline__ void stage_raw(WarpSmem &W, const uint8_t *src, uint32_t lane) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(W.raw) + lane * 16;
+#ifndef V_NO_STREAM_HINT
+    const unsigned long long pol = W.pol_stream;
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(dst), "l"(src + lane * 16), "l"(pol) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(dst + 512), "l"(src + 512 + lane * 16), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + lane * 16) : "memory");
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 512), "l"(src + 512 + lane * 16) : "memory");
+#endif
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -404,8 +444,19 @@ __device__ __noinline__ void convert_chunk_edge(const ScanSmem &S, WarpSmem &W, 
 }
 
 // One round of full slices: the first `cnt` (<= 32) queued survivors, one per lane; live records go to the warp's staging area.
-__device__ __forceinline__ void slice_round(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t cnt, const uint32_t *tickg, PosEntry *run_pos,
-                                            uint32_t lane, uint32_t &n_stage, Rec *stage, uint32_t *stage_key) {
+// This warp's private global areas, recomputed from the thread index where they are needed (measured: holding them in shared
+// memory puts a shared-memory load in front of every global store of the tick copy and is 1.5 % slower)
+#define WARP_GLOBAL() (blockIdx.x * SC_WARPS + (threadIdx.x >> 5))
+#define W_TICKG(W, P) ((P).tick_scratch + (size_t)WARP_GLOBAL() * TICKG_WORDS)
+#define W_STAGE(W, P) ((P).stage_rec + (size_t)WARP_GLOBAL() * (P).stage_cap)
+#define W_STAGE_KEY(W, P) ((P).stage_key + (size_t)WARP_GLOBAL() * (P).stage_cap)
+#define W_Q1_OVER(W, P) ((P).q1_over + (size_t)WARP_GLOBAL() * CHUNK)
+
+__device__ __forceinline__ void slice_round(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t cnt, uint32_t lane, uint32_t &n_stage) {
+    const uint32_t *tickg = W_TICKG(W, P);
+    Rec *stage = W_STAGE(W, P);
+    uint32_t *stage_key = W_STAGE_KEY(W, P);
+    PosEntry *run_pos = P.pos_pool + (size_t)W.ctx.tile0 * SCAN_TILE;
     uint32_t rw[8];
     uint32_t kind = 0;
     SCAN_COUNT(SCN_SLICE_ROUNDS, 1);
@@ -442,51 +493,46 @@ __device__ __forceinline__ void slice_round(const ScanSmem &S, WarpSmem &W, cons
 
 // Candidates of one chunk: its pre-check passers (q1, ascending) -> thresholds -> PosEntries; DF gate -> survivor queue,
 // sliced 32 at a time whenever the queue fills (the rest waits for later chunks of the run).
-__device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t n_q1, uint32_t warp_global,
-                                                   uint32_t chunk_p0, uint32_t mslot, uint32_t tslot, uint32_t lane,
-                                                   uint32_t &n_surv, uint32_t &n_stage) {
+__device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t n_q1, uint32_t chunk_p0, uint32_t mslot,
+                                                   uint32_t tslot, uint32_t lane, uint32_t &n_surv, uint32_t &n_stage) {
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t m = chunk_p0 / SCAN_TILE;                     // tile of the run this chunk belongs to
-    const uint16_t *q1_over = P.q1_over + (size_t)warp_global * CHUNK;
-    const uint32_t *tickg = P.tick_scratch + (size_t)warp_global * TICKG_WORDS;
-    Rec *stage = P.stage_rec + (size_t)warp_global * P.stage_cap;
-    uint32_t *stage_key = P.stage_key + (size_t)warp_global * P.stage_cap;
-    PosEntry *run_pos = P.pos_pool + (size_t)W.ctx.tile0 * SCAN_TILE;
-    PosEntry *pos_out = run_pos + (size_t)m * SCAN_TILE;
+    PosEntry *pos_out = P.pos_pool + (size_t)(W.ctx.tile0 + m) * SCAN_TILE;
+    const uint32_t pe_base = (chunk_p0 & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE);    // PosEntry position of chunk-local position 0
+    const uint16_t *mag0 = &W.mag[mslot * CHUNK];
     // Threshold passers wait in W.pass (32 entries) until the chunk's last batch is through or the next batch's passers would
-    // not fit: their DF gates are evaluated five lanes per passer, and a single batch rarely has more than three (one gate
-    // trip per batch left most lanes idle: 1.76 trips per chunk on the bench workload against 1.1 now).
+    // not fit: their DF gates are evaluated five lanes per passer, and a single batch rarely has more than three.
     uint32_t n_pass = 0, pos_base = W.n_pos[m];                 // passers waiting in W.pass; PosEntry index (in the tile) of W.pass[0]
     for (uint32_t b0 = 0;; b0 += 32) {
         const bool have_batch = b0 < n_q1;
-        uint32_t p = 0, tried = 0, bal = 0;
+        uint32_t pl = 0, tried = 0, bal = 0;
         if (have_batch) {
             SCAN_COUNT(SCN_THR_BATCHES, 1);
             const uint32_t e = b0 + lane;
             if (e < n_q1) {
-                p = e < Q1_SMEM ? W.q1[e] : q1_over[e - Q1_SMEM];    // run-relative position
-                tried = threshold_phases(&W.mag[mslot * CHUNK + (p - chunk_p0)], P.thr);
+                pl = (Q1_SMEM >= CHUNK || e < Q1_SMEM) ? W.q1[e] : W_Q1_OVER(W, P)[e - Q1_SMEM];      // chunk-local position
+                tried = threshold_phases(mag0 + pl, P.thr);
             }
             bal = __ballot_sync(FULLMASK, tried != 0);
         }
         const uint32_t n_b = __popc(bal);
         if (n_pass && (!have_batch || n_pass + n_b > 32)) {      // ---- DF gates of the waiting passers
             __syncwarp();
-            for (uint32_t i0 = 0; i0 < 5 * n_pass; i0 += 32) {
+            for (uint32_t i0 = 0; i0 < 5 * n_pass; i0 += 32) {          // five lanes per passer, one per phase
                 SCAN_COUNT(SCN_GATE_TRIPS, 1);
-                const uint32_t i = i0 + lane, r = i / 5, ph = i - 5 * r;
+                const uint32_t i_ = i0 + lane, r = i_ / 5, gph = i_ - 5 * r;
                 uint32_t g = 0, pe = 0;
                 if (r < n_pass) {
                     pe = W.pass[r];
-                    if ((pe >> (16 + ph)) & 1u) g = df_gate(W, P, first_tick(tslot, (pe & 0x3fffu) - chunk_p0, ph));
+                    if ((pe >> (16 + gph)) & 1u) g = df_gate(W, P, first_tick(tslot, pe & 0xffffu, gph));
                 }
                 const uint32_t bal2 = __ballot_sync(FULLMASK, g & 1u);
-                if (g & 1u) W.surv[n_surv + __popc(bal2 & lt)] = (pe & 0x3fffu) | (ph << 14) | ((g >> 1) << 17) | ((pos_base + r) << 18);
+                if (g & 1u) W.surv[n_surv + __popc(bal2 & lt)] = (chunk_p0 + (pe & 0xffffu)) | (gph << 14) | ((g >> 1) << 17) | ((pos_base + r) << 18);
                 n_surv += __popc(bal2);
                 SCAN_COUNT(SCN_SURVIVORS, __popc(bal2));
                 __syncwarp();
                 if (n_surv >= 32) {
-                    slice_round(S, W, P, 32, tickg, run_pos, lane, n_stage, stage, stage_key);
+                    slice_round(S, W, P, 32, lane, n_stage);
                     const uint32_t moved = lane + 32 < n_surv ? W.surv[lane + 32] : 0;
                     __syncwarp();
                     W.surv[lane] = moved;
@@ -502,8 +548,8 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
             SCAN_COUNT(SCN_PASS_BATCHES, 1); SCAN_COUNT(SCN_PASSERS, n_b);
             if (tried) {
                 const uint32_t r = n_pass + __popc(bal & lt);
-                W.pass[r] = p | (tried << 16);
-                pos_out[pos_base + r] = (p & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE) | (tried << 16);   // live bits are OR-ed in when its phases are sliced
+                W.pass[r] = pl | (tried << 16);
+                pos_out[pos_base + r] = (pe_base + pl) | (tried << 16);   // live bits are OR-ed in when its phases are sliced
             }
             n_pass += n_b;
         }
@@ -531,7 +577,14 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
 
     WarpSmem &W = F.w[wid];
     RunCtx &T = W.ctx;
-    const uint32_t warp_global = blockIdx.x * NW + wid;
+    if (lane == 0) {
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        W.pol_stream = pol;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+        W.pol_keep = pol;
+    }
+    __syncwarp();
 
     uint32_t pend_tile = 0, pend_n = 0;       // tiles already claimed but not processed yet (a claim that crossed a segment boundary)
     for (;;) {
@@ -594,8 +647,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
             if (k >= 0) {
                 SCAN_COUNT(SCN_WINDOW_CHUNKS, 1);
                 // ---- window(k): pre-check + tick map -----------------------------------------------------------------
-                mask = window_pass(W, ms * CHUNK + lane * 16, (k & 1) * TICK_CW, lane, (k & 1) == 0,
-                                   P.tick_scratch + (size_t)warp_global * TICKG_WORDS + k * TICK_CW);
+                mask = window_pass(W, ms * CHUNK + lane * 16, (k & 1) * TICK_CW, lane, (k & 1) == 0, W_TICKG(W, P) + k * TICK_CW);
                 if ((uint32_t)k < k_int_lo || (uint32_t)k >= k_int_hi) {      // positions outside [p_lo, p_hi) are not preamble starts
                     const uint32_t i0 = k * CHUNK + lane * 16;               // run-relative
                     const uint32_t p_lo = T.p_lo, p_hi = T.p_hi;
@@ -640,7 +692,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
             if (more) { if (all_data) stage_raw(W, T.tile_base + (size_t)cn * CHUNK * 2, lane); else prefetch_raw(T, cn, lane); }
             __syncwarp();                                        // ticks of chunk k visible to the warp
             // ---- candidates(k-1) --------------------------------------------------------------------------------------
-            if (n_q1) process_candidates(S, W, P, n_q1, warp_global, (uint32_t)(k - 1) * CHUNK, ms == 0 ? 2 : ms - 1, (uint32_t)(k - 1) & 1u, lane, n_surv, n_stage);
+            if (n_q1) process_candidates(S, W, P, n_q1, (uint32_t)(k - 1) * CHUNK, ms == 0 ? 2 : ms - 1, (uint32_t)(k - 1) & 1u, lane, n_surv, n_stage);
             __syncwarp();                                        // chunk k-1's magnitudes are dead now
             // ---- convert(k+2) into the slot chunk k-1 occupied ------------------------------------------------------
             if (more) {
@@ -654,16 +706,15 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
             }
             // ---- q1 <- pre-check passers of chunk k -------------------------------------------------------------------
             if (k >= 0) {
-                uint16_t *q1_over = P.q1_over + (size_t)warp_global * CHUNK;
                 uint32_t off = warp_excl_scan(__popc(mask), lane, &n_q1);
-                const uint32_t i0 = k * CHUNK + lane * 16;
+                const uint32_t i0 = lane * 16;                   // chunk-local
                 uint32_t mb = mask;
 #ifdef B200_SCAN_COUNTERS
                 { const uint32_t trips = __reduce_max_sync(FULLMASK, (uint32_t)__popc(mask)); SCAN_COUNT(SCN_Q1_LOOP_TRIPS, trips); SCAN_COUNT(SCN_Q1_ENTRIES, n_q1); }
 #endif
                 while (mb) {
                     const uint32_t b = __ffs(mb) - 1; mb &= mb - 1;
-                    if (off < Q1_SMEM) W.q1[off] = (uint16_t)(i0 + b); else q1_over[off - Q1_SMEM] = (uint16_t)(i0 + b);
+                    if (Q1_SMEM >= CHUNK || off < Q1_SMEM) W.q1[off] = (uint16_t)(i0 + b); else W_Q1_OVER(W, P)[off - Q1_SMEM] = (uint16_t)(i0 + b);
                     off++;
                 }
                 ms = ms == 2 ? 0 : ms + 1;
@@ -672,10 +723,10 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
         }
 
         // ---- end of run: remaining slices, one record-pool reservation, copy of the staged records ------------------------
-        Rec *stage = P.stage_rec + (size_t)warp_global * P.stage_cap;
-        uint32_t *stage_key = P.stage_key + (size_t)warp_global * P.stage_cap;
+        Rec *stage = W_STAGE(W, P);
+        uint32_t *stage_key = W_STAGE_KEY(W, P);
         const uint32_t tile0 = T.tile0, n_tiles_run = T.n_tiles;
-        if (n_surv) slice_round(S, W, P, n_surv, P.tick_scratch + (size_t)warp_global * TICKG_WORDS, P.pos_pool + (size_t)tile0 * SCAN_TILE, lane, n_stage, stage, stage_key);
+        if (n_surv) slice_round(S, W, P, n_surv, lane, n_stage);
         __syncwarp();
         uint32_t off = 0, ok = 1;
         if (lane == 0) {

@@ -188,6 +188,8 @@ template <class T, class V> static inline T atomicCAS(T *p, V cmp, V v) { const 
 // ---- inline PTX (build_emu.py rewrites every asm statement into a call of emu_asm_<opcode>(outputs..., inputs..., immediates...)) ----
 static inline void emu_asm_dp2a_lo_u32_s32(int &d, unsigned a, unsigned b, int c) { d = c + (int)(a & 0xffffu) * (int)(int8_t)(b & 0xffu) + (int)(a >> 16) * (int)(int8_t)((b >> 8) & 0xffu); }
 static inline void emu_asm_dp2a_hi_u32_s32(int &d, unsigned a, unsigned b, int c) { d = c + (int)(a & 0xffffu) * (int)(int8_t)((b >> 16) & 0xffu) + (int)(a >> 16) * (int)(int8_t)(b >> 24); }
+static inline void emu_asm_min_u16x2(unsigned &d, unsigned a, unsigned b) { const unsigned lo = (a & 0xffffu) < (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu), hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16); d = lo | (hi << 16); }
+static inline void emu_asm_max_u16x2(unsigned &d, unsigned a, unsigned b) { const unsigned lo = (a & 0xffffu) > (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu), hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16); d = lo | (hi << 16); }
 static inline void emu_asm_prmt_b32(unsigned &d, unsigned a, unsigned b, unsigned sel) { d = emu_prmt(a, b, sel, true); }
 static inline void emu_asm_mad_wide_u32(unsigned long long &acc, unsigned a, unsigned b) { acc += (unsigned long long)a * b; }
 static inline void emu_asm_ld_global_nc_L1__no_allocate_v4_u32(unsigned &x, unsigned &y, unsigned &z, unsigned &w, const void *p) {
@@ -195,6 +197,10 @@ static inline void emu_asm_ld_global_nc_L1__no_allocate_v4_u32(unsigned &x, unsi
 }
 static inline void emu_asm_cp_async_cg_shared_global(unsigned dst, const void *src, int bytes) { memcpy(emu_smem + dst, src, (size_t)bytes); }
 static inline void emu_asm_cp_async_ca_shared_global(unsigned dst, const void *src, int bytes) { memcpy(emu_smem + dst, src, (size_t)bytes); }
+static inline void emu_asm_cp_async_cg_shared_global_L2__cache_hint(unsigned dst, const void *src, unsigned long long, int bytes) { memcpy(emu_smem + dst, src, (size_t)bytes); }
+static inline void emu_asm_createpolicy_fractional_L2__evict_first_b64(unsigned long long &p) { p = 1; }
+static inline void emu_asm_createpolicy_fractional_L2__evict_last_b64(unsigned long long &p) { p = 2; }
+static inline void emu_asm_st_global_L2__cache_hint_b32(unsigned *p, unsigned v, unsigned long long) { *p = v; }
 static inline void emu_asm_cp_async_commit_group() {}
 static inline void emu_asm_cp_async_wait_group(int) {}
 static inline void emu_asm_prefetch_global_L2(const void *) {}
