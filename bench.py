@@ -610,7 +610,7 @@ def b200_arm(args, rank, world, local):
         ms_e, _, launches_e, frames_e, clk_e = timed(host_step_async, args.steps * LPS, args.warmup * LPS, pipelined=True, sample=True)
         e2e = {"value": world * step_samples * args.steps / (ms_e * 1e-3) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": (launch_samples * 2 + S * 64 + 64) * LPS,           # IQ slab + segment table + control block, per launch
-               "d2h_bytes_per_step": int(frames_e / args.steps * 64) + (S * 4 + S * B * 80 + 32) * LPS,   # frames + counts + buffer results
+               "d2h_bytes_per_step": int(frames_e / args.steps * 64) + (S * 4 + S * B * 144 + 32 + 16 * 64) * LPS,   # frames + counts + buffer results
                "ms_per_step": ms_e / args.steps, "frames_per_step": frames_e / args.steps, "host_placement": numa_note, "clocks": clk_e}
         d = d_dev
         d2.close()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200_DEMOD_ABI_VERSION 1
+#define B200_DEMOD_ABI_VERSION 2
 
 /* readsb.c:288  trailing_samples = (8 + 112 + 16) us * 2.4 = 326 */
 #define B200_TRAILING_SAMPLES 326
@@ -95,6 +95,15 @@ typedef struct b200_buffer_result {
     uint32_t n_frames;          /* frames accepted in this buffer */
     uint32_t buffer_seq;
     uint32_t icao_flipped;      /* 1 if the ICAO filter tables were flipped after this buffer */
+    /* what demodulate2400() added to Modes.stats_current while it worked on this buffer (stats.h:62-83): a caller that keeps
+     * readsb's statistics needs no second call per buffer */
+    uint32_t demod_preambles;
+    uint32_t demod_rejected_bad;
+    uint32_t demod_rejected_unknown_icao;
+    uint32_t demod_accepted[2];         /* by correctedbits */
+    uint32_t demod_preamblePhase[5];    /* every phase tried (demod_2400.c:216) */
+    uint32_t demod_bestPhase[5];
+    uint32_t pad_;
 } b200_buffer_result;
 
 /* Cumulative per-stream counters = Modes.stats_current demod_* (stats.h:62-83). */

@@ -27,7 +27,6 @@
 #include "b200_demod.h"
 
 static b200_demod_ctx *g_ctx;
-static b200_demod_stats g_prev;      /* cumulative counters at the previous buffer */
 static int g_in_shim;                /* adds that come from our own decodeModesMessage calls are already on the device */
 static b200_frame g_frames[2048];
 static b200_modeac *g_ac;            /* replies of the buffer demodulate2400 just handed to the library */
@@ -69,7 +68,6 @@ static int shim_open(void) {
         fprintf(stderr, "b200 demodulator: %s\n", b200_demod_last_error(NULL));
         return -1;
     }
-    memset(&g_prev, 0, sizeof g_prev);
     g_thr = cfg.preamble_threshold;
     return 0;
 }
@@ -130,15 +128,14 @@ void __wrap_demodulate2400(struct mag_buf *mag) {
         netUseMessage(mm);                                                       /* :471 */
     }
 
-    /* the counters the scan itself increments (stats.h:62-83) */
-    b200_demod_stats s;
-    if (b200_demod_get_stats(g_ctx, 0, &s) == B200_OK) {
-        Modes.stats_current.demod_preambles += (uint32_t) (s.demod_preambles - g_prev.demod_preambles);
-        Modes.stats_current.demod_rejected_bad += (uint32_t) (s.demod_rejected_bad - g_prev.demod_rejected_bad);
-        Modes.stats_current.demod_rejected_unknown_icao += (uint32_t) (s.demod_rejected_unknown_icao - g_prev.demod_rejected_unknown_icao);
-        for (int p = 0; p < 5; p++)
-            Modes.stats_current.demod_preamblePhase[p] += (uint32_t) (s.demod_preamblePhase[p] - g_prev.demod_preamblePhase[p]);
-        g_prev = s;
+    /* the counters the scan itself increments (stats.h:62-83): what this call added, delivered with the buffer's result */
+    b200_buffer_result br;
+    uint32_t nbr = 0;
+    if (b200_demod_buffer_results(g_ctx, 0, &br, 1, &nbr) == B200_OK && nbr == 1) {
+        Modes.stats_current.demod_preambles += br.demod_preambles;
+        Modes.stats_current.demod_rejected_bad += br.demod_rejected_bad;
+        Modes.stats_current.demod_rejected_unknown_icao += br.demod_rejected_unknown_icao;
+        for (int p = 0; p < 5; p++) Modes.stats_current.demod_preamblePhase[p] += br.demod_preamblePhase[p];
     }
     /* demod_2400.c:474-479 */
     double sum_signal_power = sum_scaled_signal_power / 65535.0 / 65535.0;

@@ -379,6 +379,7 @@ int oracle_demodulate2400(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64
                           uint64_t sum_level, uint64_t sum_power,
                           b200_frame *out, unsigned cap, unsigned *n_out, b200_buffer_result *res) {
     b200_demod_stats *st = &o->st;
+    const b200_demod_stats before = *st;        /* the buffer result reports what this call added to the counters */
     uint64_t sum_sig = 0;
     unsigned nfr = 0;
     int overflow = 0;
@@ -513,6 +514,15 @@ int oracle_demodulate2400(oracle_ctx *o, const uint16_t *m, unsigned mlen, int64
         res->sample_timestamp = sample_ts; res->sum_level = sum_level; res->sum_power = sum_power;
         res->sum_signal_power = sum_sig; res->length = mlen; res->n_frames = nfr;
         res->buffer_seq = o->buffer_seq; res->icao_flipped = (uint32_t)flipped;
+        res->demod_preambles = (uint32_t)(st->demod_preambles - before.demod_preambles);
+        res->demod_rejected_bad = (uint32_t)(st->demod_rejected_bad - before.demod_rejected_bad);
+        res->demod_rejected_unknown_icao = (uint32_t)(st->demod_rejected_unknown_icao - before.demod_rejected_unknown_icao);
+        for (int i = 0; i < 2; i++) res->demod_accepted[i] = (uint32_t)(st->demod_accepted[i] - before.demod_accepted[i]);
+        for (int i = 0; i < 5; i++) {
+            res->demod_preamblePhase[i] = (uint32_t)(st->demod_preamblePhase[i] - before.demod_preamblePhase[i]);
+            res->demod_bestPhase[i] = (uint32_t)(st->demod_bestPhase[i] - before.demod_bestPhase[i]);
+        }
+        res->pad_ = 0;
     }
     o->buffer_seq++;
     return overflow ? -1 : 0;

@@ -194,6 +194,7 @@ int ref_demodulate2400(uint16_t *data, unsigned length, int64_t sample_ts, doubl
     mb.data = data;
     g_out = out; g_levels = levels; g_cap = cap; g_n = *n_out; g_overflow = 0;
     g_cur_sample_ts = sample_ts; g_buf_frames = 0;
+    const struct stats before = Modes.stats_current;
     demodulate2400(&mb);                                         /* readsb.c:871 */
     Modes.stats_current.samples_processed += length;             /* readsb.c:876 */
     *n_out = g_n;
@@ -209,6 +210,15 @@ int ref_demodulate2400(uint16_t *data, unsigned length, int64_t sample_ts, doubl
         memset(res, 0, sizeof *res);
         res->sample_timestamp = sample_ts; res->length = length; res->n_frames = g_buf_frames;
         res->buffer_seq = g_buffer_seq; res->icao_flipped = (uint32_t)flipped;
+        const struct stats *s = &Modes.stats_current;             /* what this call added (stats.h:62-83) */
+        res->demod_preambles = s->demod_preambles - before.demod_preambles;
+        res->demod_rejected_bad = s->demod_rejected_bad - before.demod_rejected_bad;
+        res->demod_rejected_unknown_icao = s->demod_rejected_unknown_icao - before.demod_rejected_unknown_icao;
+        for (int i = 0; i < 2; i++) res->demod_accepted[i] = s->demod_accepted[i] - before.demod_accepted[i];
+        for (int i = 0; i < 5; i++) {
+            res->demod_preamblePhase[i] = s->demod_preamblePhase[i] - before.demod_preamblePhase[i];
+            res->demod_bestPhase[i] = s->demod_bestPhase[i] - before.demod_bestPhase[i];
+        }
     }
     g_buffer_seq++;
     return g_overflow ? -1 : 0;

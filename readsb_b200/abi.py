@@ -19,7 +19,10 @@ class Frame(C.Structure):
 class BufferResult(C.Structure):
     _fields_ = [("sample_timestamp", C.c_int64), ("sum_level", C.c_uint64), ("sum_power", C.c_uint64),
                 ("sum_signal_power", C.c_uint64), ("length", C.c_uint32), ("n_frames", C.c_uint32),
-                ("buffer_seq", C.c_uint32), ("icao_flipped", C.c_uint32)]
+                ("buffer_seq", C.c_uint32), ("icao_flipped", C.c_uint32),
+                ("demod_preambles", C.c_uint32), ("demod_rejected_bad", C.c_uint32), ("demod_rejected_unknown_icao", C.c_uint32),
+                ("demod_accepted", C.c_uint32 * 2), ("demod_preamblePhase", C.c_uint32 * 5), ("demod_bestPhase", C.c_uint32 * 5),
+                ("pad_", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -49,7 +52,7 @@ class Config(C.Structure):
 MODEAC_DTYPE = np.dtype([("timestamp", "<i8"), ("f1_sample", "<u4"), ("modeac", "<u2"), ("buffer_idx", "<u2")])
 CFG_MODE_AC = 0x1
 
-assert C.sizeof(Frame) == 64 and C.sizeof(BufferResult) == 48 and MODEAC_DTYPE.itemsize == 16
+assert C.sizeof(Frame) == 64 and C.sizeof(BufferResult) == 112 and MODEAC_DTYPE.itemsize == 16
 
 FRAME_DTYPE = np.dtype([("timestamp", "<i8"), ("sigpow_sum", "<u8"), ("j", "<u4"), ("crc", "<u4"), ("addr", "<u4"),
                         ("score", "<i4"), ("buffer_seq", "<u4"), ("signal_len", "<u2"), ("phase", "u1"),
@@ -57,8 +60,11 @@ FRAME_DTYPE = np.dtype([("timestamp", "<i8"), ("sigpow_sum", "<u8"), ("j", "<u4"
                         ("flags", "u1"), ("msg", "u1", (14,)), ("pad_", "u1", (6,))])
 BUFRES_DTYPE = np.dtype([("sample_timestamp", "<i8"), ("sum_level", "<u8"), ("sum_power", "<u8"),
                          ("sum_signal_power", "<u8"), ("length", "<u4"), ("n_frames", "<u4"),
-                         ("buffer_seq", "<u4"), ("icao_flipped", "<u4")])
-assert FRAME_DTYPE.itemsize == 64 and BUFRES_DTYPE.itemsize == 48
+                         ("buffer_seq", "<u4"), ("icao_flipped", "<u4"),
+                         ("demod_preambles", "<u4"), ("demod_rejected_bad", "<u4"), ("demod_rejected_unknown_icao", "<u4"),
+                         ("demod_accepted", "<u4", (2,)), ("demod_preamblePhase", "<u4", (5,)), ("demod_bestPhase", "<u4", (5,)),
+                         ("pad_", "<u4")])
+assert FRAME_DTYPE.itemsize == 64 and BUFRES_DTYPE.itemsize == 112
 
 # fields of a frame that the reference itself defines (flags is this library's own annotation)
 FRAME_PARITY_FIELDS = ("timestamp", "sigpow_sum", "j", "crc", "addr", "score", "buffer_seq", "signal_len",

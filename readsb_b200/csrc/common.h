@@ -117,7 +117,7 @@ struct StreamState {
 // ---- run-wide control block (device) ------------------------------------------------------------
 struct RunCtl {
     uint32_t rec_alloc;      // atomic bump pointer into rec_pool
-    uint32_t rec_cap;
+    uint32_t pad0_;
     uint32_t overflow;       // bit0: rec_pool exhausted, bit1: per-tile queue capacity exceeded, bit2: frame capacity,
                              // bit3: a receiver's ICAO tables have to grow before this run (StreamState.grow_log2), bit4: stage B skipped
                              // because the step ahead has to be repeated, bit5: Mode A/C candidate / output capacity exceeded
@@ -139,6 +139,7 @@ struct ScanParams {
     TileOut *tile_out;
     BufAcc *buf_acc;
     RunCtl *ctl;
+    uint32_t rec_cap;            // records rec_pool / key_pool hold
     int32_t thr;                 // Modes.preambleThreshold
     uint32_t long_set, short_set; // valid DF bitsets (demod_2400.c:98-128)
     int32_t nfix, fixdf;

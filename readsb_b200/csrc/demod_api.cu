@@ -43,7 +43,13 @@ struct DeviceArgs {      // what a device-resident step was asked to do (kept fo
 struct Slot {
     bool allocated = false, in_flight = false, completed = false;
     uint32_t rec_cap = 0;
-    Segment *d_segs = nullptr, *h_segs = nullptr;
+    // Descriptors of a run travel in ONE host-to-device copy and its results in ONE device-to-host copy: two blocks per slot, laid
+    // out per run (layout_run); the d_* / h_* members below point into them.
+    //   descriptor block  [stream_seg_begin (S+1) | segs (nseg) | tile_seg (ntile)]
+    //   result block      [RunCtl | buf_acc (nbuf) | frame_prefix (S+1) | buf_out (nbuf) | packed frames ...]
+    uint8_t *d_desc = nullptr, *h_desc = nullptr, *d_res = nullptr, *h_res = nullptr;
+    size_t desc_cap = 0, res_cap = 0, res_head = 0;     // res_head: bytes in front of the packed frames in this run's result block
+    Segment *d_segs = nullptr, *h_segs = nullptr;       // h_segs / h_tile_seg / h_stream_seg_begin: where the host BUILDS the run (copied into h_desc)
     uint32_t *d_tile_seg = nullptr, *h_tile_seg = nullptr;
     uint32_t *d_stream_seg_begin = nullptr, *h_stream_seg_begin = nullptr;
     uint32_t cached_tiles = 0;        // tile_seg on the device is valid for this many tiles (device-resident path)
@@ -65,6 +71,7 @@ struct Slot {
     AcLevel *d_ac_levels = nullptr, *h_ac_levels = nullptr;                           // per reference buffer of the run: source of the noise floor
     // the run this slot holds
     uint32_t nseg = 0, ntile = 0, nbuf = 0, run_frames = 0;
+    size_t desc_bytes = 0;            // bytes of the descriptor block this run uploads
     bool upload_tiles = true, is_device = false;
     DeviceArgs dargs = {};
     std::vector<uint32_t> stream_buf_begin;   // [n_streams+1] into h_buf_out
@@ -72,7 +79,10 @@ struct Slot {
                                               // 5 result copies done, 6 Mode A/C scan + walk done, 7 descriptors uploaded
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t launches = 0;
+    uint32_t first_frames = 0;        // packed frames that came with the result block's copy
 };
+
+#define FIRST_COPY_FRAMES 16
 
 #define NSLOT 3      // steps in flight in the asynchronous modes; the blocking calls use slot 0
 
@@ -167,15 +177,20 @@ API int b200_demod_uc8_lut(uint16_t *out) {
     return B200_OK;
 }
 
+static inline size_t pad16(size_t n) { return (n + 15) & ~(size_t)15; }
+
+// Lays this run's descriptors and results out in the slot's two blocks (nseg / ntile / nbuf are final) and copies what the host
+// built into the descriptor block's host copy.
+static void layout_run(b200_demod_ctx *c, Slot &sl);
+
 static void free_slot(Slot &s) {
-    cudaFree(s.d_segs); cudaFree(s.d_tile_seg); cudaFree(s.d_stream_seg_begin); cudaFree(s.d_ctl); cudaFree(s.d_pos_pool);
-    cudaFree(s.d_rec_pool); cudaFree(s.d_key_pool); cudaFree(s.d_tile_out); cudaFree(s.d_buf_acc); cudaFree(s.d_buf_out);
-    cudaFree(s.d_frames); cudaFree(s.d_packed); cudaFree(s.d_frame_count); cudaFree(s.d_frame_prefix); cudaFree(s.d_addable);
+    cudaFree(s.d_desc); cudaFree(s.d_res); cudaFreeHost(s.h_desc); cudaFreeHost(s.h_res); cudaFree(s.d_pos_pool);
+    cudaFree(s.d_rec_pool); cudaFree(s.d_key_pool); cudaFree(s.d_tile_out);
+    cudaFree(s.d_frames); cudaFree(s.d_frame_count); cudaFree(s.d_addable);
     cudaFree(s.d_ac_bitmap); cudaFree(s.d_ac_noise); cudaFree(s.d_ac_count); cudaFree(s.d_ac_prefix); cudaFree(s.d_ac_out); cudaFree(s.d_ac_packed);
     cudaFreeHost(s.h_ac_prefix); cudaFreeHost(s.h_ac_packed);
     cudaFree(s.d_ac_levels); cudaFreeHost(s.h_ac_levels);
-    cudaFreeHost(s.h_segs); cudaFreeHost(s.h_tile_seg); cudaFreeHost(s.h_stream_seg_begin); cudaFreeHost(s.h_ctl);
-    cudaFreeHost(s.h_buf_acc); cudaFreeHost(s.h_buf_out); cudaFreeHost(s.h_packed); cudaFreeHost(s.h_frame_prefix);
+    free(s.h_segs); free(s.h_tile_seg); free(s.h_stream_seg_begin);
     for (auto &e : s.ev) if (e) cudaEventDestroy(e);
     s = Slot();
 }
@@ -185,21 +200,25 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
 #define A(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
     for (auto &e : s.ev) A(cudaEventCreate(&e));
     s.rec_cap = rec_cap;
-    A(dev_alloc(&s.d_segs, c->seg_cap)); A(pin_alloc(&s.h_segs, c->seg_cap));
-    A(dev_alloc(&s.d_tile_seg, c->tile_cap)); A(pin_alloc(&s.h_tile_seg, c->tile_cap));
-    A(dev_alloc(&s.d_stream_seg_begin, S + 1)); A(pin_alloc(&s.h_stream_seg_begin, S + 1));
-    A(dev_alloc(&s.d_ctl, 1)); A(pin_alloc(&s.h_ctl, 1));
+    s.h_segs = (Segment *)malloc((size_t)c->seg_cap * sizeof(Segment));
+    s.h_tile_seg = (uint32_t *)malloc((size_t)c->tile_cap * 4);
+    s.h_stream_seg_begin = (uint32_t *)malloc(((size_t)S + 1) * 4);
+    if (!s.h_segs || !s.h_tile_seg || !s.h_stream_seg_begin) return cudaErrorMemoryAllocation;
+    s.desc_cap = pad16(((size_t)S + 1) * 4) + (size_t)c->seg_cap * sizeof(Segment) + (size_t)c->tile_cap * 4 + 64;
+    s.res_cap = sizeof(RunCtl) + (size_t)c->buf_cap * (sizeof(BufAcc) + sizeof(b200_buffer_result)) + pad16(((size_t)S + 1) * 4)
+              + (size_t)S * c->frame_cap * sizeof(b200_frame) + 64;
+    A(cudaMalloc((void **)&s.d_desc, s.desc_cap)); A(cudaHostAlloc((void **)&s.h_desc, s.desc_cap, cudaHostAllocDefault));
+    A(cudaMalloc((void **)&s.d_res, s.res_cap)); A(cudaHostAlloc((void **)&s.h_res, s.res_cap, cudaHostAllocDefault));
+    A(cudaMemset(s.d_res, 0, sizeof(RunCtl)));
+    memset(s.h_res, 0, sizeof(RunCtl) + pad16(((size_t)S + 1) * 4));
+    s.d_ctl = reinterpret_cast<RunCtl *>(s.d_res); s.h_ctl = reinterpret_cast<RunCtl *>(s.h_res);     // fixed: the next step reads it as prev_ctl
     A(dev_alloc(&s.d_pos_pool, (size_t)c->tile_cap * SCAN_TILE));
     A(dev_alloc(&s.d_rec_pool, s.rec_cap)); A(dev_alloc(&s.d_key_pool, s.rec_cap));
     A(dev_alloc(&s.d_tile_out, c->tile_cap));
-    A(dev_alloc(&s.d_buf_acc, c->buf_cap)); A(pin_alloc(&s.h_buf_acc, c->buf_cap));
-    A(dev_alloc(&s.d_buf_out, c->buf_cap)); A(pin_alloc(&s.h_buf_out, c->buf_cap));
     A(dev_alloc(&s.d_frames, (size_t)S * c->frame_cap));
-    A(dev_alloc(&s.d_packed, (size_t)S * c->frame_cap)); A(pin_alloc(&s.h_packed, (size_t)S * c->frame_cap));
     A(dev_alloc(&s.d_frame_count, S)); A(cudaMemset(s.d_frame_count, 0, S * 4));
     A(dev_alloc(&s.d_addable, S)); A(cudaMemset(s.d_addable, 0, S * 4));
-    A(dev_alloc(&s.d_frame_prefix, S + 1)); A(pin_alloc(&s.h_frame_prefix, S + 1));
-    A(cudaMemset(s.d_ctl, 0, sizeof(RunCtl)));
+
     if (c->cfg.flags & B200_CFG_MODE_AC) {
         // one bit per position, and room for every reply a buffer can hold: nothing here depends on the input
         const size_t ac_total = (size_t)c->buf_cap * c->ac_cap;
@@ -213,11 +232,32 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
         memset(s.h_ac_prefix, 0, (S + 1) * 4);
     }
 #undef A
-    memset(s.h_frame_prefix, 0, (S + 1) * 4);
-    memset(s.h_ctl, 0, sizeof(RunCtl));
     s.stream_buf_begin.assign(S + 1, 0);
+    layout_run(c, s);       // results of "no run yet": zero frames, zero buffers
     s.allocated = true;
     return cudaSuccess;
+}
+
+static void layout_run(b200_demod_ctx *c, Slot &sl) {
+    const size_t S = c->cfg.n_streams;
+    size_t o = 0;
+    const size_t o_ssb = o; o += pad16((S + 1) * 4);
+    const size_t o_seg = o; o += (size_t)sl.nseg * sizeof(Segment);
+    const size_t o_tile = o;
+    sl.d_stream_seg_begin = reinterpret_cast<uint32_t *>(sl.d_desc + o_ssb);
+    sl.d_segs = reinterpret_cast<Segment *>(sl.d_desc + o_seg);
+    sl.d_tile_seg = reinterpret_cast<uint32_t *>(sl.d_desc + o_tile);
+    memcpy(sl.h_desc + o_ssb, sl.h_stream_seg_begin, (S + 1) * 4);
+    if (sl.nseg) memcpy(sl.h_desc + o_seg, sl.h_segs, (size_t)sl.nseg * sizeof(Segment));
+    if (sl.upload_tiles && sl.ntile) memcpy(sl.h_desc + o_tile, sl.h_tile_seg, (size_t)sl.ntile * 4);
+    sl.desc_bytes = o_tile + (sl.upload_tiles ? (size_t)sl.ntile * 4 : 0);
+    size_t r = sizeof(RunCtl);
+    sl.d_buf_acc = reinterpret_cast<BufAcc *>(sl.d_res + r); sl.h_buf_acc = reinterpret_cast<BufAcc *>(sl.h_res + r); r += (size_t)sl.nbuf * sizeof(BufAcc);
+    sl.d_frame_prefix = reinterpret_cast<uint32_t *>(sl.d_res + r); sl.h_frame_prefix = reinterpret_cast<uint32_t *>(sl.h_res + r); r += pad16((S + 1) * 4);
+    sl.d_buf_out = reinterpret_cast<b200_buffer_result *>(sl.d_res + r); sl.h_buf_out = reinterpret_cast<b200_buffer_result *>(sl.h_res + r); r += (size_t)sl.nbuf * sizeof(b200_buffer_result);
+    r = pad16(r);
+    sl.d_packed = reinterpret_cast<b200_frame *>(sl.d_res + r); sl.h_packed = reinterpret_cast<b200_frame *>(sl.h_res + r);
+    sl.res_head = r;
 }
 
 API void b200_demod_destroy(b200_demod_ctx *c) {
@@ -309,7 +349,7 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     c->seg_cap = S * K;
     c->tile_cap = S * K * tiles_per_buf;
     c->buf_cap = S * K;
-    c->frame_cap = K * (BUF / 113 + 2);
+    c->frame_cap = K * (BUF / 113 + 2 + 32);         // + what the sub-ranges of a buffer add by rounding (stage B, resolve_stream)
     c->ac_cap = BUF / 70 + 2;                       // per reference buffer: a Mode A/C reply hides the next 69 positions
     {
         const size_t warps = (size_t)b200_scan_warps(c->n_sm);
@@ -464,20 +504,17 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
         Slot &succ = c->slot[((&sl - c->slot) + 1) % NSLOT];
         if (succ.in_flight) CU(c, cudaStreamWaitEvent(pre, succ.ev[2], 0));
     }
-    CU(c, cudaMemcpyAsync(sl.d_segs, sl.h_segs, sl.nseg * sizeof(Segment), cudaMemcpyHostToDevice, pre));
-    if (sl.upload_tiles && sl.ntile) CU(c, cudaMemcpyAsync(sl.d_tile_seg, sl.h_tile_seg, sl.ntile * 4, cudaMemcpyHostToDevice, pre));
-    CU(c, cudaMemcpyAsync(sl.d_stream_seg_begin, sl.h_stream_seg_begin, (S + 1) * 4, cudaMemcpyHostToDevice, pre));
-    memset(sl.h_ctl, 0, sizeof(RunCtl));
-    sl.h_ctl->rec_cap = sl.rec_cap;
+    layout_run(c, sl);
+    CU(c, cudaMemcpyAsync(sl.d_desc, sl.h_desc, sl.desc_bytes, cudaMemcpyHostToDevice, pre));
     if (c->beast_slot == (int)(&sl - c->slot)) c->beast_slot = -1;      // the encoded records belong to the run being replaced
-    CU(c, cudaMemcpyAsync(sl.d_ctl, sl.h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pre));
-    CU(c, cudaMemsetAsync(sl.d_buf_acc, 0, (size_t)sl.nbuf * sizeof(BufAcc), pre));
+    CU(c, cudaMemsetAsync(sl.d_res, 0, sizeof(RunCtl) + (size_t)sl.nbuf * sizeof(BufAcc), pre));       // control block + per-buffer sums
     if (pre != scan) { CU(c, cudaEventRecord(sl.ev[7], pre)); CU(c, cudaStreamWaitEvent(scan, sl.ev[7], 0)); }
     sl.launches = 0;
 
     ScanParams sp;
     sp.segs = sl.d_segs; sp.tile_seg = sl.d_tile_seg; sp.n_tiles = sl.ntile; sp.pos_pool = sl.d_pos_pool; sp.rec_pool = sl.d_rec_pool;
     sp.key_pool = sl.d_key_pool; sp.tile_out = sl.d_tile_out; sp.buf_acc = sl.d_buf_acc; sp.ctl = sl.d_ctl; sp.thr = c->cfg.preamble_threshold;
+    sp.rec_cap = sl.rec_cap;
     sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df;
     sp.stage_rec = c->d_stage_rec; sp.stage_key = c->d_stage_key; sp.stage_cap = c->stage_cap; sp.q1_over = c->d_q1_over; sp.tick_scratch = c->d_tick_scratch;
     sp.stream_addable = sl.d_addable;
@@ -530,12 +567,9 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
         CU(c, cudaMemcpyAsync(sl.h_ac_prefix, sl.d_ac_prefix, ((size_t)sl.nbuf + 1) * 4, cudaMemcpyDeviceToHost, res));
     }
 
-    CU(c, cudaMemcpyAsync(sl.h_ctl, sl.d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, res));
-    CU(c, cudaMemcpyAsync(sl.h_frame_prefix, sl.d_frame_prefix, (S + 1) * 4, cudaMemcpyDeviceToHost, res));
-    if (sl.nbuf) {
-        CU(c, cudaMemcpyAsync(sl.h_buf_out, sl.d_buf_out, (size_t)sl.nbuf * sizeof(b200_buffer_result), cudaMemcpyDeviceToHost, res));
-        CU(c, cudaMemcpyAsync(sl.h_buf_acc, sl.d_buf_acc, (size_t)sl.nbuf * sizeof(BufAcc), cudaMemcpyDeviceToHost, res));
-    }
+    // control block, per-buffer sums, frame prefix, buffer results and the first frames: one copy (small runs need no second one)
+    sl.first_frames = (uint32_t)std::min<size_t>(FIRST_COPY_FRAMES, (size_t)S * c->frame_cap);
+    CU(c, cudaMemcpyAsync(sl.h_res, sl.d_res, sl.res_head + (size_t)sl.first_frames * sizeof(b200_frame), cudaMemcpyDeviceToHost, res));
     CU(c, cudaEventRecord(sl.ev[4], res));
     return B200_OK;
 }
@@ -561,12 +595,14 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     if (total_ac) CU(c, cudaMemcpyAsync(sl.h_ac_packed, sl.d_ac_packed, (size_t)total_ac * sizeof(b200_modeac), cudaMemcpyDeviceToHost, c->copy_stream));
     const uint32_t total = sl.h_frame_prefix[S];
     sl.run_frames = total;
-    if (total_ac && !total) { CU(c, cudaEventRecord(sl.ev[5], c->copy_stream)); CU(c, cudaEventSynchronize(sl.ev[5])); }
-    if (total) {
+    if (total_ac && total <= sl.first_frames) { CU(c, cudaEventRecord(sl.ev[5], c->copy_stream)); CU(c, cudaEventSynchronize(sl.ev[5])); }
+    const bool more_frames = total > sl.first_frames;
+    if (more_frames) {
         // The frame copy must not queue behind the NEXT step's stage B on the resolve stream: its own stream,
         // ordered after this slot's finalize only (ev[4] already completed: finalize is done).
         (void)res;
-        CU(c, cudaMemcpyAsync(sl.h_packed, sl.d_packed, (size_t)total * sizeof(b200_frame), cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(c, cudaMemcpyAsync(sl.h_packed + sl.first_frames, sl.d_packed + sl.first_frames, (size_t)(total - sl.first_frames) * sizeof(b200_frame),
+                              cudaMemcpyDeviceToHost, c->copy_stream));
         CU(c, cudaEventRecord(sl.ev[5], c->copy_stream));
         CU(c, cudaEventSynchronize(sl.ev[5]));
     }
@@ -577,8 +613,8 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     }
     cudaEventElapsedTime(&sl.ms[1], sl.ev[0], sl.ev[1]);
     cudaEventElapsedTime(&sl.ms[2], sl.ev[1], sl.ev[2]);
-    cudaEventElapsedTime(&sl.ms[0], sl.ev[0], total ? sl.ev[5] : sl.ev[4]);
-    cudaEventElapsedTime(&sl.ms[4], sl.ev[3], total ? sl.ev[5] : sl.ev[4]);
+    cudaEventElapsedTime(&sl.ms[0], sl.ev[0], (more_frames || total_ac) ? sl.ev[5] : sl.ev[4]);
+    cudaEventElapsedTime(&sl.ms[4], sl.ev[3], (more_frames || total_ac) ? sl.ev[5] : sl.ev[4]);
     return B200_OK;
 }
 
@@ -712,7 +748,9 @@ API int b200_demod_run(b200_demod_ctx *c) {
     }
     c->n_fsum = 0;
     // next run: move each IQ stream's tail to the front of its region
-    if (rc == B200_OK) {
+    bool any_carry = false;
+    for (uint32_t s = 0; s < S; s++) any_carry = any_carry || c->h_carry_src[s] != 0xffffffffu;
+    if (rc == B200_OK && any_carry) {          // (magnitude hand-offs bring their halo with them: nothing to carry)
         cudaMemcpyAsync(c->d_carry_src, c->h_carry_src, S * 4, cudaMemcpyHostToDevice, c->stream);
         carry_halo_kernel<<<S, 128, 0, c->stream>>>(c->d_arena, c->stream_stride, c->d_carry_src, S);
         sl.launches++;

@@ -72,6 +72,7 @@ struct WarpRing {
 struct BufResult {
     long long now_ms;          // Modes.synthetic_now at the end of the buffer (demod_2400.c:283-285, 409-414)
     uint32_t n_frames, n_new, fail;
+    uint32_t skip_out;         // the reference's `pa` after the range: positions below it are inside the last accepted frame
     uint32_t n_add;            // icaoFilterAdd calls of this buffer (mode_s.c:778) whose address the ACTIVE generation did not hold when the
                                // buffer was speculated: at most so many insertions into it
     uint32_t stats[15];        // preambles, bad, unknown, accepted[2], tried phases[5], best phases[5]
@@ -94,6 +95,7 @@ struct ResolveSmem {
     uint32_t old_bits[OLD_BITS / 32];
     WarpRing ring[RS_WARPS];
     BufResult res[RS_WARPS];
+    uint32_t tot[16], bstat[16];             // counters of the run / of the buffer being committed (lane k owns counter k)
 };
 
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
@@ -123,15 +125,19 @@ __device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
 // Frames are written to fout[0 .. n_frames); `old_gen` is the older generation's exact table in global memory.
 template <bool DEFER, bool BIG>
 __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSmem &S, WarpRing &R, BufResult &out, const Segment &seg, uint32_t si,
-                                               uint32_t b, uint32_t seq, const FilterRef &F, b200_frame *fout, uint32_t fcap, uint32_t lane) {
+                                               uint32_t b, uint32_t d_lo, uint32_t d_hi, uint32_t skip_in, uint32_t seq, const FilterRef &F,
+                                               b200_frame *fout, uint32_t fcap, uint32_t lane) {
+    // [d_lo, d_hi): the positions of reference buffer b this call walks - the whole buffer, or one of the sub-ranges a buffer is cut
+    // into when a receiver has fewer buffers in the run than stage B has warps (a sub-range is speculated like a buffer: it assumes
+    // that no frame accepted before it reaches into it, skip_in = d_lo, and is redone with the real skip_in when one does).
     const uint32_t LOG2 = BIG ? F.log2 : (uint32_t)ICAO_CAP_LOG2;
     const uint32_t tile_end = seg.tile_begin + seg.n_tiles;
     const uint32_t n_quads = (seg.n_tiles + 3) / 4;
     const uint32_t d_begin = b * seg.buf_len;
-    const uint32_t d_end = min(d_begin + seg.buf_len, seg.npos);
+    const uint32_t d_end = d_hi;
     const int64_t buf_ts = seg.first_ts + (int64_t)d_begin * 5;
     int64_t now_ms = buf_ts / 12000;          // demod_2400.c:283-285
-    uint32_t skip_until = d_begin;            // data-index form of the reference's `pa` skip
+    uint32_t skip_until = skip_in;            // data-index form of the reference's `pa` skip
     uint32_t nframes = 0, n_new = 0, fail = 0, c_add = 0;
     uint32_t c_pre = 0, c_bad = 0, c_unk = 0, c_acc0 = 0, c_acc1 = 0, c_tp[5] = {0, 0, 0, 0, 0}, c_bp[5] = {0, 0, 0, 0, 0};
 
@@ -146,7 +152,7 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
     // Quad cursor: stage B walks QUADS of four consecutive scan tiles (8192 positions; PosEntry positions are quad-relative).
     // The quad's four PosEntry / key lists are staged back to back in ring slot q % RS_RING, one quad ahead; the TileOut
     // descriptors run one more ahead in registers: lane l < 4 holds the descriptor of the quad's tile l.
-    uint32_t quad = (seg.lead + d_begin) / (4 * SCAN_TILE), idx = 0, rec_rel = 0, cur_npos = 0, cur_recbase = 0, sub = 4;
+    uint32_t quad = (seg.lead + d_lo) / (4 * SCAN_TILE), idx = 0, rec_rel = 0, cur_npos = 0, cur_recbase = 0, sub = 4;
     bool staged = true;
     uint4 to = make_uint4(0, 0, 0, 0), d1 = to, d2 = to;
     const PosEntry *pe_ptr = nullptr;
@@ -200,6 +206,7 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
         }
         return true;
     };
+    if (d_lo >= d_hi) quad = n_quads;         // empty range: nothing to walk
     if (quad < n_quads) {
         d1 = load_desc(quad); d2 = load_desc(quad + 1);
         issue_stage(quad, d1);
@@ -373,7 +380,7 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c_add += __shfl_xor_sync(FULLMASK, c_add, o);
-    if (lane == 0) { out.now_ms = now_ms; out.n_frames = min(nframes, fcap); out.n_new = n_new; out.fail = fail; out.n_add = c_add; }
+    if (lane == 0) { out.now_ms = now_ms; out.n_frames = min(nframes, fcap); out.n_new = n_new; out.fail = fail; out.n_add = c_add; out.skip_out = skip_until; }
     __syncwarp();
 }
 
@@ -387,6 +394,7 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
 
     if (tid == 0) { s_active = st->active; s_gcount[0] = st->gen_count[0]; s_gcount[1] = st->gen_count[1]; s_bits = st->filter_bits; }
     for (uint32_t i = tid; i < OLD_BITS / 32; i += blockDim.x) S.old_bits[i] = 0;
+    if (tid < 16) { S.tot[tid] = 0; S.bstat[tid] = 0; }
     __syncthreads();
     {
         const uint32_t active = s_active;
@@ -403,41 +411,58 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
     uint32_t armed = st->flip_armed, seq = st->buffer_seq;
     int64_t next_flip = st->next_flip_ms;
     bool dirty_act = false;                  // the shared-memory table differs from the global copy of the active generation
-    uint32_t tot[15];
-#pragma unroll
-    for (int k = 0; k < 15; k++) tot[k] = 0;
     unsigned long long c_samples = 0;
     uint32_t c_bufs = 0, c_flips = 0, nframes = 0;
     b200_frame *fstream = P.frames + (size_t)stream * P.frame_cap;
-    uint32_t jbuf = 0;                       // buffers of this receiver before the current round
+    uint32_t cap_base = 0;                   // frame slots handed to the units of earlier rounds (each unit speculates into a region of its own)
 
     for (uint32_t si = P.stream_seg_begin[stream]; si < P.stream_seg_begin[stream + 1]; si++) {
         const Segment seg = P.segs[si];
-        for (uint32_t b0 = 0; b0 < seg.n_bufs; b0 += RS_WARPS) {
-            const uint32_t n_round = min((uint32_t)RS_WARPS, seg.n_bufs - b0);
-            // ---- speculation: warp w resolves buffer b0 + w against the filter as it stands ---------------------------------
+        // Work units of a round: whole buffers when the receiver has at least RS_WARPS of them in this run, otherwise every buffer is
+        // cut into sub-ranges of whole scan tiles so that all warps have work (a single 65536-sample mag_buf: eight ranges of 8192).
+        const uint32_t nsplit = seg.n_bufs >= RS_WARPS ? 1u : max(1u, min((uint32_t)RS_WARPS / max(seg.n_bufs, 1u), (seg.buf_len + 4 * SCAN_TILE - 1) / (4 * SCAN_TILE)));
+        const uint32_t sub_len = nsplit == 1 ? seg.buf_len : (((seg.buf_len + nsplit - 1) / nsplit + SCAN_TILE - 1) & ~(uint32_t)(SCAN_TILE - 1));
+        const uint32_t ucap = nsplit == 1 ? P.per_buf_cap : sub_len / 113 + 3;          // frames one unit can hold (a frame hides the next 112 positions)
+        const uint32_t n_units = seg.n_bufs * nsplit;
+        auto unit_range = [&](uint32_t u, uint32_t &ub, uint32_t &lo, uint32_t &hi) {
+            ub = u / nsplit;
+            const uint32_t d_begin = ub * seg.buf_len, d_end = min(d_begin + seg.buf_len, seg.npos);
+            lo = min(d_begin + (u - ub * nsplit) * sub_len, d_end); hi = min(lo + sub_len, d_end);
+        };
+        // per-buffer accumulation over its units (warp 0)
+        uint32_t bframes = 0, skip_prev = 0;
+        int64_t buf_now = 0;
+
+        for (uint32_t u0 = 0; u0 < n_units; u0 += RS_WARPS) {
+            const uint32_t n_round = min((uint32_t)RS_WARPS, n_units - u0);
+            // ---- speculation: warp w resolves unit u0 + w against the filter as it stands ---------------------------------
             if (wid < n_round) {
-                const uint32_t b = b0 + wid;
+                uint32_t b, lo, hi;
+                unit_range(u0 + wid, b, lo, hi);
                 FilterRef F;
                 F.act = tab(s_active); F.old_gen = tab(s_active ^ 1u); F.log2 = LOG2; F.counts = nullptr; F.bits = nullptr; F.active = s_active;
-                resolve_buffer<true, BIG>(P, S, S.ring[wid], S.res[wid], seg, si, b, 0 /* buffer_seq is stamped at commit */, F,
-                                          fstream + (size_t)(jbuf + wid) * P.per_buf_cap, P.per_buf_cap, lane);
+                resolve_buffer<true, BIG>(P, S, S.ring[wid], S.res[wid], seg, si, b, lo, hi, lo, 0 /* buffer_seq is stamped at commit */, F,
+                                          fstream + cap_base + (size_t)wid * ucap, ucap, lane);
             }
             __syncthreads();
             // ---- commit, in order -----------------------------------------------------------------------------------------------
             if (wid == 0) {
                 bool spec_ok = true;
                 for (uint32_t i = 0; i < n_round; i++) {
-                    const uint32_t b = b0 + i;
+                    uint32_t b, lo, hi;
+                    unit_range(u0 + i, b, lo, hi);
+                    const bool first_of_buf = (u0 + i) % nsplit == 0, last_of_buf = (u0 + i) % nsplit == nsplit - 1;
                     BufResult &r = S.res[i];
                     const uint32_t d_begin = b * seg.buf_len, d_end = min(d_begin + seg.buf_len, seg.npos);
+                    if (first_of_buf) { skip_prev = d_begin; buf_now = (seg.first_ts + (int64_t)d_begin * 5) / 12000; bframes = 0; }
                     b200_frame *fdst = fstream + nframes;
                     // A speculation cannot know about the reference's table resize (icao_filter.c:126-128), which forgets the older
-                    // generation in the middle of a buffer: if this buffer's adds could reach the resize threshold it is resolved directly.
+                    // generation in the middle of a buffer: if this unit's adds could reach the resize threshold it is resolved directly.
                     const bool resize_possible = s_bits < ICAO_MAXBITS && s_gcount[s_active] + r.n_add > (1u << s_bits) / 3u;
-                    if (spec_ok && !r.fail && !resize_possible) {
-                        // the speculation holds: teach the filter what this buffer learned, move its frames into place
-                        const b200_frame *fsrc = fstream + (size_t)(jbuf + i) * P.per_buf_cap;
+                    const bool skip_reaches_in = skip_prev > lo;        // a frame accepted before this range hides its first positions
+                    if (spec_ok && !r.fail && !resize_possible && !skip_reaches_in) {
+                        // the speculation holds: teach the filter what this unit learned, move its frames into place
+                        const b200_frame *fsrc = fstream + cap_base + (size_t)i * ucap;
                         const uint32_t n = r.n_frames;
                         uint32_t *act = BIG ? tab(s_active) : S.act;
                         for (uint32_t k0 = 0; k0 < n; k0 += 32) {
@@ -457,23 +482,26 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
                             else if (has) { const_cast<b200_frame *>(fsrc)[k0 + lane].buffer_seq = seq; }
                             __syncwarp();
                         }
-                        if (r.n_new) spec_ok = false;                   // later buffers of the round saw a filter without these addresses
+                        if (r.n_new) spec_ok = false;                   // later units of the round saw a filter without these addresses
                     } else {
-                        spec_ok = false;
+                        if (!skip_reaches_in || r.fail || resize_possible || !spec_ok) spec_ok = false;      // (a skip alone does not change the filter)
                         FilterRef F;
                         F.act = tab(s_active); F.old_gen = tab(s_active ^ 1u); F.log2 = LOG2; F.counts = s_gcount; F.bits = &s_bits; F.active = s_active;
-                        resolve_buffer<false, BIG>(P, S, S.ring[0], r, seg, si, b, seq, F, fdst, P.frame_cap - nframes, lane);
+                        resolve_buffer<false, BIG>(P, S, S.ring[0], r, seg, si, b, lo, hi, max(skip_prev, lo), seq, F, fdst, P.frame_cap - nframes, lane);
                         dirty_act = true;
+                        spec_ok = false;
                     }
                     __syncwarp();
-#pragma unroll
-                    for (int k = 0; k < 15; k++) tot[k] += r.stats[k];
-                    const uint32_t nfr_buf = r.n_frames;
-                    nframes += nfr_buf;
+                    if (lane < 15) { S.tot[lane] += r.stats[lane]; S.bstat[lane] += r.stats[lane]; }
+                    __syncwarp();
+                    nframes += r.n_frames; bframes += r.n_frames;
+                    if (r.n_frames) buf_now = r.now_ms;
+                    skip_prev = max(skip_prev, r.skip_out);
+                    if (!last_of_buf) continue;
                     // end of buffer: readsb.c:876, then backgroundTasks' filter flip (readsb.c:1227-1231)
                     c_samples += d_end - d_begin; c_bufs++;
                     uint32_t flipped = 0;
-                    const int64_t now_ms = r.now_ms;
+                    const int64_t now_ms = buf_now;
                     if (P.ttl_ms > 0 && (!armed || now_ms >= next_flip)) {
                         // icaoFilterExpire (icao_filter.c:96-110): the active generation becomes the older one (its exact table in global
                         // memory, its hash bits here); the other generation is emptied and becomes active
@@ -501,13 +529,20 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
                     if (lane == 0) {
                         b200_buffer_result br;
                         br.sample_timestamp = seg.first_ts + (int64_t)d_begin * 5; br.sum_level = 0; br.sum_power = 0; br.sum_signal_power = 0;
-                        br.length = d_end - d_begin; br.n_frames = nfr_buf; br.buffer_seq = seq; br.icao_flipped = flipped;
+                        br.length = d_end - d_begin; br.n_frames = bframes; br.buffer_seq = seq; br.icao_flipped = flipped;
+                        br.demod_preambles = S.bstat[0]; br.demod_rejected_bad = S.bstat[1]; br.demod_rejected_unknown_icao = S.bstat[2];
+                        br.demod_accepted[0] = S.bstat[3]; br.demod_accepted[1] = S.bstat[4];
+                        for (int p = 0; p < 5; p++) { br.demod_preamblePhase[p] = S.bstat[5 + p]; br.demod_bestPhase[p] = S.bstat[10 + p]; }
+                        br.pad_ = 0;
                         P.buf_out[seg.first_buf + b] = br;
                     }
+                    __syncwarp();
+                    if (lane < 16) S.bstat[lane] = 0;
+                    __syncwarp();
                     seq++;
                 }
             }
-            jbuf += n_round;
+            cap_base += n_round * ucap;
             __syncthreads();
         }
     }
@@ -520,6 +555,7 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
             st->gen_count[0] = s_gcount[0]; st->gen_count[1] = s_gcount[1];
             st->active = active; st->filter_bits = s_bits; st->flip_armed = armed; st->next_flip_ms = next_flip; st->buffer_seq = seq;
             b200_demod_stats &s = st->stats;
+            const uint32_t *tot = S.tot;
             s.samples_processed += c_samples; s.demod_preambles += tot[0]; s.demod_rejected_bad += tot[1];
             s.demod_rejected_unknown_icao += tot[2]; s.demod_accepted[0] += tot[3]; s.demod_accepted[1] += tot[4];
             for (int p = 0; p < 5; p++) { s.demod_preamblePhase[p] += tot[5 + p]; s.demod_bestPhase[p] += tot[10 + p]; }

@@ -733,7 +733,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
             if (n_stage > P.stage_cap) { atomicOr(&P.ctl->overflow, 2u); atomicMax(&P.ctl->stage_need, n_stage); ok = 0; }   // host grows the staging areas and reruns
             else if (n_stage) {
                 off = atomicAdd(&P.ctl->rec_alloc, n_stage);
-                if (off + n_stage > P.ctl->rec_cap) { atomicOr(&P.ctl->overflow, 1u); ok = 0; }                              // host regrows the pool and reruns
+                if (off + n_stage > P.rec_cap) { atomicOr(&P.ctl->overflow, 1u); ok = 0; }                              // host regrows the pool and reruns
             }
         }
         off = __shfl_sync(FULLMASK, off, 0); ok = __shfl_sync(FULLMASK, ok, 0);

@@ -6,7 +6,8 @@ import numpy as np
 from readsb_b200.abi import FRAME_PARITY_FIELDS, frame_hex
 
 BUFRES_FIELDS = ("sample_timestamp", "sum_level", "sum_power", "sum_signal_power", "length", "n_frames",
-                 "buffer_seq", "icao_flipped")
+                 "buffer_seq", "icao_flipped", "demod_preambles", "demod_rejected_bad", "demod_rejected_unknown_icao",
+                 "demod_accepted", "demod_preamblePhase", "demod_bestPhase")
 STATS_INT_FIELDS = ("samples_processed", "demod_preambles", "demod_rejected_bad", "demod_rejected_unknown_icao",
                     "demod_accepted", "demod_preamblePhase", "demod_bestPhase", "signal_power_count",
                     "sum_signal_power", "strong_signal_count", "buffers", "icao_flips")
@@ -37,8 +38,10 @@ def diff_bufres(a: np.ndarray, b: np.ndarray, fields=BUFRES_FIELDS) -> list[str]
     msgs = []
     if len(a) != len(b):
         return [f"buffer count {len(a)} vs {len(b)}"]
+    if len(a) == 0:
+        return msgs
     for f in fields:
-        ne = np.nonzero(a[f] != b[f])[0]
+        ne = np.nonzero((a[f] != b[f]).reshape(len(a), -1).any(axis=1))[0]
         if len(ne):
             i = ne[0]
             msgs.append(f"bufres {f}[{i}]: {a[f][i]} vs {b[f][i]} ({len(ne)} differ)")

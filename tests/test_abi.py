@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(lib_path):
         assert hasattr(L, n), f"{n} declared in include/b200_demod.h but not exported"
     from readsb_b200.demod import EXPORTED_SYMBOLS
     assert sorted(EXPORTED_SYMBOLS) == names
-    assert L.b200_demod_abi_version() == 1
+    assert L.b200_demod_abi_version() == 2
 
 
 def test_no_internal_symbols_leak(lib_path):
@@ -51,7 +51,7 @@ def test_library_is_sm100a_and_has_no_cpu_path(lib_path):
 def test_struct_layouts_match_header():
     from readsb_b200 import abi
     assert ctypes.sizeof(abi.Frame) == 64 and abi.FRAME_DTYPE.itemsize == 64
-    assert ctypes.sizeof(abi.BufferResult) == 48
+    assert ctypes.sizeof(abi.BufferResult) == 112
     assert ctypes.sizeof(abi.Config) == 40
     assert ctypes.sizeof(abi.Stats) == 8 * (4 + 2 + 5 + 5 + 3 + 2 + 2)
     for name, _ in abi.Frame._fields_:

@@ -22,8 +22,7 @@ def _oracle_buffers(o, iq, cuts, ts_of):
         data = np.concatenate([halo, mag]).astype(np.uint16)
         f, r = o.demodulate(data, hi - lo, ts_of(b, lo), sl, sp)
         frames.append(f)
-        bufres.append(np.array([(r.sample_timestamp, r.sum_level, r.sum_power, r.sum_signal_power, r.length, r.n_frames, r.buffer_seq,
-                                 r.icao_flipped)], dtype=BUFRES_DTYPE))
+        bufres.append(np.frombuffer(bytes(r), dtype=BUFRES_DTYPE).copy())
         halo = data[hi - lo: hi - lo + 326].copy() if hi - lo >= 326 else np.zeros(326, dtype=np.uint16)
     return (np.concatenate(frames) if frames else np.zeros(0, FRAME_DTYPE)), (np.concatenate(bufres) if bufres else np.zeros(0, BUFRES_DTYPE))
 

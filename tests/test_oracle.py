@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oraclelib import Oracle, Reference, have_ref
-from paritylib import diff_frames, diff_stats
+from paritylib import diff_bufres, diff_frames, diff_stats
 from readsb_b200 import synth
 
 GOLDEN = sorted(p for p in (Path(__file__).parent / "golden").glob("*.npz") if p.stem not in ("beast_stream", "sc16_converters"))
@@ -182,6 +182,9 @@ def test_oracle_matches_reference_live(kind, seed, buf):
     sr["sum_signal_power"] = so["sum_signal_power"]       # the reference keeps this one as fp64 only
     assert not diff_stats(so, sr)
     assert np.array_equal(bo["sum_level"] / 65536.0 / bo["length"], ml)
+    # what each demodulate2400() call added to Modes.stats_current (the per-buffer counters of b200_buffer_result)
+    assert not diff_bufres(bo, br, fields=("sample_timestamp", "length", "n_frames", "buffer_seq", "icao_flipped", "demod_preambles", "demod_rejected_bad",
+                                           "demod_rejected_unknown_icao", "demod_accepted", "demod_preamblePhase", "demod_bestPhase"))
 
 
 @needs_ref
