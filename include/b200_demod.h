@@ -159,6 +159,10 @@ int b200_demod_set_stream(b200_demod_ctx *ctx, void *cuda_stream);
 /* pinned host memory for zero-staging submits (optional; any host pointer is accepted) */
 void *b200_demod_host_alloc(size_t bytes);
 void  b200_demod_host_free(void *p);
+/* ... or page-lock memory the caller already owns - e.g. readsb's ring of mag_bufs (readsb.h:113,855), allocated once at start-up:
+ * a submit from pageable memory is staged by the driver and costs several times the copy itself. */
+int   b200_demod_host_register(void *p, size_t bytes);
+int   b200_demod_host_unregister(void *p);
 
 /* host-buffer path (the drop-in) ---------------------------------------------------------------
  * submit_iq_uc8 replaces the converter call a frontend makes (sdr_ifile.c:241, sdr_rtlsdr.c:395):

@@ -32,6 +32,17 @@ static b200_frame g_frames[2048];
 static b200_modeac *g_ac;            /* replies of the buffer demodulate2400 just handed to the library */
 static uint32_t g_ac_cap;
 static int32_t g_thr;                /* threshold the library currently uses */
+static void *g_pinned[MODES_MAG_BUFFERS + 4];   /* mag_buf.data arrays already page-locked for the GPU's copy engine */
+static int g_npinned;
+
+/* readsb allocates its ring of mag_bufs once (readsb.c:283-300) and re-uses the same `data` arrays for ever: page-lock each one the
+ * first time it is handed over, so that the upload is a direct DMA instead of a staged copy. */
+static void pin_once(struct mag_buf *mag) {
+    for (int i = 0; i < g_npinned; i++) if (g_pinned[i] == (void *) mag->data) return;
+    if (g_npinned >= (int) (sizeof g_pinned / sizeof g_pinned[0])) return;
+    if (b200_demod_host_register(mag->data, ((size_t) Modes.sdr_buf_samples + Modes.trailing_samples) * sizeof(uint16_t)) == B200_OK)
+        g_pinned[g_npinned++] = mag->data;
+}
 
 void __real_icaoFilterAdd(uint32_t addr);
 void __real_icaoFilterExpire(void);
@@ -83,6 +94,7 @@ void __wrap_demodulate2400(struct mag_buf *mag) {
     if (Modes.stats_15min.samples_dropped && thr < PREAMBLE_THRESHOLD_PIZERO) thr = PREAMBLE_THRESHOLD_PIZERO;
     if (thr != g_thr && b200_demod_set_preamble_threshold(g_ctx, thr) == B200_OK) g_thr = thr;
 
+    pin_once(mag);
     uint32_t n = 0;
     /* mean_level / mean_power travel with the buffer: demodulate2400AC's noise floor is made from them (demod_2400.c:580-581),
      * whatever converter filled the mag_buf */

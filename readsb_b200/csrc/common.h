@@ -140,6 +140,8 @@ struct ScanParams {
     BufAcc *buf_acc;
     RunCtl *ctl;
     uint32_t rec_cap;            // records rec_pool / key_pool hold
+    uint32_t warps_per_cta;      // set by the launcher: warps of each CTA that take work (a small run is spread over many SMs, few warps each)
+    uint32_t need_lut;           // some segment holds uc8 IQ: the magnitude table has to be staged (a pure magnitude hand-off skips it)
     int32_t thr;                 // Modes.preambleThreshold
     uint32_t long_set, short_set; // valid DF bitsets (demod_2400.c:98-128)
     int32_t nfix, fixdf;
@@ -150,6 +152,22 @@ struct ScanParams {
     uint16_t *q1_over;           // [warp][512] pre-check passers beyond the shared-memory queue (dense input)
     uint32_t *tick_scratch;      // [warp][b200_scan_tick_words()] the ticks of the run in progress (deferred, pooled slicing)
     uint32_t *stream_addable;    // [stream] records of this run that could teach the receiver's filter an address (clean DF17, DF11 with IID 0)
+};
+
+struct FinalizeParams {
+    const Segment *segs;
+    const uint32_t *stream_seg_begin;
+    uint32_t n_streams;
+    b200_frame *frames;
+    const uint32_t *frame_count;
+    const uint32_t *frame_prefix;     // exclusive prefix of frame_count (device computed)
+    uint32_t *frame_prefix_out;       // the same array, for the one-receiver launch that computes it itself
+    uint32_t frame_cap;
+    b200_frame *packed;               // all frames of the run, stream-major
+    const Rec *rec_pool;
+    BufAcc *buf_acc;
+    StreamState *state;
+    const uint16_t *lut_full;         // 65536-entry UC8 table in global memory
 };
 
 struct ResolveParams {
@@ -171,22 +189,10 @@ struct ResolveParams {
     const RunCtl *prev_ctl;           // asynchronous pipeline: control block of the step ahead of this one (or nullptr)
     int32_t ttl_ms;
     uint32_t *stream_addable;         // [n_streams] upper bound of the filter adds of this run (scan kernel); read and zeroed by the capacity check
+    uint32_t solo;                    // one receiver in the context: capacity check, stage B, frame prefix and finalizer in ONE launch
+    FinalizeParams fin;               // (solo) what the finalizer needs
 };
 
-struct FinalizeParams {
-    const Segment *segs;
-    const uint32_t *stream_seg_begin;
-    uint32_t n_streams;
-    b200_frame *frames;
-    const uint32_t *frame_count;
-    const uint32_t *frame_prefix;     // exclusive prefix of frame_count (device computed)
-    uint32_t frame_cap;
-    b200_frame *packed;               // all frames of the run, stream-major
-    const Rec *rec_pool;
-    BufAcc *buf_acc;
-    StreamState *state;
-    const uint16_t *lut_full;         // 65536-entry UC8 table in global memory
-};
 
 // ---- Mode A/C (modeac_kernel.cu) -------------------------------------------------------------------
 struct DeviceTables;

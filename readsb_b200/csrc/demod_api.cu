@@ -89,7 +89,8 @@ struct Slot {
 struct b200_demod_ctx {
     b200_demod_config cfg;
     int device = 0, n_sm = 148;
-    int n_sm_scan = 148;              // CTAs of the persistent scan kernel (one per SM); < n_sm leaves SMs to stage B of the step before (B200_SCAN_SMS)
+    int n_sm_scan = 148;              // CTAs of the persistent scan kernel (one per SM) in blocking runs
+    int n_sm_scan_async = 144;        // ... in pipelined runs: fewer than n_sm leaves SMs to stage B of the step before (B200_SCAN_SMS overrides both)
     cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
     std::string err;
 
@@ -170,6 +171,13 @@ API void *b200_demod_host_alloc(size_t bytes) {
     return p;
 }
 API void b200_demod_host_free(void *p) { if (p) cudaFreeHost(p); }
+API int b200_demod_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return B200_E_INVAL;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B200_OK; }
+    return e == cudaSuccess ? B200_OK : B200_E_CUDA;
+}
+API int b200_demod_host_unregister(void *p) { return p && cudaHostUnregister(p) == cudaSuccess ? B200_OK : B200_E_INVAL; }
 
 API int b200_demod_uc8_lut(uint16_t *out) {
     if (!out) return B200_E_INVAL;
@@ -301,9 +309,12 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
     c->n_sm_scan = c->n_sm;
+    // Pipelined steps: the persistent scan grid leaves four SMs to stage B + finalize of the step before, which then run beside the
+    // scan instead of alternating with it (measured on 148 SMs: 148 -> 0.519, 144 -> 0.472, 140 -> 0.475 ms per step).
+    c->n_sm_scan_async = c->n_sm > 32 ? c->n_sm - 4 : c->n_sm;
     if (const char *e = getenv("B200_SCAN_SMS")) {       // experiment knob (tools/): in the pipelined modes the scan of step n+1 and stage B of
         const int v = atoi(e);                           // step n alternate on the SMs; a scan grid smaller than the chip lets them overlap
-        if (v >= 1 && v <= c->n_sm) c->n_sm_scan = v;
+        if (v >= 1 && v <= c->n_sm) c->n_sm_scan = c->n_sm_scan_async = v;
     }
     {   // With several steps in flight the scan kernels of later steps are already queued when a scan ends; stage B of the step
         // that just finished scanning must not wait behind them (its results gate the host), so its stream has the higher
@@ -514,7 +525,8 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     ScanParams sp;
     sp.segs = sl.d_segs; sp.tile_seg = sl.d_tile_seg; sp.n_tiles = sl.ntile; sp.pos_pool = sl.d_pos_pool; sp.rec_pool = sl.d_rec_pool;
     sp.key_pool = sl.d_key_pool; sp.tile_out = sl.d_tile_out; sp.buf_acc = sl.d_buf_acc; sp.ctl = sl.d_ctl; sp.thr = c->cfg.preamble_threshold;
-    sp.rec_cap = sl.rec_cap;
+    sp.rec_cap = sl.rec_cap; sp.warps_per_cta = 0; sp.need_lut = 0;
+    for (uint32_t i = 0; i < sl.nseg; i++) if (!(sl.h_segs[i].flags & SEG_MAG)) sp.need_lut = 1;
     sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df;
     sp.stage_rec = c->d_stage_rec; sp.stage_key = c->d_stage_key; sp.stage_cap = c->stage_cap; sp.q1_over = c->d_q1_over; sp.tick_scratch = c->d_tick_scratch;
     sp.stream_addable = sl.d_addable;
@@ -523,7 +535,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
     if (sp.nfix && sp.fixdf) for (int b = 0; b < 5; b++) sp.long_set |= 1u << (17 ^ (1 << b));
     CU(c, cudaEventRecord(sl.ev[0], scan));
-    if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, c->n_sm_scan, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
+    if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, scan != res ? c->n_sm_scan_async : c->n_sm_scan, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
     CU(c, cudaEventRecord(sl.ev[1], scan));
     if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[1], 0));
 
@@ -544,20 +556,21 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
         CU(c, cudaEventRecord(sl.ev[6], scan));
     }
 
+    FinalizeParams fp;
+    fp.segs = sl.d_segs; fp.stream_seg_begin = sl.d_stream_seg_begin; fp.n_streams = S; fp.frames = sl.d_frames;
+    fp.frame_count = sl.d_frame_count; fp.frame_prefix = sl.d_frame_prefix; fp.frame_prefix_out = sl.d_frame_prefix; fp.frame_cap = c->frame_cap; fp.packed = sl.d_packed;
+    fp.buf_acc = sl.d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = sl.d_rec_pool;
+    const bool solo = S == 1;          // one receiver: stage B, frame prefix and finalizer are one launch (resolve_kernel, solo)
     ResolveParams rp;
     rp.segs = sl.d_segs; rp.stream_seg_begin = sl.d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = sl.d_pos_pool;
     rp.rec_pool = sl.d_rec_pool; rp.key_pool = sl.d_key_pool; rp.tile_out = sl.d_tile_out; rp.buf_acc = sl.d_buf_acc; rp.buf_out = sl.d_buf_out;
     rp.state = c->d_state; rp.frames = sl.d_frames; rp.frame_count = sl.d_frame_count; rp.frame_cap = c->frame_cap; rp.per_buf_cap = c->cfg.buf_samples / 113 + 2;
     rp.ctl = sl.d_ctl; rp.prev_ctl = prev_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms; rp.stream_addable = sl.d_addable;
+    rp.solo = solo ? 1u : 0u; rp.fin = fp;
     { const int grown = !c->icao_grown.empty();
-      int r = b200_launch_resolve(&rp, grown, res); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2 + grown; }
+      int r = b200_launch_resolve(&rp, grown, res); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += solo ? 1 : 2 + grown; }
     CU(c, cudaEventRecord(sl.ev[2], res));
-
-    FinalizeParams fp;
-    fp.segs = sl.d_segs; fp.stream_seg_begin = sl.d_stream_seg_begin; fp.n_streams = S; fp.frames = sl.d_frames;
-    fp.frame_count = sl.d_frame_count; fp.frame_prefix = sl.d_frame_prefix; fp.frame_cap = c->frame_cap; fp.packed = sl.d_packed;
-    fp.buf_acc = sl.d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = sl.d_rec_pool;
-    { int r = b200_launch_finalize(&fp, sl.d_frame_prefix, sl.d_ctl, c->n_sm, res); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
+    if (!solo) { int r = b200_launch_finalize(&fp, sl.d_frame_prefix, sl.d_ctl, c->n_sm, res); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
     CU(c, cudaEventRecord(sl.ev[3], res));
 
     if (mode_ac) {      // per-buffer reply lists -> one packed array in buffer order, receiver statistics

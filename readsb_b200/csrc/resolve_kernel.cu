@@ -571,6 +571,8 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
 // changed the filter's membership: then its adds are applied and its frames moved into place.  Otherwise it is resolved
 // again, directly, with the filter as the reference would have it at that point.  In steady state (aircraft already
 // known, no flip) every speculation holds; the results are the sequential ones by construction either way.
+__device__ __forceinline__ void finalize_frames(const FinalizeParams &P, uint32_t warp_global, uint32_t n_warps, uint32_t lane);
+
 // Receivers with grown tables (BIG) are rare: they get an instantiation of their own, launched only when there is one, so that
 // the common case does not share its register allocation; each CTA of either launch leaves the other kind alone.
 template <bool BIG>
@@ -585,6 +587,44 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
     if (P.ctl->overflow & RUN_REPEAT_BITS) return;
     if ((st->cap_log2 != ICAO_CAP_LOG2) != BIG) return;
     resolve_stream<BIG>(P, S, st, stream);
+}
+
+__device__ __noinline__ void resolve_stream_big(const ResolveParams &P, ResolveSmem &S, StreamState *st, uint32_t stream) { resolve_stream<true>(P, S, st, stream); }
+
+// A context with ONE receiver (the drop-in's shape: one readsb process, one mag_buf per call) needs no grid-wide agreement: this
+// single CTA makes the capacity check for its receiver itself, and assembles the frames when it is done - stage B, the frame
+// prefix and the finalizer in one launch.
+__global__ void __launch_bounds__(RS_WARPS * 32, 1) resolve_solo_kernel(const ResolveParams P) {
+    extern __shared__ uint4 resolve_smem_raw[];
+    ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
+    const uint32_t stream = 0;
+    StreamState *st = &P.state[0];
+    __shared__ uint32_t s_go;
+    if (threadIdx.x == 0) {
+        const uint32_t add = P.stream_addable[0];
+        P.stream_addable[0] = 0;
+        uint32_t go = (P.ctl->overflow & RUN_REPEAT_BITS) ? 0u : 1u;
+        if (P.prev_ctl && (P.prev_ctl->overflow & RUN_REPEAT_BITS)) { atomicOr(&P.ctl->overflow, 16u); go = 0; }
+        const uint32_t need = max(st->gen_count[0], st->gen_count[1]) + add;
+        if (go && 2u * need > (1u << st->cap_log2)) {
+            uint32_t lg = st->cap_log2 + 1;
+            while ((1u << lg) < 4u * need && lg < ICAO_MAXBITS + 1) lg++;
+            st->grow_log2 = lg;
+            atomicOr(&P.ctl->overflow, 8u);
+            go = 0;
+        }
+        s_go = go;
+    }
+    __syncthreads();
+    if (s_go) {
+        if (st->cap_log2 == ICAO_CAP_LOG2) resolve_stream<false>(P, S, st, stream);
+        else resolve_stream_big(P, S, st, stream);
+    }
+    __syncthreads();
+    const uint32_t n = s_go ? P.frame_count[0] : 0;
+    if (threadIdx.x == 0) { P.fin.frame_prefix_out[0] = 0; P.fin.frame_prefix_out[1] = n; P.ctl->total_frames = n; }
+    __syncthreads();
+    finalize_frames(P.fin, threadIdx.x >> 5, RS_WARPS, threadIdx.x & 31);
 }
 
 // Runs ahead of resolve_kernel on its stream: (1) the asynchronous pipeline's "the step ahead has to be repeated" test, once
@@ -630,11 +670,9 @@ __global__ void __launch_bounds__(1024) frame_prefix_kernel(const uint32_t *coun
 
 __device__ __forceinline__ unsigned long long dmax_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
 
-// Small CTAs (128 threads x 48 registers): they have to fit into what the persistent scan kernel of the NEXT step leaves free on an SM.
-__global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams P) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+// One warp per accepted frame: the frame from its record, its signal power, the statistics (see the file header).  `warp_global` of
+// `n_warps` warps share the frames of the run.
+__device__ __forceinline__ void finalize_frames(const FinalizeParams &P, uint32_t warp_global, uint32_t n_warps, uint32_t lane) {
     const uint32_t total = P.frame_prefix[P.n_streams];
     for (uint32_t fi = warp_global; fi < total; fi += n_warps) {
         // stream = last s with prefix[s] <= fi.  The whole kernel is one dependent-load chain per frame, so the search is done by
@@ -721,6 +759,11 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams P) {
     }
 }
 
+// Small CTAs (128 threads x 48 registers): they have to fit into what the persistent scan kernel of the NEXT step leaves free on an SM.
+__global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams P) {
+    finalize_frames(P, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
+}
+
 // ------------------------------------------------------------------------------------------------
 // tiny control-plane kernels: ICAO filter operations from the host API
 // ------------------------------------------------------------------------------------------------
@@ -800,11 +843,16 @@ __global__ void init_state_kernel(StreamState *st, uint32_t n, uint32_t *slab) {
 extern "C" int b200_prepare_resolve(void) {      // per device, from b200_demod_create
     cudaError_t e = cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resolve_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem));
     return (int)e;
 }
 
 // any_grown: some receiver of the context has filter tables of its own (then the second instantiation runs too; returns the launches made)
 extern "C" int b200_launch_resolve(const ResolveParams *p, int any_grown, void *stream) {
+    if (p->solo) {          // one receiver: capacity check, stage B, frame prefix and finalizer in one launch
+        resolve_solo_kernel<<<1, RS_WARPS * 32, sizeof(ResolveSmem), (cudaStream_t)stream>>>(*p);
+        return (int)cudaGetLastError();
+    }
     icao_capacity_kernel<<<(p->n_streams + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->state, p->stream_addable, p->n_streams, p->ctl, p->prev_ctl);
     resolve_kernel<false><<<p->n_streams, RS_WARPS * 32, sizeof(ResolveSmem), (cudaStream_t)stream>>>(*p);
     if (any_grown) resolve_kernel<true><<<p->n_streams, RS_WARPS * 32, sizeof(ResolveSmem), (cudaStream_t)stream>>>(*p);

@@ -567,13 +567,14 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
     {   // one-time table staging (persistent CTA)
         const uint4 *src = reinterpret_cast<const uint4 *>(tables->lut_fold);
         uint4 *dst = reinterpret_cast<uint4 *>(S.lut);
-        for (uint32_t i = tid; i < sizeof(S.lut) / 16; i += SC_THREADS) dst[i] = src[i];
+        if (P.need_lut) for (uint32_t i = tid; i < sizeof(S.lut) / 16; i += SC_THREADS) dst[i] = src[i];
         for (uint32_t i = tid; i < 256; i += SC_THREADS) S.crc_tab[i] = tables->crc_tab[i];
         for (uint32_t i = tid; i < 112; i += SC_THREADS) S.bit_syn[i] = tables->bit_syn[i];
         for (uint32_t i = tid; i < 512; i += SC_THREADS) S.syn_hash[i] = tables->syn_hash[i];
         if (tid == 0) S.syn_mul = tables->syn_hash_mul;
     }
     __syncthreads();      // the only block barrier: from here on every warp is on its own
+    if (wid >= P.warps_per_cta) return;      // small run: the launcher spread it over more SMs with fewer warps each
 
     WarpSmem &W = F.w[wid];
     RunCtx &T = W.ctx;
@@ -594,7 +595,8 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const Scan
             if (lane == 0) {
                 const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&P.ctl->tile_counter);
                 if (cur < P.n_tiles) {
-                    n = min(max((P.n_tiles - cur + gridDim.x * NW - 1u) / (gridDim.x * NW), 1u), (uint32_t)RUN_MAX);   // ceil(remaining / warps): single tiles only for the last round
+                    const uint32_t workers = gridDim.x * P.warps_per_cta;
+                    n = min(max((P.n_tiles - cur + workers - 1u) / workers, 1u), (uint32_t)RUN_MAX);   // ceil(remaining / warps): single tiles only for the last round
                     start = atomicAdd(&P.ctl->tile_counter, n);
                     if (start >= P.n_tiles) n = 0; else n = min(n, P.n_tiles - start);
                 }
@@ -763,10 +765,16 @@ extern "C" int b200_prepare_scan(void) {
 }
 
 template <int NW> static int launch_scan_t(const ScanParams *p, const DeviceTables *d_tables, int n_sm, cudaStream_t stream) {
+    // One persistent CTA per SM.  A run with fewer tiles than the chip has warps is spread out: as many CTAs as there are tiles (at
+    // most one per SM) and only as many warps of each as it takes - a lone warp on an SM runs several times faster than one of 28.
+    ScanParams q = *p;
     uint32_t grid = (uint32_t)n_sm;
-    const uint32_t need = (p->n_tiles + NW - 1) / NW;
-    if (grid > need) grid = need;
-    scan_kernel<NW><<<grid, NW * 32, sizeof(ScanSmemFull<NW>), stream>>>(*p, d_tables);
+    q.warps_per_cta = NW;
+    if (q.n_tiles < grid * NW) {
+        if (grid > q.n_tiles) grid = q.n_tiles;
+        q.warps_per_cta = (q.n_tiles + grid - 1) / grid;
+    }
+    scan_kernel<NW><<<grid, NW * 32, sizeof(ScanSmemFull<NW>), stream>>>(q, d_tables);
     return (int)cudaGetLastError();
 }
 

@@ -42,6 +42,8 @@ def lib():
         L.b200_demod_host_alloc.restype = vp
         L.b200_demod_host_alloc.argtypes = [C.c_size_t]
         L.b200_demod_host_free.argtypes = [vp]
+        L.b200_demod_host_register.argtypes = [vp, C.c_size_t]
+        L.b200_demod_host_unregister.argtypes = [vp]
         L.b200_demod_submit_iq_uc8.argtypes = [vp, u32, vp, u32, i64]
         L.b200_demod_submit_mag_u16.argtypes = [vp, u32, vp, u32, i64]
         L.b200_demod_submit_mag_u16_levels.argtypes = [vp, u32, vp, u32, i64, C.c_double, C.c_double]
@@ -74,7 +76,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "b200_demod_abi_version", "b200_demod_create", "b200_demod_destroy", "b200_demod_last_error",
-    "b200_demod_host_alloc", "b200_demod_host_free", "b200_demod_submit_iq_uc8", "b200_demod_submit_mag_u16",
+    "b200_demod_host_alloc", "b200_demod_host_free", "b200_demod_host_register", "b200_demod_host_unregister", "b200_demod_submit_iq_uc8", "b200_demod_submit_mag_u16",
     "b200_demod_run", "b200_demod_run_device_uc8", "b200_demod_frame_count", "b200_demod_fetch",
     "b200_demod_buffer_results", "b200_demod_total_frames", "b200_demod_get_stats", "b200_demod_icao_add",
     "b200_demod_fetch_beast", "b200_demod_submit_iq_sc16", "b200_demod_icao_test", "b200_demod_icao_expire", "b200_demod_icao_reset", "b200_demod_last_timing",

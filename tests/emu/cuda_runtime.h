@@ -207,7 +207,8 @@ static inline void emu_asm_prefetch_global_L2(const void *) {}
 
 // ---- runtime API (emu_rt.cpp): synchronous, host memory ------------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorHostMemoryAlreadyRegistered = 712 };
+enum { cudaHostRegisterDefault = 0 };
 typedef struct EmuStream *cudaStream_t;
 typedef struct EmuEvent *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
@@ -238,6 +239,8 @@ cudaError_t cudaFree(void *p);
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned flags);
 cudaError_t cudaMallocHost(void **p, size_t n);
 cudaError_t cudaFreeHost(void *p);
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t st = nullptr);
 cudaError_t cudaMemcpy2DAsync(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k, cudaStream_t st = nullptr);
