@@ -384,23 +384,29 @@ def latency_leg(local, hbm_peak, cpu_pool):
     pin_iq.array[:] = iq
     out = {"shape": "1 receiver, 1 buffer of 65536 samples per blocking call (submit -> run -> fetch), pinned host memory, timed in C"}
 
-    def run(is_iq, ptr, stride):
-        d = Demodulator(n_streams=1, buf_samples=BUF, max_buffers_per_run=1, device=local)
+    def run(is_iq, ptr, stride, no_timing=True):
+        # no_timing: the configuration integration/readsb_shim.c uses (no CUDA events between the kernels); the timed variant below
+        # gives the device-side timeline and costs a few microseconds per call
+        d = Demodulator(n_streams=1, buf_samples=BUF, max_buffers_per_run=1, device=local, no_timing=no_timing)
         us = (C.c_double * (reps + warm))()
         frames = C.c_uint64(0)
         fn = lambda name: C.cast(getattr(L, name), C.c_void_p)
         P.probe_latency.argtypes = [C.c_void_p] * 6 + [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         rc = P.probe_latency(d.h, fn("b200_demod_submit_mag_u16"), fn("b200_demod_submit_iq_uc8"), fn("b200_demod_run"), fn("b200_demod_fetch"),
                              C.c_void_p(ptr), stride, BUF, nbuf, reps + warm, 1 if is_iq else 0, us, C.byref(frames))
-        launches = d.timing()["launches"]
+        t = d.timing()
+        launches = t["launches"]
         d.close()
         if rc != 0:
             return {"error": rc}
         v = np.sort(np.array(us[warm:]))
         return {"median_us": float(np.median(v)), "p99_us": float(v[int(0.99 * (len(v) - 1))]), "min_us": float(v[0]), "mean_us": float(v.mean()),
-                "calls": reps, "frames": int(frames.value), "kernel_launches_per_call": launches}
+                "calls": reps, "frames": int(frames.value), "kernel_launches_per_call": launches,
+                "device_timeline_of_last_call_us": None if no_timing else {"scan_kernel": t["scan_ms"] * 1e3, "stage_b": t["resolve_ms"] * 1e3,
+                                                                           "scan_begin_to_stage_b_end": t["run_ms"] * 1e3}}
     out["mag_handoff"] = run(False, pin.ptr, row * 2)              # demodulate2400(mag_buf) call site
     out["iq_handoff"] = run(True, pin_iq.ptr, BUF * 2)             # converter call site: uc8 IQ in, magnitudes made on the GPU
+    out["mag_handoff_with_cuda_events"] = run(False, pin.ptr, row * 2, no_timing=False)
     med = out["mag_handoff"].get("median_us")
     if med:
         out["msamples_per_s"] = BUF / med

@@ -138,6 +138,8 @@ typedef struct b200_demod_config {
 } b200_demod_config;
 
 #define B200_CFG_MODE_AC 0x1u   /* also run the Mode A/C demodulator on every buffer (--modeac, readsb.c:872-874) */
+#define B200_CFG_NO_TIMING 0x2u /* blocking runs record no CUDA events between the kernels (b200_demod_last_timing then reports zeros): every
+                                   event is an operation of its own in the stream, and a one-buffer run is short enough for that to show */
 
 typedef struct b200_demod_ctx b200_demod_ctx;
 

@@ -69,6 +69,7 @@ static int shim_open(void) {
     cfg.nfix_crc = Modes.nfix_crc ? 1 : 0;
     cfg.fix_df = Modes.fixDF;
     cfg.icao_ttl_ms = -1;                                /* flips are driven by backgroundTasks through the wrap above */
+    cfg.flags |= B200_CFG_NO_TIMING;                     /* one buffer per call: keep CUDA events out of the stream */
     if (Modes.mode_ac || Modes.mode_ac_auto) {           /* readsb.c:872: Mode A/C runs on the same buffers */
         cfg.flags |= B200_CFG_MODE_AC;
         g_ac_cap = cfg.buf_samples / 70 + 2;

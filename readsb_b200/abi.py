@@ -51,6 +51,7 @@ class Config(C.Structure):
 
 MODEAC_DTYPE = np.dtype([("timestamp", "<i8"), ("f1_sample", "<u4"), ("modeac", "<u2"), ("buffer_idx", "<u2")])
 CFG_MODE_AC = 0x1
+CFG_NO_TIMING = 0x2
 
 assert C.sizeof(Frame) == 64 and C.sizeof(BufferResult) == 112 and MODEAC_DTYPE.itemsize == 16
 

@@ -191,6 +191,15 @@ struct ResolveParams {
     uint32_t *stream_addable;         // [n_streams] upper bound of the filter adds of this run (scan kernel); read and zeroed by the capacity check
     uint32_t solo;                    // one receiver in the context: capacity check, stage B, frame prefix and finalizer in ONE launch
     FinalizeParams fin;               // (solo) what the finalizer needs
+    // (solo, optional) the kernel PUBLISHES the run's result block itself: copies publish_head bytes + the packed frames from
+    // publish_src (device) to publish_dst (the host's pinned copy, mapped into the device's address space) - no device-to-host
+    // copy operation in the stream - and then zeroes the control block and the per-buffer sums for the next run (no memset either)
+    const uint4 *publish_src;
+    uint4 *publish_dst;
+    uint32_t publish_head;            // bytes in front of the packed frames
+    uint32_t publish_clear;           // bytes at the start of the block (RunCtl + BufAcc[]) to zero afterwards
+    uint16_t *carry_dst;              // (solo, optional) the receiver's arena region: its last 326 samples go to the front for the next run
+    const uint16_t *carry_src;        //   (the mag_buf overlap copy, sdr_ifile.c:209-213), or null
 };
 
 

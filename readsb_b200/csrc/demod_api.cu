@@ -48,6 +48,8 @@ struct Slot {
     //   descriptor block  [stream_seg_begin (S+1) | segs (nseg) | tile_seg (ntile)]
     //   result block      [RunCtl | buf_acc (nbuf) | frame_prefix (S+1) | buf_out (nbuf) | packed frames ...]
     uint8_t *d_desc = nullptr, *h_desc = nullptr, *d_res = nullptr, *h_res = nullptr;
+    uint8_t *d_res_host = nullptr;    // h_res as the device sees it (mapped pinned memory): the one-receiver kernel publishes its results there
+    bool res_clean = false;           // RunCtl + BufAcc[] in d_res are zero (the one-receiver kernel cleans up after itself)
     size_t desc_cap = 0, res_cap = 0, res_head = 0;     // res_head: bytes in front of the packed frames in this run's result block
     Segment *d_segs = nullptr, *h_segs = nullptr;       // h_segs / h_tile_seg / h_stream_seg_begin: where the host BUILDS the run (copied into h_desc)
     uint32_t *d_tile_seg = nullptr, *h_tile_seg = nullptr;
@@ -80,6 +82,8 @@ struct Slot {
     float ms[5] = {0, 0, 0, 0, 0};
     uint32_t launches = 0;
     uint32_t first_frames = 0;        // packed frames that came with the result block's copy
+    uint32_t carry_in_kernel = 0xffffffffu;   // one-receiver host run: byte offset of the tail the stage B kernel carries to the front
+    bool published = false, timed = true;   // this run: results published by the kernel / events recorded between the kernels
 };
 
 #define FIRST_COPY_FRAMES 16
@@ -216,7 +220,8 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
     s.res_cap = sizeof(RunCtl) + (size_t)c->buf_cap * (sizeof(BufAcc) + sizeof(b200_buffer_result)) + pad16(((size_t)S + 1) * 4)
               + (size_t)S * c->frame_cap * sizeof(b200_frame) + 64;
     A(cudaMalloc((void **)&s.d_desc, s.desc_cap)); A(cudaHostAlloc((void **)&s.h_desc, s.desc_cap, cudaHostAllocDefault));
-    A(cudaMalloc((void **)&s.d_res, s.res_cap)); A(cudaHostAlloc((void **)&s.h_res, s.res_cap, cudaHostAllocDefault));
+    A(cudaMalloc((void **)&s.d_res, s.res_cap)); A(cudaHostAlloc((void **)&s.h_res, s.res_cap, cudaHostAllocMapped));
+    A(cudaHostGetDevicePointer((void **)&s.d_res_host, s.h_res, 0));
     A(cudaMemset(s.d_res, 0, sizeof(RunCtl)));
     memset(s.h_res, 0, sizeof(RunCtl) + pad16(((size_t)S + 1) * 4));
     s.d_ctl = reinterpret_cast<RunCtl *>(s.d_res); s.h_ctl = reinterpret_cast<RunCtl *>(s.h_res);     // fixed: the next step reads it as prev_ctl
@@ -518,7 +523,13 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     layout_run(c, sl);
     CU(c, cudaMemcpyAsync(sl.d_desc, sl.h_desc, sl.desc_bytes, cudaMemcpyHostToDevice, pre));
     if (c->beast_slot == (int)(&sl - c->slot)) c->beast_slot = -1;      // the encoded records belong to the run being replaced
-    CU(c, cudaMemsetAsync(sl.d_res, 0, sizeof(RunCtl) + (size_t)sl.nbuf * sizeof(BufAcc), pre));       // control block + per-buffer sums
+    // One receiver, no Mode A/C: the stage B kernel publishes the results into the host's (mapped) copy itself and zeroes the control
+    // block and the per-buffer sums when it is done - no memset, no device-to-host copy in the stream.
+    const bool publish = S == 1 && !(c->cfg.flags & B200_CFG_MODE_AC) && scan == res;
+    const bool timing = !((c->cfg.flags & B200_CFG_NO_TIMING) && scan == res);
+    if (!(publish && sl.res_clean))
+        CU(c, cudaMemsetAsync(sl.d_res, 0, sizeof(RunCtl) + (size_t)sl.nbuf * sizeof(BufAcc), pre));       // control block + per-buffer sums
+    sl.res_clean = false; sl.published = publish; sl.timed = timing;
     if (pre != scan) { CU(c, cudaEventRecord(sl.ev[7], pre)); CU(c, cudaStreamWaitEvent(scan, sl.ev[7], 0)); }
     sl.launches = 0;
 
@@ -534,9 +545,9 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     sp.short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
     sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
     if (sp.nfix && sp.fixdf) for (int b = 0; b < 5; b++) sp.long_set |= 1u << (17 ^ (1 << b));
-    CU(c, cudaEventRecord(sl.ev[0], scan));
+    if (timing) CU(c, cudaEventRecord(sl.ev[0], scan));
     if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, scan != res ? c->n_sm_scan_async : c->n_sm_scan, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
-    CU(c, cudaEventRecord(sl.ev[1], scan));
+    if (timing) CU(c, cudaEventRecord(sl.ev[1], scan));
     if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[1], 0));
 
     // demodulate2400AC on the same buffers (readsb.c:872-874).  Its scan and walk are stateless, so they stay on the
@@ -567,11 +578,21 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     rp.state = c->d_state; rp.frames = sl.d_frames; rp.frame_count = sl.d_frame_count; rp.frame_cap = c->frame_cap; rp.per_buf_cap = c->cfg.buf_samples / 113 + 2;
     rp.ctl = sl.d_ctl; rp.prev_ctl = prev_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms; rp.stream_addable = sl.d_addable;
     rp.solo = solo ? 1u : 0u; rp.fin = fp;
+    rp.publish_src = nullptr; rp.publish_dst = nullptr; rp.publish_head = 0; rp.publish_clear = 0;
+    rp.carry_dst = nullptr; rp.carry_src = nullptr;
+    if (solo && sl.carry_in_kernel != 0xffffffffu) {      // host-buffer run of one receiver: the halo carry rides in the stage B kernel
+        rp.carry_dst = reinterpret_cast<uint16_t *>(c->d_arena);
+        rp.carry_src = reinterpret_cast<const uint16_t *>(c->d_arena + sl.carry_in_kernel);
+    }
+    if (publish) {
+        rp.publish_src = reinterpret_cast<const uint4 *>(sl.d_res); rp.publish_dst = reinterpret_cast<uint4 *>(sl.d_res_host);
+        rp.publish_head = (uint32_t)sl.res_head; rp.publish_clear = (uint32_t)(sizeof(RunCtl) + (size_t)sl.nbuf * sizeof(BufAcc));
+    }
     { const int grown = !c->icao_grown.empty();
       int r = b200_launch_resolve(&rp, grown, res); if (r) return fail(c, B200_E_CUDA, "resolve launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += solo ? 1 : 2 + grown; }
-    CU(c, cudaEventRecord(sl.ev[2], res));
+    if (timing) CU(c, cudaEventRecord(sl.ev[2], res));
     if (!solo) { int r = b200_launch_finalize(&fp, sl.d_frame_prefix, sl.d_ctl, c->n_sm, res); if (r) return fail(c, B200_E_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches += 2; }
-    CU(c, cudaEventRecord(sl.ev[3], res));
+    if (timing) CU(c, cudaEventRecord(sl.ev[3], res));
 
     if (mode_ac) {      // per-buffer reply lists -> one packed array in buffer order, receiver statistics
         if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[6], 0));
@@ -582,8 +603,9 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
 
     // control block, per-buffer sums, frame prefix, buffer results and the first frames: one copy (small runs need no second one)
     sl.first_frames = (uint32_t)std::min<size_t>(FIRST_COPY_FRAMES, (size_t)S * c->frame_cap);
-    CU(c, cudaMemcpyAsync(sl.h_res, sl.d_res, sl.res_head + (size_t)sl.first_frames * sizeof(b200_frame), cudaMemcpyDeviceToHost, res));
-    CU(c, cudaEventRecord(sl.ev[4], res));
+    if (publish) sl.first_frames = 0xffffffffu;          // the kernel has put every frame into the host's copy
+    else CU(c, cudaMemcpyAsync(sl.h_res, sl.d_res, sl.res_head + (size_t)sl.first_frames * sizeof(b200_frame), cudaMemcpyDeviceToHost, res));
+    if (timing) CU(c, cudaEventRecord(sl.ev[4], res));
     return B200_OK;
 }
 
@@ -592,7 +614,8 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
 // because the step before it had to be repeated, 4 = a receiver's ICAO filter tables have to grow first.
 static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     const uint32_t S = c->cfg.n_streams;
-    CU(c, cudaEventSynchronize(sl.ev[4]));
+    if (sl.timed) CU(c, cudaEventSynchronize(sl.ev[4])); else CU(c, cudaStreamSynchronize(res));
+    if (sl.published) sl.res_clean = true;               // the kernel zeroed RunCtl + BufAcc[] after publishing them
     const uint32_t ov = sl.h_ctl->overflow;
     if (ov & 1u) return 1;
     if ((ov & 2u) && sl.h_ctl->stage_need > c->stage_cap) return 2;
@@ -604,7 +627,7 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
     const bool mode_ac = (c->cfg.flags & B200_CFG_MODE_AC) != 0;
     const uint32_t total_ac = mode_ac ? sl.h_ac_prefix[sl.nbuf] : 0;
     sl.ms[3] = 0;
-    if (mode_ac) cudaEventElapsedTime(&sl.ms[3], sl.ev[1], sl.ev[6]);       // Mode A/C noise + scan + walk kernels
+    if (mode_ac && sl.timed) cudaEventElapsedTime(&sl.ms[3], sl.ev[1], sl.ev[6]);       // Mode A/C noise + scan + walk kernels
     if (total_ac) CU(c, cudaMemcpyAsync(sl.h_ac_packed, sl.d_ac_packed, (size_t)total_ac * sizeof(b200_modeac), cudaMemcpyDeviceToHost, c->copy_stream));
     const uint32_t total = sl.h_frame_prefix[S];
     sl.run_frames = total;
@@ -624,10 +647,12 @@ static int collect(b200_demod_ctx *c, Slot &sl, cudaStream_t res) {
         sl.h_buf_out[b].sum_power = sl.h_buf_acc[b].sum_power;
         sl.h_buf_out[b].sum_signal_power = sl.h_buf_acc[b].sum_signal_power;
     }
-    cudaEventElapsedTime(&sl.ms[1], sl.ev[0], sl.ev[1]);
-    cudaEventElapsedTime(&sl.ms[2], sl.ev[1], sl.ev[2]);
-    cudaEventElapsedTime(&sl.ms[0], sl.ev[0], (more_frames || total_ac) ? sl.ev[5] : sl.ev[4]);
-    cudaEventElapsedTime(&sl.ms[4], sl.ev[3], (more_frames || total_ac) ? sl.ev[5] : sl.ev[4]);
+    if (sl.timed) {
+        cudaEventElapsedTime(&sl.ms[1], sl.ev[0], sl.ev[1]);
+        cudaEventElapsedTime(&sl.ms[2], sl.ev[1], sl.ev[2]);
+        cudaEventElapsedTime(&sl.ms[0], sl.ev[0], (more_frames || total_ac) ? sl.ev[5] : sl.ev[4]);
+        cudaEventElapsedTime(&sl.ms[4], sl.ev[3], (more_frames || total_ac) ? sl.ev[5] : sl.ev[4]);
+    } else sl.ms[0] = sl.ms[1] = sl.ms[2] = sl.ms[4] = 0;
     return B200_OK;
 }
 
@@ -749,6 +774,7 @@ API int b200_demod_run(b200_demod_ctx *c) {
         for (const auto &g : given_levels) { AcLevel &l = sl.h_ac_levels[g.first]; l.mode = AC_LEVEL_GIVEN; l.mean_level = g.second->mean_level; l.mean_power = g.second->mean_power; }
         for (const auto &bf : fsum_of_buf) { AcLevel &l = sl.h_ac_levels[bf.first]; l.mode = AC_LEVEL_FSUM; l.idx = (uint32_t)bf.second; }
     }
+    sl.carry_in_kernel = S == 1 ? c->h_carry_src[0] : 0xffffffffu;
     int rc = execute_blocking(c, sl);
     if (rc == B200_OK && !fsum_of_buf.empty()) {      // sc16 input: the reference's float accumulators instead of the integer sums
         if (cudaMemcpyAsync(c->h_fsum, c->d_fsum, (size_t)c->n_fsum * sizeof(float2), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
@@ -763,6 +789,8 @@ API int b200_demod_run(b200_demod_ctx *c) {
     // next run: move each IQ stream's tail to the front of its region
     bool any_carry = false;
     for (uint32_t s = 0; s < S; s++) any_carry = any_carry || c->h_carry_src[s] != 0xffffffffu;
+    if (S == 1) any_carry = false;             // carried by the stage B kernel itself (enqueue: carry_in_kernel)
+    sl.carry_in_kernel = 0xffffffffu;
     if (rc == B200_OK && any_carry) {          // (magnitude hand-offs bring their halo with them: nothing to carry)
         cudaMemcpyAsync(c->d_carry_src, c->h_carry_src, S * 4, cudaMemcpyHostToDevice, c->stream);
         carry_halo_kernel<<<S, 128, 0, c->stream>>>(c->d_arena, c->stream_stride, c->d_carry_src, S);
@@ -1039,6 +1067,10 @@ API int b200_demod_debug_counters(b200_demod_ctx *c, uint64_t out[8]) {
     out[5] = sl.nseg; out[6] = sl.nbuf; out[7] = sl.run_frames;
     return B200_OK;
 }
+
+#ifdef B200_SOLO_CLOCKS
+API int b200_demod_debug_ctl(b200_demod_ctx *c, uint32_t out[8]) { memcpy(out, c->slot[c->cur].h_ctl, 32); return B200_OK; }
+#endif
 
 // ---- ICAO filter control -------------------------------------------------------------------------
 static int icao_op(b200_demod_ctx *c, uint32_t s, int op, uint32_t addr, int *result) {

@@ -123,10 +123,13 @@ __device__ __forceinline__ int rec_score(uint32_t kind, bool known) {
 //                 frames carry B200_FRAME_ICAO_ADDED — the commit step applies them if the speculation holds.
 //   DEFER = false (direct): adds go straight into the shared-memory table, exactly as the reference does.
 // Frames are written to fout[0 .. n_frames); `old_gen` is the older generation's exact table in global memory.
-template <bool DEFER, bool BIG>
-__device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSmem &S, WarpRing &R, BufResult &out, const Segment &seg, uint32_t si,
-                                               uint32_t b, uint32_t d_lo, uint32_t d_hi, uint32_t skip_in, uint32_t seq, const FilterRef &F,
-                                               b200_frame *fout, uint32_t fcap, uint32_t lane) {
+// DEFER is a function parameter: the many-receiver kernels pass a literal and get two specialised inlined copies (measured faster
+// there: 256 CTAs share the instruction cache); the one-receiver kernel runs cold every call and goes through resolve_buffer_call,
+// a single real function (its fully inlined form was 64 000 instructions, most of its time instruction fetch).
+template <bool BIG>
+__device__ __forceinline__ void resolve_buffer(const bool DEFER, const ResolveParams &P, ResolveSmem &S, WarpRing &R, BufResult &out, const Segment &seg, uint32_t si,
+                                            uint32_t b, uint32_t d_lo, uint32_t d_hi, uint32_t skip_in, uint32_t seq, const FilterRef &F,
+                                            b200_frame *fout, uint32_t fcap, uint32_t lane) {
     // [d_lo, d_hi): the positions of reference buffer b this call walks - the whole buffer, or one of the sub-ranges a buffer is cut
     // into when a receiver has fewer buffers in the run than stage B has warps (a sub-range is speculated like a buffer: it assumes
     // that no frame accepted before it reaches into it, skip_in = d_lo, and is redone with the real skip_in when one does).
@@ -162,20 +165,22 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
         return (lane < 4 && q < n_quads && t < tile_end) ? *reinterpret_cast<const uint4 *>(&P.tile_out[t]) : make_uint4(0, 0, 0, 0);
     };
     auto issue_stage = [&](uint32_t q, const uint4 &piece) {
-        uint32_t np[4], nr[4], ro[4], tp = 0, tr = 0;
+        // lane l < 4 holds the TileOut of the quad's tile l: totals first, then the four lists back to back
+        uint32_t tp = 0, tr = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { np[i] = __shfl_sync(FULLMASK, piece.x, i); nr[i] = __shfl_sync(FULLMASK, piece.y, i); ro[i] = __shfl_sync(FULLMASK, piece.z, i); tp += np[i]; tr += nr[i]; }
+        for (int i = 0; i < 4; i++) { tp += __shfl_sync(FULLMASK, piece.x, i); tr += __shfl_sync(FULLMASK, piece.y, i); }
         if (q < n_quads && tp <= RS_STAGE && tr <= RS_STAGE) {
             const uint32_t buf = q % RS_RING;
             uint32_t bp = 0, br = 0;
-#pragma unroll
+#pragma unroll 1                 // (unrolled, these loops were 12 000 of the kernel's 41 000 instructions)
             for (int i = 0; i < 4; i++) {
+                const uint32_t np = __shfl_sync(FULLMASK, piece.x, i), nr = __shfl_sync(FULLMASK, piece.y, i), ro = __shfl_sync(FULLMASK, piece.z, i);
                 const PosEntry *src = P.pos_pool + (size_t)(seg.tile_begin + 4 * q + i) * SCAN_TILE;
-#pragma unroll 1                 // one trip almost always; unrolled four-fold these two loops were 12 000 of the kernel's 41 000 instructions
-                for (uint32_t e = lane; e < np[i]; e += 32) cp_async4(&R.pos[buf][bp + e], &src[e]);
 #pragma unroll 1
-                for (uint32_t e = lane; e < nr[i]; e += 32) cp_async4(&R.key[buf][br + e], &P.key_pool[ro[i] + e]);
-                bp += np[i]; br += nr[i];
+                for (uint32_t e = lane; e < np; e += 32) cp_async4(&R.pos[buf][bp + e], &src[e]);
+#pragma unroll 1
+                for (uint32_t e = lane; e < nr; e += 32) cp_async4(&R.key[buf][br + e], &P.key_pool[ro + e]);
+                bp += np; br += nr;
             }
         }
         cp_async_commit();
@@ -371,42 +376,94 @@ __device__ __forceinline__ void resolve_buffer(const ResolveParams &P, ResolveSm
     cp_async_wait_all();      // nothing may land in this warp's ring after the next buffer starts to use it
     __syncwarp();
 
-    uint32_t red[15] = {c_pre, c_bad, c_unk, c_acc0, c_acc1, c_tp[0], c_tp[1], c_tp[2], c_tp[3], c_tp[4], c_bp[0], c_bp[1], c_bp[2], c_bp[3], c_bp[4]};
+    const uint32_t red[15] = {c_pre, c_bad, c_unk, c_acc0, c_acc1, c_tp[0], c_tp[1], c_tp[2], c_tp[3], c_tp[4], c_bp[0], c_bp[1], c_bp[2], c_bp[3], c_bp[4]};
 #pragma unroll
     for (int k = 0; k < 15; k++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) red[k] += __shfl_xor_sync(FULLMASK, red[k], o);
-        if (lane == 0) out.stats[k] = red[k];
+        const uint32_t t = __reduce_add_sync(FULLMASK, red[k]);       // REDUX: one instruction per counter
+        if (lane == 0) out.stats[k] = t;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c_add += __shfl_xor_sync(FULLMASK, c_add, o);
+    c_add = __reduce_add_sync(FULLMASK, c_add);
     if (lane == 0) { out.now_ms = now_ms; out.n_frames = min(nframes, fcap); out.n_new = n_new; out.fail = fail; out.n_add = c_add; out.skip_out = skip_until; }
     __syncwarp();
 }
 
 template <bool BIG>
-__device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSmem &S, StreamState *st, uint32_t stream) {
-    __shared__ uint32_t s_active, s_gcount[2], s_bits;
+__device__ __noinline__ void resolve_buffer_call(bool defer, const ResolveParams &P, ResolveSmem &S, WarpRing &R, BufResult &out, const Segment &seg, uint32_t si,
+                                                 uint32_t b, uint32_t d_lo, uint32_t d_hi, uint32_t skip_in, uint32_t seq, const FilterRef &F,
+                                                 b200_frame *fout, uint32_t fcap, uint32_t lane) {
+    resolve_buffer<BIG>(defer, P, S, R, out, seg, si, b, d_lo, d_hi, skip_in, seq, F, fout, fcap, lane);
+}
+
+#ifdef B200_SOLO_CLOCKS      // analysis build only (tools/gpu_latency.py): where the one-receiver kernel's microseconds go
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long g_solo_t[8];
+#define SOLO_T(i) do { if (COMPACT && threadIdx.x == 0) g_solo_t[i] = gtime(); } while (0)
+#else
+#define SOLO_T(i) do { } while (0)
+#endif
+
+// COMPACT (the one-receiver kernel): the capacity check of icao_capacity_kernel is made here, by the CTA itself, while the other
+// threads already fetch the tables; *n_frames_out (shared memory) receives the receiver's frame count, or ~0 when stage B must not run.
+template <bool BIG, bool COMPACT>
+__device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSmem &S, StreamState *st, uint32_t stream, uint32_t *n_frames_out = nullptr) {
+    __shared__ uint32_t s_active, s_gcount[2], s_bits, s_go;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t LOG2 = BIG ? st->cap_log2 : (uint32_t)ICAO_CAP_LOG2, CAP = 1u << LOG2;
     uint32_t *const tab0 = st->tab[0], *const tab1 = st->tab[1];
     auto tab = [&](uint32_t g) { return g ? tab1 : tab0; };
 
-    if (tid == 0) { s_active = st->active; s_gcount[0] = st->gen_count[0]; s_gcount[1] = st->gen_count[1]; s_bits = st->filter_bits; }
+    if (tid == 0) {
+        const uint32_t g0 = st->gen_count[0], g1 = st->gen_count[1];
+        s_active = st->active; s_gcount[0] = g0; s_gcount[1] = g1; s_bits = st->filter_bits;
+        uint32_t go = 1;
+        if (COMPACT) {
+            const uint32_t add = P.stream_addable[stream];
+            P.stream_addable[stream] = 0;
+            if (P.ctl->overflow & RUN_REPEAT_BITS) go = 0;
+            if (P.prev_ctl && (P.prev_ctl->overflow & RUN_REPEAT_BITS)) { atomicOr(&P.ctl->overflow, 16u); go = 0; }
+            const uint32_t need = max(g0, g1) + add;
+            if (go && 2u * need > CAP) {
+                uint32_t lg = LOG2 + 1;
+                while ((1u << lg) < 4u * need && lg < ICAO_MAXBITS + 1) lg++;
+                st->grow_log2 = lg;
+                atomicOr(&P.ctl->overflow, 8u);
+                go = 0;
+            }
+            if (!go) *n_frames_out = ~0u;
+        }
+        s_go = go;
+    }
     for (uint32_t i = tid; i < OLD_BITS / 32; i += blockDim.x) S.old_bits[i] = 0;
     if (tid < 16) { S.tot[tid] = 0; S.bstat[tid] = 0; }
+    // the tables, four slots per load and all of a thread's loads in flight together (a receiver's default tables: 2 x 16 KB)
+    constexpr uint32_t TL = ICAO_CAP / 4 / (RS_WARPS * 32);     // uint4 loads per thread and table for the default size
+    uint4 va[BIG ? 1 : TL], vo[BIG ? 1 : TL];
+    const uint32_t active0 = st->active;
+    if (!BIG) {
+        const uint4 *ta4 = reinterpret_cast<const uint4 *>(active0 ? tab1 : tab0), *to4 = reinterpret_cast<const uint4 *>(active0 ? tab0 : tab1);
+#pragma unroll
+        for (uint32_t k = 0; k < TL; k++) { va[k] = ta4[tid + k * RS_WARPS * 32]; vo[k] = to4[tid + k * RS_WARPS * 32]; }
+    }
     __syncthreads();
-    {
-        const uint32_t active = s_active;
-        const uint32_t *ta = tab(active), *to = tab(active ^ 1u);
+    if (COMPACT && !s_go) return;
+    if (!BIG) {
+#pragma unroll
+        for (uint32_t k = 0; k < TL; k++) {
+            reinterpret_cast<uint4 *>(S.act)[tid + k * RS_WARPS * 32] = va[k];
+            const uint32_t o[4] = {vo[k].x, vo[k].y, vo[k].z, vo[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (o[j] != ICAO_EMPTY) { const uint32_t h = old_bit(o[j]); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
+        }
+    } else {
+        const uint32_t *to = tab(s_active ^ 1u);
         for (uint32_t i = tid; i < CAP; i += blockDim.x) {
-            if (!BIG) S.act[i] = ta[i];
             const uint32_t v = to[i];
             if (v != ICAO_EMPTY) { const uint32_t h = old_bit(v); atomicOr(&S.old_bits[h >> 5], 1u << (h & 31)); }
         }
     }
     __syncthreads();
 
+    SOLO_T(1);
     // state only warp 0 touches (the commit step)
     uint32_t armed = st->flip_armed, seq = st->buffer_seq;
     int64_t next_flip = st->next_flip_ms;
@@ -441,10 +498,12 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
                 unit_range(u0 + wid, b, lo, hi);
                 FilterRef F;
                 F.act = tab(s_active); F.old_gen = tab(s_active ^ 1u); F.log2 = LOG2; F.counts = nullptr; F.bits = nullptr; F.active = s_active;
-                resolve_buffer<true, BIG>(P, S, S.ring[wid], S.res[wid], seg, si, b, lo, hi, lo, 0 /* buffer_seq is stamped at commit */, F,
-                                          fstream + cap_base + (size_t)wid * ucap, ucap, lane);
+                if (COMPACT) resolve_buffer_call<BIG>(true, P, S, S.ring[wid], S.res[wid], seg, si, b, lo, hi, lo, 0, F, fstream + cap_base + (size_t)wid * ucap, ucap, lane);
+                else resolve_buffer<BIG>(true, P, S, S.ring[wid], S.res[wid], seg, si, b, lo, hi, lo, 0 /* buffer_seq is stamped at commit */, F,
+                                         fstream + cap_base + (size_t)wid * ucap, ucap, lane);
             }
             __syncthreads();
+            SOLO_T(2);
             // ---- commit, in order -----------------------------------------------------------------------------------------------
             if (wid == 0) {
                 bool spec_ok = true;
@@ -487,7 +546,8 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
                         if (!skip_reaches_in || r.fail || resize_possible || !spec_ok) spec_ok = false;      // (a skip alone does not change the filter)
                         FilterRef F;
                         F.act = tab(s_active); F.old_gen = tab(s_active ^ 1u); F.log2 = LOG2; F.counts = s_gcount; F.bits = &s_bits; F.active = s_active;
-                        resolve_buffer<false, BIG>(P, S, S.ring[0], r, seg, si, b, lo, hi, max(skip_prev, lo), seq, F, fdst, P.frame_cap - nframes, lane);
+                        if (COMPACT) resolve_buffer_call<BIG>(false, P, S, S.ring[0], r, seg, si, b, lo, hi, max(skip_prev, lo), seq, F, fdst, P.frame_cap - nframes, lane);
+                        else resolve_buffer<BIG>(false, P, S, S.ring[0], r, seg, si, b, lo, hi, max(skip_prev, lo), seq, F, fdst, P.frame_cap - nframes, lane);
                         dirty_act = true;
                         spec_ok = false;
                     }
@@ -547,6 +607,7 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
         }
     }
 
+    SOLO_T(3);
     // write back
     if (wid == 0) {
         const uint32_t active = s_active;
@@ -554,13 +615,20 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
         if (lane == 0) {
             st->gen_count[0] = s_gcount[0]; st->gen_count[1] = s_gcount[1];
             st->active = active; st->filter_bits = s_bits; st->flip_armed = armed; st->next_flip_ms = next_flip; st->buffer_seq = seq;
-            b200_demod_stats &s = st->stats;
+            // counters: reductions into memory (nothing here waits for a load; the finalizer adds to the same block with atomics too)
+            // (addressed through the kernel parameter so that the compiler emits global reductions, not generic atomics)
+            unsigned long long *sv = reinterpret_cast<unsigned long long *>(&P.state[stream].stats);
             const uint32_t *tot = S.tot;
-            s.samples_processed += c_samples; s.demod_preambles += tot[0]; s.demod_rejected_bad += tot[1];
-            s.demod_rejected_unknown_icao += tot[2]; s.demod_accepted[0] += tot[3]; s.demod_accepted[1] += tot[4];
-            for (int p = 0; p < 5; p++) { s.demod_preamblePhase[p] += tot[5 + p]; s.demod_bestPhase[p] += tot[10 + p]; }
-            s.buffers += c_bufs; s.icao_flips += c_flips;
+#define STAT_AT(field) (sv + offsetof(b200_demod_stats, field) / 8)
+            atomicAdd(STAT_AT(samples_processed), c_samples); atomicAdd(STAT_AT(demod_preambles), (unsigned long long)tot[0]);
+            atomicAdd(STAT_AT(demod_rejected_bad), (unsigned long long)tot[1]); atomicAdd(STAT_AT(demod_rejected_unknown_icao), (unsigned long long)tot[2]);
+            atomicAdd(STAT_AT(demod_accepted), (unsigned long long)tot[3]); atomicAdd(STAT_AT(demod_accepted) + 1, (unsigned long long)tot[4]);
+#pragma unroll
+            for (int p = 0; p < 5; p++) { atomicAdd(STAT_AT(demod_preamblePhase) + p, (unsigned long long)tot[5 + p]); atomicAdd(STAT_AT(demod_bestPhase) + p, (unsigned long long)tot[10 + p]); }
+            atomicAdd(STAT_AT(buffers), (unsigned long long)c_bufs); atomicAdd(STAT_AT(icao_flips), (unsigned long long)c_flips);
+#undef STAT_AT
             P.frame_count[stream] = min(nframes, P.frame_cap);
+            if (COMPACT) *n_frames_out = min(nframes, P.frame_cap);
         }
     }
 }
@@ -586,10 +654,10 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const Resolve
     // repairs and repeats the run(s) in order.
     if (P.ctl->overflow & RUN_REPEAT_BITS) return;
     if ((st->cap_log2 != ICAO_CAP_LOG2) != BIG) return;
-    resolve_stream<BIG>(P, S, st, stream);
+    resolve_stream<BIG, false>(P, S, st, stream);
 }
 
-__device__ __noinline__ void resolve_stream_big(const ResolveParams &P, ResolveSmem &S, StreamState *st, uint32_t stream) { resolve_stream<true>(P, S, st, stream); }
+__device__ __noinline__ void resolve_stream_big(const ResolveParams &P, ResolveSmem &S, StreamState *st, uint32_t stream, uint32_t *n_frames_out) { resolve_stream<true, true>(P, S, st, stream, n_frames_out); }
 
 // A context with ONE receiver (the drop-in's shape: one readsb process, one mag_buf per call) needs no grid-wide agreement: this
 // single CTA makes the capacity check for its receiver itself, and assembles the frames when it is done - stage B, the frame
@@ -599,32 +667,42 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 1) resolve_solo_kernel(const Re
     ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
     const uint32_t stream = 0;
     StreamState *st = &P.state[0];
-    __shared__ uint32_t s_go;
-    if (threadIdx.x == 0) {
-        const uint32_t add = P.stream_addable[0];
-        P.stream_addable[0] = 0;
-        uint32_t go = (P.ctl->overflow & RUN_REPEAT_BITS) ? 0u : 1u;
-        if (P.prev_ctl && (P.prev_ctl->overflow & RUN_REPEAT_BITS)) { atomicOr(&P.ctl->overflow, 16u); go = 0; }
-        const uint32_t need = max(st->gen_count[0], st->gen_count[1]) + add;
-        if (go && 2u * need > (1u << st->cap_log2)) {
-            uint32_t lg = st->cap_log2 + 1;
-            while ((1u << lg) < 4u * need && lg < ICAO_MAXBITS + 1) lg++;
-            st->grow_log2 = lg;
-            atomicOr(&P.ctl->overflow, 8u);
-            go = 0;
-        }
-        s_go = go;
-    }
+    __shared__ uint32_t s_nframes;
+#ifdef B200_SOLO_CLOCKS
+    if (threadIdx.x == 0) g_solo_t[0] = gtime();
+#endif
+    if (st->cap_log2 == ICAO_CAP_LOG2) resolve_stream<false, true>(P, S, st, stream, &s_nframes);
+    else resolve_stream_big(P, S, st, stream, &s_nframes);
     __syncthreads();
-    if (s_go) {
-        if (st->cap_log2 == ICAO_CAP_LOG2) resolve_stream<false>(P, S, st, stream);
-        else resolve_stream_big(P, S, st, stream);
-    }
-    __syncthreads();
-    const uint32_t n = s_go ? P.frame_count[0] : 0;
+    const uint32_t n = s_nframes == ~0u ? 0u : s_nframes;         // ~0: stage B did not run (the step is going to be repeated)
     if (threadIdx.x == 0) { P.fin.frame_prefix_out[0] = 0; P.fin.frame_prefix_out[1] = n; P.ctl->total_frames = n; }
     __syncthreads();
+#ifdef B200_SOLO_CLOCKS
+    if (threadIdx.x == 0) g_solo_t[4] = gtime();
+#endif
     finalize_frames(P.fin, threadIdx.x >> 5, RS_WARPS, threadIdx.x & 31);
+    if (P.carry_src && s_nframes != ~0u) {      // (not when the step is going to be repeated: it needs its halo again) every reader of this
+                                                // run's samples - scan kernel, finalizer above - is done: move the tail to the front
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < B200_TRAIL; i += blockDim.x) P.carry_dst[i] = P.carry_src[i];
+    }
+    if (P.publish_dst) {
+        __syncthreads();                                    // the finalizer's writes (all warps) are in place
+        const uint32_t n16 = (P.publish_head + n * (uint32_t)sizeof(b200_frame)) / 16;
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) P.publish_dst[i] = P.publish_src[i];
+        __syncthreads();
+        uint4 *clr = const_cast<uint4 *>(P.publish_src);
+        for (uint32_t i = threadIdx.x; i < P.publish_clear / 16; i += blockDim.x) clr[i] = make_uint4(0, 0, 0, 0);
+    }
+#ifdef B200_SOLO_CLOCKS
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        g_solo_t[5] = gtime();
+        P.ctl->pad0_ = (uint32_t)(g_solo_t[1] - g_solo_t[0]); P.ctl->pad_[0] = (uint32_t)(g_solo_t[2] - g_solo_t[1]);
+        P.ctl->pad_[1] = (uint32_t)(g_solo_t[3] - g_solo_t[2]); P.ctl->stage_need = (uint32_t)(g_solo_t[4] - g_solo_t[3]);
+        P.ctl->rec_alloc = (uint32_t)(g_solo_t[5] - g_solo_t[4]);
+    }
+#endif
 }
 
 // Runs ahead of resolve_kernel on its stream: (1) the asynchronous pipeline's "the step ahead has to be repeated" test, once

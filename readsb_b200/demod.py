@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .abi import BUFRES_DTYPE, CFG_MODE_AC, FRAME_DTYPE, MODEAC_DTYPE, Config, Stats
+from .abi import BUFRES_DTYPE, CFG_MODE_AC, CFG_NO_TIMING, FRAME_DTYPE, MODEAC_DTYPE, Config, Stats
 
 _LIB = None
 LIB_PATH = Path(__file__).resolve().parent / "libb200demod.so"
@@ -112,10 +112,10 @@ class PinnedBuffer:
 class Demodulator:
     def __init__(self, n_streams: int = 1, buf_samples: int = 131072, max_buffers_per_run: int = 1,
                  preamble_threshold: int = 58, nfix_crc: int = 1, fix_df: int = 1, icao_ttl_ms: int = 60000,
-                 device: int = -1, mode_ac: bool = False):
+                 device: int = -1, mode_ac: bool = False, no_timing: bool = False):
         self.L = lib()
         self.cfg = Config(C.sizeof(Config), device, n_streams, buf_samples, max_buffers_per_run,
-                          preamble_threshold, nfix_crc, fix_df, icao_ttl_ms, CFG_MODE_AC if mode_ac else 0)
+                          preamble_threshold, nfix_crc, fix_df, icao_ttl_ms, (CFG_MODE_AC if mode_ac else 0) | (CFG_NO_TIMING if no_timing else 0))
         self.n_streams, self.buf_samples, self.max_buffers_per_run = n_streams, buf_samples, max_buffers_per_run
         h = C.c_void_p()
         rc = self.L.b200_demod_create(C.byref(self.cfg), C.byref(h))

@@ -212,7 +212,7 @@ enum { cudaHostRegisterDefault = 0 };
 typedef struct EmuStream *cudaStream_t;
 typedef struct EmuEvent *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
-enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEventDefault = 0 };
+enum { cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEventDefault = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; size_t totalGlobalMem; size_t sharedMemPerBlockOptin; };
 
@@ -240,6 +240,7 @@ cudaError_t cudaHostAlloc(void **p, size_t n, unsigned flags);
 cudaError_t cudaMallocHost(void **p, size_t n);
 cudaError_t cudaFreeHost(void *p);
 static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t st = nullptr);
