@@ -44,6 +44,9 @@ static void pin_once(struct mag_buf *mag) {
         g_pinned[g_npinned++] = mag->data;
 }
 
+/* readsb_shim_iq.c (optional, -Wl,--wrap=init_converter): the raw IQ the converter hook kept for a mag_buf */
+int b200_shim_iq_lookup(const uint16_t *mag_data, const uint8_t **iq, unsigned *n) __attribute__((weak));
+
 void __real_icaoFilterAdd(uint32_t addr);
 void __real_icaoFilterExpire(void);
 
@@ -95,11 +98,21 @@ void __wrap_demodulate2400(struct mag_buf *mag) {
     if (Modes.stats_15min.samples_dropped && thr < PREAMBLE_THRESHOLD_PIZERO) thr = PREAMBLE_THRESHOLD_PIZERO;
     if (thr != g_thr && b200_demod_set_preamble_threshold(g_ctx, thr) == B200_OK) g_thr = thr;
 
-    pin_once(mag);
     uint32_t n = 0;
-    /* mean_level / mean_power travel with the buffer: demodulate2400AC's noise floor is made from them (demod_2400.c:580-581),
-     * whatever converter filled the mag_buf */
-    if (b200_demod_submit_mag_u16_levels(g_ctx, 0, mag->data, mag->length, mag->sampleTimestamp, mag->mean_level, mag->mean_power) != B200_OK ||
+    const uint8_t *iq = NULL;
+    unsigned iq_n = 0;
+    int rc_submit;
+    if (b200_shim_iq_lookup && b200_shim_iq_lookup(mag->data + Modes.trailing_samples, &iq, &iq_n) && iq_n == mag->length) {
+        /* converter hook active: the frontend's raw uc8 IQ goes up, convert_uc8_nodc (convert.c:64-108) runs on the GPU */
+        rc_submit = b200_demod_submit_iq_uc8(g_ctx, 0, iq, mag->length, mag->sampleTimestamp);
+    } else {
+        iq = NULL;
+        pin_once(mag);
+        /* mean_level / mean_power travel with the buffer: demodulate2400AC's noise floor is made from them (demod_2400.c:580-581),
+         * whatever converter filled the mag_buf */
+        rc_submit = b200_demod_submit_mag_u16_levels(g_ctx, 0, mag->data, mag->length, mag->sampleTimestamp, mag->mean_level, mag->mean_power);
+    }
+    if (rc_submit != B200_OK ||
         b200_demod_run(g_ctx) != B200_OK ||
         b200_demod_fetch(g_ctx, 0, g_frames, sizeof g_frames / sizeof g_frames[0], &n) != B200_OK) {
         fprintf(stderr, "b200 demodulator: %s\n", b200_demod_last_error(g_ctx));
@@ -145,6 +158,10 @@ void __wrap_demodulate2400(struct mag_buf *mag) {
     b200_buffer_result br;
     uint32_t nbr = 0;
     if (b200_demod_buffer_results(g_ctx, 0, &br, 1, &nbr) == B200_OK && nbr == 1) {
+        if (iq && mag->length) {          /* what convert_uc8_nodc would have returned (convert.c:100-107), from the GPU's exact sums */
+            mag->mean_level = br.sum_level / 65536.0 / mag->length;
+            mag->mean_power = br.sum_power / 65535.0 / 65535.0 / mag->length;
+        }
         Modes.stats_current.demod_preambles += br.demod_preambles;
         Modes.stats_current.demod_rejected_bad += br.demod_rejected_bad;
         Modes.stats_current.demod_rejected_unknown_icao += br.demod_rejected_unknown_icao;

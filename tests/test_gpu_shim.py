@@ -20,6 +20,7 @@ from readsb_b200 import synth
 ROOT = Path(__file__).resolve().parent.parent
 CPU = ROOT / "oracle" / "_ref" / "readsb_cpu"
 GPU = ROOT / "oracle" / "_ref" / "readsb_b200"
+GPU_IQ = ROOT / "oracle" / "_ref" / "readsb_b200_iq"      # + integration/readsb_shim_iq.c: the converter call site keeps the raw IQ, the GPU converts
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (CPU.exists() and GPU.exists()), reason="oracle/_ref/readsb_{cpu,b200} not built")]
 
@@ -32,7 +33,7 @@ def _env_for(exe):
     is searched before the binary's RUNPATH — so the whole unmodified reference program runs against the kernels' source on the CPU."""
     global _EMU_DIR
     env = dict(os.environ)
-    if exe == GPU and os.environ.get("B200_EMU") == "1":
+    if exe in (GPU, GPU_IQ) and os.environ.get("B200_EMU") == "1":
         if _EMU_DIR is None:
             import tempfile
             _EMU_DIR = tempfile.mkdtemp(prefix="b200emu_")
@@ -41,8 +42,8 @@ def _env_for(exe):
     return env
 
 
-def _run_pair(args, timeout=180):
-    procs = [subprocess.Popen([str(exe)] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=_env_for(exe)) for exe in (CPU, GPU)]
+def _run_pair(args, timeout=180, exes=(CPU, GPU)):
+    procs = [subprocess.Popen([str(exe)] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=_env_for(exe)) for exe in exes]
     outs = []
     for p in procs:
         out, _ = p.communicate(timeout=timeout)
@@ -85,4 +86,27 @@ def test_reference_program_with_swapped_demodulator(cuda, tmp_path, name, extra,
     assert any(re.search(r"[1-9]\d* accepted with correct CRC", l) for l in block_cpu)
     if "--modeac" in extra:
         assert any(re.search(r"[1-9]\d* Mode A/C messages received", l) for l in block_cpu)
+    assert block_gpu == block_cpu, "\n".join(f"{a!r} | {b!r}" for a, b in zip(block_cpu, block_gpu) if a != b)
+
+
+@pytest.mark.skipif(not GPU_IQ.exists(), reason="oracle/_ref/readsb_b200_iq not built")
+@pytest.mark.parametrize("extra", [["--modeac"], ["--sdr-buffer-size=128"]])
+def test_reference_program_with_converter_hook(cuda, tmp_path, extra):
+    """SURVEY.md 8(b), upstream hand-off #1 / north_star "drops in behind the existing sdr.c callback": init_converter is wrapped
+    too (integration/readsb_shim_iq.c), the frontend's converter call only keeps the raw uc8 IQ and convert_uc8_nodc
+    (convert.c:64-108) runs on the GPU, fused into the scan kernel.  Frames, every demodulator counter and the noise / signal power
+    lines of --stats (which need the converter's exact mean_power) equal the stock program's."""
+    nsamples = 2_400_000 * 2 + 4321
+    cap = tmp_path / "iqhook.bin"
+    synth.generate(nsamples, seed=77, frames_per_sec=3000.0, df_mask=synth.MODEAC | synth.DF17 | synth.DF11 | synth.AP, n_icao=24,
+                   amp=(0.3, 0.9), p_bit_error=0.2).tofile(cap)
+    base = ["--device-type", "ifile", "--ifile", str(cap)] + extra
+    raw_cpu, raw_gpu = _run_pair(base + ["--mlat", "--raw"], exes=(CPU, GPU_IQ))
+    assert "UC8 conversion moved to the GPU" in raw_gpu and "b200 demodulator" not in raw_gpu
+    frames_cpu = [l for l in raw_cpu.splitlines() if l.startswith("@")]
+    frames_gpu = [l for l in raw_gpu.splitlines() if l.startswith("@")]
+    assert len(frames_cpu) > 500 and frames_gpu == frames_cpu
+    st_cpu, st_gpu = _run_pair(base + ["--quiet", "--stats"], exes=(CPU, GPU_IQ))
+    block_cpu, block_gpu = _stats_block(st_cpu), _stats_block(st_gpu)
+    assert any("noise power" in l for l in block_cpu)
     assert block_gpu == block_cpu, "\n".join(f"{a!r} | {b!r}" for a, b in zip(block_cpu, block_gpu) if a != b)
