@@ -20,21 +20,7 @@
 #include "common.h"
 #include "device_utils.cuh"
 
-#define AC_THREADS 512
-#define AC_WARPS (AC_THREADS / 32)
-#define AC_BEHIND 8            // magnitudes kept before the tile origin (1 needed, 8 keeps 16-byte alignment)
-#define AC_AHEAD 80            // after the last position (<= f1 + 69 is read)
-#define AC_TILE 8192           // positions per block iteration = AC_TILE / SCAN_TILE consecutive scan tiles of one segment
-#define AC_NMAG (AC_BEHIND + AC_TILE + AC_AHEAD)
 #define AC_SKIP (20 * 87 / 25 + 1)   // positions hidden by an accepted reply (demod_2400.c:753 + the loop increment)
-
-struct AcSmem {
-    uint16_t lut[128 * 128];                 // folded + swizzled uc8 table, as in the scan kernel
-    alignas(16) uint16_t mag[AC_NMAG + 8];
-    uint16_t q1[AC_TILE];                    // positions that passed the F1 tests (at most 2 of 3 can), then in place: F2 survivors
-    uint32_t bitmap[AC_TILE / 32];
-    uint32_t q1n;
-};
 
 // ---- the reply detector, shared by the scan (magnitudes in shared memory) and the walk (samples from global memory) ----
 
@@ -132,30 +118,63 @@ __global__ void modeac_noise_kernel(const AcScanParams P) {
 }
 
 // ---- stateless scan: one bit per position ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(AC_THREADS, 2) modeac_scan_kernel(const AcScanParams P) {
+// Warp-autonomous, like the Mode S scan: one persistent CTA per SM shares the folded magnitude table; every warp claims scan
+// tiles (2048 positions) from an atomic counter and works on them alone - no block barrier after the table is staged:
+//   convert   the tile's samples (8 before, 104 after: m[-1] .. m[+75] of every position) -> magnitudes in the warp's own shared memory
+//   window    per chunk of 512 positions, 16 per lane: the noise-independent part of the F1 test (rising edge, quiet third sample,
+//             demod_2400.c:630-640) on packed 16-bit halves -> 13 % of the positions on receiver noise
+//   front     the survivors 32 at a time: level against the buffer's noise floor, clock phase, F2 tests (:641-672) -> < 1 %
+//   bits      those few: 20 bit cells against the thresholds, framing (:674-731) -> the position's bit in the map
+// (The block-phased predecessor - load a quad, barrier, F1 tests, barrier, F2 / bit cells, barrier - took 0.58 ms per 134 M
+// samples at 2.6 warp instructions per sample; see profiles/.)
+#define AC2_WARPS 28
+#define AC2_BEHIND 8
+#define AC2_AHEAD 104
+#define AC2_NMAG (AC2_BEHIND + SCAN_TILE + AC2_AHEAD)      // 2160 = 270 pieces of 8
+#define AC2_Q2 64                                          // pooled over the tile and worked off 32 at a time (they are < 1 % of the positions)
+
+struct AcWarpSmem {
+    alignas(16) uint16_t mag[AC2_NMAG];      // mag[AC2_BEHIND + p] = magnitude at tile position p
+    uint16_t q1[512];                        // positions of the chunk that passed the edge test (tile-relative, ascending)
+    uint4 q2[AC2_Q2];                        // survivors of the front tests waiting for their bit cells: position, f1_sample, f1_clock, f1f2 level
+    uint32_t q2_noise[AC2_Q2];
+    uint32_t bits[SCAN_TILE / 32];
+};
+
+struct Ac2Smem {
+    uint16_t lut[128 * 128];
+    AcWarpSmem w[AC2_WARPS];
+};
+
+__device__ __forceinline__ uint32_t ac_vmin2(uint32_t a, uint32_t b) { uint32_t d; asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+
+__global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const AcScanParams P) {
     extern __shared__ __align__(16) unsigned char ac_smem_raw[];
-    AcSmem &S = *reinterpret_cast<AcSmem *>(ac_smem_raw);
+    Ac2Smem &S = *reinterpret_cast<Ac2Smem *>(ac_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (P.ctl->overflow & 3u) return;
     {   // the folded table, once per CTA
         const uint4 *src = reinterpret_cast<const uint4 *>(P.tables->lut_fold);
         uint4 *dst = reinterpret_cast<uint4 *>(S.lut);
-        for (uint32_t i = tid; i < 128 * 128 * 2 / 16; i += AC_THREADS) dst[i] = src[i];
+        for (uint32_t i = tid; i < 128 * 128 * 2 / 16; i += AC2_WARPS * 32) dst[i] = src[i];
     }
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const uint32_t ts = P.tile_seg[tile];
-        if (!(ts & TILE_QUAD_START)) continue;                              // a block iteration covers one quad: the scan tiles [tile, tile + 4) of the segment
-        const Segment seg = P.segs[ts & ~TILE_QUAD_START];
-        const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;
+    __syncthreads();          // the only block barrier
+    AcWarpSmem &W = S.w[wid];
+    const uint32_t lt = (1u << lane) - 1u;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&P.ctl->pad_[0], 1u);
+        tile = __shfl_sync(FULLMASK, tile, 0);
+        if (tile >= P.n_tiles) break;
+        const Segment seg = P.segs[P.tile_seg[tile] & ~TILE_QUAD_START];
+        const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;               // tile coordinate x = data index + lead
         const uint32_t x_data_end = seg.lead + seg.npos + B200_TRAIL;
         const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;
         const bool is_mag = seg.flags & SEG_MAG;
-        __syncthreads();                                                   // the previous iteration's bitmap has been written out
-        if (tid < AC_TILE / 32) S.bitmap[tid] = 0;
-        if (tid == 0) S.q1n = 0;
-        // magnitudes of tile coordinates [x0 - AC_BEHIND, x0 + AC_TILE + AC_AHEAD): shared index = x - x0 + AC_BEHIND
-        for (uint32_t c = tid; c < AC_NMAG / 8; c += AC_THREADS) {
-            const int64_t xc = (int64_t)x0 - AC_BEHIND + (int64_t)c * 8;
+        __syncwarp();
+        // ---- convert: magnitudes of tile coordinates [x0 - 8, x0 + 2048 + 104) ------------------------------------------
+        for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32) {
+            const int64_t xc = (int64_t)x0 - AC2_BEHIND + (int64_t)c * 8;
             uint32_t m[8];
             if (xc < 0 || xc + 8 <= (int64_t)x_zero_end || xc >= (int64_t)x_data_end) {
 #pragma unroll
@@ -174,110 +193,95 @@ __global__ void __launch_bounds__(AC_THREADS, 2) modeac_scan_kernel(const AcScan
                 }
             }
             uint4 packed;
-            packed.x = m[0] | (m[1] << 16); packed.y = m[2] | (m[3] << 16);
-            packed.z = m[4] | (m[5] << 16); packed.w = m[6] | (m[7] << 16);
-            *reinterpret_cast<uint4 *>(&S.mag[c * 8]) = packed;
+            packed.x = __byte_perm(m[0], m[1], 0x5410); packed.y = __byte_perm(m[2], m[3], 0x5410);
+            packed.z = __byte_perm(m[4], m[5], 0x5410); packed.w = __byte_perm(m[6], m[7], 0x5410);
+            *reinterpret_cast<uint4 *>(&W.mag[c * 8]) = packed;
         }
-        __syncthreads();
+        W.bits[lane] = 0; W.bits[lane + 32] = 0;
+        __syncwarp();
 
         // position p of the tile = data index d_tile0 + p of the segment = f1_sample (d mod buf_len) of buffer d / buf_len
         const int64_t d_tile0 = (int64_t)x0 - (int64_t)seg.lead;
         const uint32_t bt = d_tile0 > 0 ? (uint32_t)d_tile0 / seg.buf_len : 0;     // buffer of the tile's first position
         const int64_t bt_d0 = (int64_t)bt * seg.buf_len;
 
-        // ---- phase A: F1 edge / quiet / level for 8 consecutive positions per thread, two passes ------------------
+        uint32_t n2 = 0;                   // survivors waiting in W.q2
 #pragma unroll 1
-        for (uint32_t pass = 0; pass < AC_TILE / (8 * AC_THREADS); pass++) {
-            const uint32_t p = 8 * (pass * AC_THREADS + tid);
-            const uint16_t *mp = &S.mag[p + AC_BEHIND];
-            uint32_t v[11];
-            v[0] = mp[-1];
+        for (uint32_t c = 0; c < SCAN_TILE / 512; c++) {
+            // ---- window: rising edge and quiet third sample for this lane's 16 positions, two per step on packed halves ----
+            const uint32_t p0 = c * 512 + lane * 16;
+            uint32_t mask;
             {
-                const uint4 B = *reinterpret_cast<const uint4 *>(mp);
-                const uint32_t Cw = *reinterpret_cast<const uint32_t *>(mp + 8);
-                v[1] = B.x & 0xffffu; v[2] = B.x >> 16; v[3] = B.y & 0xffffu; v[4] = B.y >> 16;
-                v[5] = B.z & 0xffffu; v[6] = B.z >> 16; v[7] = B.w & 0xffffu; v[8] = B.w >> 16;
-                v[9] = Cw & 0xffffu; v[10] = Cw >> 16;
-            }
-            // which of the 8 positions are f1_sample values of this segment (1 <= f1_sample < length), and their noise floor
-            const int64_t d0 = d_tile0 + p;
-            uint32_t valid = 0, noise2 = 0;
-            if (d0 + 8 > 0 && d0 < (int64_t)seg.npos) {
-                uint32_t b = bt;
-                int64_t jj = d0 - bt_d0;
-                while (jj >= (int64_t)seg.buf_len) { jj -= seg.buf_len; b++; }
-                const uint32_t len_b = b < seg.n_bufs ? min(seg.buf_len, seg.npos - b * seg.buf_len) : 0;
-                if (d0 >= 0 && jj + 8 <= (int64_t)len_b) {          // all eight in buffer b: level test here, with its noise floor
-                    valid = jj == 0 ? 0xfeu : 0xffu;
-                    noise2 = 2 * P.noise[seg.first_buf + b];
-                } else {                                             // straddles a buffer edge: level test left to phase B
+                const uint4 *src = reinterpret_cast<const uint4 *>(&W.mag[p0]);          // samples p0 - 8 .. p0 + 23
+                const uint4 q0 = src[0], q1v = src[1], q2 = src[2], q3 = src[3];
+                const uint32_t wv[16] = {q0.x, q0.y, q0.z, q0.w, q1v.x, q1v.y, q1v.z, q1v.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                // wv[4 + k] = (m[2k], m[2k+1]) relative to p0; xs[k] = (m[2k+1], m[2k+2]); xs[-1] = (m[-1], m[0])
+                uint32_t acc2 = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int64_t d = d0 + i;
-                        if (d < 0 || d >= (int64_t)seg.npos) continue;
-                        const int64_t ji = jj + i < (int64_t)seg.buf_len ? jj + i : jj + i - seg.buf_len;
-                        if (ji >= 1) valid |= 1u << i;
+                for (int k = 7; k >= 0; k--) {
+                    const uint32_t bq = wv[4 + k];                                        // b: m[0] of both positions
+                    const uint32_t aq = __funnelshift_r(wv[3 + k], wv[4 + k], 16);        // a: m[-1]
+                    const uint32_t cq = __funnelshift_r(wv[4 + k], wv[5 + k], 16);        // c: m[1]
+                    const uint32_t eq = wv[5 + k];                                        // e: m[2]
+                    const uint32_t d1 = bq - ac_vmin2(aq, bq);                            // != 0  <=>  m[-1] < m[0]
+                    const uint32_t d2 = eq - ac_vmin2(eq, ac_vmin2(bq, cq));              // == 0  <=>  m[2] <= m[0] && m[2] <= m[1]
+                    const uint32_t okq = ac_vmin2(d1, 0x00010001u) & ~ac_vmin2(d2, 0x00010001u);
+                    acc2 = acc2 * 4u + okq;
+                }
+                mask = (acc2 & 0xffffu) | (acc2 >> 15);
+            }
+            // ---- the passers, in order ------------------------------------------------------------------------------------
+            uint32_t n1;
+            uint32_t off = warp_excl_scan(__popc(mask), lane, &n1);
+            while (mask) { const uint32_t i = __ffs(mask) - 1; mask &= mask - 1; W.q1[off++] = (uint16_t)(p0 + i); }
+            __syncwarp();
+            // ---- front: level, clock phase, F2 (32 passers at a time); bits: the survivors of the batch ---------------------
+            for (uint32_t r0 = 0; r0 < n1; r0 += 32) {
+                const bool has = r0 + lane < n1;
+                const uint32_t p = has ? W.q1[r0 + lane] : 0;
+                bool surv = false;
+                uint32_t f1_clock = 0, f1f2 = 0, jj32 = 0, noise = 0;
+                if (has) {
+                    const int64_t d = d_tile0 + p;
+                    if (d >= 0 && d < (int64_t)seg.npos) {
+                        uint32_t b = bt;
+                        int64_t jj = d - bt_d0;
+                        while (jj >= (int64_t)seg.buf_len) { jj -= seg.buf_len; b++; }
+                        if (jj >= 1) {                                       // f1_sample runs from 1 (demod_2400.c:612)
+                            jj32 = (uint32_t)jj;
+                            noise = P.noise[seg.first_buf + b];
+                            surv = ac_front(SmemMag{&W.mag[p + AC2_BEHIND]}, jj32, noise, &f1_clock, &f1f2);
+                        }
                     }
                 }
-            }
-            uint32_t mask = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint32_t a = v[i], b = v[i + 1], c = v[i + 2], e = v[i + 3];
-                const bool ok = a < b && e <= b && e <= c && ((b + c) >> 1) >= noise2;
-                mask |= ok ? 1u << i : 0u;
-            }
-            mask &= valid;
-            uint32_t wtot;
-            uint32_t off = warp_excl_scan(__popc(mask), lane, &wtot);
-            uint32_t base = 0;
-            if (lane == 0 && wtot) base = atomicAdd(&S.q1n, wtot);
-            off += __shfl_sync(FULLMASK, base, 0);
-            while (mask) { const uint32_t i = __ffs(mask) - 1; mask &= mask - 1; S.q1[off++] = (uint16_t)(p + i); }
-        }
-        __syncthreads();
-
-        // ---- phase B: clock phase + F2 tests over the warp's slice of the queue, survivors compacted in place;
-        //      phase C: bit cells of the survivors ----------------------------------------------------------------
-        {
-            const uint32_t n1 = S.q1n;
-            const uint32_t lo = n1 * wid / AC_WARPS, hi = n1 * (wid + 1) / AC_WARPS;
-            uint32_t wr = lo;
-            for (uint32_t r0 = lo; r0 < hi; r0 += 32) {
-                const bool has = r0 + lane < hi;
-                const uint32_t p = has ? S.q1[r0 + lane] : 0;
-                bool surv = false;
-                if (has) {
-                    uint32_t b = bt;
-                    int64_t jj = d_tile0 + p - bt_d0;
-                    while (jj >= (int64_t)seg.buf_len) { jj -= seg.buf_len; b++; }
-                    uint32_t f1_clock, f1f2;
-                    surv = ac_front(SmemMag{&S.mag[p + AC_BEHIND]}, (uint32_t)jj, P.noise[seg.first_buf + b], &f1_clock, &f1f2);
-                }
                 const uint32_t bal = __ballot_sync(FULLMASK, surv);
-                if (surv) S.q1[wr + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
-                wr += __popc(bal);
+                if (surv) { const uint32_t at = n2 + __popc(bal & lt); W.q2[at] = make_uint4(p, jj32, f1_clock, f1f2); W.q2_noise[at] = noise; }
+                n2 += __popc(bal);
                 __syncwarp();
-            }
-            for (uint32_t r0 = lo; r0 < wr; r0 += 32) {
-                if (r0 + lane < wr) {
-                    const uint32_t p = S.q1[r0 + lane];
-                    uint32_t b = bt;
-                    int64_t jj = d_tile0 + p - bt_d0;
-                    while (jj >= (int64_t)seg.buf_len) { jj -= seg.buf_len; b++; }
-                    const uint32_t noise = P.noise[seg.first_buf + b];
-                    const SmemMag m{&S.mag[p + AC_BEHIND]};
-                    uint32_t f1_clock = 0, f1f2 = 0;
-                    ac_front(m, (uint32_t)jj, noise, &f1_clock, &f1f2);
-                    if (ac_bits(m, (uint32_t)jj, noise, f1_clock, f1f2) != 0xffffffffu) atomicOr(&S.bitmap[p >> 5], 1u << (p & 31));
+                if (n2 >= 32) {            // bit cells of 32 pooled survivors
+                    const uint4 e = W.q2[lane];
+                    if (ac_bits(SmemMag{&W.mag[e.x + AC2_BEHIND]}, e.y, W.q2_noise[lane], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[e.x >> 5], 1u << (e.x & 31));
+                    __syncwarp();
+                    const uint4 mv = lane + 32 < n2 ? W.q2[lane + 32] : make_uint4(0, 0, 0, 0);
+                    const uint32_t mn = lane + 32 < n2 ? W.q2_noise[lane + 32] : 0;
+                    __syncwarp();
+                    W.q2[lane] = mv; W.q2_noise[lane] = mn;
+                    n2 -= 32;
+                    __syncwarp();
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();
-        {   // one bit per position; only the words of this segment's own scan tiles
-            const uint32_t words = min((uint32_t)(AC_TILE / 32), (seg.tile_begin + seg.n_tiles - tile) * (SCAN_TILE / 32));
-            if (tid < words) P.bitmap[(size_t)tile * (SCAN_TILE / 32) + tid] = S.bitmap[tid];
+        if (n2) {                          // the rest of the tile's survivors
+            if (lane < n2) {
+                const uint4 e = W.q2[lane];
+                if (ac_bits(SmemMag{&W.mag[e.x + AC2_BEHIND]}, e.y, W.q2_noise[lane], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[e.x >> 5], 1u << (e.x & 31));
+            }
+            __syncwarp();
         }
+        // one bit per position of this scan tile
+        uint32_t *dst = P.bitmap + (size_t)tile * (SCAN_TILE / 32);
+        dst[lane] = W.bits[lane]; dst[lane + 32] = W.bits[lane + 32];
     }
 }
 
@@ -352,17 +356,17 @@ __global__ void modeac_stats_kernel(const AcWalkParams P, const uint32_t *prefix
 }
 
 extern "C" int b200_prepare_modeac(void) {      // per device, from b200_demod_create
-    return (int)cudaFuncSetAttribute(modeac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcSmem));
+    return (int)cudaFuncSetAttribute(modeac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ac2Smem));
 }
 
 extern "C" int b200_launch_modeac(const AcScanParams *sp, const AcWalkParams *wp, int n_sm, void *stream) {
     if (sp->n_segs) {       // also for a run of empty buffers only (no tiles): the walk is what sets every buffer's reply count, zero included
         modeac_noise_kernel<<<min(sp->n_segs, 1024u), 32, 0, (cudaStream_t)stream>>>(*sp);
         if (sp->n_tiles) {
-            // three of four scan tiles are skipped (AC_TILE = 4 scan tiles): an odd grid gives every block the same share of the fourth
-            uint32_t grid = (uint32_t)n_sm * 2 - 1;       // odd and not more than one wave (2 CTAs per SM)
-            if (grid > sp->n_tiles) grid = sp->n_tiles;
-            modeac_scan_kernel<<<grid, AC_THREADS, sizeof(AcSmem), (cudaStream_t)stream>>>(*sp);
+            uint32_t grid = (uint32_t)n_sm;               // one persistent CTA per SM, its warps claim scan tiles
+            const uint32_t need = (sp->n_tiles + AC2_WARPS - 1) / AC2_WARPS;
+            if (grid > need) grid = need;
+            modeac_scan_kernel<<<grid, AC2_WARPS * 32, sizeof(Ac2Smem), (cudaStream_t)stream>>>(*sp);
         }
         modeac_walk_kernel<<<wp->n_segs, 256, 0, (cudaStream_t)stream>>>(*wp);
     }
