@@ -121,9 +121,9 @@ __global__ void modeac_noise_kernel(const AcScanParams P) {
 // Warp-autonomous, like the Mode S scan: one persistent CTA per SM shares the folded magnitude table; every warp claims scan
 // tiles (2048 positions) from an atomic counter and works on them alone - no block barrier after the table is staged:
 //   convert   the tile's samples (8 before, 104 after: m[-1] .. m[+75] of every position) -> magnitudes in the warp's own shared memory
-//   window    per chunk of 512 positions, 16 per lane: the noise-independent part of the F1 test (rising edge, quiet third sample,
-//             demod_2400.c:630-640) on packed 16-bit halves -> 13 % of the positions on receiver noise
-//   front     the survivors 32 at a time: level against the buffer's noise floor, clock phase, F2 tests (:641-672) -> < 1 %
+//   window    16 positions per lane: the noise-independent part of the F1 test (rising edge, quiet third sample, demod_2400.c:630-640)
+//             on packed 16-bit halves -> a bit per position; F2 must pass the same test 48 or 49 positions on -> 3 % candidates
+//   front     the candidates 32 at a time: level against the buffer's noise floor, clock phase, F2 tests (:641-672) -> < 1 %
 //   bits      those few: 20 bit cells against the thresholds, framing (:674-731) -> the position's bit in the map
 // (The block-phased predecessor - load a quad, barrier, F1 tests, barrier, F2 / bit cells, barrier - took 0.58 ms per 134 M
 // samples at 2.6 warp instructions per sample; see profiles/.)
@@ -135,9 +135,9 @@ __global__ void modeac_noise_kernel(const AcScanParams P) {
 
 struct AcWarpSmem {
     alignas(16) uint16_t mag[AC2_NMAG];      // mag[AC2_BEHIND + p] = magnitude at tile position p
-    uint16_t q1[512];                        // positions of the chunk that passed the edge test (tile-relative, ascending)
-    uint4 q2[AC2_Q2];                        // survivors of the front tests waiting for their bit cells: position, f1_sample, f1_clock, f1f2 level
-    uint32_t q2_noise[AC2_Q2];
+    uint16_t edge[SCAN_TILE / 16 + 8];       // 16 positions per entry: bit i = position 16 e + i passes the edge / quiet-sample test
+    uint16_t q1[512 + 32];                   // candidate positions (tile-relative, ascending): a chunk's, behind up to 31 left over
+    uint4 q2[AC2_Q2];                        // survivors of the front tests waiting for their bit cells: position | buffer << 16, f1_sample, f1_clock, f1f2 level
     uint32_t bits[SCAN_TILE / 32];
 };
 
@@ -205,42 +205,57 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
         const uint32_t bt = d_tile0 > 0 ? (uint32_t)d_tile0 / seg.buf_len : 0;     // buffer of the tile's first position
         const int64_t bt_d0 = (int64_t)bt * seg.buf_len;
 
-        uint32_t n2 = 0;                   // survivors waiting in W.q2
+        // ---- window: rising edge and quiet third sample (demod_2400.c:630-640: m[-1] < m[0], m[2] <= m[0], m[2] <= m[1]) for every
+        //      position of the tile and the 64 after it, two positions per step on packed halves -> one bit each in W.edge.
+        //      The F2 pulse of a reply whose F1 starts at p starts at p + 48 or p + 49 (f1_clock lies in [25 j, 25 j + 25], :651-660)
+        //      and has to pass the very same three tests (:662-668): only positions with edge(p) && (edge(p+48) || edge(p+49)) can
+        //      be replies - 3 % of the positions on receiver noise instead of 13 %, by bit arithmetic alone.
 #pragma unroll 1
-        for (uint32_t c = 0; c < SCAN_TILE / 512; c++) {
-            // ---- window: rising edge and quiet third sample for this lane's 16 positions, two per step on packed halves ----
+        for (uint32_t c = 0; c < SCAN_TILE / 512 + 1; c++) {
+            if (c == SCAN_TILE / 512 && lane >= 4) break;                                     // look-ahead: 64 positions
             const uint32_t p0 = c * 512 + lane * 16;
-            uint32_t mask;
-            {
-                const uint4 *src = reinterpret_cast<const uint4 *>(&W.mag[p0]);          // samples p0 - 8 .. p0 + 23
-                const uint4 q0 = src[0], q1v = src[1], q2 = src[2], q3 = src[3];
-                const uint32_t wv[16] = {q0.x, q0.y, q0.z, q0.w, q1v.x, q1v.y, q1v.z, q1v.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-                // wv[4 + k] = (m[2k], m[2k+1]) relative to p0; xs[k] = (m[2k+1], m[2k+2]); xs[-1] = (m[-1], m[0])
-                uint32_t acc2 = 0;
+            const uint4 *src = reinterpret_cast<const uint4 *>(&W.mag[p0]);                   // samples p0 - 8 .. p0 + 23
+            const uint4 q0 = src[0], q1v = src[1], q2 = src[2], q3 = src[3];
+            const uint32_t wv[16] = {q0.x, q0.y, q0.z, q0.w, q1v.x, q1v.y, q1v.z, q1v.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+            // wv[4 + k] = (m[2k], m[2k+1]) relative to p0
+            uint32_t acc2 = 0;
 #pragma unroll
-                for (int k = 7; k >= 0; k--) {
-                    const uint32_t bq = wv[4 + k];                                        // b: m[0] of both positions
-                    const uint32_t aq = __funnelshift_r(wv[3 + k], wv[4 + k], 16);        // a: m[-1]
-                    const uint32_t cq = __funnelshift_r(wv[4 + k], wv[5 + k], 16);        // c: m[1]
-                    const uint32_t eq = wv[5 + k];                                        // e: m[2]
-                    const uint32_t d1 = bq - ac_vmin2(aq, bq);                            // != 0  <=>  m[-1] < m[0]
-                    const uint32_t d2 = eq - ac_vmin2(eq, ac_vmin2(bq, cq));              // == 0  <=>  m[2] <= m[0] && m[2] <= m[1]
-                    const uint32_t okq = ac_vmin2(d1, 0x00010001u) & ~ac_vmin2(d2, 0x00010001u);
-                    acc2 = acc2 * 4u + okq;
-                }
-                mask = (acc2 & 0xffffu) | (acc2 >> 15);
+            for (int k = 7; k >= 0; k--) {
+                const uint32_t bq = wv[4 + k];                                        // b: m[0] of both positions
+                const uint32_t aq = __funnelshift_r(wv[3 + k], wv[4 + k], 16);        // a: m[-1]
+                const uint32_t cq = __funnelshift_r(wv[4 + k], wv[5 + k], 16);        // c: m[1]
+                const uint32_t eq = wv[5 + k];                                        // e: m[2]
+                const uint32_t d1 = bq - ac_vmin2(aq, bq);                            // != 0  <=>  m[-1] < m[0]
+                const uint32_t d2 = eq - ac_vmin2(eq, ac_vmin2(bq, cq));              // == 0  <=>  m[2] <= m[0] && m[2] <= m[1]
+                const uint32_t okq = ac_vmin2(d1, 0x00010001u) & ~ac_vmin2(d2, 0x00010001u);
+                acc2 = acc2 * 4u + okq;
             }
-            // ---- the passers, in order ------------------------------------------------------------------------------------
-            uint32_t n1;
-            uint32_t off = warp_excl_scan(__popc(mask), lane, &n1);
-            while (mask) { const uint32_t i = __ffs(mask) - 1; mask &= mask - 1; W.q1[off++] = (uint16_t)(p0 + i); }
-            __syncwarp();
-            // ---- front: level, clock phase, F2 (32 passers at a time); bits: the survivors of the batch ---------------------
-            for (uint32_t r0 = 0; r0 < n1; r0 += 32) {
+            W.edge[c * 32 + lane] = (uint16_t)((acc2 & 0xffffu) | (acc2 >> 15));
+        }
+        __syncwarp();
+
+        uint32_t n1 = 0, n2 = 0;           // candidates waiting in W.q1, front-test survivors waiting in W.q2
+#pragma unroll 1
+        for (uint32_t c = 0; c <= SCAN_TILE / 512; c++) {
+            const bool last = c == SCAN_TILE / 512;
+            if (!last) {
+                // ---- candidates of this chunk, in order, behind those left over from the chunk before -----------------------
+                const uint32_t p0 = c * 512 + lane * 16, e = c * 32 + lane;
+                const uint32_t f2 = (uint32_t)W.edge[e + 3] | ((uint32_t)W.edge[e + 4] << 16);     // edge bits of p0 + 48 ...
+                uint32_t mask = (uint32_t)W.edge[e] & (f2 | (f2 >> 1)) & 0xffffu;
+                uint32_t tot;
+                uint32_t off = n1 + warp_excl_scan(__popc(mask), lane, &tot);
+                while (mask) { const uint32_t i = __ffs(mask) - 1; mask &= mask - 1; W.q1[off++] = (uint16_t)(p0 + i); }
+                n1 += tot;
+                __syncwarp();
+            }
+            // ---- front: level, clock phase, F2 (demod_2400.c:641-672), 32 candidates at a time (the rest waits for the next chunk) ----
+            uint32_t r0 = 0;
+            for (; r0 + 32 <= n1 || (last && r0 < n1); r0 += 32) {
                 const bool has = r0 + lane < n1;
                 const uint32_t p = has ? W.q1[r0 + lane] : 0;
                 bool surv = false;
-                uint32_t f1_clock = 0, f1f2 = 0, jj32 = 0, noise = 0;
+                uint32_t f1_clock = 0, f1f2 = 0, jj32 = 0, brel = 0;
                 if (has) {
                     const int64_t d = d_tile0 + p;
                     if (d >= 0 && d < (int64_t)seg.npos) {
@@ -248,34 +263,42 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
                         int64_t jj = d - bt_d0;
                         while (jj >= (int64_t)seg.buf_len) { jj -= seg.buf_len; b++; }
                         if (jj >= 1) {                                       // f1_sample runs from 1 (demod_2400.c:612)
-                            jj32 = (uint32_t)jj;
-                            noise = P.noise[seg.first_buf + b];
+                            jj32 = (uint32_t)jj; brel = b - bt;
+                            const uint32_t noise = P.noise[seg.first_buf + b];
                             surv = ac_front(SmemMag{&W.mag[p + AC2_BEHIND]}, jj32, noise, &f1_clock, &f1f2);
                         }
                     }
                 }
                 const uint32_t bal = __ballot_sync(FULLMASK, surv);
-                if (surv) { const uint32_t at = n2 + __popc(bal & lt); W.q2[at] = make_uint4(p, jj32, f1_clock, f1f2); W.q2_noise[at] = noise; }
+                if (surv) W.q2[n2 + __popc(bal & lt)] = make_uint4(p | (brel << 16), jj32, f1_clock, f1f2);
                 n2 += __popc(bal);
                 __syncwarp();
                 if (n2 >= 32) {            // bit cells of 32 pooled survivors
                     const uint4 e = W.q2[lane];
-                    if (ac_bits(SmemMag{&W.mag[e.x + AC2_BEHIND]}, e.y, W.q2_noise[lane], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[e.x >> 5], 1u << (e.x & 31));
+                    const uint32_t ep = e.x & 0xffffu;
+                    if (ac_bits(SmemMag{&W.mag[ep + AC2_BEHIND]}, e.y, P.noise[seg.first_buf + bt + (e.x >> 16)], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[ep >> 5], 1u << (ep & 31));
                     __syncwarp();
                     const uint4 mv = lane + 32 < n2 ? W.q2[lane + 32] : make_uint4(0, 0, 0, 0);
-                    const uint32_t mn = lane + 32 < n2 ? W.q2_noise[lane + 32] : 0;
                     __syncwarp();
-                    W.q2[lane] = mv; W.q2_noise[lane] = mn;
+                    W.q2[lane] = mv;
                     n2 -= 32;
                     __syncwarp();
                 }
             }
+            if (r0 && r0 < n1) {           // fewer than 32 left: to the front of the queue
+                const uint32_t keep = n1 - r0;
+                const uint32_t v = lane < keep ? W.q1[r0 + lane] : 0;
+                __syncwarp();
+                if (lane < keep) W.q1[lane] = (uint16_t)v;
+                n1 = keep;
+            } else if (r0) n1 = 0;
             __syncwarp();
         }
         if (n2) {                          // the rest of the tile's survivors
             if (lane < n2) {
                 const uint4 e = W.q2[lane];
-                if (ac_bits(SmemMag{&W.mag[e.x + AC2_BEHIND]}, e.y, W.q2_noise[lane], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[e.x >> 5], 1u << (e.x & 31));
+                const uint32_t ep = e.x & 0xffffu;
+                if (ac_bits(SmemMag{&W.mag[ep + AC2_BEHIND]}, e.y, P.noise[seg.first_buf + bt + (e.x >> 16)], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[ep >> 5], 1u << (ep & 31));
             }
             __syncwarp();
         }
