@@ -173,6 +173,24 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
         const bool is_mag = seg.flags & SEG_MAG;
         __syncwarp();
         // ---- convert: magnitudes of tile coordinates [x0 - 8, x0 + 2048 + 104) ------------------------------------------
+        if (x0 >= x_zero_end + AC2_BEHIND && x0 + SCAN_TILE + AC2_AHEAD <= x_data_end) {
+            // a tile in the interior of the data (nearly all of them): no piece needs a bounds test
+            const uint8_t *src = seg.base + 2 * ((int64_t)x0 - AC2_BEHIND - (int64_t)seg.lead);
+            for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32) {
+                const uint4 raw = ldg_stream_u4(src + (size_t)c * 16);
+                const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
+                uint4 packed;
+                if (is_mag) packed = raw;
+                else {
+                    uint32_t m[8];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) uc8_pair_to_mag(S.lut, wv[i], m[2 * i], m[2 * i + 1]);
+                    packed.x = __byte_perm(m[0], m[1], 0x5410); packed.y = __byte_perm(m[2], m[3], 0x5410);
+                    packed.z = __byte_perm(m[4], m[5], 0x5410); packed.w = __byte_perm(m[6], m[7], 0x5410);
+                }
+                *reinterpret_cast<uint4 *>(&W.mag[c * 8]) = packed;
+            }
+        } else
         for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32) {
             const int64_t xc = (int64_t)x0 - AC2_BEHIND + (int64_t)c * 8;
             uint32_t m[8];
