@@ -314,9 +314,10 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
     c->n_sm_scan = c->n_sm;
-    // Pipelined steps: the persistent scan grid leaves four SMs to stage B + finalize of the step before, which then run beside the
-    // scan instead of alternating with it (measured on 148 SMs: 148 -> 0.519, 144 -> 0.472, 140 -> 0.475 ms per step).
-    c->n_sm_scan_async = c->n_sm > 32 ? c->n_sm - 4 : c->n_sm;
+    // Pipelined steps could leave a few SMs to stage B + finalize of the step before (B200_SCAN_SMS).  Measured on 148 SMs with this
+    // code: 148 -> 0.492, 146 -> 0.494, 144 -> 0.498, 140 -> 0.507 ms per launch (tools/gpu_scan_sms.sh): the whole chip for the scan wins
+    // since stage B got shorter; with round 1's stage B it was 148 -> 0.519, 144 -> 0.472.
+    c->n_sm_scan_async = c->n_sm;
     if (const char *e = getenv("B200_SCAN_SMS")) {       // experiment knob (tools/): in the pipelined modes the scan of step n+1 and stage B of
         const int v = atoi(e);                           // step n alternate on the SMs; a scan grid smaller than the chip lets them overlap
         if (v >= 1 && v <= c->n_sm) c->n_sm_scan = c->n_sm_scan_async = v;
