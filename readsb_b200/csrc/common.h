@@ -140,6 +140,10 @@ struct ScanParams {
     BufAcc *buf_acc;
     RunCtl *ctl;
     uint32_t rec_cap;            // records rec_pool / key_pool hold
+    // A run of ONE segment (one receiver, one buffer: the drop-in's call shape) carries its descriptor in the kernel parameters: no
+    // descriptor upload in front of the kernels.  one_seg_valid: segs / tile_seg are not read, every tile belongs to one_seg.
+    Segment one_seg;
+    uint32_t one_seg_valid;
     uint32_t warps_per_cta;      // set by the launcher: warps of each CTA that take work (a small run is spread over many SMs, few warps each)
     uint32_t need_lut;           // some segment holds uc8 IQ: the magnitude table has to be staged (a pure magnitude hand-off skips it)
     int32_t thr;                 // Modes.preambleThreshold
@@ -162,6 +166,8 @@ struct FinalizeParams {
     const uint32_t *frame_count;
     const uint32_t *frame_prefix;     // exclusive prefix of frame_count (device computed)
     uint32_t *frame_prefix_out;       // the same array, for the one-receiver launch that computes it itself
+    Segment one_seg;                  // (see ScanParams) the run's only segment, when one_seg_valid
+    uint32_t one_seg_valid;
     uint32_t frame_cap;
     b200_frame *packed;               // all frames of the run, stream-major
     const Rec *rec_pool;
@@ -189,6 +195,8 @@ struct ResolveParams {
     const RunCtl *prev_ctl;           // asynchronous pipeline: control block of the step ahead of this one (or nullptr)
     int32_t ttl_ms;
     uint32_t *stream_addable;         // [n_streams] upper bound of the filter adds of this run (scan kernel); read and zeroed by the capacity check
+    Segment one_seg;                  // (see ScanParams) the run's only segment, when one_seg_valid
+    uint32_t one_seg_valid;
     uint32_t solo;                    // one receiver in the context: capacity check, stage B, frame prefix and finalizer in ONE launch
     FinalizeParams fin;               // (solo) what the finalizer needs
     // (solo, optional) the kernel PUBLISHES the run's result block itself: copies publish_head bytes + the packed frames from

@@ -83,6 +83,7 @@ struct Slot {
     uint32_t launches = 0;
     uint32_t first_frames = 0;        // packed frames that came with the result block's copy
     uint32_t carry_in_kernel = 0xffffffffu;   // one-receiver host run: byte offset of the tail the stage B kernel carries to the front
+    bool desc_on_device = true;       // false: this run's descriptors went as kernel parameters (b200_demod_fetch_beast uploads them if asked)
     bool published = false, timed = true;   // this run: results published by the kernel / events recorded between the kernels
 };
 
@@ -522,7 +523,10 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
         if (succ.in_flight) CU(c, cudaStreamWaitEvent(pre, succ.ev[2], 0));
     }
     layout_run(c, sl);
-    CU(c, cudaMemcpyAsync(sl.d_desc, sl.h_desc, sl.desc_bytes, cudaMemcpyHostToDevice, pre));
+    // One receiver, one segment, no Mode A/C (the drop-in's call shape): the descriptor rides in the kernel parameters
+    const bool one_seg = S == 1 && sl.nseg == 1 && !(c->cfg.flags & B200_CFG_MODE_AC) && scan == res;
+    sl.desc_on_device = !one_seg;
+    if (!one_seg) CU(c, cudaMemcpyAsync(sl.d_desc, sl.h_desc, sl.desc_bytes, cudaMemcpyHostToDevice, pre));
     if (c->beast_slot == (int)(&sl - c->slot)) c->beast_slot = -1;      // the encoded records belong to the run being replaced
     // One receiver, no Mode A/C: the stage B kernel publishes the results into the host's (mapped) copy itself and zeroes the control
     // block and the per-buffer sums when it is done - no memset, no device-to-host copy in the stream.
@@ -538,6 +542,8 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     sp.segs = sl.d_segs; sp.tile_seg = sl.d_tile_seg; sp.n_tiles = sl.ntile; sp.pos_pool = sl.d_pos_pool; sp.rec_pool = sl.d_rec_pool;
     sp.key_pool = sl.d_key_pool; sp.tile_out = sl.d_tile_out; sp.buf_acc = sl.d_buf_acc; sp.ctl = sl.d_ctl; sp.thr = c->cfg.preamble_threshold;
     sp.rec_cap = sl.rec_cap; sp.warps_per_cta = 0; sp.need_lut = 0;
+    sp.one_seg_valid = one_seg ? 1u : 0u;
+    if (sl.nseg) sp.one_seg = sl.h_segs[0]; else memset(&sp.one_seg, 0, sizeof sp.one_seg);
     for (uint32_t i = 0; i < sl.nseg; i++) if (!(sl.h_segs[i].flags & SEG_MAG)) sp.need_lut = 1;
     sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df;
     sp.stage_rec = c->d_stage_rec; sp.stage_key = c->d_stage_key; sp.stage_cap = c->stage_cap; sp.q1_over = c->d_q1_over; sp.tick_scratch = c->d_tick_scratch;
@@ -572,12 +578,14 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     fp.segs = sl.d_segs; fp.stream_seg_begin = sl.d_stream_seg_begin; fp.n_streams = S; fp.frames = sl.d_frames;
     fp.frame_count = sl.d_frame_count; fp.frame_prefix = sl.d_frame_prefix; fp.frame_prefix_out = sl.d_frame_prefix; fp.frame_cap = c->frame_cap; fp.packed = sl.d_packed;
     fp.buf_acc = sl.d_buf_acc; fp.state = c->d_state; fp.lut_full = c->d_lut_full; fp.rec_pool = sl.d_rec_pool;
+    fp.one_seg = sp.one_seg; fp.one_seg_valid = sp.one_seg_valid;
     const bool solo = S == 1;          // one receiver: stage B, frame prefix and finalizer are one launch (resolve_kernel, solo)
     ResolveParams rp;
     rp.segs = sl.d_segs; rp.stream_seg_begin = sl.d_stream_seg_begin; rp.n_streams = S; rp.pos_pool = sl.d_pos_pool;
     rp.rec_pool = sl.d_rec_pool; rp.key_pool = sl.d_key_pool; rp.tile_out = sl.d_tile_out; rp.buf_acc = sl.d_buf_acc; rp.buf_out = sl.d_buf_out;
     rp.state = c->d_state; rp.frames = sl.d_frames; rp.frame_count = sl.d_frame_count; rp.frame_cap = c->frame_cap; rp.per_buf_cap = c->cfg.buf_samples / 113 + 2;
     rp.ctl = sl.d_ctl; rp.prev_ctl = prev_ctl; rp.ttl_ms = c->cfg.icao_ttl_ms; rp.stream_addable = sl.d_addable;
+    rp.one_seg = sp.one_seg; rp.one_seg_valid = sp.one_seg_valid;
     rp.solo = solo ? 1u : 0u; rp.fin = fp;
     rp.publish_src = nullptr; rp.publish_dst = nullptr; rp.publish_head = 0; rp.publish_clear = 0;
     rp.carry_dst = nullptr; rp.carry_src = nullptr;
@@ -1004,6 +1012,7 @@ API int b200_demod_fetch_beast(b200_demod_ctx *c, uint32_t s, uint32_t flags, ui
         }
         c->beast_slot = -1;
         cudaStream_t st = c->copy_stream;
+        if (!sl.desc_on_device) { CU(c, cudaMemcpyAsync(sl.d_desc, sl.h_desc, sl.desc_bytes, cudaMemcpyHostToDevice, st)); sl.desc_on_device = true; }
         CU(c, cudaMemsetAsync(c->d_beast_meta, 0, (2 * (size_t)S + 1) * 4, st));
         BeastParams bp;
         bp.segs = sl.d_segs; bp.stream_seg_begin = sl.d_stream_seg_begin; bp.frames = sl.d_packed; bp.frame_prefix = sl.d_frame_prefix;

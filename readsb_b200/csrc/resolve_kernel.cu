@@ -473,8 +473,9 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
     b200_frame *fstream = P.frames + (size_t)stream * P.frame_cap;
     uint32_t cap_base = 0;                   // frame slots handed to the units of earlier rounds (each unit speculates into a region of its own)
 
-    for (uint32_t si = P.stream_seg_begin[stream]; si < P.stream_seg_begin[stream + 1]; si++) {
-        const Segment seg = P.segs[si];
+    const uint32_t si_begin = P.one_seg_valid ? 0u : P.stream_seg_begin[stream], si_end = P.one_seg_valid ? 1u : P.stream_seg_begin[stream + 1];
+    for (uint32_t si = si_begin; si < si_end; si++) {
+        const Segment seg = P.one_seg_valid ? P.one_seg : P.segs[si];
         // Work units of a round: whole buffers when the receiver has at least RS_WARPS of them in this run, otherwise every buffer is
         // cut into sub-ranges of whole scan tiles so that all warps have work (a single 65536-sample mag_buf: eight ranges of 8192).
         const uint32_t nsplit = seg.n_bufs >= RS_WARPS ? 1u : max(1u, min((uint32_t)RS_WARPS / max(seg.n_bufs, 1u), (seg.buf_len + 4 * SCAN_TILE - 1) / (4 * SCAN_TILE)));
@@ -662,7 +663,7 @@ __device__ __noinline__ void resolve_stream_big(const ResolveParams &P, ResolveS
 // A context with ONE receiver (the drop-in's shape: one readsb process, one mag_buf per call) needs no grid-wide agreement: this
 // single CTA makes the capacity check for its receiver itself, and assembles the frames when it is done - stage B, the frame
 // prefix and the finalizer in one launch.
-__global__ void __launch_bounds__(RS_WARPS * 32, 1) resolve_solo_kernel(const ResolveParams P) {
+__global__ void __launch_bounds__(RS_WARPS * 32, 1) resolve_solo_kernel(const __grid_constant__ ResolveParams P) {
     extern __shared__ uint4 resolve_smem_raw[];
     ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
     const uint32_t stream = 0;
@@ -767,12 +768,12 @@ __device__ __forceinline__ void finalize_frames(const FinalizeParams &P, uint32_
         const b200_frame *src = &P.frames[(size_t)stream * P.frame_cap + k];
         const uint32_t d = *reinterpret_cast<const uint32_t *>(&src->pad_[2]);
         // locate the segment: accept records carry the low 16 bits of the segment index; a stream has few segments
-        uint32_t seg_i = P.stream_seg_begin[stream];
+        uint32_t seg_i = P.one_seg_valid ? 0u : P.stream_seg_begin[stream];
         {
             const uint32_t low = *reinterpret_cast<const uint16_t *>(&src->pad_[0]);
             while ((seg_i & 0xffffu) != low) seg_i++;
         }
-        const Segment seg = P.segs[seg_i];
+        const Segment seg = P.one_seg_valid ? P.one_seg : P.segs[seg_i];
         const uint32_t len = src->signal_len;                    // 134 or 268 samples (demod_2400.c:439): at most 9 per lane
         // ... and the samples are fetched with all loads of a lane in flight at once (then the table lookups, likewise)
         constexpr int FIN_PER_LANE = 9;

@@ -209,6 +209,7 @@ static inline void emu_asm_prefetch_global_L2(const void *) {}
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorHostMemoryAlreadyRegistered = 712 };
 enum { cudaHostRegisterDefault = 0 };
+#define __grid_constant__
 typedef struct EmuStream *cudaStream_t;
 typedef struct EmuEvent *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
