@@ -107,11 +107,7 @@ template <int NW> struct ScanSmemFull {
 };
 
 __device__ __forceinline__ void stg_keep(uint32_t *p, uint32_t v, unsigned long long policy) {
-#ifndef V_NO_KEEP_HINT
     asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(policy) : "memory");
-#else
-    *p = v;
-#endif
 }
 
 // packed unsigned 16-bit min / max (VIMNMX.U16x2): two magnitudes per instruction
@@ -344,14 +340,9 @@ __device__ __forceinline__ uint32_t window_pass(WarpSmem &W, uint32_t mi0, uint3
 // back exactly the bytes it copied, so its own cp.async.wait_group is all the synchronisation there is.
 __device__ __forceinline__ void stage_raw(WarpSmem &W, const uint8_t *src, uint32_t lane) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(W.raw) + lane * 16;
-#ifndef V_NO_STREAM_HINT
     const unsigned long long pol = W.pol_stream;
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(dst), "l"(src + lane * 16), "l"(pol) : "memory");
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(dst + 512), "l"(src + 512 + lane * 16), "l"(pol) : "memory");
-#else
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + lane * 16) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 512), "l"(src + 512 + lane * 16) : "memory");
-#endif
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
