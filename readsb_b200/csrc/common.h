@@ -144,6 +144,7 @@ struct ScanParams {
     // descriptor upload in front of the kernels.  one_seg_valid: segs / tile_seg are not read, every tile belongs to one_seg.
     Segment one_seg;
     uint32_t one_seg_valid;
+    uint32_t static_tiles;       // set by the launcher: as many CTAs as tiles, CTA b takes tile b (no claim counter)
     uint32_t warps_per_cta;      // set by the launcher: warps of each CTA that take work (a small run is spread over many SMs, few warps each)
     uint32_t need_lut;           // some segment holds uc8 IQ: the magnitude table has to be staged (a pure magnitude hand-off skips it)
     int32_t thr;                 // Modes.preambleThreshold

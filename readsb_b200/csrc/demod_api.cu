@@ -541,7 +541,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     ScanParams sp;
     sp.segs = sl.d_segs; sp.tile_seg = sl.d_tile_seg; sp.n_tiles = sl.ntile; sp.pos_pool = sl.d_pos_pool; sp.rec_pool = sl.d_rec_pool;
     sp.key_pool = sl.d_key_pool; sp.tile_out = sl.d_tile_out; sp.buf_acc = sl.d_buf_acc; sp.ctl = sl.d_ctl; sp.thr = c->cfg.preamble_threshold;
-    sp.rec_cap = sl.rec_cap; sp.warps_per_cta = 0; sp.need_lut = 0;
+    sp.rec_cap = sl.rec_cap; sp.warps_per_cta = 0; sp.static_tiles = 0; sp.need_lut = 0;
     sp.one_seg_valid = one_seg ? 1u : 0u;
     if (sl.nseg) sp.one_seg = sl.h_segs[0]; else memset(&sp.one_seg, 0, sizeof sp.one_seg);
     for (uint32_t i = 0; i < sl.nseg; i++) if (!(sl.h_segs[i].flags & SEG_MAG)) sp.need_lut = 1;

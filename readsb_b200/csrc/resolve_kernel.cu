@@ -530,14 +530,16 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
                             b200_frame fr;
                             if (has) fr = fsrc[k0 + lane];
                             const uint32_t addm = __ballot_sync(FULLMASK, has && (fr.flags & B200_FRAME_ICAO_ADDED));
-                            uint32_t m = addm;
+                            uint32_t m = addm, inserted = 0;
                             while (m) {                                  // mode_s.c:778, in frame order
                                 const uint32_t l = __ffs(m) - 1; m &= m - 1;
                                 const uint32_t a = __shfl_sync(FULLMASK, fr.addr, l);
-                                if (lane == 0) { if (gen_insert(act, LOG2, a)) s_gcount[s_active]++; }
+                                if (lane == 0) { if (gen_insert(act, LOG2, a)) { s_gcount[s_active]++; inserted = 1; } }
                                 __syncwarp();
                             }
-                            if (addm) dirty_act = true;
+                            // (only a real insertion makes the shared-memory table differ from its global copy: frames of aircraft the
+                            // active generation already holds - the steady state - must not cost a 16 KB write-back per run)
+                            if (__shfl_sync(FULLMASK, inserted, 0)) dirty_act = true;
                             if (has && fdst != fsrc) { fr.buffer_seq = seq; fdst[k0 + lane] = fr; }
                             else if (has) { const_cast<b200_frame *>(fsrc)[k0 + lane].buffer_seq = seq; }
                             __syncwarp();

@@ -588,11 +588,16 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
     __syncwarp();
 
     uint32_t pend_tile = 0, pend_n = 0;       // tiles already claimed but not processed yet (a claim that crossed a segment boundary)
+    bool static_done = false;
     for (;;) {
         // ---- claim a run: guided self-scheduling, then cut at the segment boundary --------------------------------------
         if (!pend_n) {
             uint32_t start = 0, n = 0;
-            if (lane == 0) {
+            if (P.static_tiles) {                 // one tile per CTA (a run of a few dozen tiles): no claim, no atomic round trip
+                if (static_done) break;
+                static_done = true;
+                start = blockIdx.x; n = 1;
+            } else if (lane == 0) {
                 const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&P.ctl->tile_counter);
                 if (cur < P.n_tiles) {
                     const uint32_t workers = gridDim.x * P.warps_per_cta;
@@ -601,7 +606,8 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
                     if (start >= P.n_tiles) n = 0; else n = min(n, P.n_tiles - start);
                 }
             }
-            pend_tile = __shfl_sync(FULLMASK, start, 0); pend_n = __shfl_sync(FULLMASK, n, 0);
+            if (!P.static_tiles) { start = __shfl_sync(FULLMASK, start, 0); n = __shfl_sync(FULLMASK, n, 0); }
+            pend_tile = start; pend_n = n;
             if (!pend_n) break;
         }
         __syncwarp();
@@ -772,10 +778,11 @@ template <int NW> static int launch_scan_t(const ScanParams *p, const DeviceTabl
     // most one per SM) and only as many warps of each as it takes - a lone warp on an SM runs several times faster than one of 28.
     ScanParams q = *p;
     uint32_t grid = (uint32_t)n_sm;
-    q.warps_per_cta = NW;
+    q.warps_per_cta = NW; q.static_tiles = 0;
     if (q.n_tiles < grid * NW) {
         if (grid > q.n_tiles) grid = q.n_tiles;
         q.warps_per_cta = (q.n_tiles + grid - 1) / grid;
+        q.static_tiles = (grid == q.n_tiles) ? 1u : 0u;      // then warps_per_cta is 1: CTA b takes tile b
     }
     scan_kernel<NW><<<grid, NW * 32, sizeof(ScanSmemFull<NW>), stream>>>(q, d_tables);
     return (int)cudaGetLastError();
