@@ -111,12 +111,17 @@ def test_full_size_batch_properties(cuda, workload):
             out2[s].append(d2.frames(s))
     for s in range(S):
         assert not diff_frames(np.concatenate(out2[s]), frames[s]), f"stream {s}"
-    # (5) spot check against the oracle
-    for s in (0, 37, 128, 255):
+    # (5) every receiver against the oracle: frames, per-buffer results and counters, cumulative statistics
+    from concurrent.futures import ThreadPoolExecutor
+    stats = [d.stats(s) for s in range(S)]
+
+    def check(s):
         o = Oracle()
         fo, bo = o.run_stream(host[s], BUF)
-        problems = diff_frames(frames[s], fo) + diff_bufres(bufres[s], bo) + diff_stats(d.stats(s), o.stats())
-        assert not problems, f"stream {s}: " + "\n".join(problems)
+        return diff_frames(frames[s], fo) + diff_bufres(bufres[s], bo) + diff_stats(stats[s], o.stats())
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for s, problems in enumerate(ex.map(check, range(S))):
+            assert not problems, f"stream {s}: " + "\n".join(problems)
     d.close(); d2.close()
 
 
