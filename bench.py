@@ -618,6 +618,10 @@ def b200_arm(args, rank, world, local):
                "h2d_bytes_per_step": (launch_samples * 2 + S * 64 + 64) * LPS,           # IQ slab + segment table + control block, per launch
                "d2h_bytes_per_step": int(frames_e / args.steps * 64) + (S * 4 + S * B * 144 + 32 + 16 * 64) * LPS,   # frames + counts + buffer results
                "ms_per_step": ms_e / args.steps, "frames_per_step": frames_e / args.steps, "host_placement": numa_note, "clocks": clk_e}
+        if dist is not None:      # where every rank pinned its slab (the H2D copies of ranks on the far socket cross the interconnect)
+            notes = [None] * world
+            dist.all_gather_object(notes, f"rank {rank} gpu {local}: {numa_note}")
+            e2e["host_placement"] = notes
         d = d_dev
         d2.close()
     # --- roofline leg: blocking device-resident launches, so that the scan kernel runs alone on the GPU ----------------

@@ -367,7 +367,9 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     c->seg_cap = S * K;
     c->tile_cap = S * K * tiles_per_buf;
     c->buf_cap = S * K;
-    c->frame_cap = K * (BUF / 113 + 2 + 32);         // + what the sub-ranges of a buffer add by rounding (stage B, resolve_stream)
+    // Stage B speculates every sub-range of a buffer into a region of its own (resolve_stream): up to 8 sub-ranges, each rounded
+    // up to whole scan tiles and holding len/113 + 3 frames, so a buffer can reserve BUF/113 + 8 * (2048/113 + 4) slots.
+    c->frame_cap = K * (BUF / 113 + 2 + 8 * (2048 / 113 + 4));
     c->ac_cap = BUF / 70 + 2;                       // per reference buffer: a Mode A/C reply hides the next 69 positions
     {
         const size_t warps = (size_t)b200_scan_warps(c->n_sm);

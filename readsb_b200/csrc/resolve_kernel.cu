@@ -497,11 +497,14 @@ __device__ __forceinline__ void resolve_stream(const ResolveParams &P, ResolveSm
             if (wid < n_round) {
                 uint32_t b, lo, hi;
                 unit_range(u0 + wid, b, lo, hi);
+                // (the host sizes frame_cap so that every round's regions fit; a unit whose region would not fit holds no frames,
+                // which reports the overflow instead of writing past the receiver's slots)
+                const uint32_t ucap_fit = cap_base + (wid + 1) * ucap <= P.frame_cap ? ucap : 0u;
                 FilterRef F;
                 F.act = tab(s_active); F.old_gen = tab(s_active ^ 1u); F.log2 = LOG2; F.counts = nullptr; F.bits = nullptr; F.active = s_active;
-                if (COMPACT) resolve_buffer_call<BIG>(true, P, S, S.ring[wid], S.res[wid], seg, si, b, lo, hi, lo, 0, F, fstream + cap_base + (size_t)wid * ucap, ucap, lane);
+                if (COMPACT) resolve_buffer_call<BIG>(true, P, S, S.ring[wid], S.res[wid], seg, si, b, lo, hi, lo, 0, F, fstream + cap_base + (size_t)wid * ucap, ucap_fit, lane);
                 else resolve_buffer<BIG>(true, P, S, S.ring[wid], S.res[wid], seg, si, b, lo, hi, lo, 0 /* buffer_seq is stamped at commit */, F,
-                                         fstream + cap_base + (size_t)wid * ucap, ucap, lane);
+                                         fstream + cap_base + (size_t)wid * ucap, ucap_fit, lane);
             }
             __syncthreads();
             SOLO_T(2);

@@ -73,6 +73,31 @@ def test_timestamp_discontinuity_starts_a_new_segment(cuda):
     d.close()
 
 
+def test_one_segment_per_buffer_keeps_its_frames_inside_the_receivers_slots(cuda):
+    """Every buffer of a run a segment of its own (a clock jump before each), eight per receiver: stage B cuts each of them
+    into sub-ranges rounded up to whole scan tiles, and the frame regions the sub-ranges speculate into must still add up to
+    no more than the receiver's slots — the last receiver's last regions lie at the end of the allocation (found by the
+    emulator's fuzzer under AddressSanitizer; on the GPU the neighbouring receiver's frames would be overwritten)."""
+    from readsb_b200.demod import Demodulator
+    BUF, K, S = 37016, 8, 2
+    ts_of = lambda b, lo: lo * 5 + b * 1_000_000
+    cuts = [(i * BUF, (i + 1) * BUF) for i in range(K)]
+    d = Demodulator(n_streams=S, buf_samples=BUF, max_buffers_per_run=K)
+    want = []
+    for s in range(S):
+        iq = synth.mixed_stream(90 + s, K * BUF, frames_per_sec=9000)
+        o = Oracle(); want.append(_oracle_buffers(o, iq, cuts, ts_of) + (o.stats(),))
+        for b, (lo, hi) in enumerate(cuts):
+            d.submit_iq(s, iq[2 * lo: 2 * hi], ts_of(b, lo))
+    d.run()
+    for s in range(S):
+        fo, bo, so = want[s]
+        problems = diff_frames(d.frames(s), fo) + diff_bufres(d.buffer_results(s), bo) + diff_stats(d.stats(s), so)
+        assert not problems, f"receiver {s}\n" + "\n".join(problems)
+        assert len(fo) > 150 and fo["j"][-1] > 33000            # the last sub-range of the last buffer holds frames
+    d.close()
+
+
 def test_receivers_with_unequal_work_in_one_run(cuda):
     """Some receivers idle, some with one buffer, some with several, some ending in a partial buffer."""
     from readsb_b200.demod import Demodulator
