@@ -161,12 +161,18 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
     __syncthreads();          // the only block barrier
     AcWarpSmem &W = S.w[wid];
     const uint32_t lt = (1u << lane) - 1u;
-    for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&P.ctl->pad_[0], 1u);
-        tile = __shfl_sync(FULLMASK, tile, 0);
-        if (tile >= P.n_tiles) break;
-        const Segment seg = P.segs[P.tile_seg[tile] & ~TILE_QUAD_START];
+    // A warp's tile costs it three dependent round trips to L2 / HBM before the first magnitude is there (claim, descriptor, samples),
+    // which seven warps per scheduler do not hide: the NEXT tile is claimed while this one is worked on, the segment descriptor is kept
+    // while the tiles stay in the segment (hundreds in a row), and the next tile's samples are asked into L2 half-way through this one.
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(&P.ctl->pad_[0], 1u);
+    tile = __shfl_sync(FULLMASK, tile, 0);
+    Segment seg;
+    uint32_t seg_tile_end = 0;
+    while (tile < P.n_tiles) {
+        if (tile >= seg_tile_end) { seg = P.segs[P.tile_seg[tile] & ~TILE_QUAD_START]; seg_tile_end = seg.tile_begin + seg.n_tiles; }
+        uint32_t tile_next = 0;
+        if (lane == 0) tile_next = atomicAdd(&P.ctl->pad_[0], 1u);              // (waited for at the end of this tile)
         const uint32_t x0 = (tile - seg.tile_begin) * SCAN_TILE;               // tile coordinate x = data index + lead
         const uint32_t x_data_end = seg.lead + seg.npos + B200_TRAIL;
         const uint32_t x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;
@@ -175,20 +181,28 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
         // ---- convert: magnitudes of tile coordinates [x0 - 8, x0 + 2048 + 104) ------------------------------------------
         if (x0 >= x_zero_end + AC2_BEHIND && x0 + SCAN_TILE + AC2_AHEAD <= x_data_end) {
             // a tile in the interior of the data (nearly all of them): no piece needs a bounds test
+            // A sample is two bytes as uc8 IQ and two bytes as a magnitude: the input lands, asynchronously and all 4320 bytes at once
+            // (one exposed memory latency per tile instead of one per pair of pieces), where its magnitudes belong, and is converted
+            // in place - every lane reads back exactly the pieces it copied.  A magnitude hand-off is complete when it has landed.
             const uint8_t *src = seg.base + 2 * ((int64_t)x0 - AC2_BEHIND - (int64_t)seg.lead);
-            for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32) {
-                const uint4 raw = ldg_stream_u4(src + (size_t)c * 16);
-                const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
-                uint4 packed;
-                if (is_mag) packed = raw;
-                else {
+            const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(W.mag);
+            for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst0 + c * 16), "l"(src + (size_t)c * 16) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (!is_mag) {
+#pragma unroll 3
+                for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32) {
+                    const uint4 raw = *reinterpret_cast<const uint4 *>(&W.mag[c * 8]);
+                    const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
                     uint32_t m[8];
 #pragma unroll
                     for (int i = 0; i < 4; i++) uc8_pair_to_mag(S.lut, wv[i], m[2 * i], m[2 * i + 1]);
+                    uint4 packed;
                     packed.x = __byte_perm(m[0], m[1], 0x5410); packed.y = __byte_perm(m[2], m[3], 0x5410);
                     packed.z = __byte_perm(m[4], m[5], 0x5410); packed.w = __byte_perm(m[6], m[7], 0x5410);
+                    *reinterpret_cast<uint4 *>(&W.mag[c * 8]) = packed;
                 }
-                *reinterpret_cast<uint4 *>(&W.mag[c * 8]) = packed;
             }
         } else
         for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32) {
@@ -251,6 +265,15 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
             W.edge[c * 32 + lane] = (uint16_t)((acc2 & 0xffffu) | (acc2 >> 15));
         }
         __syncwarp();
+        tile_next = __shfl_sync(FULLMASK, tile_next, 0);
+        if (tile_next < seg_tile_end) {    // the next tile's samples (same segment: its descriptor is at hand) on their way into L2
+            const int64_t xn = (int64_t)(tile_next - seg.tile_begin) * SCAN_TILE - AC2_BEHIND - (int64_t)seg.lead;      // its first sample, as a data index
+            if (xn >= B200_TRAIL && xn + AC2_NMAG <= (int64_t)seg.npos + B200_TRAIL) {      // (memory the interior path of that tile reads anyway)
+                const uint8_t *pn = seg.base + 2 * xn;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pn + lane * 128));
+                if (lane < 2) asm volatile("prefetch.global.L2 [%0];" :: "l"(pn + 4096 + lane * 128));
+            }
+        }
 
         uint32_t n1 = 0, n2 = 0;           // candidates waiting in W.q1, front-test survivors waiting in W.q2
 #pragma unroll 1
@@ -323,11 +346,12 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
         // one bit per position of this scan tile
         uint32_t *dst = P.bitmap + (size_t)tile * (SCAN_TILE / 32);
         dst[lane] = W.bits[lane]; dst[lane + 32] = W.bits[lane + 32];
+        tile = tile_next;
     }
 }
 
 // ---- the sequential part, one warp per reference buffer ---------------------------------------------------------------
-__global__ void __launch_bounds__(256) modeac_walk_kernel(const AcWalkParams P) {
+__global__ void __launch_bounds__(256, 1) modeac_walk_kernel(const AcWalkParams P) {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (P.ctl->overflow & 3u) return;
     for (uint32_t si = blockIdx.x; si < P.n_segs; si += gridDim.x) {
@@ -344,19 +368,37 @@ __global__ void __launch_bounds__(256) modeac_walk_kernel(const AcWalkParams P) 
             const uint32_t w_first = xa >> 5, w_last = (xb - 1) >> 5;
             b200_modeac *out = P.ac_out + (size_t)(seg.first_buf + b) * P.per_buf_cap;
             uint32_t n = 0, next_ok = 0;
-            uint32_t word_next = w_first + lane <= w_last ? bits[w_first + lane] : 0;
-            for (uint32_t w0 = w_first; w0 <= w_last; w0 += 32) {
-                const uint32_t wi = w0 + lane, wx = wi * 32;
-                uint32_t word = word_next;
-                word_next = wi + 32 <= w_last ? bits[wi + 32] : 0;
-                if (wi == w_first) word &= ~0u << (xa & 31);
-                if (wi == w_last && (xb & 31)) word &= (1u << (xb & 31)) - 1u;
+            // The map is nearly empty (a reply per 10 000 positions): a lane takes four words at a time (128 words = 4096 positions per
+            // warp step) and the warp only looks closer when one of them is not zero.  The map of a segment starts at a tile boundary
+            // and every tile has 64 words of its own, so groups of four words are aligned and never leave the segment's tiles.
+            const uint32_t g_first = w_first >> 2, g_last = w_last >> 2;
+            const uint4 *bits4 = reinterpret_cast<const uint4 *>(bits);
+            uint4 grp_next = g_first + lane <= g_last ? bits4[g_first + lane] : make_uint4(0, 0, 0, 0);
+            for (uint32_t g0 = g_first; g0 <= g_last; g0 += 32) {
+                const uint32_t gi = g0 + lane;
+                const uint4 grp = grp_next;
+                grp_next = gi + 32 <= g_last ? bits4[gi + 32] : make_uint4(0, 0, 0, 0);
+                if (!__any_sync(FULLMASK, (grp.x | grp.y | grp.z | grp.w) != 0)) continue;
+                // words of the group outside the buffer, and the bits of its first / last word that belong to its neighbours, do not count
+                auto clip = [&](uint32_t v, uint32_t wi) {
+                    if (wi < w_first || wi > w_last) v = 0;
+                    if (wi == w_first) v &= ~0u << (xa & 31);
+                    if (wi == w_last && (xb & 31)) v &= (1u << (xb & 31)) - 1u;
+                    return v;
+                };
+                const uint32_t wi0 = gi * 4;
+                const uint32_t v0 = clip(grp.x, wi0), v1 = clip(grp.y, wi0 + 1), v2 = clip(grp.z, wi0 + 2), v3 = clip(grp.w, wi0 + 3);
                 for (;;) {
-                    uint32_t cand = word;
-                    if (next_ok > wx) cand = next_ok - wx >= 32 ? 0 : word & (~0u << (next_ok - wx));
-                    const uint32_t bal = __ballot_sync(FULLMASK, cand != 0);
+                    // this lane's first position that is not hidden by the reply accepted before it (demod_2400.c:747: the next 69 are skipped)
+                    auto first_in = [&](uint32_t v, uint32_t wi, uint32_t later) {
+                        const uint32_t wx = wi * 32;
+                        if (next_ok > wx) v = next_ok - wx >= 32 ? 0 : v & (~0u << (next_ok - wx));
+                        return v ? wx + __ffs(v) - 1 : later;
+                    };
+                    const uint32_t mine = first_in(v0, wi0, first_in(v1, wi0 + 1, first_in(v2, wi0 + 2, first_in(v3, wi0 + 3, 0xffffffffu))));
+                    const uint32_t bal = __ballot_sync(FULLMASK, mine != 0xffffffffu);
                     if (!bal) break;
-                    const uint32_t pos = __shfl_sync(FULLMASK, wx + __ffs(cand) - 1, __ffs(bal) - 1);
+                    const uint32_t pos = __shfl_sync(FULLMASK, mine, __ffs(bal) - 1);
                     if (lane == 0) { if (n < P.per_buf_cap) out[n].f1_sample = pos - xa; else atomicOr(&P.ctl->overflow, 32u); }
                     n++;
                     next_ok = pos + AC_SKIP;

@@ -75,6 +75,7 @@ struct RunCtx {
     uint32_t is_mag, last_tile;
     uint32_t tile0, n_tiles;
     uint32_t tile_rel0;            // tile0 - seg.tile_begin: stage B walks quads of tiles, PosEntry positions are quad-relative
+    uint32_t sub_off;              // run coordinate 0 inside its tile (0 unless the tile is shared between warps, see finish_shared_tile)
 };
 
 struct WarpSmem {
@@ -98,7 +99,9 @@ struct ScanSmem {                             // the read-only tables every warp
     uint32_t bit_syn[112];
     uint32_t syn_hash[512];
     uint32_t syn_mul;
-    uint32_t pad_[3];
+    // a tile shared between the warps of the CTA (small runs, finish_shared_tile): what each warp found, the tile's reservation
+    uint32_t sub_pos[TILE_CHUNKS], sub_rec[TILE_CHUNKS], sub_rec_off, sub_ok;
+    uint32_t pad_[1];
 };
 
 template <int NW> struct ScanSmemFull {
@@ -498,7 +501,7 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t m = chunk_p0 / SCAN_TILE;                     // tile of the run this chunk belongs to
     PosEntry *pos_out = P.pos_pool + (size_t)(W.ctx.tile0 + m) * SCAN_TILE;
-    const uint32_t pe_base = (chunk_p0 & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE);    // PosEntry position of chunk-local position 0
+    const uint32_t pe_base = ((chunk_p0 + W.ctx.sub_off) & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE);    // PosEntry position of chunk-local position 0
     const uint16_t *mag0 = &W.mag[mslot * CHUNK];
     // Threshold passers wait in W.pass (32 entries) until the chunk's last batch is through or the next batch's passers would
     // not fit: their DF gates are evaluated five lanes per passer, and a single batch rarely has more than three.
@@ -555,6 +558,68 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
         }
     }
     if (lane == 0) W.n_pos[m] = pos_base;
+}
+
+// End of a run that covers only part of a tile.  A run of a few dozen tiles (one receiver's single buffer: the drop-in's call
+// shape) leaves most of the chip idle and is latency-bound in every warp, so the launcher gives each tile to one CTA and each of
+// its chunks to a warp of its own: a quarter of the serial work per warp (one 65536-sample buffer: 24 -> see DESIGN.md 3.7).  Each
+// warp has written its PosEntries at its chunk's offset in the tile's list and staged its records privately; here the warps of
+// the CTA meet (the only barriers after table staging, and only in this mode), reserve the tile's records in one piece, copy
+// their records behind those of the warps before them and close the gaps in the PosEntry list, so that the tile's output is what
+// one warp would have produced.
+__device__ __forceinline__ void shared_tile_barrier(uint32_t n_warps) { asm volatile("bar.sync %0, %1;" :: "r"(1), "r"(n_warps * 32) : "memory"); }
+
+__device__ __noinline__ void finish_shared_tile(ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t lane, uint32_t wid, uint32_t n_stage) {
+    const RunCtx &T = W.ctx;
+    const uint32_t n_warps = TILE_CHUNKS / P.sub_chunks, tile = T.tile0;
+    PosEntry *tile_pos = P.pos_pool + (size_t)tile * SCAN_TILE;
+    const uint32_t my_pos = W.n_pos[0] - T.sub_off;
+    if (lane == 0) { S.sub_pos[wid] = my_pos; S.sub_rec[wid] = n_stage; }
+    shared_tile_barrier(n_warps);
+    uint32_t pos_before = 0, rec_before = 0, pos_tot = 0, rec_tot = 0, need = 0;
+    for (uint32_t w = 0; w < n_warps; w++) {
+        const uint32_t a = S.sub_pos[w], b = S.sub_rec[w];
+        if (w < wid) { pos_before += a; rec_before += b; }
+        pos_tot += a; rec_tot += b; need = max(need, b);
+    }
+    if (wid == 0 && lane == 0) {
+        uint32_t off = 0, ok = 1;
+        if (need > P.stage_cap) { atomicOr(&P.ctl->overflow, 2u); atomicMax(&P.ctl->stage_need, need); ok = 0; }         // as at the end of a whole-tile run
+        else if (rec_tot) {
+            off = atomicAdd(&P.ctl->rec_alloc, rec_tot);
+            if (off + rec_tot > P.rec_cap) { atomicOr(&P.ctl->overflow, 1u); ok = 0; }
+        }
+        S.sub_rec_off = off; S.sub_ok = ok;
+    }
+    shared_tile_barrier(n_warps);
+    const uint32_t off = S.sub_rec_off, ok = S.sub_ok;
+    if (ok) {
+        const Rec *stage = W_STAGE(W, P);
+        const uint32_t *stage_key = W_STAGE_KEY(W, P);
+        for (uint32_t i = lane; i < n_stage; i += 32) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(stage + i);
+            uint4 *dst = reinterpret_cast<uint4 *>(P.rec_pool + off + rec_before + i);
+            dst[0] = __ldcg(src); dst[1] = __ldcg(src + 1);
+            P.key_pool[off + rec_before + i] = __ldcg(stage_key + i);
+        }
+    }
+    // PosEntry lists: warp w's entries move down behind those of the warps before it, one warp after the other (a warp's
+    // destination may reach into the list of the warp before it, which has moved by then; within a warp the destination never
+    // lies above the source, so 32 entries at a time in ascending order is a safe forward move)
+    for (uint32_t w = 1; w < n_warps; w++) {
+        if (wid == w && pos_before != T.sub_off) {
+            for (uint32_t i0 = 0; i0 < my_pos; i0 += 32) {
+                const bool has = i0 + lane < my_pos;
+                PosEntry v = 0;
+                if (has) v = __ldcg(&tile_pos[T.sub_off + i0 + lane]);
+                __syncwarp();
+                if (has) tile_pos[pos_before + i0 + lane] = v;
+                __syncwarp();
+            }
+        }
+        shared_tile_barrier(n_warps);
+    }
+    if (wid == 0 && lane == 0) { TileOut t; t.n_pos = pos_tot; t.n_rec = ok ? rec_tot : 0; t.rec_off = off; t.n_found = rec_tot; P.tile_out[tile] = t; }
 }
 
 template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __grid_constant__ ScanParams P, const DeviceTables *__restrict__ tables) {
@@ -623,14 +688,17 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
             const uint32_t tile0 = pend_tile, n_tiles_run = min(pend_n, seg.tile_begin + seg.n_tiles - tile0);
             pend_tile += n_tiles_run; pend_n -= n_tiles_run;
             n_chunks = n_tiles_run * TILE_CHUNKS;
+            const uint32_t sub_off = P.sub_chunks ? wid * P.sub_chunks * CHUNK : 0u;  // a tile shared between warps: this warp's chunks of it
+            if (P.sub_chunks) n_chunks = P.sub_chunks;
             if (lane == 0) {
-                const uint32_t x0 = (tile0 - seg.tile_begin) * SCAN_TILE;             // run origin in tile coordinates (x = data index + lead)
-                T.x0 = x0; T.tile0 = tile0; T.n_tiles = n_tiles_run; T.n_chunks = n_chunks; T.tile_rel0 = tile0 - seg.tile_begin;
+                const uint32_t x0 = (tile0 - seg.tile_begin) * SCAN_TILE + sub_off;   // run origin in tile coordinates (x = data index + lead)
+                T.x0 = x0; T.tile0 = tile0; T.n_tiles = n_tiles_run; T.n_chunks = n_chunks; T.tile_rel0 = tile0 - seg.tile_begin; T.sub_off = sub_off;
+                W.n_pos[0] = sub_off;                                                 // (its PosEntries start at its own offset in the tile's list)
                 T.tile_base = seg.base + 2 * ((long long)x0 - (long long)seg.lead);
                 T.x_data_end = seg.lead + seg.npos + B200_TRAIL;                      // first x without data
                 T.x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;   // x below: magnitude 0, memory not read
                 T.is_mag = (seg.flags & SEG_MAG) ? 1u : 0u;
-                T.last_tile = tile0 + n_tiles_run == seg.tile_begin + seg.n_tiles;
+                T.last_tile = tile0 + n_tiles_run == seg.tile_begin + seg.n_tiles && (!P.sub_chunks || sub_off + n_chunks * CHUNK == SCAN_TILE);
                 const long long n_first = (long long)x0 - seg.lead - B200_TRAIL;
                 T.n_first = n_first;
                 T.buf_len = seg.buf_len; T.first_buf = seg.first_buf; T.npos = seg.npos;
@@ -739,6 +807,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
         const uint32_t tile0 = T.tile0, n_tiles_run = T.n_tiles;
         if (n_surv) slice_round(S, W, P, n_surv, lane, n_stage);
         __syncwarp();
+        if (P.sub_chunks) { finish_shared_tile(S, W, P, lane, wid, n_stage); break; }
         uint32_t off = 0, ok = 1;
         if (lane == 0) {
             if (n_stage > P.stage_cap) { atomicOr(&P.ctl->overflow, 2u); atomicMax(&P.ctl->stage_need, n_stage); ok = 0; }   // host grows the staging areas and reruns
@@ -779,10 +848,13 @@ template <int NW> static int launch_scan_t(const ScanParams *p, const DeviceTabl
     ScanParams q = *p;
     uint32_t grid = (uint32_t)n_sm;
     q.warps_per_cta = NW; q.static_tiles = 0;
+    const uint32_t sub = p->sub_chunks;
+    q.sub_chunks = 0;
     if (q.n_tiles < grid * NW) {
         if (grid > q.n_tiles) grid = q.n_tiles;
         q.warps_per_cta = (q.n_tiles + grid - 1) / grid;
-        q.static_tiles = (grid == q.n_tiles) ? 1u : 0u;      // then warps_per_cta is 1: CTA b takes tile b
+        q.static_tiles = (grid == q.n_tiles) ? 1u : 0u;      // then warps_per_cta is 1: CTA b takes tile b ...
+        if (q.static_tiles && (sub == 1 || sub == 2)) { q.sub_chunks = sub; q.warps_per_cta = TILE_CHUNKS / sub; }   // ... or its first warps share it (finish_shared_tile)
     }
     scan_kernel<NW><<<grid, NW * 32, sizeof(ScanSmemFull<NW>), stream>>>(q, d_tables);
     return (int)cudaGetLastError();

@@ -201,6 +201,7 @@ static inline void emu_asm_cp_async_cg_shared_global_L2__cache_hint(unsigned dst
 static inline void emu_asm_createpolicy_fractional_L2__evict_first_b64(unsigned long long &p) { p = 1; }
 static inline void emu_asm_createpolicy_fractional_L2__evict_last_b64(unsigned long long &p) { p = 2; }
 static inline void emu_asm_st_global_L2__cache_hint_b32(unsigned *p, unsigned v, unsigned long long) { *p = v; }
+static inline void emu_asm_bar_sync(int, unsigned) { emu_block_barrier(); }     // named barrier of the warps still alive (the others have returned)
 static inline void emu_asm_cp_async_commit_group() {}
 static inline void emu_asm_cp_async_wait_group(int) {}
 static inline void emu_asm_prefetch_global_L2(const void *) {}
