@@ -159,6 +159,10 @@ struct ScanParams {
     uint16_t *q1_over;           // [warp][512] pre-check passers beyond the shared-memory queue (dense input)
     uint32_t *tick_scratch;      // [warp][b200_scan_tick_words()] the ticks of the run in progress (deferred, pooled slicing)
     uint32_t *stream_addable;    // [stream] records of this run that could teach the receiver's filter an address (clean DF17, DF11 with IID 0)
+    // Mode A/C contexts: the magnitudes this kernel makes from uc8 IQ anyway, kept for modeac_scan_kernel (which would otherwise run
+    // every sample through the table a second time): sample x (tile coordinate) of a segment at mag_copy[seg.tile_begin * SCAN_TILE + x],
+    // for the x inside the segment's tiles.  Null: not kept.
+    uint16_t *mag_copy;
 };
 
 struct FinalizeParams {
@@ -238,6 +242,7 @@ struct AcScanParams {
     RunCtl *ctl;
     const AcLevel *levels;            // [buffer]
     const float2 *fsum;               // sc16 float sums (sum_level, sum_power), or null
+    const uint16_t *mag_copy;         // (ScanParams) the Mode S scan's magnitudes of the uc8 segments, or null
 };
 
 struct AcWalkParams {

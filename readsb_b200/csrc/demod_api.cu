@@ -68,6 +68,7 @@ struct Slot {
     uint32_t *d_addable = nullptr;    // [S] filter adds this run can make at most (scan kernel -> capacity check, which zeroes it again)
     // Mode A/C (contexts created with B200_CFG_MODE_AC)
     uint32_t *d_ac_bitmap = nullptr, *d_ac_noise = nullptr;
+    uint16_t *d_mag_copy = nullptr;   // Mode A/C: the Mode S scan's magnitudes of the run's uc8 tiles (ScanParams::mag_copy)
     uint32_t *d_ac_count = nullptr, *d_ac_prefix = nullptr, *h_ac_prefix = nullptr;   // per reference buffer of the run
     b200_modeac *d_ac_out = nullptr, *d_ac_packed = nullptr, *h_ac_packed = nullptr;
     AcLevel *d_ac_levels = nullptr, *h_ac_levels = nullptr;                           // per reference buffer of the run: source of the noise floor
@@ -201,7 +202,7 @@ static void free_slot(Slot &s) {
     cudaFree(s.d_desc); cudaFree(s.d_res); cudaFreeHost(s.h_desc); cudaFreeHost(s.h_res); cudaFree(s.d_pos_pool);
     cudaFree(s.d_rec_pool); cudaFree(s.d_key_pool); cudaFree(s.d_tile_out);
     cudaFree(s.d_frames); cudaFree(s.d_frame_count); cudaFree(s.d_addable);
-    cudaFree(s.d_ac_bitmap); cudaFree(s.d_ac_noise); cudaFree(s.d_ac_count); cudaFree(s.d_ac_prefix); cudaFree(s.d_ac_out); cudaFree(s.d_ac_packed);
+    cudaFree(s.d_mag_copy); cudaFree(s.d_ac_bitmap); cudaFree(s.d_ac_noise); cudaFree(s.d_ac_count); cudaFree(s.d_ac_prefix); cudaFree(s.d_ac_out); cudaFree(s.d_ac_packed);
     cudaFreeHost(s.h_ac_prefix); cudaFreeHost(s.h_ac_packed);
     cudaFree(s.d_ac_levels); cudaFreeHost(s.h_ac_levels);
     free(s.h_segs); free(s.h_tile_seg); free(s.h_stream_seg_begin);
@@ -238,6 +239,7 @@ static cudaError_t alloc_slot(b200_demod_ctx *c, Slot &s, uint32_t rec_cap) {
         // one bit per position, and room for every reply a buffer can hold: nothing here depends on the input
         const size_t ac_total = (size_t)c->buf_cap * c->ac_cap;
         A(dev_alloc(&s.d_ac_bitmap, (size_t)c->tile_cap * (SCAN_TILE / 32)));
+        A(dev_alloc(&s.d_mag_copy, (size_t)c->tile_cap * SCAN_TILE));
         A(dev_alloc(&s.d_ac_noise, c->buf_cap)); A(dev_alloc(&s.d_ac_count, c->buf_cap));
         A(cudaMemset(s.d_ac_count, 0, (size_t)c->buf_cap * 4)); A(cudaMemset(s.d_ac_noise, 0, (size_t)c->buf_cap * 4));
         A(dev_alloc(&s.d_ac_out, ac_total)); A(dev_alloc(&s.d_ac_packed, ac_total)); A(pin_alloc(&s.h_ac_packed, ac_total));
@@ -552,6 +554,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     sp.nfix = c->cfg.nfix_crc; sp.fixdf = c->cfg.fix_df;
     sp.stage_rec = c->d_stage_rec; sp.stage_key = c->d_stage_key; sp.stage_cap = c->stage_cap; sp.q1_over = c->d_q1_over; sp.tick_scratch = c->d_tick_scratch;
     sp.stream_addable = sl.d_addable;
+    sp.mag_copy = (c->cfg.flags & B200_CFG_MODE_AC) ? sl.d_mag_copy : nullptr;
     // demod_2400.c:112-127
     sp.short_set = (1u << 0) | (1u << 4) | (1u << 5) | (1u << 11);
     sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
@@ -570,7 +573,7 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
         AcScanParams as;
         as.levels = sl.d_ac_levels; as.fsum = c->d_fsum;
         as.segs = sl.d_segs; as.n_segs = sl.nseg; as.tile_seg = sl.d_tile_seg; as.n_tiles = sl.ntile; as.buf_acc = sl.d_buf_acc;
-        as.tables = c->d_tables; as.noise = sl.d_ac_noise; as.bitmap = sl.d_ac_bitmap; as.ctl = sl.d_ctl;
+        as.tables = c->d_tables; as.noise = sl.d_ac_noise; as.bitmap = sl.d_ac_bitmap; as.ctl = sl.d_ctl; as.mag_copy = sl.d_mag_copy;
         aw.segs = sl.d_segs; aw.n_segs = sl.nseg; aw.stream_seg_begin = sl.d_stream_seg_begin; aw.n_streams = S; aw.bitmap = sl.d_ac_bitmap;
         aw.noise = sl.d_ac_noise; aw.lut_full = c->d_lut_full; aw.ac_out = sl.d_ac_out; aw.ac_count = sl.d_ac_count; aw.per_buf_cap = c->ac_cap;
         aw.state = c->d_state; aw.ctl = sl.d_ctl;

@@ -185,12 +185,18 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
             // (one exposed memory latency per tile instead of one per pair of pieces), where its magnitudes belong, and is converted
             // in place - every lane reads back exactly the pieces it copied.  A magnitude hand-off is complete when it has landed.
             const uint8_t *src = seg.base + 2 * ((int64_t)x0 - AC2_BEHIND - (int64_t)seg.lead);
+            bool convert = !is_mag;
+            if (convert && P.mag_copy && x0 + SCAN_TILE + AC2_AHEAD <= seg.n_tiles * SCAN_TILE) {
+                // uc8 IQ that the Mode S scan has been through: its magnitudes are there to be read (ScanParams::mag_copy)
+                src = reinterpret_cast<const uint8_t *>(P.mag_copy + ((size_t)seg.tile_begin * SCAN_TILE + x0 - AC2_BEHIND));
+                convert = false;
+            }
             const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(W.mag);
             for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst0 + c * 16), "l"(src + (size_t)c * 16) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            if (!is_mag) {
+            if (convert) {
 #pragma unroll 3
                 for (uint32_t c = lane; c < AC2_NMAG / 8; c += 32) {
                     const uint4 raw = *reinterpret_cast<const uint4 *>(&W.mag[c * 8]);
@@ -236,6 +242,10 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
         const int64_t d_tile0 = (int64_t)x0 - (int64_t)seg.lead;
         const uint32_t bt = d_tile0 > 0 ? (uint32_t)d_tile0 / seg.buf_len : 0;     // buffer of the tile's first position
         const int64_t bt_d0 = (int64_t)bt * seg.buf_len;
+        // the noise floors the tile's candidates are measured against: those of its first buffer and the next (a tile rarely reaches further),
+        // asked for now instead of once per batch of candidates
+        const uint32_t noise_b0 = bt < seg.n_bufs ? P.noise[seg.first_buf + bt] : 0u, noise_b1 = bt + 1 < seg.n_bufs ? P.noise[seg.first_buf + bt + 1] : 0u;
+        auto noise_of = [&](uint32_t brel) { return brel == 0 ? noise_b0 : brel == 1 ? noise_b1 : P.noise[seg.first_buf + bt + brel]; };
 
         // ---- window: rising edge and quiet third sample (demod_2400.c:630-640: m[-1] < m[0], m[2] <= m[0], m[2] <= m[1]) for every
         //      position of the tile and the 64 after it, two positions per step on packed halves -> one bit each in W.edge.
@@ -269,7 +279,9 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
         if (tile_next < seg_tile_end) {    // the next tile's samples (same segment: its descriptor is at hand) on their way into L2
             const int64_t xn = (int64_t)(tile_next - seg.tile_begin) * SCAN_TILE - AC2_BEHIND - (int64_t)seg.lead;      // its first sample, as a data index
             if (xn >= B200_TRAIL && xn + AC2_NMAG <= (int64_t)seg.npos + B200_TRAIL) {      // (memory the interior path of that tile reads anyway)
-                const uint8_t *pn = seg.base + 2 * xn;
+                const uint32_t xt = (tile_next - seg.tile_begin) * SCAN_TILE;
+                const uint8_t *pn = (!is_mag && P.mag_copy && xt + SCAN_TILE + AC2_AHEAD <= seg.n_tiles * SCAN_TILE)
+                                        ? reinterpret_cast<const uint8_t *>(P.mag_copy + ((size_t)seg.tile_begin * SCAN_TILE + xt - AC2_BEHIND)) : seg.base + 2 * xn;
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(pn + lane * 128));
                 if (lane < 2) asm volatile("prefetch.global.L2 [%0];" :: "l"(pn + 4096 + lane * 128));
             }
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
                         while (jj >= (int64_t)seg.buf_len) { jj -= seg.buf_len; b++; }
                         if (jj >= 1) {                                       // f1_sample runs from 1 (demod_2400.c:612)
                             jj32 = (uint32_t)jj; brel = b - bt;
-                            const uint32_t noise = P.noise[seg.first_buf + b];
+                            const uint32_t noise = noise_of(brel);
                             surv = ac_front(SmemMag{&W.mag[p + AC2_BEHIND]}, jj32, noise, &f1_clock, &f1f2);
                         }
                     }
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
                 if (n2 >= 32) {            // bit cells of 32 pooled survivors
                     const uint4 e = W.q2[lane];
                     const uint32_t ep = e.x & 0xffffu;
-                    if (ac_bits(SmemMag{&W.mag[ep + AC2_BEHIND]}, e.y, P.noise[seg.first_buf + bt + (e.x >> 16)], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[ep >> 5], 1u << (ep & 31));
+                    if (ac_bits(SmemMag{&W.mag[ep + AC2_BEHIND]}, e.y, noise_of(e.x >> 16), e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[ep >> 5], 1u << (ep & 31));
                     __syncwarp();
                     const uint4 mv = lane + 32 < n2 ? W.q2[lane + 32] : make_uint4(0, 0, 0, 0);
                     __syncwarp();
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(AC2_WARPS * 32, 1) modeac_scan_kernel(const Ac
             if (lane < n2) {
                 const uint4 e = W.q2[lane];
                 const uint32_t ep = e.x & 0xffffu;
-                if (ac_bits(SmemMag{&W.mag[ep + AC2_BEHIND]}, e.y, P.noise[seg.first_buf + bt + (e.x >> 16)], e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[ep >> 5], 1u << (ep & 31));
+                if (ac_bits(SmemMag{&W.mag[ep + AC2_BEHIND]}, e.y, noise_of(e.x >> 16), e.z, e.w) != 0xffffffffu) atomicOr(&W.bits[ep >> 5], 1u << (ep & 31));
             }
             __syncwarp();
         }

@@ -99,9 +99,7 @@ struct ScanSmem {                             // the read-only tables every warp
     uint32_t bit_syn[112];
     uint32_t syn_hash[512];
     uint32_t syn_mul;
-    // a tile shared between the warps of the CTA (small runs, finish_shared_tile): what each warp found, the tile's reservation
-    uint32_t sub_pos[TILE_CHUNKS], sub_rec[TILE_CHUNKS], sub_rec_off, sub_ok;
-    uint32_t pad_[1];
+    uint32_t pad_[3];
 };
 
 template <int NW> struct ScanSmemFull {
@@ -360,11 +358,14 @@ __device__ __forceinline__ void prefetch_raw(const RunCtx &T, uint32_t c, uint32
     }
 }
 
-__device__ __forceinline__ void store_mags(WarpSmem &W, uint32_t slot, int r, uint32_t lane, const uint32_t m[8]) {
+// keep: where the chunk's piece r of this lane goes in ScanParams::mag_copy, or null (Mode A/C off, a magnitude segment, or outside
+// the segment's tiles)
+__device__ __forceinline__ void store_mags(WarpSmem &W, uint32_t slot, int r, uint32_t lane, const uint32_t m[8], uint16_t *keep) {
     uint4 packed;
     packed.x = __byte_perm(m[0], m[1], 0x5410); packed.y = __byte_perm(m[2], m[3], 0x5410);      // lo | hi << 16 in one PRMT (magnitudes are < 65536)
     packed.z = __byte_perm(m[4], m[5], 0x5410); packed.w = __byte_perm(m[6], m[7], 0x5410);
     *reinterpret_cast<uint4 *>(&W.mag[slot * CHUNK + r * 256 + lane * 8]) = packed;
+    if (keep) __stcs(reinterpret_cast<uint4 *>(keep), packed);
     if (slot == 0 && r == 0 && lane < MAG_MIRROR / 8) *reinterpret_cast<uint4 *>(&W.mag[MAG_RING + lane * 8]) = packed;
 }
 
@@ -379,10 +380,18 @@ __device__ __forceinline__ void to_mags(const ScanSmem &S, bool is_mag, const ui
     }
 }
 
+// ScanParams::mag_copy address of sample (chunk cn, piece r, this lane's 8) of the run, or null when it is not kept.
+template <bool KEEP> __device__ __forceinline__ uint16_t *mag_keep_at(const WarpSmem &W, const ScanParams &P, uint32_t cn, int r, uint32_t lane) {
+    if (!KEEP || W.ctx.is_mag) return nullptr;
+    const Segment &seg = *reinterpret_cast<const Segment *>(W.seg);
+    const uint32_t x = W.ctx.x0 + cn * CHUNK + r * 256 + lane * 8;
+    return x < seg.n_tiles * SCAN_TILE ? P.mag_copy + ((size_t)seg.tile_begin * SCAN_TILE + x) : nullptr;
+}
+
 // Magnitudes of one chunk into ring slot `slot` + exact statistics (convert.c:64-108), chunk entirely data; if count_buf is a
 // reference buffer the whole chunk lies in it and is counted: lane partials -> warp sum -> one pair of atomics.
-__device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &W, const ScanParams &P, bool is_mag, uint32_t slot,
-                                                   uint32_t lane, uint32_t count_buf) {
+template <bool KEEP> __device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &W, const ScanParams &P, bool is_mag, uint32_t slot,
+                                                   uint32_t lane, uint32_t count_buf, uint32_t cn) {
     stage_wait();
     const uint4 raw0 = *reinterpret_cast<const uint4 *>(&W.raw[lane * 16]), raw1 = *reinterpret_cast<const uint4 *>(&W.raw[512 + lane * 16]);
     uint32_t level = 0;
@@ -394,7 +403,7 @@ __device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &
         level += (m[0] + m[1]) + (m[2] + m[3]) + (m[4] + m[5]) + (m[6] + m[7]);
 #pragma unroll
         for (int i = 0; i < 8; i++) mad_wide(power, m[i], m[i]);
-        store_mags(W, slot, r, lane, m);
+        store_mags(W, slot, r, lane, m, mag_keep_at<KEEP>(W, P, cn, r, lane));
     }
     if (count_buf != 0xffffffffu) {
         // hardware warp reductions (REDUX) instead of 15 shuffle steps: a lane's level is < 2^20, its power < 2^36, so the
@@ -408,7 +417,7 @@ __device__ __forceinline__ void convert_chunk_fast(const ScanSmem &S, WarpSmem &
 // The same for a chunk at the edge of the data or across a buffer boundary.  Power statistics are per reference buffer:
 // new sample n = x - lead - 326 belongs to buffer n / buf_len and is counted by the run whose position range holds x
 // (the last tile of a segment also owns the tail).
-__device__ __noinline__ void convert_chunk_edge(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t c, uint32_t slot, uint32_t lane) {
+template <bool KEEP> __device__ __noinline__ void convert_chunk_edge(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t c, uint32_t slot, uint32_t lane) {
     const RunCtx &T = W.ctx;
     const bool owned = c < T.n_chunks || T.last_tile;
     unsigned long long level = 0, power = 0;
@@ -441,7 +450,7 @@ __device__ __noinline__ void convert_chunk_edge(const ScanSmem &S, WarpSmem &W, 
                 }
             }
         }
-        store_mags(W, slot, r, lane, m);
+        store_mags(W, slot, r, lane, m, mag_keep_at<KEEP>(W, P, c, r, lane));
     }
     if (buf != 0xffffffffu) { atomicAdd(&P.buf_acc[buf].sum_level, level); atomicAdd(&P.buf_acc[buf].sum_power, power); }
 }
@@ -496,12 +505,12 @@ __device__ __forceinline__ void slice_round(const ScanSmem &S, WarpSmem &W, cons
 
 // Candidates of one chunk: its pre-check passers (q1, ascending) -> thresholds -> PosEntries; DF gate -> survivor queue,
 // sliced 32 at a time whenever the queue fills (the rest waits for later chunks of the run).
-__device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t n_q1, uint32_t chunk_p0, uint32_t mslot,
+template <bool SUB> __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t n_q1, uint32_t chunk_p0, uint32_t mslot,
                                                    uint32_t tslot, uint32_t lane, uint32_t &n_surv, uint32_t &n_stage) {
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t m = chunk_p0 / SCAN_TILE;                     // tile of the run this chunk belongs to
     PosEntry *pos_out = P.pos_pool + (size_t)(W.ctx.tile0 + m) * SCAN_TILE;
-    const uint32_t pe_base = ((chunk_p0 + W.ctx.sub_off) & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE);    // PosEntry position of chunk-local position 0
+    const uint32_t pe_base = ((chunk_p0 + (SUB ? W.ctx.sub_off : 0u)) & (SCAN_TILE - 1)) | (((W.ctx.tile_rel0 + m) & 3u) * SCAN_TILE);    // PosEntry position of chunk-local position 0
     const uint16_t *mag0 = &W.mag[mslot * CHUNK];
     // Threshold passers wait in W.pass (32 entries) until the chunk's last batch is through or the next batch's passers would
     // not fit: their DF gates are evaluated five lanes per passer, and a single batch rarely has more than three.
@@ -569,7 +578,11 @@ __device__ __forceinline__ void process_candidates(const ScanSmem &S, WarpSmem &
 // one warp would have produced.
 __device__ __forceinline__ void shared_tile_barrier(uint32_t n_warps) { asm volatile("bar.sync %0, %1;" :: "r"(1), "r"(n_warps * 32) : "memory"); }
 
-__device__ __noinline__ void finish_shared_tile(ScanSmem &S, WarpSmem &W, const ScanParams &P, uint32_t lane, uint32_t wid, uint32_t n_stage) {
+// (W0 = the first warp's area: a one-tile run uses entry 0 of its per-tile counters only, the others carry what the warps tell each other
+// here - nothing is added to the shared-memory layout of the whole-tile kernel)
+__device__ __noinline__ void finish_shared_tile(WarpSmem &W0, WarpSmem &W, const ScanParams &P, uint32_t lane, uint32_t wid, uint32_t n_stage) {
+    static_assert(RUN_MAX >= TILE_CHUNKS + 3, "exchange area of finish_shared_tile");
+    struct Exchange { uint32_t *sub_pos, *sub_rec; uint32_t &sub_rec_off, &sub_ok; } S = {&W0.n_pos[1], &W0.n_rec[1], W0.n_pos[TILE_CHUNKS + 1], W0.n_pos[TILE_CHUNKS + 2]};
     const RunCtx &T = W.ctx;
     const uint32_t n_warps = TILE_CHUNKS / P.sub_chunks, tile = T.tile0;
     PosEntry *tile_pos = P.pos_pool + (size_t)tile * SCAN_TILE;
@@ -622,7 +635,11 @@ __device__ __noinline__ void finish_shared_tile(ScanSmem &S, WarpSmem &W, const 
     if (wid == 0 && lane == 0) { TileOut t; t.n_pos = pos_tot; t.n_rec = ok ? rec_tot : 0; t.rec_off = off; t.n_found = rec_tot; P.tile_out[tile] = t; }
 }
 
-template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __grid_constant__ ScanParams P, const DeviceTables *__restrict__ tables) {
+// SUB: the launcher's small-run form, a tile shared between the warps of its CTA (finish_shared_tile).  KEEP: a Mode A/C context, the
+// magnitudes are also written to ScanParams::mag_copy.  Both are compile-time so that the plain kernel - the one the throughput is
+// measured on - carries nothing of either (measured with them as run-time tests: 4 - 6 % slower).
+template <int NW, bool SUB, bool KEEP> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __grid_constant__ ScanParams P, const DeviceTables *__restrict__ tables) {
+    const uint32_t sub_chunks = SUB ? P.sub_chunks : 0u;
     constexpr uint32_t SC_THREADS = NW * 32;
     extern __shared__ uint4 smem_raw[];
     ScanSmemFull<NW> &F = *reinterpret_cast<ScanSmemFull<NW> *>(smem_raw);
@@ -680,7 +697,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
             const Segment *sg = P.one_seg_valid ? &P.one_seg : &P.segs[P.tile_seg[pend_tile] & ~TILE_QUAD_START];
             W.seg[lane] = reinterpret_cast<const uint32_t *>(sg)[lane];
         }
-        if (lane < RUN_MAX) { W.n_pos[lane] = 0; W.n_rec[lane] = 0; }
+        if (lane < (SUB ? 1u : (uint32_t)RUN_MAX)) { W.n_pos[lane] = 0; W.n_rec[lane] = 0; }      // (SUB: the other entries of warp 0 are finish_shared_tile's exchange area)
         __syncwarp();
         uint32_t n_chunks;
         {
@@ -688,8 +705,8 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
             const uint32_t tile0 = pend_tile, n_tiles_run = min(pend_n, seg.tile_begin + seg.n_tiles - tile0);
             pend_tile += n_tiles_run; pend_n -= n_tiles_run;
             n_chunks = n_tiles_run * TILE_CHUNKS;
-            const uint32_t sub_off = P.sub_chunks ? wid * P.sub_chunks * CHUNK : 0u;  // a tile shared between warps: this warp's chunks of it
-            if (P.sub_chunks) n_chunks = P.sub_chunks;
+            const uint32_t sub_off = SUB ? wid * sub_chunks * CHUNK : 0u;             // a tile shared between warps: this warp's chunks of it
+            if (SUB) n_chunks = sub_chunks;
             if (lane == 0) {
                 const uint32_t x0 = (tile0 - seg.tile_begin) * SCAN_TILE + sub_off;   // run origin in tile coordinates (x = data index + lead)
                 T.x0 = x0; T.tile0 = tile0; T.n_tiles = n_tiles_run; T.n_chunks = n_chunks; T.tile_rel0 = tile0 - seg.tile_begin; T.sub_off = sub_off;
@@ -698,7 +715,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
                 T.x_data_end = seg.lead + seg.npos + B200_TRAIL;                      // first x without data
                 T.x_zero_end = (seg.flags & SEG_HALO_ZERO) ? seg.lead + B200_TRAIL : seg.lead;   // x below: magnitude 0, memory not read
                 T.is_mag = (seg.flags & SEG_MAG) ? 1u : 0u;
-                T.last_tile = tile0 + n_tiles_run == seg.tile_begin + seg.n_tiles && (!P.sub_chunks || sub_off + n_chunks * CHUNK == SCAN_TILE);
+                T.last_tile = tile0 + n_tiles_run == seg.tile_begin + seg.n_tiles && (!SUB || sub_off + n_chunks * CHUNK == SCAN_TILE);
                 const long long n_first = (long long)x0 - seg.lead - B200_TRAIL;
                 T.n_first = n_first;
                 T.buf_len = seg.buf_len; T.first_buf = seg.first_buf; T.npos = seg.npos;
@@ -771,16 +788,16 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
             if (more) { if (all_data) stage_raw(W, T.tile_base + (size_t)cn * CHUNK * 2, lane); else prefetch_raw(T, cn, lane); }
             __syncwarp();                                        // ticks of chunk k visible to the warp
             // ---- candidates(k-1) --------------------------------------------------------------------------------------
-            if (n_q1) process_candidates(S, W, P, n_q1, (uint32_t)(k - 1) * CHUNK, ms == 0 ? 2 : ms - 1, (uint32_t)(k - 1) & 1u, lane, n_surv, n_stage);
+            if (n_q1) process_candidates<SUB>(S, W, P, n_q1, (uint32_t)(k - 1) * CHUNK, ms == 0 ? 2 : ms - 1, (uint32_t)(k - 1) & 1u, lane, n_surv, n_stage);
             __syncwarp();                                        // chunk k-1's magnitudes are dead now
             // ---- convert(k+2) into the slot chunk k-1 occupied ------------------------------------------------------
             if (more) {
                 const uint32_t msn = k < 0 ? cn : (ms == 0 ? 2 : ms - 1);       // (ms + 2) % 3; the first two chunks fill slots 0 and 1
                 SCAN_COUNT(fast ? SCN_FAST_CONVERTS : SCN_EDGE_CONVERTS, 1);
-                if (fast) convert_chunk_fast(S, W, P, T.is_mag, msn, lane, count_buf);
+                if (fast) convert_chunk_fast<KEEP>(S, W, P, T.is_mag, msn, lane, count_buf, cn);
                 else {
                     if (all_data) stage_wait();      // staged, but this chunk straddles a buffer boundary: the edge path loads it itself
-                    convert_chunk_edge(S, W, P, cn, msn, lane);
+                    convert_chunk_edge<KEEP>(S, W, P, cn, msn, lane);
                 }
             }
             // ---- q1 <- pre-check passers of chunk k -------------------------------------------------------------------
@@ -807,7 +824,7 @@ template <int NW> __global__ void __maxnreg__(SC_MAXNREG) scan_kernel(const __gr
         const uint32_t tile0 = T.tile0, n_tiles_run = T.n_tiles;
         if (n_surv) slice_round(S, W, P, n_surv, lane, n_stage);
         __syncwarp();
-        if (P.sub_chunks) { finish_shared_tile(S, W, P, lane, wid, n_stage); break; }
+        if (SUB) { finish_shared_tile(F.w[0], W, P, lane, wid, n_stage); break; }
         uint32_t off = 0, ok = 1;
         if (lane == 0) {
             if (n_stage > P.stage_cap) { atomicOr(&P.ctl->overflow, 2u); atomicMax(&P.ctl->stage_need, n_stage); ok = 0; }   // host grows the staging areas and reruns
@@ -839,7 +856,12 @@ extern "C" int b200_scan_tick_words(void) { return TICKG_WORDS; }
 
 // Kernel attributes are per device: b200_demod_create calls this for the context's device (current at that point).
 extern "C" int b200_prepare_scan(void) {
-    return (int)cudaFuncSetAttribute(scan_kernel<SC_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemFull<SC_WARPS>));
+    const int bytes = (int)sizeof(ScanSmemFull<SC_WARPS>);
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<SC_WARPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_kernel<SC_WARPS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_kernel<SC_WARPS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_kernel<SC_WARPS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return (int)e;
 }
 
 template <int NW> static int launch_scan_t(const ScanParams *p, const DeviceTables *d_tables, int n_sm, cudaStream_t stream) {
@@ -856,7 +878,9 @@ template <int NW> static int launch_scan_t(const ScanParams *p, const DeviceTabl
         q.static_tiles = (grid == q.n_tiles) ? 1u : 0u;      // then warps_per_cta is 1: CTA b takes tile b ...
         if (q.static_tiles && (sub == 1 || sub == 2)) { q.sub_chunks = sub; q.warps_per_cta = TILE_CHUNKS / sub; }   // ... or its first warps share it (finish_shared_tile)
     }
-    scan_kernel<NW><<<grid, NW * 32, sizeof(ScanSmemFull<NW>), stream>>>(q, d_tables);
+    const size_t smem = sizeof(ScanSmemFull<NW>);
+    if (q.sub_chunks) { if (q.mag_copy) scan_kernel<NW, true, true><<<grid, NW * 32, smem, stream>>>(q, d_tables); else scan_kernel<NW, true, false><<<grid, NW * 32, smem, stream>>>(q, d_tables); }
+    else { if (q.mag_copy) scan_kernel<NW, false, true><<<grid, NW * 32, smem, stream>>>(q, d_tables); else scan_kernel<NW, false, false><<<grid, NW * 32, smem, stream>>>(q, d_tables); }
     return (int)cudaGetLastError();
 }
 

@@ -169,6 +169,7 @@ template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 template <class T> static inline T __ldcs(const T *p) { return *p; }
 template <class T> static inline void __stcg(T *p, T v) { *p = v; }
+template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 static inline size_t __cvta_generic_to_shared(const void *p) {
     const ptrdiff_t off = (const unsigned char *)p - emu_smem;
     if (off < 0 || (size_t)off >= emu_smem_bytes) { fprintf(stderr, "emu: __cvta_generic_to_shared of a pointer outside dynamic shared memory\n"); abort(); }
@@ -256,4 +257,4 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 
 // kernel<<<grid, block, smem, stream>>>(args...) becomes EMU_LAUNCH(grid, block, smem, kernel(args...))
 void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()> &body);
-#define EMU_LAUNCH(grid, block, smem, call) emu_launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [=]() { call; })
+#define EMU_LAUNCH(grid, block, smem, ...) emu_launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [=]() { __VA_ARGS__; })     // (variadic: template arguments bring commas)
