@@ -155,6 +155,29 @@ def test_random_buffer_sizes_fuzz(cuda, seed):
     d.close()
 
 
+@pytest.mark.parametrize("thr", [120, 200])
+def test_few_survivors_in_long_runs(cuda, thr):
+    """A high preamble threshold leaves so few DF-gate survivors that the pooled slices (32 at a time) wait for most of a
+    run, some until its end: the ticks they are cut from must still be the run's (scan_kernel.cu, the per-warp tick copy).
+    Two receivers with eight full buffers each: runs of many tiles per warp."""
+    from readsb_b200.demod import Demodulator
+    BUF, K = 65536, 8
+    d = Demodulator(n_streams=2, buf_samples=BUF, max_buffers_per_run=K, preamble_threshold=thr)
+    want = []
+    for s in range(2):
+        iq = synth.mixed_stream(5 + s, K * BUF, frames_per_sec=800)
+        o = Oracle(thr); want.append(o.run_stream(iq, BUF) + (o.stats(),))
+        for b in range(K):
+            d.submit_iq(s, iq[2 * b * BUF: 2 * (b + 1) * BUF], b * BUF * 5)
+    d.run()
+    for s in range(2):
+        fo, bo, so = want[s]
+        problems = diff_frames(d.frames(s), fo) + diff_bufres(d.buffer_results(s), bo) + diff_stats(d.stats(s), so)
+        assert not problems, f"receiver {s}\n" + "\n".join(problems)
+        assert len(fo) > 50
+    d.close()
+
+
 def test_filter_flip_on_the_stream_clock(cuda):
     """Two-generation ICAO filter flipped by stream time (readsb.c:1227-1231), with a short TTL so several flips happen."""
     from readsb_b200.demod import Demodulator
