@@ -566,6 +566,7 @@ template <bool SUB> __device__ __forceinline__ void process_candidates(const Sca
             n_pass += n_b;
         }
     }
+    __syncwarp();                                                // (every lane has read W.n_pos[m] above; compute-sanitizer's racecheck wants the fence, not just the ballots in between)
     if (lane == 0) W.n_pos[m] = pos_base;
 }
 

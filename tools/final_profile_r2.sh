@@ -27,3 +27,5 @@ timeout 200 python tools/gpu_latency.py > gpurun_out/r02_latency.json 2> gpurun_
 # 4. parity on this box: the gpu-marked tests, then 300 fuzz cases against the oracle on the hardware (tools/emu_fuzz.py without --emu)
 ( time timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 ) > gpurun_out/r02_pytest_gpu.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu.log
 timeout 900 python tools/emu_fuzz.py --seed 2024 --cases 300 2>&1 | tail -2 | tee gpurun_out/r02_hw_fuzz.txt
+# 5. compute-sanitizer (memcheck, racecheck, synccheck) over a selection of the gpu-marked tests
+bash tools/gpu_sanitize.sh
