@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,7 @@ struct Slot {
     uint32_t first_frames = 0;        // packed frames that came with the result block's copy
     uint32_t carry_in_kernel = 0xffffffffu;   // one-receiver host run: byte offset of the tail the stage B kernel carries to the front
     bool desc_on_device = true;       // false: this run's descriptors went as kernel parameters (b200_demod_fetch_beast uploads them if asked)
+    int scan_grid = 0;                // CTAs the scan kernel of this run was launched with
     bool published = false, timed = true;   // this run: results published by the kernel / events recorded between the kernels
 };
 
@@ -92,10 +94,26 @@ struct Slot {
 
 #define NSLOT 3      // steps in flight in the asynchronous modes; the blocking calls use slot 0
 
+// measurement of the scan's share of the SMs in a pipelined session (tune_partition)
+struct PartCal {
+    enum { SAMPLES = 12 };
+    int grids[4] = {0, 0, 0, 0};      // candidates: the whole chip, 85 %, 82 % of the SMs; [3] = the winner, measured again
+    int phase = 0, n = 0, skip = 0;
+    double dt[SAMPLES] = {}, mean[4] = {0, 0, 0, 0};
+    uint32_t ntile = 0;               // size of the runs being measured
+    std::chrono::steady_clock::time_point last;
+    bool have_last = false, locked = false;
+};
+
 struct b200_demod_ctx {
     b200_demod_config cfg;
     int device = 0, n_sm = 148;
     int n_sm_scan = 148;              // CTAs of the persistent scan kernel (one per SM) in blocking runs
+    // Pipelined steps: how the SMs are shared between the scan of step n+1 and stage B + finalizer of step n (tune_partition)
+    int part_n = 0;                   // CTAs of the scan kernel in pipelined runs; 0 = the whole chip (the two alternate on all SMs)
+    bool part_debug = false;
+    bool part_fixed = false, part_off = false;     // B200_SCAN_SMS given: no tuning; B200_SCAN_PART=0: always the whole chip
+    PartCal cal;
     int scan_sub = 1;                 // chunks per warp when a run is small enough for one CTA per tile (scan_kernel.cu, finish_shared_tile); B200_SCAN_SUB: 0 = whole tiles
     int n_sm_scan_async = 144;        // ... in pipelined runs: fewer than n_sm leaves SMs to stage B of the step before (B200_SCAN_SMS overrides both)
     cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
@@ -324,8 +342,9 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     c->n_sm_scan_async = c->n_sm;
     if (const char *e = getenv("B200_SCAN_SMS")) {       // experiment knob (tools/): in the pipelined modes the scan of step n+1 and stage B of
         const int v = atoi(e);                           // step n alternate on the SMs; a scan grid smaller than the chip lets them overlap
-        if (v >= 1 && v <= c->n_sm) c->n_sm_scan = c->n_sm_scan_async = v;
+        if (v >= 1 && v <= c->n_sm) { c->n_sm_scan = c->n_sm_scan_async = v; c->part_fixed = true; }
     }
+    if (const char *e = getenv("B200_SCAN_PART")) { c->part_off = atoi(e) == 0; c->part_debug = atoi(e) == 2; }
     if (const char *e = getenv("B200_SCAN_SUB")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->scan_sub = v; }     // experiment knob (tools/gpu_latency.py)
     {   // With several steps in flight the scan kernels of later steps are already queued when a scan ends; stage B of the step
         // that just finished scanning must not wait behind them (its results gate the host), so its stream has the higher
@@ -333,8 +352,9 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
         // the small finalize CTAs fit next to them.
         int prio_lo = 0, prio_hi = 0;
         CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUC(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_lo));
-        CUC(cudaStreamCreateWithPriority(&c->res_stream, cudaStreamNonBlocking, prio_hi));
+        const bool scan_first = getenv("B200_SCAN_PRIO") != nullptr;        // experiment knob (tools/gpu_partition.sh): the scan's stream gets the high priority
+        CUC(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, scan_first ? prio_hi : prio_lo));
+        CUC(cudaStreamCreateWithPriority(&c->res_stream, cudaStreamNonBlocking, scan_first ? prio_lo : prio_hi));
         CUC(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_lo));
         CUC(cudaStreamCreateWithPriority(&c->in_stream, cudaStreamNonBlocking, prio_lo));
     }
@@ -560,7 +580,8 @@ static int enqueue(b200_demod_ctx *c, Slot &sl, cudaStream_t scan, cudaStream_t 
     sp.long_set = (1u << 16) | (1u << 17) | (1u << 18) | (1u << 20) | (1u << 21);
     if (sp.nfix && sp.fixdf) for (int b = 0; b < 5; b++) sp.long_set |= 1u << (17 ^ (1 << b));
     if (timing) CU(c, cudaEventRecord(sl.ev[0], scan));
-    if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, scan != res ? c->n_sm_scan_async : c->n_sm_scan, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
+    sl.scan_grid = scan != res ? ((c->part_fixed || !c->part_n) ? c->n_sm_scan_async : c->part_n) : c->n_sm_scan;
+    if (sl.ntile) { int r = b200_launch_scan(&sp, c->d_tables, sl.scan_grid, scan); if (r) return fail(c, B200_E_CUDA, "scan launch: %s", cudaGetErrorString((cudaError_t)r)); sl.launches++; }
     if (timing) CU(c, cudaEventRecord(sl.ev[1], scan));
     if (res != scan) CU(c, cudaStreamWaitEvent(res, sl.ev[1], 0));
 
@@ -933,6 +954,56 @@ API int b200_demod_run_host_uc8_async(b200_demod_ctx *c, const uint8_t *h_iq, ui
     return launch_async(c, sl);
 }
 
+// Pipelined steps keep three kernels' worth of work in flight: the scan of step n+1 (one persistent CTA per SM, the whole SM each)
+// and stage B + finalizer of step n (one CTA of 8 warps per receiver, two per SM, latency-bound: a third of the issue slots).
+// Launched over the whole chip they take turns on all SMs.  With a scan grid smaller than the chip the scan runs back to back on
+// its SMs and stage B lives on the rest, in several waves.  Measured on 148 SMs (tools/gpu_partition.sh, bench workload, ms per
+// launch): 148 -> 0.488, 140 -> 0.507, 132 -> 0.520 (stage B does not fit into what is left and holds the scans up: worse than
+// taking turns), 126 -> 0.469, 124 -> 0.476, 120 -> 0.490 (it fits: the step costs what the scan costs on its SMs); the dense
+// stress: 148 -> 1.140, 126 -> 1.232 (stage B is a third of the step there and wants the whole chip).  Where the edge lies depends
+// on the workload, and the kernels' event times say little while they overlap, so a pipelined session MEASURES it: after its first
+// steps it runs with the whole chip, then with 85 % and 82 % of the SMs for the scan (twelve step periods each: host clock between
+// completed steps, the longest dropped), measures the winner once more and keeps it - the whole chip unless a partition wins by
+// 1.5 % and again by 1 %.  A run of a different size (tiles +- 1/8) starts over.
+static void tune_partition(b200_demod_ctx *c, Slot &sl) {
+    if (c->part_fixed || c->part_off || (c->cfg.flags & B200_CFG_MODE_AC) || !sl.ntile || c->n_sm < 16) return;
+    PartCal &k = c->cal;
+    const auto now = std::chrono::steady_clock::now();
+    if (!k.grids[0]) { k.grids[0] = c->n_sm; k.grids[1] = (c->n_sm * 85 + 50) / 100; k.grids[2] = (c->n_sm * 82 + 50) / 100; k.grids[3] = c->n_sm; k.skip = 8; }
+    if (k.locked) {
+        const uint32_t d = sl.ntile > k.ntile ? sl.ntile - k.ntile : k.ntile - sl.ntile;
+        if (d * 8 > k.ntile) { k = PartCal(); c->part_n = 0; }         // another workload: measure again
+        return;
+    }
+    const double dt = k.have_last ? std::chrono::duration<double, std::milli>(now - k.last).count() : 0.0;
+    const bool first = !k.have_last;
+    k.last = now; k.have_last = true;
+    if (first || sl.scan_grid != k.grids[k.phase]) { if (k.skip < 2) k.skip = 2; return; }     // a step launched before the grid was switched
+    if (k.n == 0 && !k.skip) k.ntile = sl.ntile;
+    if (k.skip) { k.skip--; return; }                     // (the session's first steps, the first periods with a new grid: not steady yet)
+    if (sl.ntile != k.ntile) { k.n = 0; return; }          // the size changed in the middle of a measurement: start this phase over
+    k.dt[k.n++] = dt;
+    if (k.n < PartCal::SAMPLES) return;
+    std::sort(k.dt, k.dt + PartCal::SAMPLES);
+    double sum = 0;
+    for (int i = 0; i < PartCal::SAMPLES - 1; i++) sum += k.dt[i];           // (the longest one may hold a pause of the caller)
+    k.mean[k.phase] = sum / (PartCal::SAMPLES - 1);
+    k.n = 0; k.phase++;
+    if (k.phase < 3) { c->part_n = k.grids[k.phase]; return; }
+    if (k.phase == 3) {                                    // candidates measured: the better partition, if it wins by 1.5 %, is measured once more
+        int best = 0;
+        for (int i = 1; i < 3; i++) if (k.mean[i] < 0.985 * k.mean[0] && (best == 0 || k.mean[i] < k.mean[best])) best = i;
+        k.grids[3] = k.grids[best];
+        c->part_n = best ? k.grids[best] : 0;
+        if (best) return;
+        k.mean[3] = k.mean[0];
+    }
+    if (k.mean[3] >= 0.99 * k.mean[0]) c->part_n = 0;      // ... and kept only if it wins again
+    k.locked = true;
+    if (c->part_debug) fprintf(stderr, "b200 partition: %u tiles: step period %.4f ms on %d SMs, %.4f on %d, %.4f on %d, again %.4f on %d -> scan grid %d\n", k.ntile,
+                               k.mean[0], k.grids[0], k.mean[1], k.grids[1], k.mean[2], k.grids[2], k.mean[3], k.grids[3], c->part_n ? c->part_n : c->n_sm);
+}
+
 API int b200_demod_wait(b200_demod_ctx *c) {
     if (!c) return B200_E_INVAL;
     CU(c, cudaSetDevice(c->device));
@@ -958,6 +1029,7 @@ API int b200_demod_wait(b200_demod_ctx *c) {
             }
         }
     }
+    if (rc == B200_OK && !sl.completed) tune_partition(c, sl);
     sl.in_flight = false;
     c->head = (idx + 1) % NSLOT;
     c->n_flight--;

@@ -649,8 +649,11 @@ __device__ __forceinline__ void finalize_frames(const FinalizeParams &P, uint32_
 
 // Receivers with grown tables (BIG) are rare: they get an instantiation of their own, launched only when there is one, so that
 // the common case does not share its register allocation; each CTA of either launch leaves the other kind alone.
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 2         // CTAs per SM the register allocation aims at (128 registers; 3 -> 85: see DESIGN.md 6, SM partition experiment)
+#endif
 template <bool BIG>
-__global__ void __launch_bounds__(RS_WARPS * 32, 2) resolve_kernel(const ResolveParams P) {
+__global__ void __launch_bounds__(RS_WARPS * 32, RS_MIN_CTAS) resolve_kernel(const ResolveParams P) {
     extern __shared__ uint4 resolve_smem_raw[];
     ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(resolve_smem_raw);
     const uint32_t stream = blockIdx.x;

@@ -211,6 +211,40 @@ def test_async_pipeline_matches_oracle(cuda, depth):
     d.close()
 
 
+def test_long_pipelined_session_stays_exact_while_the_sm_partition_is_measured(cuda):
+    """A pipelined session measures how many SMs the scan should take (whole chip / 85 % / 82 %, demod_api.cu tune_partition):
+    the scan grid changes between steps during the first ~60 of them, and once more when the size of the runs changes.  Grid
+    size is a launch parameter only - every step's frames must be the oracle's.  90 steps of 8192 samples, then 20 of two buffers."""
+    from readsb_b200.demod import Demodulator
+    S, buf = 3, 8192
+    calls_a, calls_b = 90, 20
+    total = buf * (calls_a + 2 * calls_b)
+    iqs = [synth.mixed_stream(4100 + s, total, frames_per_sec=3000) for s in range(S)]
+    dev, stride, pad = _device_streams(iqs, total)
+    d = Demodulator(n_streams=S, buf_samples=buf, max_buffers_per_run=2)
+    got = [[] for _ in range(S)]; gotb = [[] for _ in range(S)]
+
+    def collect():
+        d.wait()
+        for s in range(S):
+            got[s].append(d.frames(s)); gotb[s].append(d.buffer_results(s))
+    flying, off = 0, 0
+    for c in range(calls_a + calls_b):
+        nb = 1 if c < calls_a else 2
+        d.run_device_async(dev.data_ptr() + pad + off * 2, stride, nb, buf, continues=c > 0, first_sample_timestamp=off * 5)
+        off += nb * buf
+        flying += 1
+        if flying == 3:
+            collect(); flying -= 1
+    while flying:
+        collect(); flying -= 1
+    for s in range(S):
+        o = Oracle()
+        fo, bo = o.run_stream(iqs[s], buf)
+        _check(d, o, np.concatenate(got[s]), np.concatenate(gotb[s]), fo, bo, stream=s)
+    d.close()
+
+
 def test_host_async_pipeline_matches_oracle(cuda):
     """run_host_uc8_async / wait: pinned host slabs, the copy of step n+1 overlapping the kernels of step n; halo carried
     between the two library-owned input buffers; unpinned memory and a restart (continues=0) in the middle."""
