@@ -451,7 +451,8 @@ def dense_leg(local, args, hbm_peak):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ev0.record()
-        for k in range(phase * 1000, phase * 1000 + (12 if phase == 0 else n_launch)):
+        # (warm-up: long enough for the pipelined session to have measured its SM partition, ~70 steps - demod_api.cu tune_partition)
+        for k in range(phase * 1000, phase * 1000 + (96 if phase == 0 else n_launch)):
             go_async(k); flying += 1
             if flying == PIPE_DEPTH:
                 d.wait(); flying -= 1; frames += d.total_frames() if phase else 0
