@@ -115,7 +115,7 @@ struct b200_demod_ctx {
     bool part_fixed = false, part_off = false;     // B200_SCAN_SMS given: no tuning; B200_SCAN_PART=0: always the whole chip
     PartCal cal;
     int scan_sub = 1;                 // chunks per warp when a run is small enough for one CTA per tile (scan_kernel.cu, finish_shared_tile); B200_SCAN_SUB: 0 = whole tiles
-    int n_sm_scan_async = 144;        // ... in pipelined runs: fewer than n_sm leaves SMs to stage B of the step before (B200_SCAN_SMS overrides both)
+    int n_sm_scan_async = 148;        // ... in pipelined runs, unless the session's measurement chose fewer (part_n, tune_partition) or B200_SCAN_SMS fixed it
     cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
     std::string err;
 
@@ -336,12 +336,11 @@ API int b200_demod_create(const b200_demod_config *cfg, b200_demod_ctx **out) {
     if (prop.major < 10) { fail(nullptr, B200_E_NODEV, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor); b200_demod_destroy(c); return B200_E_NODEV; }
     c->n_sm = prop.multiProcessorCount;
     c->n_sm_scan = c->n_sm;
-    // Pipelined steps could leave a few SMs to stage B + finalize of the step before (B200_SCAN_SMS).  Measured on 148 SMs with this
-    // code: 148 -> 0.492, 146 -> 0.494, 144 -> 0.498, 140 -> 0.507 ms per launch (tools/gpu_scan_sms.sh): the whole chip for the scan wins
-    // since stage B got shorter; with round 1's stage B it was 148 -> 0.519, 144 -> 0.472.
+    // Pipelined steps start with the whole chip for the scan; the session then measures whether a smaller grid - stage B + finalizer
+    // of the step before on the remaining SMs - is faster (tune_partition).  B200_SCAN_SMS fixes the grid of both kinds of run.
     c->n_sm_scan_async = c->n_sm;
-    if (const char *e = getenv("B200_SCAN_SMS")) {       // experiment knob (tools/): in the pipelined modes the scan of step n+1 and stage B of
-        const int v = atoi(e);                           // step n alternate on the SMs; a scan grid smaller than the chip lets them overlap
+    if (const char *e = getenv("B200_SCAN_SMS")) {       // experiment knob (tools/gpu_partition.sh)
+        const int v = atoi(e);
         if (v >= 1 && v <= c->n_sm) { c->n_sm_scan = c->n_sm_scan_async = v; c->part_fixed = true; }
     }
     if (const char *e = getenv("B200_SCAN_PART")) { c->part_off = atoi(e) == 0; c->part_debug = atoi(e) == 2; }
