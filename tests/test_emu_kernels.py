@@ -20,8 +20,8 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def _run_gpu_tests_emulated(*modules: str, timeout: int = 900, sanitize: str | None = None, select: str | None = None,
-                            sched_seed: int | None = None) -> str:
-    env = dict(os.environ, B200_EMU="1")
+                            sched_seed: int | None = None, extra_env: dict | None = None) -> str:
+    env = dict(os.environ, B200_EMU="1", **(extra_env or {}))
     if sched_seed is not None:
         env["B200_EMU_SCHED_SEED"] = str(sched_seed)
     env.pop("B200_DEMOD_LIB", None)
@@ -37,6 +37,8 @@ def _run_gpu_tests_emulated(*modules: str, timeout: int = 900, sanitize: str | N
         env["ASAN_OPTIONS"] = "detect_leaks=0:detect_stack_use_after_return=0"      # fibers switch stacks by hand
         env["UBSAN_OPTIONS"] = "halt_on_error=1:print_stacktrace=0"
         cmd += ["-s"]                                                                # a sanitizer report must reach our pipe
+    elif extra_env:
+        cmd += ["-s"]                                                                # ... and so must what the library prints when asked to
     res = subprocess.run(cmd, cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=timeout)
     tail = (res.stdout + res.stderr)[-3000:]
     assert res.returncode == 0, "gpu-marked tests failed against the emulated kernels:\n" + tail
@@ -82,6 +84,15 @@ def test_parity_does_not_depend_on_the_order_lanes_and_warps_run_in(seed):
     """The emulator's default schedule runs lane 0 first and warp 0 first; here every scheduling round uses a fresh random order
     of the CTA's fibers (lanes within a warp, warps within the CTA) — code that leans on the default order fails."""
     _run_gpu_tests_emulated("tests/test_gpu_parity.py", "tests/test_gpu_edges.py", sched_seed=seed)
+
+
+def test_pipelined_session_measures_its_sm_partition_on_a_larger_emulated_chip():
+    """The host code that measures a pipelined session's SM partition (demod_api.cu tune_partition) only runs on chips with
+    at least 16 SMs: a 20-SM emulated device takes the long-session test through its phases - whole chip, 85 %, 82 %, the
+    decision, and the new measurement when the size of the runs changes (the periods themselves mean nothing here) - and the
+    asynchronous tests through changing scan grids, all still bit-exact."""
+    out = _run_gpu_tests_emulated("tests/test_gpu_parity.py", select="long_pipelined or async_pipeline_matches", extra_env={"B200_EMU_SMS": "20", "B200_SCAN_PART": "2"})
+    assert "passed" in out and "b200 partition: 15 tiles" in out and "-> scan grid" in out, out
 
 
 def test_every_allocation_failure_is_reported_not_fatal():
