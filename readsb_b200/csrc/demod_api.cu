@@ -114,6 +114,7 @@ struct b200_demod_ctx {
     bool part_debug = false;
     bool part_fixed = false, part_off = false;     // B200_SCAN_SMS given: no tuning; B200_SCAN_PART=0: always the whole chip
     PartCal cal;
+    int cal_restarts = 0;
     int scan_sub = 1;                 // chunks per warp when a run is small enough for one CTA per tile (scan_kernel.cu, finish_shared_tile); B200_SCAN_SUB: 0 = whole tiles
     int n_sm_scan_async = 148;        // ... in pipelined runs, unless the session's measurement chose fewer (part_n, tune_partition) or B200_SCAN_SMS fixed it
     cudaStream_t stream = nullptr, own_stream = nullptr, res_stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
@@ -963,7 +964,7 @@ API int b200_demod_run_host_uc8_async(b200_demod_ctx *c, const uint8_t *h_iq, ui
 // on the workload, and the kernels' event times say little while they overlap, so a pipelined session MEASURES it: after its first
 // steps it runs with the whole chip, then with 85 % and 82 % of the SMs for the scan (twelve step periods each: host clock between
 // completed steps, the longest dropped), measures the winner once more and keeps it - the whole chip unless a partition wins by
-// 1.5 % and again by 1 %.  A run of a different size (tiles +- 1/8) starts over.
+// 1.5 % and again by 1 %.  A run of a different size (tiles +- 1/8) starts over, up to four times per session.
 static void tune_partition(b200_demod_ctx *c, Slot &sl) {
     if (c->part_fixed || c->part_off || (c->cfg.flags & B200_CFG_MODE_AC) || !sl.ntile || c->n_sm < 16) return;
     PartCal &k = c->cal;
@@ -971,7 +972,10 @@ static void tune_partition(b200_demod_ctx *c, Slot &sl) {
     if (!k.grids[0]) { k.grids[0] = c->n_sm; k.grids[1] = (c->n_sm * 85 + 50) / 100; k.grids[2] = (c->n_sm * 82 + 50) / 100; k.grids[3] = c->n_sm; k.skip = 8; }
     if (k.locked) {
         const uint32_t d = sl.ntile > k.ntile ? sl.ntile - k.ntile : k.ntile - sl.ntile;
-        if (d * 8 > k.ntile) { k = PartCal(); c->part_n = 0; }         // another workload: measure again
+        if (d * 8 > k.ntile) {                                          // another workload: measure again - a few times; a session whose
+            k = PartCal(); c->part_n = 0;                               // runs keep changing size stays with the whole chip
+            if (++c->cal_restarts > 4) c->part_off = true;
+        }
         return;
     }
     const double dt = k.have_last ? std::chrono::duration<double, std::milli>(now - k.last).count() : 0.0;
