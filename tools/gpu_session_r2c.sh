@@ -2,7 +2,7 @@
 # Round 2, third measurement session: A/B of the scan kernel against the build before the shared-tile change (same box, alternating),
 # Mode A/C with the Mode S scan's magnitudes.
 mkdir -p gpurun_out
-OLD=tools/_ab/libb200demod_f0af209.so
+OLD=${1:?path of the library build to compare with}
 for i in 1 2; do
   echo "--- new"; timeout 100 python tools/gpu_scan_probe.py 2>&1 | tail -4
   echo "--- old"; B200_DEMOD_LIB=$OLD timeout 100 python tools/gpu_scan_probe.py 2>&1 | tail -4

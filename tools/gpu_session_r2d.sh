@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2: A/B of the working tree against a variant build of the library (default: the build before the shared-tile change), same box, alternating.
 mkdir -p gpurun_out
-V=${1:-tools/_ab/libb200demod_f0af209.so}
+V=${1:?path of the variant build of libb200demod.so (readsb_b200.build.build_demod(defines=..., out=...))}
 for i in 1 2; do
   echo "--- head";  timeout 100 python tools/gpu_scan_probe.py 2>&1 | tail -4
   echo "--- variant"; B200_DEMOD_LIB=$V timeout 100 python tools/gpu_scan_probe.py 2>&1 | tail -4
